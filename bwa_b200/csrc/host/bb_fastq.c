@@ -1,0 +1,145 @@
+/* bb_fastq.c -- FASTA/FASTQ (optionally gzip'd) batch reader behind bseq_read (reference bwa.c:79-112,
+ * grammar of kseq.h:175-215): header '>'/'@', name up to the first white space, rest of the line is the
+ * comment, sequence may span lines, '+' line, quality may span lines and must match the sequence length.
+ */
+#include <zlib.h>
+#include <ctype.h>
+#include "bb_host.h"
+
+struct bb_fq {
+	gzFile fp;
+	unsigned char *buf;
+	int beg, end, eof;
+	int pending_hdr;          /* header character already consumed ('>' or '@'), or 0 */
+	bb_str_t name, comment, seq, qual;
+};
+
+#define FQ_BUFSZ (1 << 20)
+
+bb_fq_t *bb_fq_open(const char *fn)
+{
+	bb_fq_t *f = bb_calloc(1, sizeof(*f));
+	f->fp = strcmp(fn, "-") == 0 ? gzdopen(0, "r") : gzopen(fn, "r");
+	if (!f->fp) { free(f); return 0; }
+	gzbuffer(f->fp, 1 << 18);
+	f->buf = bb_malloc(FQ_BUFSZ);
+	return f;
+}
+
+void bb_fq_close(bb_fq_t *f)
+{
+	if (!f) return;
+	gzclose(f->fp);
+	free(f->buf); free(f->name.s); free(f->comment.s); free(f->seq.s); free(f->qual.s);
+	free(f);
+}
+
+static inline int fq_fill(bb_fq_t *f)
+{
+	if (f->eof) return 0;
+	f->beg = 0;
+	f->end = gzread(f->fp, f->buf, FQ_BUFSZ);
+	if (f->end <= 0) { f->end = 0; f->eof = 1; return 0; }
+	return 1;
+}
+
+static inline int fq_getc(bb_fq_t *f)
+{
+	if (f->beg >= f->end && !fq_fill(f)) return -1;
+	return f->buf[f->beg++];
+}
+
+/* append bytes up to (not including) the delimiter: '\n' when line!=0, else any white space.
+ * Returns -1 if nothing could be read at EOF, else the new length; *dret = delimiter met (0 at EOF). */
+static int fq_until(bb_fq_t *f, int line, bb_str_t *s, int *dret, int append)
+{
+	int any = 0;
+	if (dret) *dret = 0;
+	if (!append) s->l = 0;
+	for (;;) {
+		int i;
+		if (f->beg >= f->end && !fq_fill(f)) break;
+		if (line) { unsigned char *p = memchr(f->buf + f->beg, '\n', f->end - f->beg); i = p ? (int)(p - f->buf) : f->end; }
+		else for (i = f->beg; i < f->end && !isspace(f->buf[i]); ++i) {}
+		any = 1;
+		bb_putsn(s, (char *)f->buf + f->beg, (size_t)(i - f->beg));
+		f->beg = i + 1;
+		if (i < f->end) { if (dret) *dret = f->buf[i]; break; }
+	}
+	if (!any && f->eof) return -1;
+	bb_str_need(s, 1);
+	if (line && s->l > 1 && s->s[s->l - 1] == '\r') --s->l;
+	s->s[s->l] = 0;
+	return (int)s->l;
+}
+
+/* >=0 sequence length; -1 end of file; -2 truncated quality */
+static int fq_next(bb_fq_t *f)
+{
+	int c;
+	if (f->pending_hdr == 0) {
+		while ((c = fq_getc(f)) != -1 && c != '>' && c != '@') {}
+		if (c == -1) return -1;
+		f->pending_hdr = c;
+	}
+	f->comment.l = f->seq.l = f->qual.l = 0;
+	if (fq_until(f, 0, &f->name, &c, 0) < 0) return -1;
+	if (c != '\n') fq_until(f, 1, &f->comment, 0, 0);
+	bb_str_need(&f->seq, 256);
+	while ((c = fq_getc(f)) != -1 && c != '>' && c != '+' && c != '@') {
+		if (c == '\n') continue;
+		bb_putc(&f->seq, c);
+		fq_until(f, 1, &f->seq, 0, 1);
+	}
+	if (c == '>' || c == '@') f->pending_hdr = c;
+	f->seq.s[f->seq.l] = 0;
+	if (c != '+') return (int)f->seq.l;
+	while ((c = fq_getc(f)) != -1 && c != '\n') {}
+	if (c == -1) return -2;
+	while (fq_until(f, 1, &f->qual, 0, 1) >= 0 && f->qual.l < f->seq.l) {}
+	f->pending_hdr = 0;
+	if (f->seq.l != f->qual.l) return -2;
+	return (int)f->seq.l;
+}
+
+static char *dup_str(const bb_str_t *s, int dup_empty)
+{
+	char *p;
+	if (s->l == 0 && !dup_empty) return 0;
+	p = bb_malloc(s->l + 1);
+	if (s->l) memcpy(p, s->s, s->l);
+	p[s->l] = 0;
+	return p;
+}
+
+static void take_record(bb_fq_t *f, bseq1_t *s, int id)
+{
+	if (f->name.l > 2 && f->name.s[f->name.l - 2] == '/' && isdigit((unsigned char)f->name.s[f->name.l - 1])) { f->name.l -= 2; f->name.s[f->name.l] = 0; }
+	s->name = dup_str(&f->name, 1);
+	s->comment = dup_str(&f->comment, 0);
+	s->seq = dup_str(&f->seq, 1);
+	s->qual = dup_str(&f->qual, 0);
+	s->l_seq = (int)f->seq.l;
+	s->sam = 0;
+	s->id = id;
+}
+
+bseq1_t *bseq_read(int chunk_size, int *n_, void *ks1_, void *ks2_)
+{
+	bb_fq_t *f1 = ks1_, *f2 = ks2_;
+	int size = 0, m = 0, n = 0;
+	bseq1_t *seqs = 0;
+	while (fq_next(f1) >= 0) {
+		if (f2 && fq_next(f2) < 0) {
+			fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", __func__);
+			break;
+		}
+		if (n + 2 > m) { m = m ? m << 1 : 256; seqs = bb_realloc(seqs, (size_t)m * sizeof(bseq1_t)); }
+		take_record(f1, &seqs[n], n); size += seqs[n++].l_seq;
+		if (f2) { take_record(f2, &seqs[n], n); size += seqs[n++].l_seq; }
+		if (size >= chunk_size && (n & 1) == 0) break;
+	}
+	if (size == 0 && f2 && fq_next(f2) >= 0) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", __func__);
+	*n_ = n;
+	return seqs;
+}

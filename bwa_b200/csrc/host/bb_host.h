@@ -1,0 +1,117 @@
+/* bb_host.h -- internal interfaces of the host glue of libbwa_b200 (C).
+ *
+ * The host side keeps what the reference keeps per read around its kernels: chaining and chain
+ * filtering, region de-duplication, primary marking, MAPQ, pairing and SAM text.  Everything that
+ * walks the FM-index or fills a DP matrix is behind include/bwa_b200_dev.h (CUDA).
+ */
+#ifndef BB_HOST_H
+#define BB_HOST_H
+
+#include "bwa_b200.h"
+#include "bwa_b200_dev.h"
+#include "bb_util.h"
+#include "bb_str.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- sequence / coordinate helpers (bb_index.c) ---- */
+extern unsigned char bb_nt4_table[256];
+static inline int bb_pac_get(const uint8_t *pac, int64_t k) { return pac[k >> 2] >> ((~k & 3) << 1) & 3; }
+static inline int64_t bb_depos(const bntseq_t *bns, int64_t pos, int *is_rev)
+{
+	*is_rev = pos >= bns->l_pac;
+	return *is_rev ? (bns->l_pac << 1) - 1 - pos : pos;
+}
+int bb_pos2rid(const bntseq_t *bns, int64_t pos_f);
+int bb_intv2rid(const bntseq_t *bns, int64_t rb, int64_t re);
+uint8_t *bb_get_seq(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, int64_t *len);
+uint8_t *bb_fetch_seq(const bntseq_t *bns, const uint8_t *pac, int64_t *beg, int64_t mid, int64_t *end, int *rid);
+void bb_clamp_to_contig(const bntseq_t *bns, int64_t *beg, int64_t mid, int64_t *end, int *rid);
+
+/* ---- device residency keyed by host index pointer (bb_process.c) ---- */
+bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac);
+void bb_device_release(const bwt_t *bwt);
+
+/* ---- chaining (bb_chain.c) ---- */
+typedef struct { int64_t rbeg; int32_t qbeg, len; int score; } bb_seed_t;
+typedef struct {
+	int n, m, first, rid;
+	uint32_t w, kept, is_alt;
+	float frac_rep;
+	int64_t pos;
+	bb_seed_t *seeds;
+} bb_chain_t;
+typedef BB_VEC(bb_chain_t) bb_chain_v;
+
+typedef struct bb_chainer bb_chainer_t; /* per-thread scratch: ordered map + seed arena */
+bb_chainer_t *bb_chainer_new(void);
+void bb_chainer_free(bb_chainer_t *c);
+/* Chains of one read from its sorted SA intervals and their suffix-array positions.  Output chains
+ * (and their seed arrays) live in the chainer's arena until the next call. */
+void bb_chain_build(bb_chainer_t *c, const mem_opt_t *opt, const bntseq_t *bns, int l_query,
+                    int n_intv, const bwtintv_t *intv, const int64_t *seed_off, const int64_t *rbeg, bb_chain_v *out);
+int bb_chain_weight(const bb_chain_t *c);
+int bb_chain_filter(const mem_opt_t *opt, int n, bb_chain_t *a);
+void bb_chain_seed_sw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, int n, bb_chain_t *a);
+int bb_cal_max_gap(const mem_opt_t *opt, int qlen);
+
+/* ---- local Smith-Waterman used by mate rescue and seed filtering (bb_localsw.c) ---- */
+#define BB_SW_XBYTE  0x10000
+#define BB_SW_XSTOP  0x20000
+#define BB_SW_XSUBO  0x40000
+#define BB_SW_XSTART 0x80000
+typedef struct { int score, te, qe, score2, te2, tb, qb; } bb_swr_t;
+bb_swr_t bb_local_sw(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int xtra);
+
+/* ---- global-alignment service with memoisation (bb_process.c) ---- */
+typedef struct {
+	int64_t rb, re;
+	int32_t qb, qe, w, truesc, mode;
+	int32_t score, n_cigar, NM, l_md;
+	uint32_t *cigar; /* malloc'd: n_cigar ops followed by the MD string */
+	int done;
+} bb_galn_t;
+typedef BB_VEC(bb_galn_t) bb_galn_v;
+/* Look up / request an alignment for a read.  Returns the cached entry, or NULL after recording the
+ * request (the caller then abandons this read's current pass; it is re-run after the next device round). */
+typedef struct {
+	bb_galn_v memo;
+	int pending;     /* requests recorded in this pass */
+} bb_gcache_t;
+const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc);
+
+/* ---- regions (bb_reg.c) ---- */
+int bb_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, int l_query, int n, mem_alnreg_t *a);
+int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id);
+void bb_reorder_primary5(int T, mem_alnreg_v *a);
+int bb_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a);
+
+/* ---- SAM (bb_sam.c) ---- */
+typedef struct {
+	const mem_opt_t *opt;
+	const bntseq_t *bns;
+	const uint8_t *pac;
+	bb_gcache_t *gc;   /* of the read being formatted */
+	int dry;           /* pass that only discovers which alignments are needed: skip text */
+} bb_samctx_t;
+mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query, const mem_alnreg_t *ar);
+void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_t *s, int n, const mem_aln_t *list, int which, const mem_aln_t *m_);
+void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, const mem_aln_t *m);
+char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const char *query);
+
+/* ---- paired-end (bb_pair.c) ---- */
+int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a, int l_ms, const uint8_t *ms, mem_alnreg_v *ma);
+int bb_sam_pe(bb_samctx_t sc[2], const mem_pestat_t pes[4], uint64_t id, bseq1_t s[2], mem_alnreg_v a[2], int rescue_done);
+int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], bseq1_t s[2], mem_alnreg_v a[2]);
+
+/* ---- FASTA/FASTQ input (bb_fastq.c) ---- */
+typedef struct bb_fq bb_fq_t;
+bb_fq_t *bb_fq_open(const char *fn);
+void bb_fq_close(bb_fq_t *f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

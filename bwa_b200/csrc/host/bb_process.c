@@ -1,0 +1,539 @@
+/* bb_process.c -- mem_process_seqs: the drop-in boundary (reference bwamem.c:1191-1264).
+ *
+ * The reference runs, per read and on a CPU thread, seeding -> chaining -> extension -> (PE stats) ->
+ * CIGAR -> SAM.  Here a batch goes through the same stages, but every stage that walks the FM-index
+ * or fills a DP matrix is ONE device call for the whole batch (include/bwa_b200_dev.h):
+ *
+ *   host  encode reads to 0..4 codes in place (bwamem.c:1087), pack, upload
+ *   GPU   bwag_seed    : SMEM intervals + suffix-array positions of every read
+ *   host  chain, filter chains (bb_chain.c), lay out extension work             [threads]
+ *   GPU   bwag_extend  : mem_chain2aln loops with banded extension
+ *   host  dedup/patch regions (bb_reg.c), insert-size model, mate rescue        [threads]
+ *   GPU   bwag_global  : banded global alignment -> CIGAR/NM/MD (as many rounds as the host asks)
+ *   host  MAPQ, pairing, SAM text (bb_sam.c, bb_pair.c)                          [threads]
+ *
+ * Host steps that need a global alignment (mem_patch_reg, mem_reg2aln) look it up in a per-read
+ * cache; a miss records a request and abandons that read's pass, and the pass is repeated after the
+ * device has served all requests of the batch.  There is no CPU implementation of the device stages.
+ */
+#include <pthread.h>
+#include <assert.h>
+#include <math.h>
+#include "bb_host.h"
+
+/* ---------------------------------------------------------------- device residency */
+typedef struct { const bwt_t *bwt; bwag_ctx_t *ctx; } dev_slot_t;
+static dev_slot_t g_dev[8];
+static pthread_mutex_t g_dev_mu = PTHREAD_MUTEX_INITIALIZER;
+
+bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
+{
+	int i;
+	bwag_ctx_t *ctx = 0;
+	pthread_mutex_lock(&g_dev_mu);
+	for (i = 0; i < 8; ++i) if (g_dev[i].bwt == bwt && g_dev[i].ctx) { ctx = g_dev[i].ctx; break; }
+	if (!ctx) {
+		for (i = 0; i < 8 && g_dev[i].ctx; ++i) {}
+		if (i == 8) bb_fatal("bb_device_attach", "too many resident indexes");
+		ctx = bwag_ctx_create(-1, bwt, bns->l_pac, pac);
+		if (!ctx) bb_fatal("bb_device_attach", "cannot place the index on the GPU: %s", bwag_last_error());
+		g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
+	}
+	pthread_mutex_unlock(&g_dev_mu);
+	return ctx;
+}
+
+void bb_device_release(const bwt_t *bwt)
+{
+	int i;
+	pthread_mutex_lock(&g_dev_mu);
+	for (i = 0; i < 8; ++i)
+		if (g_dev[i].bwt == bwt && g_dev[i].ctx) { bwag_ctx_destroy(g_dev[i].ctx); g_dev[i].ctx = 0; g_dev[i].bwt = 0; }
+	pthread_mutex_unlock(&g_dev_mu);
+}
+
+/* ---------------------------------------------------------------- alignment cache */
+const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc)
+{
+	size_t i;
+	bb_galn_t e;
+	for (i = 0; i < gc->memo.n; ++i) {
+		const bb_galn_t *g = &gc->memo.a[i];
+		if (g->mode == mode && g->qb == qb && g->qe == qe && g->rb == rb && g->re == re && g->w == w && g->truesc == truesc) {
+			if (g->done) return g;
+			++gc->pending;
+			return 0;
+		}
+	}
+	memset(&e, 0, sizeof(e));
+	e.mode = mode; e.qb = qb; e.qe = qe; e.rb = rb; e.re = re; e.w = w; e.truesc = truesc;
+	bb_vec_push(gc->memo, e);
+	++gc->pending;
+	return 0;
+}
+
+static void gcache_free(bb_gcache_t *gc)
+{
+	size_t i;
+	for (i = 0; i < gc->memo.n; ++i) free(gc->memo.a[i].cigar);
+	free(gc->memo.a);
+	memset(gc, 0, sizeof(*gc));
+}
+
+/* ---------------------------------------------------------------- batch state */
+typedef struct {
+	mem_alnreg_v regs;   /* regions after de-duplication (and mate rescue), pristine */
+	bb_gcache_t gc;
+	int done;            /* SAM written */
+	int dedup_done;
+	int n_raw;           /* regions straight from the extension stage */
+} rstate_t;
+
+typedef struct { /* per-thread output of the chaining step */
+	bb_chainer_t *chainer;
+	bb_chain_v chains;
+	BB_VEC(bwag_xchain_t) xc;
+	BB_VEC(bwag_xseed_t) xs;
+	BB_VEC(int) c_rid;
+	BB_VEC(float) c_frac;
+	BB_VEC(uint64_t) srt;
+} tls_t;
+
+typedef struct { int tid; int64_t c0, s0; int nc, ns; } rslice_t; /* where read i's chains sit in its thread's buffers */
+
+typedef struct {
+	const mem_opt_t *opt;
+	const bwt_t *bwt;
+	const bntseq_t *bns;
+	const uint8_t *pac;
+	const mem_pestat_t *pes;
+	int64_t n_processed;
+	int n;
+	bseq1_t *seqs;
+	int64_t *off;
+	uint8_t *codes;
+	rstate_t *rs;
+	/* stage 1 results */
+	bwag_seeds_t seeds;
+	/* chaining */
+	tls_t *tls;
+	rslice_t *slice;
+	/* flattened extension work */
+	int32_t *chain_off;
+	bwag_xchain_t *xchains;
+	bwag_xseed_t *xseeds;
+	int *chain_rid;
+	float *chain_frac;
+	int64_t n_xchains, n_xseeds;
+	bwag_regs_t xregs;
+	int pass_dry;
+} job_t;
+
+static void w_encode(void *d, long i, int tid)
+{
+	job_t *j = d;
+	bseq1_t *s = &j->seqs[i];
+	uint8_t *dst = j->codes + j->off[i];
+	int k;
+	(void)tid;
+	for (k = 0; k < s->l_seq; ++k) {
+		unsigned char c = (unsigned char)s->seq[k];
+		c = c < 4 ? c : bb_nt4_table[c];
+		s->seq[k] = (char)c;
+		dst[k] = c > 4 ? 4 : c; /* the reference table maps '-' to 5; every kernel treats >3 as N */
+	}
+}
+
+static void w_chain(void *d, long i, int tid)
+{
+	job_t *j = d;
+	tls_t *t = &j->tls[tid];
+	const mem_opt_t *opt = j->opt;
+	const bwag_seeds_t *sd = &j->seeds;
+	int l_query = j->seqs[i].l_seq, n_chn, c;
+	int64_t i0 = sd->intv_off[i], i1 = sd->intv_off[i + 1], l_pac = j->bns->l_pac;
+	rslice_t *sl = &j->slice[i];
+	const uint8_t *query = (const uint8_t *)j->seqs[i].seq;
+	if (!t->chainer) t->chainer = bb_chainer_new();
+	sl->tid = tid; sl->c0 = (int64_t)t->xc.n; sl->s0 = (int64_t)t->xs.n; sl->nc = sl->ns = 0;
+	bb_chain_build(t->chainer, opt, j->bns, l_query, (int)(i1 - i0), sd->intv + i0, sd->seed_off + i0, sd->rbeg, &t->chains);
+	n_chn = bb_chain_filter(opt, (int)t->chains.n, t->chains.a);
+	bb_chain_seed_sw(opt, j->bns, j->pac, l_query, query, n_chn, t->chains.a);
+	for (c = 0; c < n_chn; ++c) { /* window and seed order of mem_chain2aln (bwamem.c:666-691) */
+		const bb_chain_t *ch = &t->chains.a[c];
+		bwag_xchain_t xc;
+		int64_t rmax0 = l_pac << 1, rmax1 = 0;
+		int k, rid;
+		if (ch->n == 0) continue;
+		for (k = 0; k < ch->n; ++k) {
+			const bb_seed_t *s = &ch->seeds[k];
+			int64_t b = s->rbeg - (s->qbeg + bb_cal_max_gap(opt, s->qbeg));
+			int64_t e = s->rbeg + s->len + ((l_query - s->qbeg - s->len) + bb_cal_max_gap(opt, l_query - s->qbeg - s->len));
+			if (b < rmax0) rmax0 = b;
+			if (e > rmax1) rmax1 = e;
+		}
+		if (rmax0 < 0) rmax0 = 0;
+		if (rmax1 > l_pac << 1) rmax1 = l_pac << 1;
+		if (rmax0 < l_pac && l_pac < rmax1) {
+			if (ch->seeds[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac;
+		}
+		bb_clamp_to_contig(j->bns, &rmax0, ch->seeds[0].rbeg, &rmax1, &rid);
+		assert(rid == ch->rid);
+		t->srt.n = 0;
+		for (k = 0; k < ch->n; ++k) bb_vec_push(t->srt, (uint64_t)ch->seeds[k].score << 32 | (uint32_t)k);
+		bb_sort_u64(t->srt.n, t->srt.a);
+		xc.rmax0 = rmax0; xc.rmax1 = rmax1; xc.seed_off = (int32_t)(t->xs.n - sl->s0); xc.n_seeds = ch->n;
+		for (k = 0; k < ch->n; ++k) {
+			const bb_seed_t *s = &ch->seeds[(uint32_t)t->srt.a[k]];
+			bwag_xseed_t xs;
+			xs.rbeg = s->rbeg; xs.qbeg = s->qbeg; xs.len = (uint32_t)s->len | (t->srt.a[k] == 0 ? BWAG_XSEED_ZEROKEY : 0);
+			bb_vec_push(t->xs, xs);
+		}
+		bb_vec_push(t->xc, xc);
+		bb_vec_push(t->c_rid, ch->rid);
+		bb_vec_push(t->c_frac, ch->frac_rep);
+		++sl->nc; sl->ns += ch->n;
+	}
+}
+
+static void w_flatten(void *d, long i, int tid)
+{
+	job_t *j = d;
+	const rslice_t *sl = &j->slice[i];
+	const tls_t *t = &j->tls[sl->tid];
+	int64_t c0 = j->chain_off[i], s0, k;
+	(void)tid;
+	if (sl->nc == 0) return;
+	s0 = j->xchains[c0].seed_off; /* pre-filled by the serial prefix pass with the read's global seed base */
+	for (k = 0; k < sl->nc; ++k) {
+		bwag_xchain_t xc = t->xc.a[sl->c0 + k];
+		xc.seed_off += (int32_t)s0;
+		j->xchains[c0 + k] = xc;
+		j->chain_rid[c0 + k] = t->c_rid.a[sl->c0 + k];
+		j->chain_frac[c0 + k] = t->c_frac.a[sl->c0 + k];
+	}
+	memcpy(j->xseeds + s0, t->xs.a + sl->s0, sizeof(bwag_xseed_t) * sl->ns);
+}
+
+/* regions of read i from the extension stage -> pristine mem_alnreg_t array */
+static void load_raw_regs(job_t *j, long i, mem_alnreg_v *v)
+{
+	int64_t c0 = j->chain_off[i], c1 = j->chain_off[i + 1];
+	int k, n = c1 > c0 ? j->xregs.n_regs[i] : 0;
+	const bwag_xreg_t *x = c1 > c0 ? j->xregs.regs + j->xchains[c0].seed_off : 0;
+	v->n = 0;
+	bb_vec_reserve(*v, (size_t)n + 4);
+	for (k = 0; k < n; ++k) {
+		mem_alnreg_t *a = &v->a[k];
+		memset(a, 0, sizeof(*a));
+		a->rb = x[k].rb; a->re = x[k].re; a->qb = x[k].qb; a->qe = x[k].qe;
+		a->score = x[k].score; a->truesc = x[k].truesc; a->w = x[k].w;
+		a->seedcov = x[k].seedcov; a->seedlen0 = x[k].seedlen0;
+		a->rid = j->chain_rid[c0 + x[k].chain];
+		a->frac_rep = j->chain_frac[c0 + x[k].chain];
+	}
+	v->n = (size_t)n;
+}
+
+static void w_dedup(void *d, long i, int tid)
+{
+	job_t *j = d;
+	rstate_t *r = &j->rs[i];
+	int n;
+	size_t k;
+	(void)tid;
+	if (r->dedup_done) return;
+	load_raw_regs(j, i, &r->regs);
+	r->gc.pending = 0;
+	n = bb_sort_dedup_patch(j->opt, j->bns, &r->gc, j->seqs[i].l_seq, (int)r->regs.n, r->regs.a);
+	if (n < 0) return; /* a merge candidate needs a device alignment first */
+	r->regs.n = (size_t)n;
+	for (k = 0; k < r->regs.n; ++k) {
+		mem_alnreg_t *p = &r->regs.a[k];
+		if (p->rid >= 0 && j->bns->anns[p->rid].is_alt) p->is_alt = 1;
+	}
+	r->dedup_done = 1;
+}
+
+/* serve every outstanding alignment request of the batch with one device call; returns #requests */
+static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *swp)
+{
+	BB_VEC(bwag_gtask_t) tasks = {0, 0, 0};
+	bwag_galn_t out;
+	int64_t i, t = 0;
+	size_t k;
+	for (i = 0; i < j->n; ++i)
+		for (k = 0; k < j->rs[i].gc.memo.n; ++k) {
+			const bb_galn_t *g = &j->rs[i].gc.memo.a[k];
+			bwag_gtask_t x;
+			if (g->done) continue;
+			x.rb = g->rb; x.re = g->re; x.read = (int32_t)i; x.qb = g->qb; x.qe = g->qe; x.w = g->w; x.truesc = g->truesc; x.mode = g->mode;
+			bb_vec_push(tasks, x);
+		}
+	if (tasks.n == 0) return 0;
+	if (bwag_global(batch, swp, (int)tasks.n, tasks.a, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
+	for (i = 0; i < j->n; ++i)
+		for (k = 0; k < j->rs[i].gc.memo.n; ++k) {
+			bb_galn_t *g = &j->rs[i].gc.memo.a[k];
+			const bwag_gres_t *r;
+			if (g->done) continue;
+			r = &out.res[t++];
+			g->score = r->score; g->n_cigar = r->n_cigar; g->NM = r->NM; g->l_md = r->l_md > 0 ? r->l_md : 1;
+			g->cigar = bb_malloc(4 * (size_t)r->n_cigar + g->l_md);
+			memcpy(g->cigar, out.cigar + r->cigar_off, 4 * (size_t)r->n_cigar);
+			if (r->l_md > 0) memcpy((char *)(g->cigar + r->n_cigar), out.md + r->md_off, r->l_md);
+			else *(char *)(g->cigar + r->n_cigar) = 0;
+			g->done = 1;
+		}
+	t = (int64_t)tasks.n;
+	free(tasks.a);
+	return t;
+}
+
+static void w_rescue(void *d, long i, int tid)
+{
+	job_t *j = d;
+	mem_alnreg_v a[2];
+	(void)tid;
+	a[0] = j->rs[i << 1].regs; a[1] = j->rs[i << 1 | 1].regs;
+	bb_rescue_pe(j->opt, j->bns, j->pac, j->pes, &j->seqs[i << 1], a);
+	j->rs[i << 1].regs = a[0]; j->rs[i << 1 | 1].regs = a[1];
+}
+
+static void copy_regs(mem_alnreg_v *dst, const mem_alnreg_v *src)
+{
+	dst->n = 0;
+	bb_vec_reserve(*dst, src->n + 1);
+	memcpy(dst->a, src->a, src->n * sizeof(mem_alnreg_t));
+	dst->n = src->n;
+}
+
+/* worker2 of the reference (bwamem.c:1217-1233) for read / pair i, on a scratch copy of the regions */
+static void run_sam(job_t *j, long i, int dry)
+{
+	const mem_opt_t *opt = j->opt;
+	if (!(opt->flag & MEM_F_PE)) {
+		rstate_t *r = &j->rs[i];
+		mem_alnreg_v w = {0, 0, 0};
+		bb_samctx_t sc = { opt, j->bns, j->pac, &r->gc, dry };
+		copy_regs(&w, &r->regs);
+		bb_mark_primary_se(opt, (int)w.n, w.a, j->n_processed + i);
+		if (opt->flag & MEM_F_PRIMARY5) bb_reorder_primary5(opt->T, &w);
+		bb_reg2sam(&sc, &j->seqs[i], &w, 0, 0);
+		free(w.a);
+	} else {
+		mem_alnreg_v w[2] = {{0, 0, 0}, {0, 0, 0}};
+		bb_samctx_t sc[2] = { { opt, j->bns, j->pac, &j->rs[i << 1].gc, dry }, { opt, j->bns, j->pac, &j->rs[i << 1 | 1].gc, dry } };
+		copy_regs(&w[0], &j->rs[i << 1].regs); copy_regs(&w[1], &j->rs[i << 1 | 1].regs);
+		bb_sam_pe(sc, j->pes, (uint64_t)((j->n_processed >> 1) + i), &j->seqs[i << 1], w, 1);
+		free(w[0].a); free(w[1].a);
+	}
+}
+
+static void w_sam(void *d, long i, int tid)
+{
+	job_t *j = d;
+	int pe = !!(j->opt->flag & MEM_F_PE);
+	rstate_t *r0 = pe ? &j->rs[i << 1] : &j->rs[i], *r1 = pe ? &j->rs[i << 1 | 1] : 0;
+	int dry = j->pass_dry;
+	(void)tid;
+	if (r0->done) return;
+	for (;;) {
+		r0->gc.pending = 0; if (r1) r1->gc.pending = 0;
+		run_sam(j, i, dry);
+		if (r0->gc.pending || (r1 && r1->gc.pending)) {
+			if (!dry) { /* text built on incomplete data: discard */
+				if (pe) { free(j->seqs[i << 1].sam); free(j->seqs[i << 1 | 1].sam); j->seqs[i << 1].sam = j->seqs[i << 1 | 1].sam = 0; }
+				else { free(j->seqs[i].sam); j->seqs[i].sam = 0; }
+			}
+			return;
+		}
+		if (!dry) { r0->done = 1; if (r1) r1->done = 1; return; }
+		dry = 0; /* everything this read needs is cached: produce the text now */
+	}
+}
+
+static void sw_par_from_opt(const mem_opt_t *opt, bwag_sw_par_t *p)
+{
+	p->a = opt->a; p->b = opt->b; p->o_del = opt->o_del; p->e_del = opt->e_del; p->o_ins = opt->o_ins; p->e_ins = opt->e_ins;
+	p->w = opt->w; p->zdrop = opt->zdrop; p->pen_clip5 = opt->pen_clip5; p->pen_clip3 = opt->pen_clip3;
+	memcpy(p->mat, opt->mat, 25);
+}
+
+/* stages up to de-duplicated regions for all reads of the job (worker1 of the reference) */
+static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t *swp)
+{
+	const mem_opt_t *opt = j->opt;
+	bwag_batch_t *batch;
+	bwag_seed_par_t sp;
+	int nt = opt->n_threads > 0 ? opt->n_threads : 1, t, n = j->n;
+	int64_t i, tot = 0, nc = 0, ns = 0;
+
+	j->off = bb_malloc(sizeof(int64_t) * ((size_t)n + 1));
+	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
+	j->off[n] = tot;
+	j->codes = bb_malloc((size_t)tot + 16);
+	bb_parallel_for(nt, w_encode, j, n);
+
+	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
+	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
+	sp.min_seed_len = opt->min_seed_len;
+	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+	sp.split_width = opt->split_width;
+	sp.max_occ = opt->max_occ;
+	sp.max_mem_intv = opt->max_mem_intv;
+	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
+
+	j->tls = bb_calloc(nt, sizeof(tls_t));
+	j->slice = bb_calloc((size_t)n + 1, sizeof(rslice_t));
+	bb_parallel_for(nt, w_chain, j, n);
+
+	j->chain_off = bb_malloc(sizeof(int32_t) * ((size_t)n + 1));
+	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
+	j->n_xchains = nc; j->n_xseeds = ns;
+	j->xchains = bb_malloc(sizeof(bwag_xchain_t) * ((size_t)nc + 1));
+	j->xseeds = bb_malloc(sizeof(bwag_xseed_t) * ((size_t)ns + 1));
+	j->chain_rid = bb_malloc(sizeof(int) * ((size_t)nc + 1));
+	j->chain_frac = bb_malloc(sizeof(float) * ((size_t)nc + 1));
+	for (i = 0, nc = ns = 0; i < n; ++i) {
+		j->chain_off[i] = (int32_t)nc;
+		if (j->slice[i].nc) j->xchains[nc].seed_off = (int32_t)ns; /* read's seed base, consumed by w_flatten */
+		nc += j->slice[i].nc; ns += j->slice[i].ns;
+	}
+	j->chain_off[n] = (int32_t)nc;
+	bb_parallel_for(nt, w_flatten, j, n);
+	for (t = 0; t < nt; ++t) {
+		tls_t *x = &j->tls[t];
+		bb_chainer_free(x->chainer);
+		free(x->chains.a); free(x->xc.a); free(x->xs.a); free(x->c_rid.a); free(x->c_frac.a); free(x->srt.a);
+	}
+	free(j->tls); j->tls = 0;
+	free(j->slice); j->slice = 0;
+
+	if (bwag_extend(batch, swp, j->chain_off, j->xchains, j->n_xseeds, j->xseeds, &j->xregs) != 0)
+		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
+
+	j->rs = bb_calloc((size_t)n + 1, sizeof(rstate_t));
+	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
+		int64_t left = 0;
+		bb_parallel_for(nt, w_dedup, j, n);
+		for (i = 0; i < n; ++i) left += !j->rs[i].dedup_done;
+		if (left == 0) break;
+		if (global_round(j, batch, swp) == 0) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
+	}
+	return batch;
+}
+
+static void job_free(job_t *j)
+{
+	int64_t i;
+	if (j->rs) for (i = 0; i < j->n; ++i) { free(j->rs[i].regs.a); gcache_free(&j->rs[i].gc); }
+	free(j->rs); free(j->off); free(j->codes); free(j->chain_off); free(j->xchains); free(j->xseeds); free(j->chain_rid); free(j->chain_frac);
+}
+
+void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                      int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	job_t j;
+	mem_pestat_t pes[4];
+	bwag_sw_par_t swp;
+	bwag_ctx_t *ctx;
+	bwag_batch_t *batch;
+	double ctime = bb_cputime(), rtime = bb_realtime();
+	int nt = opt->n_threads > 0 ? opt->n_threads : 1, pe = !!(opt->flag & MEM_F_PE);
+	long n_units = pe ? n >> 1 : n;
+
+	if (n <= 0) return;
+	memset(&j, 0, sizeof(j));
+	j.opt = opt; j.bwt = bwt; j.bns = bns; j.pac = pac; j.n_processed = n_processed; j.n = n; j.seqs = seqs; j.pes = pes;
+	sw_par_from_opt(opt, &swp);
+	ctx = bb_device_attach(bwt, bns, pac);
+	batch = run_to_regs(&j, ctx, &swp);
+
+	if (pe) {
+		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
+		else {
+			mem_alnreg_v *rv = bb_malloc(sizeof(mem_alnreg_v) * (size_t)n);
+			int i;
+			for (i = 0; i < n; ++i) rv[i] = j.rs[i].regs;
+			mem_pestat(opt, bns->l_pac, n, rv, pes);
+			free(rv);
+		}
+		bb_parallel_for(nt, w_rescue, &j, n_units);
+	}
+	for (j.pass_dry = 1;; j.pass_dry = 0) { /* SAM: discover needed alignments, serve them on the device, write */
+		long i, left = 0;
+		bb_parallel_for(nt, w_sam, &j, n_units);
+		for (i = 0; i < n; ++i) left += !j.rs[i].done;
+		if (left == 0) break;
+		if (global_round(&j, batch, &swp) == 0) bb_fatal("mem_process_seqs", "internal error: unfinished reads without requests");
+	}
+	bwag_batch_end(batch);
+	job_free(&j);
+	if (bwa_verbose >= 3)
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec\n", __func__, n, bb_cputime() - ctime, bb_realtime() - rtime);
+}
+
+/* ---------------------------------------------------------------- single-read conveniences of the reference API */
+
+mem_alnreg_v mem_align1(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int l_seq, const char *seq_)
+{
+	job_t j;
+	bseq1_t s;
+	bwag_sw_par_t swp;
+	bwag_batch_t *batch;
+	mem_alnreg_v out;
+	memset(&j, 0, sizeof(j)); memset(&s, 0, sizeof(s));
+	s.l_seq = l_seq; s.seq = bb_malloc((size_t)l_seq + 1); memcpy(s.seq, seq_, l_seq);
+	j.opt = opt; j.bwt = bwt; j.bns = bns; j.pac = pac; j.n = 1; j.seqs = &s;
+	sw_par_from_opt(opt, &swp);
+	batch = run_to_regs(&j, bb_device_attach(bwt, bns, pac), &swp);
+	bwag_batch_end(batch);
+	out = j.rs[0].regs; j.rs[0].regs.a = 0;
+	bb_mark_primary_se(opt, (int)out.n, out.a, lrand48());
+	job_free(&j);
+	free(s.seq);
+	return out;
+}
+
+static const bwt_t *any_resident_bwt(const uint8_t *pac_unused)
+{
+	int i;
+	(void)pac_unused;
+	for (i = 0; i < 8; ++i) if (g_dev[i].ctx) return g_dev[i].bwt;
+	return 0;
+}
+
+mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_seq, const char *seq, const mem_alnreg_t *ar)
+{
+	/* needs the index on the device: the caller must have aligned with this index before (as example.c does) */
+	job_t j;
+	bseq1_t s;
+	rstate_t rs;
+	bwag_sw_par_t swp;
+	bwag_batch_t *batch;
+	bb_samctx_t sc = { opt, bns, pac, &rs.gc, 1 };
+	mem_aln_t a;
+	int64_t off[2] = {0, l_seq};
+	int k;
+	const bwt_t *bwt = any_resident_bwt(pac);
+	if (!bwt) bb_fatal("mem_reg2aln", "no index resident on the GPU; call mem_align1/mem_process_seqs first");
+	memset(&j, 0, sizeof(j)); memset(&s, 0, sizeof(s)); memset(&rs, 0, sizeof(rs));
+	s.l_seq = l_seq; s.seq = bb_malloc((size_t)l_seq + 1);
+	for (k = 0; k < l_seq; ++k) { unsigned char c = (unsigned char)seq[k]; c = c < 5 ? c : bb_nt4_table[c]; s.seq[k] = (char)(c > 4 ? 4 : c); }
+	a = bb_reg2aln(&sc, l_seq, s.seq, ar);
+	if (rs.gc.pending) {
+		free(a.cigar);
+		j.opt = opt; j.bns = bns; j.pac = pac; j.n = 1; j.seqs = &s; j.rs = &rs;
+		sw_par_from_opt(opt, &swp);
+		batch = bwag_batch_begin(bb_device_attach(bwt, bns, pac), 1, (const uint8_t *)s.seq, off);
+		if (!batch) bb_fatal("mem_reg2aln", "cannot start a device batch: %s", bwag_last_error());
+		global_round(&j, batch, &swp);
+		bwag_batch_end(batch);
+		rs.gc.pending = 0;
+		a = bb_reg2aln(&sc, l_seq, s.seq, ar);
+	}
+	gcache_free(&rs.gc);
+	free(s.seq);
+	return a;
+}

@@ -1,0 +1,117 @@
+/* bwa_b200_dev.h -- device-batch entry points (C ABI) of the B200 seed-and-extend path.
+ *
+ * These are the calls the host glue (mem_process_seqs) makes where the reference's worker threads
+ * call bwt_smem1/bwt_seed_strategy1/bwt_sa (bwamem.c:140-188,309), mem_chain2aln/ksw_extend2
+ * (bwamem.c:658-812, ksw.c:416) and bwa_gen_cigar2/ksw_global2 (bwa.c:148, ksw.c:540) once per read.
+ * Here each is ONE call per batch; the work runs in hand-written sm_100a kernels.  Plain pointers and
+ * sizes only.  Every function returns 0 on success and a non-zero CUDA/driver error otherwise; there
+ * is no CPU implementation behind them in the product library.
+ *
+ * Host-visible result buffers are owned by the batch object (pinned memory) and stay valid until the
+ * next call of the same stage on that batch or bwag_batch_end().
+ */
+#ifndef BWA_B200_DEV_H
+#define BWA_B200_DEV_H
+
+#include "bwa_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bwag_ctx bwag_ctx_t;     /* one per (GPU, index): FM-index + SA + pac resident in HBM */
+typedef struct bwag_batch bwag_batch_t; /* the reads of one mem_process_seqs call, resident in HBM */
+
+/* ---- index residency ------------------------------------------------------------------------ */
+/* Size in bytes of the device index blob for this index (header + Occ/BWT blocks + SA + pac). */
+size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac);
+/* Fill a device blob (d_blob: device pointer, >= bwag_blob_bytes) from the host index
+ * (bwt_restore_bwt/bwt_restore_sa layout, bwt.c:421-462; pac: bwa.c:308). */
+int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac);
+/* Create a context over a filled blob (e.g. after an NCCL broadcast of the blob).  own_blob!=0: the
+ * context frees the blob with cudaFree on destroy. */
+bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob);
+/* Convenience: allocate + fill + create.  device < 0 -> current device. */
+bwag_ctx_t *bwag_ctx_create(int device, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac);
+void bwag_ctx_destroy(bwag_ctx_t *ctx);
+/* Replace the every-32nd-row suffix-array sample by a denser one computed on the device (values are
+ * exact; only the number of LF steps per bwt_sa changes).  intv must be a power of two <= 32. */
+int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
+const char *bwag_last_error(void);
+
+/* ---- batch ------------------------------------------------------------------------------------ */
+/* codes: concatenated reads, one byte per base, values 0..4 (bwamem.c:1087-1088); off[n_reads+1]. */
+bwag_batch_t *bwag_batch_begin(bwag_ctx_t *ctx, int n_reads, const uint8_t *codes, const int64_t *off);
+void bwag_batch_end(bwag_batch_t *b);
+
+/* ---- stage 1: SMEM seeding + suffix-array lookup (replaces mem_collect_intv + bwt_sa) --------- */
+typedef struct {
+	int min_seed_len;        /* opt->min_seed_len */
+	int split_len;           /* (int)(min_seed_len*split_factor+.499)  bwamem.c:144 */
+	int split_width;         /* opt->split_width */
+	int max_occ;             /* opt->max_occ */
+	uint64_t max_mem_intv;   /* opt->max_mem_intv */
+} bwag_seed_par_t;
+
+typedef struct {
+	const int64_t *intv_off;   /* [n_reads+1] range of each read in intv[] */
+	const bwtintv_t *intv;     /* per read: sorted by info, exactly smem_aux_t.mem after bwamem.c:187 */
+	const int64_t *seed_off;   /* [n_intv+1] range of each interval in rbeg[] */
+	const int64_t *rbeg;       /* bwt_sa(x[0]+k) for k = 0, step, 2*step ... (bwamem.c:304-309) */
+	int64_t n_intv, n_seeds;
+} bwag_seeds_t;
+
+int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out);
+
+/* ---- stage 2: chain -> alignment regions (replaces the mem_chain2aln loop + ksw_extend2) ------ */
+typedef struct {
+	int a, b, o_del, e_del, o_ins, e_ins, w, zdrop, pen_clip5, pen_clip3;
+	int8_t mat[25];
+} bwag_sw_par_t;
+
+#define BWAG_XSEED_ZEROKEY 0x80000000u   /* the seed's sort key (score<<32|index) is 0, see bwamem.c:720 */
+typedef struct { int64_t rbeg; int32_t qbeg; uint32_t len; } bwag_xseed_t;  /* seeds of a chain in ks_introsort_64 order (bwamem.c:688-691) */
+typedef struct { int64_t rmax0, rmax1; int32_t seed_off, n_seeds; } bwag_xchain_t; /* rmax after bns_fetch_seq clamping (bwamem.c:668-685) */
+typedef struct { int64_t rb, re; int32_t qb, qe, score, truesc, w, seedcov, seedlen0, chain; } bwag_xreg_t;
+
+typedef struct {
+	const int32_t *n_regs;     /* [n_reads] */
+	const bwag_xreg_t *regs;   /* regs of read r: regs[reg_base(r) ... + n_regs[r]), reg_base(r) = chains[chain_off[r]].seed_off */
+} bwag_regs_t;
+
+int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par,
+                const int32_t *chain_off /* [n_reads+1] */, const bwag_xchain_t *chains,
+                int64_t n_seeds, const bwag_xseed_t *seeds, bwag_regs_t *out);
+
+/* ---- stage 3: banded global alignment -> CIGAR/NM/MD (replaces bwa_gen_cigar2 + ksw_global2) -- */
+#define BWAG_G_REG2ALN 0   /* the do-while of mem_reg2aln (bwamem.c:1144-1152): up to 3 band doublings, CIGAR+NM+MD */
+#define BWAG_G_SCORE   1   /* one bwa_gen_cigar2 call, score only (mem_patch_reg, bwamem.c:454) */
+typedef struct { int64_t rb, re; int32_t read, qb, qe, w, truesc, mode; } bwag_gtask_t;
+typedef struct { int32_t score, n_cigar, NM, l_md; int64_t cigar_off, md_off; } bwag_gres_t;
+
+typedef struct {
+	const bwag_gres_t *res;    /* [n_tasks] */
+	const uint32_t *cigar;     /* pool; task t: cigar[res[t].cigar_off ... + n_cigar) , len<<4|op */
+	const char *md;            /* pool; task t: md[res[t].md_off ... + l_md), NUL-terminated (l_md counts the NUL) */
+} bwag_galn_t;
+
+int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out);
+
+/* ---- work / time counters for the roofline ---------------------------------------------------- */
+typedef struct {
+	uint64_t occ_touches;      /* 64-byte Occ blocks touched by bwt_extend (1 or 2 per call, bwt.c:194-197) */
+	uint64_t sa_touches;       /* 64-byte blocks touched by LF steps in bwt_sa */
+	uint64_t sa_touches_algo;  /* same, had the walk used the on-disk sa_intv=32 sample */
+	uint64_t ext_cells;        /* sum over ksw_extend2 rows of (end-beg) */
+	uint64_t glb_cells;        /* sum over ksw_global2 rows of (end-beg) */
+	double ms_smem, ms_sa, ms_extend, ms_global;   /* CUDA-event time of the kernels, accumulated */
+	double ms_h2d, ms_d2h;
+	uint64_t n_launch;         /* kernels launched */
+} bwag_stats_t;
+void bwag_stats_get(bwag_ctx_t *ctx, bwag_stats_t *s);
+void bwag_stats_reset(bwag_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
