@@ -1,0 +1,50 @@
+# Build of the B200 BWA-MEM path.
+#   make            -> bwa_b200/libbwa_b200.so (host glue in C + sm_100a CUDA kernels) and bwa_b200/bwa-b200 (CLI)
+#   make oracle     -> oracle/_build/liboracle.so, oracle/_ref/* (needs /root/reference or a prebuilt _ref)
+#   make testbin    -> tests/_build/bwa-b200-oracle : host glue linked against the CPU oracle stages (TEST ONLY)
+#   make cusim      -> tests/_build/libbwa_b200_cusim.so : the CUDA kernels compiled for the CPU SIMT emulator (TEST ONLY)
+NVCC  ?= /usr/local/cuda/bin/nvcc
+CC    ?= gcc
+CXX   ?= g++
+HOST  := bwa_b200/csrc/host
+CUDA  := bwa_b200/csrc/cuda
+CFLAGS := -O2 -g -Wall -Wno-unused-function -fPIC -Iinclude -I$(HOST) -pthread
+NVFLAGS := -O3 -lineinfo -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -I$(CUDA)
+HOST_SRC := $(filter-out $(HOST)/bb_cli.c,$(wildcard $(HOST)/*.c))
+HOST_OBJ := $(patsubst $(HOST)/%.c,build/host/%.o,$(HOST_SRC))
+CUDA_SRC := $(wildcard $(CUDA)/*.cu)
+CUDA_OBJ := $(patsubst $(CUDA)/%.cu,build/cuda/%.o,$(CUDA_SRC))
+CUDA_HDR := $(wildcard $(CUDA)/*.cuh) $(wildcard $(CUDA)/*.h) $(wildcard include/*.h)
+
+all: bwa_b200/libbwa_b200.so bwa_b200/bwa-b200
+
+build/host/%.o: $(HOST)/%.c $(wildcard $(HOST)/*.h) $(wildcard include/*.h)
+	@mkdir -p build/host
+	$(CC) $(CFLAGS) -c $< -o $@
+
+build/cuda/%.o: $(CUDA)/%.cu $(CUDA_HDR)
+	@mkdir -p build/cuda
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+bwa_b200/libbwa_b200.so: $(HOST_OBJ) build/host/bb_cli.o $(CUDA_OBJ)
+	$(NVCC) -shared -o $@ $^ -lz -lm -lpthread -cudart shared
+
+build/host/bb_main.o: $(HOST)/bb_cli.c
+	@mkdir -p build/host
+	$(CC) $(CFLAGS) -DBB_MAIN -c $< -o $@
+
+bwa_b200/bwa-b200: build/host/bb_main.o bwa_b200/libbwa_b200.so
+	$(CC) -o $@ build/host/bb_main.o $(filter-out build/host/bb_cli.o,$(HOST_OBJ)) $(CUDA_OBJ) -L/usr/local/cuda/lib64 -lcudart -lstdc++ -lz -lm -lpthread -Wl,-rpath,/usr/local/cuda/lib64
+
+oracle:
+	$(MAKE) -C oracle all
+
+# ---- test-only artefacts ----
+testbin: tests/_build/bwa-b200-oracle
+tests/_build/bwa-b200-oracle: $(HOST_OBJ) build/host/bb_main.o oracle/oracle_fm.c oracle/oracle_sw.c oracle/oracle_stages.c
+	@mkdir -p tests/_build
+	$(CC) $(CFLAGS) -O3 -Ioracle -o $@ build/host/bb_main.o $(HOST_OBJ) oracle/oracle_fm.c oracle/oracle_sw.c oracle/oracle_stages.c -lz -lm -lpthread
+
+clean:
+	rm -rf build bwa_b200/libbwa_b200.so bwa_b200/bwa-b200 tests/_build
+.PHONY: all oracle testbin clean
