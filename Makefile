@@ -48,3 +48,18 @@ tests/_build/bwa-b200-oracle: $(HOST_OBJ) build/host/bb_main.o oracle/oracle_fm.
 clean:
 	rm -rf build bwa_b200/libbwa_b200.so bwa_b200/bwa-b200 tests/_build
 .PHONY: all oracle testbin clean
+
+# CUDA kernels compiled for the CPU SIMT emulator (tests/cusim): TEST ONLY, checks kernel logic without a GPU
+CUSIM_FLAGS := -O2 -g -std=c++17 -fPIC -x c++ -include tests/cusim/cusim.h -DBWAG_CUSIM -Iinclude -I$(CUDA) -Itests/cusim -Wall -Wno-unused-function -Wno-unknown-pragmas -Wno-unused-variable
+cusim: tests/_build/libbwa_b200_cusim.so tests/_build/bwa-b200-cusim
+tests/_build/cusim_%.o: $(CUDA)/%.cu $(CUDA_HDR) tests/cusim/cusim.h
+	@mkdir -p tests/_build
+	$(CXX) $(CUSIM_FLAGS) -c $< -o $@
+tests/_build/cusim_rt.o: tests/cusim/cusim.cpp tests/cusim/cusim.h
+	@mkdir -p tests/_build
+	$(CXX) -O2 -g -std=c++17 -fPIC -Itests/cusim -c $< -o $@
+CUSIM_OBJ := $(patsubst $(CUDA)/%.cu,tests/_build/cusim_%.o,$(CUDA_SRC)) tests/_build/cusim_rt.o
+tests/_build/libbwa_b200_cusim.so: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_cli.o
+	$(CXX) -shared -o $@ $^ -lz -lm -lpthread
+tests/_build/bwa-b200-cusim: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_main.o
+	$(CXX) -o $@ build/host/bb_main.o $(HOST_OBJ) $(CUSIM_OBJ) -lz -lm -lpthread

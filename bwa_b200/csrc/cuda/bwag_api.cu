@@ -1,0 +1,496 @@
+/* bwag_api.cu -- host side of the device-batch C ABI (include/bwa_b200_dev.h): index residency in HBM,
+ * batch upload, kernel launches on the context's stream, result download into pinned buffers, and
+ * the work/time counters the roofline is computed from.
+ *
+ * HBM layout of the index blob (all offsets 256-byte aligned):
+ *   [ header 256 B | Occ/BWT blocks (bwt_size*4 B) | sampled SA (n_sa*8 B) | pac (l_pac/4+1 B) ]
+ * The blob is position independent (the header holds sizes, not pointers) so that it can be filled
+ * on one GPU and broadcast to the others with a single collective.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "bwag_dev.cuh"
+#include "bwag_kernels.h"
+
+struct BlobHeader {
+	u64 magic, primary, seq_len, bwt_size, n_sa, l_pac;
+	u64 L2[5];
+	u64 sa_shift;
+	u64 off_bwt, off_sa, off_pac, total;
+};
+#define BLOB_MAGIC 0x3042574142323030ull
+#define ALIGN256(x) (((x) + 255) & ~(size_t)255)
+
+static __thread char g_err[512];
+extern "C" const char *bwag_last_error(void) { return g_err[0] ? g_err : "no error"; }
+static int set_err(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); return 0; } } while (0)
+
+/* device counters, mirrored in pinned host memory */
+struct Counters {
+	int next_read, next_task, pad0, pad1;
+	u64 next_seed;
+	u64 n_intv, n_seeds;
+	u64 occ_touches, sa_touches, ext_cells, glb_cells;
+	u64 n_cig, n_md;
+	u32 flags, pad2;
+};
+
+struct DevBuf { void *p; size_t cap; };
+static int buf_reserve(DevBuf *b, size_t bytes)
+{
+	if (bytes <= b->cap) return 0;
+	if (b->p) cudaFree(b->p);
+	b->p = 0; b->cap = 0;
+	size_t want = bytes + bytes / 4 + 256;
+	CK(cudaMalloc(&b->p, want));
+	b->cap = want;
+	return 0;
+}
+struct HostBuf { void *p; size_t cap; };
+static int hbuf_reserve(HostBuf *b, size_t bytes)
+{
+	if (bytes <= b->cap) return 0;
+	if (b->p) cudaFreeHost(b->p);
+	b->p = 0; b->cap = 0;
+	size_t want = bytes + bytes / 4 + 256;
+	CK(cudaMallocHost(&b->p, want));
+	b->cap = want;
+	return 0;
+}
+
+struct bwag_ctx {
+	int device, own_blob, n_sm;
+	void *blob;
+	DevIndex ix;
+	u64 *dense_sa;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	Counters *d_cnt, *h_cnt;
+	bwag_stats_t st;
+	int sa_intv_disk;
+	/* scratch reused across batches */
+	DevBuf s_k1, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
+	int grid_k1, grid_k2, grid_k4, grid_k5;
+};
+
+struct bwag_batch {
+	bwag_ctx_t *ctx;
+	int n;
+	i64 total_bases;
+	int max_len;
+	const i64 *h_off;
+	DevBuf d_codes, d_off;
+	/* stage 1 */
+	DevBuf d_intv_beg, d_intv_n, d_intv, d_seed_beg, d_rbeg;
+	HostBuf h_intv_beg, h_intv_n, h_intv, h_seed_beg, h_rbeg;
+	/* stage 2 */
+	DevBuf d_chain_off, d_chains, d_seeds, d_regs, d_nregs;
+	HostBuf h_regs, h_nregs;
+	/* stage 3 */
+	DevBuf d_tasks, d_res, d_cig, d_md;
+	HostBuf h_res, h_cig, h_md;
+};
+
+static void free_dev(DevBuf *b) { if (b->p) cudaFree(b->p); b->p = 0; b->cap = 0; }
+static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->cap = 0; }
+
+/* ------------------------------------------------------------------------------------------------ index */
+
+extern "C" size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac)
+{
+	return ALIGN256(sizeof(BlobHeader)) + ALIGN256((size_t)bwt->bwt_size * 4 + 64) + ALIGN256((size_t)bwt->n_sa * 8) + ALIGN256((size_t)l_pac / 4 + 1 + 64);
+}
+
+extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac)
+{
+	BlobHeader h;
+	if (device >= 0) CK(cudaSetDevice(device));
+	memset(&h, 0, sizeof(h));
+	h.magic = BLOB_MAGIC; h.primary = bwt->primary; h.seq_len = bwt->seq_len; h.bwt_size = bwt->bwt_size; h.n_sa = bwt->n_sa; h.l_pac = (u64)l_pac;
+	for (int i = 0; i < 5; ++i) h.L2[i] = bwt->L2[i];
+	{
+		int s = 0;
+		while ((1 << s) < bwt->sa_intv) ++s;
+		if ((1 << s) != bwt->sa_intv) return set_err("suffix-array interval %d is not a power of two", bwt->sa_intv);
+		h.sa_shift = (u64)s;
+	}
+	h.off_bwt = ALIGN256(sizeof(BlobHeader));
+	h.off_sa = h.off_bwt + ALIGN256((size_t)bwt->bwt_size * 4 + 64);
+	h.off_pac = h.off_sa + ALIGN256((size_t)bwt->n_sa * 8);
+	h.total = h.off_pac + ALIGN256((size_t)l_pac / 4 + 1 + 64);
+	char *d = (char *)d_blob;
+	CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d + h.off_bwt, bwt->bwt, (size_t)bwt->bwt_size * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d + h.off_sa, bwt->sa, (size_t)bwt->n_sa * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d + h.off_pac, pac, (size_t)l_pac / 4 + 1, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+static int pick_grid(bwag_ctx_t *c)
+{
+#ifdef BWAG_CUSIM
+	c->n_sm = 2;
+	c->grid_k1 = c->grid_k2 = c->grid_k4 = c->grid_k5 = 2;
+#else
+	cudaDeviceProp prop;
+	int nb;
+	CK(cudaGetDeviceProperties(&prop, c->device));
+	c->n_sm = prop.multiProcessorCount;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, 0)); c->grid_k1 = c->n_sm * (nb > 0 ? nb : 1);
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
+#endif
+	return 0;
+}
+
+extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob)
+{
+	BlobHeader h;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device is visible: this library has no CPU path"); return 0; }
+	if (device < 0) CKP(cudaGetDevice(&device));
+	CKP(cudaSetDevice(device));
+	CKP(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
+	if (h.magic != BLOB_MAGIC) { set_err("index blob has a bad magic number"); return 0; }
+	bwag_ctx_t *c = (bwag_ctx_t *)calloc(1, sizeof(*c));
+	c->device = device; c->own_blob = own_blob; c->blob = d_blob;
+	char *d = (char *)d_blob;
+	c->ix.bwt = (const uint4 *)(d + h.off_bwt);
+	c->ix.sa = (const u64 *)(d + h.off_sa);
+	c->ix.pac = (const uint8_t *)(d + h.off_pac);
+	c->ix.primary = h.primary; c->ix.seq_len = h.seq_len; c->ix.n_sa = h.n_sa; c->ix.l_pac = (i64)h.l_pac; c->ix.sa_shift = (int)h.sa_shift;
+	for (int i = 0; i < 5; ++i) c->ix.L2[i] = h.L2[i];
+	c->sa_intv_disk = 1 << h.sa_shift;
+	CKP(cudaStreamCreate(&c->stream));
+	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
+	CKP(cudaMalloc((void **)&c->d_cnt, sizeof(Counters)));
+	CKP(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
+	if (pick_grid(c)) { free(c); return 0; }
+	return c;
+}
+
+extern "C" bwag_ctx_t *bwag_ctx_create(int device, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac)
+{
+	int ndev = 0;
+	void *blob = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device is visible: this library has no CPU path"); return 0; }
+	if (device < 0) CKP(cudaGetDevice(&device));
+	CKP(cudaSetDevice(device));
+	CKP(cudaMalloc(&blob, bwag_blob_bytes(bwt, l_pac)));
+	if (bwag_blob_fill(device, blob, bwt, l_pac, pac)) { cudaFree(blob); return 0; }
+	bwag_ctx_t *c = bwag_ctx_from_blob(device, blob, 1);
+	if (!c) cudaFree(blob);
+	return c;
+}
+
+extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	free_dev(&c->s_k1); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
+	if (c->dense_sa) cudaFree(c->dense_sa);
+	if (c->own_blob && c->blob) cudaFree(c->blob);
+	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	free(c);
+}
+
+extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
+{
+	int s = 0;
+	while ((1 << s) < intv) ++s;
+	if ((1 << s) != intv || s > c->ix.sa_shift) return set_err("dense suffix-array interval must be a power of two not above the current %d", 1 << c->ix.sa_shift);
+	if (s == c->ix.sa_shift) return 0;
+	CK(cudaSetDevice(c->device));
+	u64 n_out = (c->ix.seq_len + (u64)intv) / (u64)intv, *out = 0;
+	CK(cudaMalloc((void **)&out, n_out * 8));
+	BWAG_LAUNCH(k_sa_densify, c->n_sm * 8, 256, 0, c->stream, c->ix, out, s, n_out);
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->dense_sa) cudaFree(c->dense_sa);
+	c->dense_sa = out;
+	c->ix.sa = out; c->ix.sa_shift = s; c->ix.n_sa = n_out;
+	++c->st.n_launch;
+	return 0;
+}
+
+extern "C" void bwag_stats_get(bwag_ctx_t *c, bwag_stats_t *s) { *s = c->st; }
+extern "C" void bwag_stats_reset(bwag_ctx_t *c) { memset(&c->st, 0, sizeof(c->st)); }
+
+/* ------------------------------------------------------------------------------------------------ batch */
+
+extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *codes, const int64_t *off)
+{
+	bwag_batch_t *b = (bwag_batch_t *)calloc(1, sizeof(*b));
+	CKP(cudaSetDevice(c->device));
+	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
+	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
+	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { free(b); return 0; }
+	CKP(cudaEventRecord(c->ev0, c->stream));
+	CKP(cudaMemcpyAsync(b->d_codes.p, codes, (size_t)b->total_bases, cudaMemcpyHostToDevice, c->stream));
+	CKP(cudaMemcpyAsync(b->d_off.p, off, sizeof(i64) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+	CKP(cudaEventRecord(c->ev1, c->stream));
+	CKP(cudaStreamSynchronize(c->stream));
+	{ float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->st.ms_h2d += ms; }
+	return b;
+}
+
+extern "C" void bwag_batch_end(bwag_batch_t *b)
+{
+	if (!b) return;
+	cudaSetDevice(b->ctx->device);
+	cudaStreamSynchronize(b->ctx->stream);
+	free_dev(&b->d_codes); free_dev(&b->d_off);
+	free_dev(&b->d_intv_beg); free_dev(&b->d_intv_n); free_dev(&b->d_intv); free_dev(&b->d_seed_beg); free_dev(&b->d_rbeg);
+	free_host(&b->h_intv_beg); free_host(&b->h_intv_n); free_host(&b->h_intv); free_host(&b->h_seed_beg); free_host(&b->h_rbeg);
+	free_dev(&b->d_chain_off); free_dev(&b->d_chains); free_dev(&b->d_seeds); free_dev(&b->d_regs); free_dev(&b->d_nregs);
+	free_host(&b->h_regs); free_host(&b->h_nregs);
+	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
+	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
+	free(b);
+}
+
+static int reset_counters(bwag_ctx_t *c)
+{
+	CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
+	return 0;
+}
+static int fetch_counters(bwag_ctx_t *c)
+{
+	CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+static double elapsed(bwag_ctx_t *c) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); return ms; }
+
+/* ------------------------------------------------------------------------------------------------ stage 1 */
+
+extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out)
+{
+	bwag_ctx_t *c = b->ctx;
+	CK(cudaSetDevice(c->device));
+	const int n = b->n;
+	i64 cap_intv = (i64)n * 16 + b->total_bases / 8 + 1024, cap_seeds = (i64)n * 32 + b->total_bases / 4 + 4096;
+	int cap_list = b->max_len + 1, cap_mem = 2 * b->max_len + 64;
+	SeedArgs a;
+	memset(&a, 0, sizeof(a));
+	for (int attempt = 0;; ++attempt) {
+		const int groups_per_block = K1_THREADS / 8;
+		int grid = c->grid_k1;
+		size_t per_group = (size_t)(3 * cap_list + cap_mem) * 32;
+		{   /* keep the per-group scratch within ~6 GB: very long reads get fewer groups */
+			size_t budget = (size_t)6 << 30;
+			i64 max_groups = (i64)(budget / per_group);
+			if (max_groups < groups_per_block) max_groups = groups_per_block;
+			if ((i64)grid * groups_per_block > max_groups) grid = (int)(max_groups / groups_per_block);
+			i64 need_groups = ((i64)n + groups_per_block - 1) / groups_per_block;
+			if (grid > need_groups) grid = (int)(need_groups > 0 ? need_groups : 1);
+		}
+		if (buf_reserve(&c->s_k1, per_group * (size_t)grid * groups_per_block)) return 1;
+		if (buf_reserve(&b->d_intv_beg, sizeof(i64) * (size_t)(n + 1)) || buf_reserve(&b->d_intv_n, sizeof(int) * (size_t)(n + 1)) ||
+		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
+		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
+		a.min_seed_len = par->min_seed_len; a.split_len = par->split_len; a.split_width = par->split_width; a.max_occ = par->max_occ; a.max_mem_intv = par->max_mem_intv;
+		a.scratch = (Intv *)c->s_k1.p; a.cap_list = cap_list; a.cap_mem = cap_mem;
+		a.intv_beg = (i64 *)b->d_intv_beg.p; a.intv_n = (int *)b->d_intv_n.p; a.intv = (bwtintv_t *)b->d_intv.p; a.seed_beg = (i64 *)b->d_seed_beg.p; a.rbeg = (i64 *)b->d_rbeg.p;
+		a.cap_intv = cap_intv; a.cap_seeds = cap_seeds;
+		a.next_read = &c->d_cnt->next_read; a.n_intv = &c->d_cnt->n_intv; a.n_seeds = &c->d_cnt->n_seeds; a.occ_touches = &c->d_cnt->occ_touches; a.flags = &c->d_cnt->flags;
+		if (reset_counters(c)) return 1;
+		CK(cudaEventRecord(c->ev0, c->stream));
+		BWAG_LAUNCH(k_smem, grid, K1_THREADS, 0, c->stream, c->ix, a);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev1, c->stream));
+		if (fetch_counters(c)) return 1;
+		c->st.ms_smem += elapsed(c); ++c->st.n_launch;
+		if (!(c->h_cnt->flags & 9u)) break;
+		if (attempt >= 6) return set_err("seeding: output pools keep overflowing (intervals %llu, seeds %llu)", (unsigned long long)c->h_cnt->n_intv, (unsigned long long)c->h_cnt->n_seeds);
+		if (c->h_cnt->flags & 1u) { /* pools too small: the counters say how much is needed */
+			if ((i64)c->h_cnt->n_intv > cap_intv) cap_intv = (i64)c->h_cnt->n_intv + 1024;
+			if ((i64)c->h_cnt->n_seeds > cap_seeds) cap_seeds = (i64)c->h_cnt->n_seeds + 4096;
+		}
+		if (c->h_cnt->flags & 8u) cap_mem *= 4;
+	}
+	c->st.occ_touches += c->h_cnt->occ_touches;
+	const i64 n_intv = (i64)c->h_cnt->n_intv, n_seeds = (i64)c->h_cnt->n_seeds;
+	/* K2: resolve the BWT rows left in rbeg[] to suffix-array positions, in place */
+	if (n_seeds > 0) {
+		SaArgs s;
+		s.rbeg = (i64 *)b->d_rbeg.p; s.n = n_seeds; s.next = &c->d_cnt->next_seed; s.sa_touches = &c->d_cnt->sa_touches;
+		int grid = c->grid_k2;
+		i64 need = (n_seeds + K2_THREADS - 1) / K2_THREADS;
+		if (grid > need) grid = (int)need;
+		CK(cudaEventRecord(c->ev0, c->stream));
+		BWAG_LAUNCH(k_sa, grid, K2_THREADS, 0, c->stream, c->ix, s);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev1, c->stream));
+		if (fetch_counters(c)) return 1;
+		c->st.ms_sa += elapsed(c); ++c->st.n_launch;
+		c->st.sa_touches += c->h_cnt->sa_touches;
+	}
+	if (hbuf_reserve(&b->h_intv_beg, sizeof(i64) * (size_t)(n + 1)) || hbuf_reserve(&b->h_intv_n, sizeof(int) * (size_t)(n + 1)) ||
+	    hbuf_reserve(&b->h_intv, 32 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_seed_beg, 8 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_rbeg, 8 * (size_t)(n_seeds + 1))) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	CK(cudaMemcpyAsync(b->h_intv_beg.p, b->d_intv_beg.p, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(b->h_intv_n.p, b->d_intv_n.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	if (n_intv) CK(cudaMemcpyAsync(b->h_intv.p, b->d_intv.p, 32 * (size_t)n_intv, cudaMemcpyDeviceToHost, c->stream));
+	if (n_intv) CK(cudaMemcpyAsync(b->h_seed_beg.p, b->d_seed_beg.p, 8 * (size_t)n_intv, cudaMemcpyDeviceToHost, c->stream));
+	if (n_seeds) CK(cudaMemcpyAsync(b->h_rbeg.p, b->d_rbeg.p, 8 * (size_t)n_seeds, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_d2h += elapsed(c);
+	out->intv_beg = (const int64_t *)b->h_intv_beg.p; out->intv_n = (const int32_t *)b->h_intv_n.p; out->intv = (const bwtintv_t *)b->h_intv.p;
+	out->seed_beg = (const int64_t *)b->h_seed_beg.p; out->rbeg = (const int64_t *)b->h_rbeg.p; out->n_intv = n_intv; out->n_seeds = n_seeds;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ stage 2 */
+
+extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int32_t *chain_off, const bwag_xchain_t *chains,
+                           int64_t n_seeds, const bwag_xseed_t *seeds, bwag_regs_t *out)
+{
+	bwag_ctx_t *c = b->ctx;
+	CK(cudaSetDevice(c->device));
+	const int n = b->n;
+	const i64 n_chains = chain_off[n];
+	int cap_r = 16;
+	for (i64 i = 0; i < n_chains; ++i) { i64 l = chains[i].rmax1 - chains[i].rmax0; if (l > cap_r) cap_r = (int)l; }
+	cap_r = (cap_r + 15) & ~15;
+	const int cap_q = (b->max_len + 3) & ~3;
+	int grid = c->grid_k4;
+	{
+		i64 need = ((i64)n + (K4_THREADS / 32) - 1) / (K4_THREADS / 32);
+		if (grid > need) grid = (int)(need > 0 ? need : 1);
+	}
+	const size_t n_warps = (size_t)grid * (K4_THREADS / 32);
+	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r)) return 1;
+	if (buf_reserve(&b->d_chain_off, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_chains, sizeof(bwag_xchain_t) * (size_t)(n_chains + 1)) ||
+	    buf_reserve(&b->d_seeds, sizeof(bwag_xseed_t) * (size_t)(n_seeds + 1)) || buf_reserve(&b->d_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) ||
+	    buf_reserve(&b->d_nregs, 4 * (size_t)(n + 1))) return 1;
+	if (reset_counters(c)) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	CK(cudaMemcpyAsync(b->d_chain_off.p, chain_off, 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+	if (n_chains) CK(cudaMemcpyAsync(b->d_chains.p, chains, sizeof(bwag_xchain_t) * (size_t)n_chains, cudaMemcpyHostToDevice, c->stream));
+	if (n_seeds) CK(cudaMemcpyAsync(b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_h2d += elapsed(c);
+	ExtArgs a;
+	memset(&a, 0, sizeof(a));
+	a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n; a.par = *par;
+	a.chain_off = (const int32_t *)b->d_chain_off.p; a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
+	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
+	a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.cap_q = cap_q; a.cap_r = cap_r;
+	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	if (fetch_counters(c)) return 1;
+	c->st.ms_extend += elapsed(c); ++c->st.n_launch;
+	if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
+	c->st.ext_cells += c->h_cnt->ext_cells;
+	if (hbuf_reserve(&b->h_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) || hbuf_reserve(&b->h_nregs, 4 * (size_t)(n + 1))) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	if (n_seeds) CK(cudaMemcpyAsync(b->h_regs.p, b->d_regs.p, sizeof(bwag_xreg_t) * (size_t)n_seeds, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_d2h += elapsed(c);
+	out->n_regs = (const int32_t *)b->h_nregs.p; out->regs = (const bwag_xreg_t *)b->h_regs.p;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ stage 3 */
+
+extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out)
+{
+	bwag_ctx_t *c = b->ctx;
+	CK(cudaSetDevice(c->device));
+	if (n_tasks <= 0) { out->res = 0; out->cigar = 0; out->md = 0; return 0; }
+	i64 cap_z = 64, n_aln = 0;
+	int cap_q = 4, cap_r = 16;
+	for (int t = 0; t < n_tasks; ++t) {
+		i64 lq = tasks[t].qe - tasks[t].qb, rl = tasks[t].re - tasks[t].rb;
+		if (lq > cap_q) cap_q = (int)lq;
+		if (rl > cap_r) cap_r = (int)rl;
+		if (tasks[t].mode == BWAG_G_REG2ALN) { /* backtrack bytes of the widest band this task can reach */
+			i64 d = rl > lq ? rl - lq : lq - rl, wmax = (i64)par->w << 2;
+			if (d + 3 > wmax) wmax = d + 3;
+			i64 ncol = lq < 2 * wmax + 1 ? lq : 2 * wmax + 1;
+			if (ncol * rl > cap_z) cap_z = ncol * rl;
+			++n_aln;
+		}
+	}
+	cap_q = (cap_q + 3) & ~3; cap_r = (cap_r + 15) & ~15; cap_z = (cap_z + 15) & ~(i64)15;
+	/* one task's CIGAR has at most lq+rlen ops, its MD at most 3 characters per reference base */
+	const int cap_wcig = cap_q + cap_r + 4, cap_wmd = 3 * cap_r + cap_q + 16;
+	int grid = c->grid_k5;
+	{
+		i64 need = ((i64)n_tasks + (K5_THREADS / 32) - 1) / (K5_THREADS / 32);
+		if (grid > need) grid = (int)(need > 0 ? need : 1);
+		i64 max_warps = ((i64)8 << 30) / cap_z;    /* bound the per-warp backtrack scratch to ~8 GB */
+		if (max_warps < K5_THREADS / 32) max_warps = K5_THREADS / 32;
+		if ((i64)grid * (K5_THREADS / 32) > max_warps) grid = (int)(max_warps / (K5_THREADS / 32));
+	}
+	const size_t n_warps = (size_t)grid * (K5_THREADS / 32);
+	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r) ||
+	    buf_reserve(&c->s_qseq, n_warps * (size_t)(cap_q + 2)) || buf_reserve(&c->s_z, n_warps * (size_t)cap_z) ||
+	    buf_reserve(&c->s_wcig, n_warps * (size_t)cap_wcig * 4) || buf_reserve(&c->s_wmd, n_warps * (size_t)cap_wmd)) return 1;
+	if (buf_reserve(&b->d_tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	CK(cudaMemcpyAsync(b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_h2d += elapsed(c);
+	i64 cap_cig = n_aln * 6 + 1024, cap_md = n_aln * 24 + 4096;   /* typical short-read sizes; grown on demand */
+	for (int attempt = 0;; ++attempt) {
+		if (buf_reserve(&b->d_cig, 4 * (size_t)cap_cig) || buf_reserve(&b->d_md, (size_t)cap_md)) return 1;
+		GlbArgs a;
+		memset(&a, 0, sizeof(a));
+		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.par = *par;
+		a.tasks = (const bwag_gtask_t *)b->d_tasks.p; a.n_tasks = n_tasks;
+		a.res = (bwag_gres_t *)b->d_res.p; a.cigar = (u32 *)b->d_cig.p; a.md = (char *)b->d_md.p;
+		a.cap_cig = cap_cig; a.cap_md = cap_md; a.n_cig = &c->d_cnt->n_cig; a.n_md = &c->d_cnt->n_md;
+		a.w_cig = (u32 *)c->s_wcig.p; a.w_md = (char *)c->s_wmd.p; a.cap_wcig = cap_wcig; a.cap_wmd = cap_wmd;
+		a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.qseq = (uint8_t *)c->s_qseq.p; a.z = (uint8_t *)c->s_z.p;
+		a.cap_q = cap_q; a.cap_r = cap_r; a.cap_z = cap_z;
+		a.next_task = &c->d_cnt->next_task; a.cells = &c->d_cnt->glb_cells; a.flags = &c->d_cnt->flags;
+		if (reset_counters(c)) return 1;
+		CK(cudaEventRecord(c->ev0, c->stream));
+		BWAG_LAUNCH(k_global, grid, K5_THREADS, 0, c->stream, c->ix, a);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev1, c->stream));
+		if (fetch_counters(c)) return 1;
+		c->st.ms_global += elapsed(c); ++c->st.n_launch;
+		if (c->h_cnt->flags & 4u) return set_err("global alignment: a task exceeded the scratch capacity");
+		if (!(c->h_cnt->flags & 16u)) break;
+		if (attempt >= 3) return set_err("global alignment: output pools keep overflowing");
+		cap_cig = (i64)c->h_cnt->n_cig + 1024; cap_md = (i64)c->h_cnt->n_md + 4096;
+	}
+	c->st.glb_cells += c->h_cnt->glb_cells;
+	const i64 nc = (i64)c->h_cnt->n_cig, nm = (i64)c->h_cnt->n_md;
+	if (hbuf_reserve(&b->h_res, sizeof(bwag_gres_t) * (size_t)n_tasks) || hbuf_reserve(&b->h_cig, 4 * (size_t)(nc + 1)) || hbuf_reserve(&b->h_md, (size_t)nm + 16)) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	CK(cudaMemcpyAsync(b->h_res.p, b->d_res.p, sizeof(bwag_gres_t) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
+	if (nc) CK(cudaMemcpyAsync(b->h_cig.p, b->d_cig.p, 4 * (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
+	if (nm) CK(cudaMemcpyAsync(b->h_md.p, b->d_md.p, (size_t)nm, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_d2h += elapsed(c);
+	out->res = (const bwag_gres_t *)b->h_res.p; out->cigar = (const uint32_t *)b->h_cig.p; out->md = (const char *)b->h_md.p;
+	return 0;
+}

@@ -1,0 +1,245 @@
+/* bwag_global.cu -- stage 3 kernel (K5): banded global alignment -> CIGAR, NM, MD.
+ *
+ * Replaces bwa_gen_cigar2 (bwa.c:148-234) with ksw_global2 (ksw.c:540-642) and, in mode
+ * BWAG_G_REG2ALN, the band-doubling loop of mem_reg2aln around it (bwamem.c:1143-1152).
+ *
+ * Mapping to the machine.  One warp per task (persistent warps, atomic task counter).  The DP is
+ * swept row by row with the 32 lanes on consecutive query columns of the band, exactly like the
+ * extension kernel: M/E per column depend on the previous row only, F along the row is a max-plus
+ * prefix scan (shuffles), and the three direction bits of each cell (ksw.c:587-600) are derived per
+ * lane from the scanned F.  One byte per cell goes to a per-warp backtrack matrix in global memory
+ * (n_col x tlen, the only HBM traffic of the stage); the backtrack itself is a short serial walk
+ * done by lane 0, after which NM/MD are produced from 32-base mismatch ballots.
+ * The gap-free fast path of bwa_gen_cigar2 (equal lengths, band 0) never touches the DP.
+ * Integer-ALU bound (cells), int32 cells with the reference's -2^30 sentinel.
+ */
+#include "bwag_dev.cuh"
+#include "bwag_kernels.h"
+
+#define NEG_INF (-0x40000000)
+
+/* Banded global alignment score of q[0..qlen) vs t[0..tlen), band w; z != 0: record directions
+ * (n_col bytes per row).  Restatement of ksw_global2 (ksw.c:552-611), lanes across columns. */
+__device__ int warp_ksw_global(int lane, int qlen, const uint8_t *q, int tlen, const uint8_t *t, const int8_t *mat,
+                               int o_del, int e_del, int o_ins, int e_ins, int w, int *H, int *E, uint8_t *z, int n_col, u64 *cells)
+{
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	for (int j = lane; j <= qlen; j += 32) {
+		H[j] = j == 0 ? 0 : (j <= w ? -(o_ins + e_ins * j) : NEG_INF);
+		E[j] = NEG_INF;
+	}
+	__syncwarp();
+	for (int i = 0; i < tlen; ++i) {
+		const int8_t *srow = mat + t[i] * 5;
+		const int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+		int carry_h = beg == 0 ? -(o_del + e_del * (i + 1)) : NEG_INF;
+		int carry_f = NEG_INF;
+		uint8_t *zi = z ? z + (i64)i * n_col : 0;
+		if (end > beg) *cells += (u64)(end - beg);
+		for (int j0 = beg; j0 < end; j0 += 32) {
+			const int j = j0 + lane;
+			const bool act = j < end;
+			int m = NEG_INF, e = NEG_INF, tt, s, f, h, hp;
+			if (act) { m = H[j] + srow[q[j]]; e = E[j]; }
+			tt = act ? m - oe_ins : -0x7f000000;       /* inactive lanes (only ever at the end of the last chunk) must not feed the scan */
+			s = tt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				int v = __shfl_up_sync(FULL_MASK, s, d) - d * e_ins;
+				if (lane >= d && v > s) s = v;
+			}
+			{
+				int sl = __shfl_up_sync(FULL_MASK, s, 1);
+				f = carry_f - lane * e_ins;
+				if (lane > 0 && sl > f) f = sl;
+			}
+			uint8_t d;
+			d = m >= e ? 0 : 1; h = m >= e ? m : e;
+			d = h >= f ? d : 2; h = h >= f ? h : f;
+			if (!act) h = NEG_INF;
+			hp = __shfl_up_sync(FULL_MASK, h, 1);
+			if (lane == 0) hp = carry_h;
+			{
+				int la = end - 1 - j0; la = la < 31 ? la : 31;
+				int s31 = __shfl_sync(FULL_MASK, s, 31);
+				int cf = carry_f - 32 * e_ins;
+				carry_f = s31 > cf ? s31 : cf;
+				carry_h = __shfl_sync(FULL_MASK, h, la);
+			}
+			if (act) {
+				int te = m - oe_del;
+				e -= e_del; d |= e > te ? 1 << 2 : 0; e = e > te ? e : te;
+				d |= (f - e_ins) > tt ? 2 << 4 : 0;
+				H[j] = hp; E[j] = e;
+				if (zi) zi[j - beg] = d;
+			}
+		}
+		if (lane == 0) { H[end] = carry_h; E[end] = NEG_INF; }
+		__syncwarp();
+	}
+	return H[qlen];
+}
+
+__device__ __forceinline__ void cig_push(u32 *cig, int *n, int op, int len)
+{
+	if (*n && (cig[*n - 1] & 0xf) == (u32)op) cig[*n - 1] += (u32)len << 4;
+	else cig[(*n)++] = (u32)len << 4 | (u32)op;
+}
+
+__device__ __forceinline__ int md_put_num(char *md, int l, int v)
+{
+	char buf[12];
+	int n = 0;
+	do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+	while (n) md[l++] = buf[--n];
+	return l;
+}
+
+__global__ void __launch_bounds__(K5_THREADS)
+k_global(DevIndex ix, GlbArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int *H = a.eh + wid * (i64)(2 * (a.cap_q + 2)), *E = H + a.cap_q + 2;
+	uint8_t *rseq = a.rseq + wid * (i64)a.cap_r, *qseq = a.qseq + wid * (i64)(a.cap_q + 2), *z = a.z + wid * a.cap_z;
+	const bwag_sw_par_t &p = a.par;
+	__shared__ int8_t s_mat[32];
+	if (threadIdx.x < 25) s_mat[threadIdx.x] = p.mat[threadIdx.x];
+	__syncthreads();
+	u64 cells = 0;
+	int overflow = 0;
+
+	for (;;) {
+		int tix = 0;
+		if (lane == 0) tix = atomicAdd(a.next_task, 1);
+		tix = __shfl_sync(FULL_MASK, tix, 0);
+		if (tix >= a.n_tasks) break;
+		const bwag_gtask_t tk = a.tasks[tix];
+		const int lq = tk.qe - tk.qb;
+		const i64 rb = tk.rb, re = tk.re;
+		u32 *cig = a.w_cig + wid * (i64)a.cap_wcig;   /* built in per-warp scratch, then appended to the compact pools */
+		char *md = a.w_md + wid * (i64)a.cap_wmd;
+		int score = 0, n_cigar = 0, NM = -1, l_md = 0;
+		bool ok = !(lq <= 0 || rb >= re || (rb < ix.l_pac && re > ix.l_pac)) && rb >= 0 && re <= ix.l_pac << 1;
+		const int rlen = (int)(re - rb);
+		if (ok && (lq > a.cap_q || rlen > a.cap_r)) { ok = false; overflow |= 4; }
+		if (ok) {
+			const uint8_t *query = a.codes + a.off[tk.read] + tk.qb;
+			const bool rev = rb >= ix.l_pac;   /* reverse both so that gaps are left-aligned on the forward strand (bwa.c:162-167) */
+			__syncwarp();
+			for (int x = lane; x < rlen; x += 32) rseq[rev ? rlen - 1 - x : x] = (uint8_t)bwag_ref_base(ix, rb + x);
+			for (int x = lane; x < lq; x += 32) qseq[rev ? lq - 1 - x : x] = query[x];
+			__syncwarp();
+			const int want = tk.mode == BWAG_G_REG2ALN;
+			int w2 = tk.w, it = 0, last_sc = -(1 << 30);
+			for (;;) {
+				if (want) w2 = w2 < p.w << 2 ? w2 : p.w << 2;
+				n_cigar = 0;
+				if (lq == rlen && w2 == 0) {    /* no gap possible: score the diagonal */
+					int sc = 0;
+					for (int x = lane; x < lq; x += 32) sc += s_mat[rseq[x] * 5 + qseq[x]];
+					score = __reduce_add_sync(FULL_MASK, sc);
+					if (want) { cig[0] = (u32)lq << 4; n_cigar = 1; }
+				} else {
+					int w, max_gap, max_ins, max_del, min_w, d = rlen - lq;
+					d = d < 0 ? -d : d;
+					max_ins = (int)((double)(((lq + 1) >> 1) * s_mat[0] - p.o_ins) / p.e_ins + 1.);
+					max_del = (int)((double)(((lq + 1) >> 1) * s_mat[0] - p.o_del) / p.e_del + 1.);
+					max_gap = max_ins > max_del ? max_ins : max_del;
+					max_gap = max_gap > 1 ? max_gap : 1;
+					w = (max_gap + d + 1) >> 1;
+					w = w < w2 ? w : w2;
+					min_w = d + 3;
+					w = w > min_w ? w : min_w;
+					const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
+					if (want && (i64)n_col * rlen > a.cap_z) { overflow |= 4; score = 0; break; }
+					score = warp_ksw_global(lane, lq, qseq, rlen, rseq, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, H, E, want ? z : 0, n_col, &cells);
+					if (want) {
+						if (lane == 0) {        /* backtrack (ksw.c:613-627) */
+							int i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1, which = 0, n = 0;
+							while (i >= 0 && k >= 0) {
+								which = z[(i64)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+								if (which == 0) { cig_push(cig, &n, 0, 1); --i; --k; }
+								else if (which == 1) { cig_push(cig, &n, 2, 1); --i; }
+								else { cig_push(cig, &n, 1, 1); --k; }
+							}
+							if (i >= 0) cig_push(cig, &n, 2, i + 1);
+							if (k >= 0) cig_push(cig, &n, 1, k + 1);
+							for (int x = 0; x < n >> 1; ++x) { u32 tmp = cig[x]; cig[x] = cig[n - 1 - x]; cig[n - 1 - x] = tmp; }
+							n_cigar = n;
+						}
+						n_cigar = __shfl_sync(FULL_MASK, n_cigar, 0);
+						__syncwarp();
+					}
+				}
+				if (want) {                     /* NM and MD (bwa.c:196-226) */
+					const char *b2c = rev ? "TGCAN" : "ACGTN";
+					int x = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
+					l_md = 0;
+					for (int k = 0; k < n_cigar; ++k) {
+						const int op = cig[k] & 0xf, len = (int)(cig[k] >> 4);
+						if (op == 0) {
+							for (int b0 = 0; b0 < len; b0 += 32) {
+								const int b = b0 + lane;
+								const bool mm = b < len && qseq[x + b] != rseq[y + b];
+								u32 bal = __ballot_sync(FULL_MASK, mm);
+								n_mm += __popc(bal);
+								if (lane == 0) {
+									int done = 0;       /* positions of this 32-block already accounted in u */
+									while (bal) {
+										int pos = __ffs(bal) - 1;
+										u += pos - done;
+										l_md = md_put_num(md, l_md, u);
+										md[l_md++] = b2c[rseq[y + b0 + pos]];
+										u = 0; done = pos + 1;
+										bal &= bal - 1;
+									}
+									int blk = len - b0 < 32 ? len - b0 : 32;
+									u += blk - done;
+								}
+							}
+							x += len; y += len;
+						} else if (op == 2) {
+							if (k > 0 && k < n_cigar - 1) {
+								if (lane == 0) {
+									l_md = md_put_num(md, l_md, u);
+									md[l_md++] = '^';
+									for (int b = 0; b < len; ++b) md[l_md++] = b2c[rseq[y + b]];
+									u = 0;
+								}
+								n_gap += len;
+							}
+							y += len;
+						} else if (op == 1) { x += len; n_gap += len; }
+					}
+					if (lane == 0) { l_md = md_put_num(md, l_md, u); md[l_md++] = 0; }
+					l_md = __shfl_sync(FULL_MASK, l_md, 0);
+					NM = n_mm + n_gap;
+				}
+				if (!want) break;
+				if (score == last_sc || w2 == p.w << 2) break;
+				last_sc = score;
+				w2 <<= 1;
+				if (!(++it < 3 && score < tk.truesc - p.a)) break;
+			}
+		}
+		i64 co = 0, mo = 0;
+		if (n_cigar || l_md) {
+			if (lane == 0) { co = (i64)atomicAdd(a.n_cig, (u64)n_cigar); mo = (i64)atomicAdd(a.n_md, (u64)((l_md + 3) & ~3)); }
+			co = __shfl_sync(FULL_MASK, co, 0); mo = __shfl_sync(FULL_MASK, mo, 0);
+			__syncwarp();
+			if (co + n_cigar <= a.cap_cig && mo + l_md <= a.cap_md) {
+				for (int x = lane; x < n_cigar; x += 32) a.cigar[co + x] = cig[x];
+				for (int x = lane; x < l_md; x += 32) a.md[mo + x] = md[x];
+			} else overflow |= 16;
+			__syncwarp();
+		}
+		if (lane == 0) {
+			bwag_gres_t r;
+			r.score = score; r.n_cigar = n_cigar; r.NM = NM; r.l_md = l_md; r.cigar_off = co; r.md_off = mo;
+			a.res[tix] = r;
+		}
+	}
+	if (lane == 0 && cells) atomicAdd(a.cells, cells);
+	if (overflow && lane == 0) atomicOr(a.flags, (u32)overflow);
+}

@@ -1,0 +1,64 @@
+/* bwag_kernels.h -- argument blocks and launch constants shared by the kernels and their host drivers. */
+#ifndef BWAG_KERNELS_H
+#define BWAG_KERNELS_H
+#include "bwag_dev.cuh"
+
+#define K1_THREADS 128
+#define K2_THREADS 128
+#define K4_THREADS 128
+#define K5_THREADS 128
+
+struct Intv;
+
+struct SeedArgs {
+	/* batch */
+	const uint8_t *codes; const i64 *off; int n_reads;
+	/* parameters (bwag_seed_par_t) */
+	int min_seed_len, split_len, split_width, max_occ; u64 max_mem_intv;
+	/* per-group scratch */
+	Intv *scratch; int cap_list, cap_mem;
+	/* outputs */
+	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
+	i64 cap_intv, cap_seeds;
+	/* counters: [0] next read, n_intv, n_seeds, occ touches, flags */
+	int *next_read; u64 *n_intv; u64 *n_seeds; u64 *occ_touches; u32 *flags;
+};
+
+struct SaArgs { i64 *rbeg; i64 n; u64 *next; u64 *sa_touches; };
+
+struct ExtArgs {
+	const uint8_t *codes; const i64 *off; int n_reads;
+	bwag_sw_par_t par;
+	const int32_t *chain_off; const bwag_xchain_t *chains; const bwag_xseed_t *seeds;
+	bwag_xreg_t *regs; int32_t *n_regs;
+	/* per-warp scratch: H, E (int32 each, cap_q+2), reference window (cap_r bytes) */
+	int *eh; uint8_t *rseq; int cap_q, cap_r;
+	int *next_read; u64 *cells; u32 *flags;
+};
+
+struct GlbArgs {
+	const uint8_t *codes; const i64 *off;
+	bwag_sw_par_t par;
+	const bwag_gtask_t *tasks; int n_tasks;
+	bwag_gres_t *res; u32 *cigar; char *md;   /* compact output pools, filled with atomicAdd on n_cig / n_md */
+	i64 cap_cig, cap_md; u64 *n_cig, *n_md;
+	u32 *w_cig; char *w_md; int cap_wcig, cap_wmd;   /* per-warp staging of one task's CIGAR / MD */
+	int *eh; uint8_t *rseq; uint8_t *qseq; uint8_t *z;   /* per-warp scratch: H/E rows, reference, query, backtrack matrix */
+	int cap_q, cap_r; i64 cap_z;
+	int *next_task; u64 *cells; u32 *flags;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#ifdef __cplusplus
+}
+#endif
+
+__global__ void k_smem(DevIndex ix, SeedArgs a);
+__global__ void k_sa(DevIndex ix, SaArgs a);
+__global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
+__global__ void k_extend(DevIndex ix, ExtArgs a);
+__global__ void k_global(DevIndex ix, GlbArgs a);
+
+#endif

@@ -196,7 +196,7 @@ static int try_merge(bb_chainer_t *ws, const mem_opt_t *opt, int64_t l_pac, bb_c
 }
 
 void bb_chain_build(bb_chainer_t *ws, const mem_opt_t *opt, const bntseq_t *bns, int l_query,
-                    int n_intv, const bwtintv_t *intv, const int64_t *seed_off, const int64_t *rbeg, bb_chain_v *out)
+                    int n_intv, const bwtintv_t *intv, const int64_t *seed_beg, const int64_t *rbeg, bb_chain_v *out)
 {
 	int i, b = 0, e = 0, l_rep = 0;
 	int64_t l_pac = bns->l_pac;
@@ -216,7 +216,7 @@ void bb_chain_build(bb_chainer_t *ws, const mem_opt_t *opt, const bntseq_t *bns,
 	l_rep += e - b;
 	for (i = 0; i < n_intv; ++i) {
 		int slen = (int)((uint32_t)intv[i].info - (uint32_t)(intv[i].info >> 32));
-		int64_t s0 = seed_off[i], s1 = seed_off[i + 1], j;
+		int64_t s0 = seed_beg[i], s1 = s0 + (int64_t)(intv[i].x[2] < (uint64_t)opt->max_occ ? intv[i].x[2] : (uint64_t)opt->max_occ), j;
 		for (j = s0; j < s1; ++j) { /* the device already applied the max_occ subsampling (bwamem.c:304-305) */
 			bb_seed_t s;
 			int rid, lower;

@@ -51,7 +51,7 @@ void bb_chainer_free(bb_chainer_t *c);
 /* Chains of one read from its sorted SA intervals and their suffix-array positions.  Output chains
  * (and their seed arrays) live in the chainer's arena until the next call. */
 void bb_chain_build(bb_chainer_t *c, const mem_opt_t *opt, const bntseq_t *bns, int l_query,
-                    int n_intv, const bwtintv_t *intv, const int64_t *seed_off, const int64_t *rbeg, bb_chain_v *out);
+                    int n_intv, const bwtintv_t *intv, const int64_t *seed_beg, const int64_t *rbeg, bb_chain_v *out);
 int bb_chain_weight(const bb_chain_t *c);
 int bb_chain_filter(const mem_opt_t *opt, int n, bb_chain_t *a);
 void bb_chain_seed_sw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, int n, bb_chain_t *a);

@@ -151,12 +151,12 @@ static void w_chain(void *d, long i, int tid)
 	const mem_opt_t *opt = j->opt;
 	const bwag_seeds_t *sd = &j->seeds;
 	int l_query = j->seqs[i].l_seq, n_chn, c;
-	int64_t i0 = sd->intv_off[i], i1 = sd->intv_off[i + 1], l_pac = j->bns->l_pac;
+	int64_t i0 = sd->intv_beg[i], i1 = i0 + sd->intv_n[i], l_pac = j->bns->l_pac;
 	rslice_t *sl = &j->slice[i];
 	const uint8_t *query = (const uint8_t *)j->seqs[i].seq;
 	if (!t->chainer) t->chainer = bb_chainer_new();
 	sl->tid = tid; sl->c0 = (int64_t)t->xc.n; sl->s0 = (int64_t)t->xs.n; sl->nc = sl->ns = 0;
-	bb_chain_build(t->chainer, opt, j->bns, l_query, (int)(i1 - i0), sd->intv + i0, sd->seed_off + i0, sd->rbeg, &t->chains);
+	bb_chain_build(t->chainer, opt, j->bns, l_query, (int)(i1 - i0), sd->intv + i0, sd->seed_beg + i0, sd->rbeg, &t->chains);
 	n_chn = bb_chain_filter(opt, (int)t->chains.n, t->chains.a);
 	bb_chain_seed_sw(opt, j->bns, j->pac, l_query, query, n_chn, t->chains.a);
 	for (c = 0; c < n_chn; ++c) { /* window and seed order of mem_chain2aln (bwamem.c:666-691) */

@@ -54,11 +54,12 @@ typedef struct {
 } bwag_seed_par_t;
 
 typedef struct {
-	const int64_t *intv_off;   /* [n_reads+1] range of each read in intv[] */
+	const int64_t *intv_beg;   /* [n_reads] first interval of each read in intv[] */
+	const int32_t *intv_n;     /* [n_reads] number of intervals of each read */
 	const bwtintv_t *intv;     /* per read: sorted by info, exactly smem_aux_t.mem after bwamem.c:187 */
-	const int64_t *seed_off;   /* [n_intv+1] range of each interval in rbeg[] */
+	const int64_t *seed_beg;   /* [n_intv] first seed of each interval in rbeg[]; it has min(x[2], max_occ) seeds */
 	const int64_t *rbeg;       /* bwt_sa(x[0]+k) for k = 0, step, 2*step ... (bwamem.c:304-309) */
-	int64_t n_intv, n_seeds;
+	int64_t n_intv, n_seeds;   /* pool sizes (reads may sit in the pools in any order) */
 } bwag_seeds_t;
 
 int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out);

@@ -28,7 +28,7 @@ struct bwag_batch {
 	const uint8_t *codes;
 	const int64_t *off;
 	/* stage outputs */
-	int64_t *intv_off, *seed_off, *rbeg;
+	int64_t *intv_off, *seed_off, *rbeg; int32_t *intv_n;
 	bwtintv_t *intv;
 	int32_t *n_regs;
 	bwag_xreg_t *regs;
@@ -94,7 +94,7 @@ bwag_batch_t *bwag_batch_begin(bwag_ctx_t *ctx, int n, const uint8_t *codes, con
 void bwag_batch_end(bwag_batch_t *b)
 {
 	if (!b) return;
-	free(b->intv_off); free(b->seed_off); free(b->rbeg); free(b->intv); free(b->n_regs); free(b->regs); free(b->gres); free(b->cig); free(b->md);
+	free(b->intv_off); free(b->intv_n); free(b->seed_off); free(b->rbeg); free(b->intv); free(b->n_regs); free(b->regs); free(b->gres); free(b->cig); free(b->md);
 	free(b);
 }
 
@@ -121,9 +121,10 @@ int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out)
 	int64_t i, n_intv = 0, n_seeds = 0, k;
 	uint64_t *steps;
 	pfor(s1_read, &s1, b->n);
-	free(b->intv_off); free(b->seed_off); free(b->rbeg); free(b->intv);
+	free(b->intv_off); free(b->intv_n); free(b->seed_off); free(b->rbeg); free(b->intv);
 	b->intv_off = malloc(sizeof(int64_t) * (b->n + 1));
-	for (i = 0; i < b->n; ++i) { b->intv_off[i] = n_intv; n_intv += (int64_t)s1.per[i].n; b->ctx->st.occ_touches += s1.touch[i]; }
+	b->intv_n = malloc(sizeof(int32_t) * (b->n + 1));
+	for (i = 0; i < b->n; ++i) { b->intv_off[i] = n_intv; b->intv_n[i] = (int32_t)s1.per[i].n; n_intv += (int64_t)s1.per[i].n; b->ctx->st.occ_touches += s1.touch[i]; }
 	b->intv_off[b->n] = n_intv;
 	b->intv = malloc(sizeof(bwtintv_t) * (n_intv + 1));
 	b->seed_off = malloc(sizeof(int64_t) * (n_intv + 1));
@@ -150,7 +151,7 @@ int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out)
 	pfor(s2_seed, &s2, n_seeds);
 	for (i = 0; i < n_seeds; ++i) { b->ctx->st.sa_touches += steps[i]; b->ctx->st.sa_touches_algo += steps[i]; }
 	free(steps); free(s2.row); free(s1.per); free(s1.touch);
-	out->intv_off = b->intv_off; out->intv = b->intv; out->seed_off = b->seed_off; out->rbeg = b->rbeg; out->n_intv = n_intv; out->n_seeds = n_seeds;
+	out->intv_beg = b->intv_off; out->intv_n = b->intv_n; out->intv = b->intv; out->seed_beg = b->seed_off; out->rbeg = b->rbeg; out->n_intv = n_intv; out->n_seeds = n_seeds;
 	return 0;
 }
 
