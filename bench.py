@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec of the BWA-MEM seed-and-extend hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of mem_process_seqs (the drop-in boundary) over one batch of synthetic reads:
+  e2e    host buffers in, SAM text out, every host<->device copy inside the timed region  (headline)
+  value  the same reads / the CUDA-event time of the four kernels (inputs resident in HBM)
+  roofline  dominant kernel = SMEM seeding: 64 B x Occ-block touches / its CUDA-event time vs measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref/bwa mem -t <cores>) on a bounded sample of the same reads
+`--impl reference` times the reference binary alone and prints the same line shape.
+
+Workload (config.workload): synthetic uniform-random reference of --ref-mbp Mbp in contigs of <= 125 Mbp,
+150-bp single-end reads with 1 % error (0.8 sub / 0.1 ins / 0.1 del), BASELINE.json configs[1].  The index is
+the reference's own on-disk format; for references too large to index with `bwa index` inside a benchmark run it
+is produced by this repo's GPU index builder, which is checked byte-for-byte against `bwa index` on small inputs.
+Inputs are larger than L2 (index >= hundreds of MB, reads >= 100 MB), so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+REF_BWA = os.path.join(ROOT, "oracle", "_ref", "bwa")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0):
+    """Reference FASTA + index (once per box) and this rank's reads."""
+    import gen_data
+    import numpy as np
+    os.makedirs(workdir, exist_ok=True)
+    fa = os.path.join(workdir, "ref_%d.fa" % ref_mbp)
+    contig_len = min(125_000_000, ref_mbp * 1_000_000)
+    n_contigs = max(1, (ref_mbp * 1_000_000) // contig_len)
+    done = fa + ".done"
+    if rank == 0 and not os.path.exists(done):
+        t0 = time.time()
+        contigs = gen_data.random_contigs(n_contigs, contig_len, 7)
+        gen_data.write_fasta(fa, contigs)
+        log("[bench] reference %d Mbp written in %.1fs" % (ref_mbp, time.time() - t0))
+        t0 = time.time()
+        build_index(fa)
+        log("[bench] index built in %.1fs" % (time.time() - t0))
+        open(done, "w").write("ok")
+    while not os.path.exists(done):
+        time.sleep(0.5)
+    fq = os.path.join(workdir, "reads_%d_%d_r%d.fq" % (n_reads, read_len, rank))
+    if not os.path.exists(fq):
+        t0 = time.time()
+        # reads are drawn without materialising the FASTA again: regenerate the contigs from the seed
+        contigs = gen_data.random_contigs(n_contigs, contig_len, 7)
+        r1, _ = gen_data.gen_reads(contigs, n_reads, read_len, seed + rank)
+        gen_data.write_fastq(fq, r1)
+        log("[bench] %d reads written in %.1fs" % (n_reads, time.time() - t0))
+    return fa, fq
+
+
+def build_index(fa):
+    """The reference's own `bwa index` (oracle/_ref) for sizes it finishes in about a minute; beyond that the
+    GPU index builder of this repo (same files, verified identical on small inputs)."""
+    size = os.path.getsize(fa)
+    try:
+        import bwa_b200.index_build as ib
+        have_gpu_builder = True
+    except Exception:
+        have_gpu_builder = False
+    if size > 60_000_000 and have_gpu_builder:
+        ib.build(fa)
+    else:
+        subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.cmd = ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"]
+        self.rows = []
+        self.p = None
+
+    def run(self):
+        try:
+            self.p = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.p.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference(fa, fq, n_sample, threads):
+    """`bwa mem -t threads` of the unmodified reference on the first n_sample reads; reads/s from its own
+    '[M::mem_process_seqs] Processed N reads in X CPU sec, Y real sec' lines (excludes index load and I/O)."""
+    sample = fq + ".sample%d" % n_sample
+    if not os.path.exists(sample):
+        with open(fq, "rb") as f, open(sample, "wb") as o:
+            for i, line in enumerate(f):
+                if i >= 4 * n_sample:
+                    break
+                o.write(line)
+    r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa, sample], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    n, real = 0, 0.0
+    for m in re.finditer(r"Processed (\d+) reads in ([\d.]+) CPU sec, ([\d.]+) real sec", r.stderr):
+        n += int(m.group(1)); real += float(m.group(3))
+    if n == 0 or real <= 0:
+        raise RuntimeError("reference run produced no timing lines:\n" + r.stderr[-2000:])
+    return n / real, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-mbp", type=int, default=int(os.environ.get("BWA_B200_BENCH_REF_MBP", "3000")))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("BWA_B200_BENCH_READS", "1000000")))
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
+    ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
+    ap.add_argument("--cpu-sample", type=int, default=100000)
+    ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncores = os.cpu_count() or 1
+    threads = a.threads or max(1, ncores // max(1, world))
+    workload = "%d synthetic %d-bp SE reads per GPU, 1%% error, vs %d Mbp uniform-random reference" % (a.reads, a.read_len, a.ref_mbp)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000)
+        n_sample = min(a.reads, a.cpu_sample)
+        vals = []
+        for s in range(a.warmup + a.steps):
+            t0 = time.time()
+            v, n = time_reference(fa, fq, n_sample, ncores)
+            if s >= a.warmup:
+                vals.append((v, n, time.time() - t0))
+            if s == 0 and (time.time() - t0) * (a.warmup + a.steps) > 240:   # keep the whole run within minutes
+                vals.append((v, n, time.time() - t0))
+                break
+        v = sum(x[0] for x in vals) / len(vals)
+        line = {"impl": "reference", "metric": "reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup,
+                "ms_per_step": 1e3 * vals[0][1] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": workload},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "first %d reads of the workload, bwa mem -t %d, rate from its own Processed-lines" % (n_sample, ncores)},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import bwa_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank)
+    if world > 1:
+        dist.barrier()
+
+    L = bwa_b200.lib()
+    idx = bwa_b200.Index(fa)
+    L.bwag_blob_bytes.restype = C.c_size_t
+    L.bwag_blob_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.bwag_blob_fill.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.bwag_ctx_from_blob.restype = C.c_void_p
+    L.bwag_ctx_from_blob.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    i = idx.p.contents
+    l_pac = C.cast(i.bns, C.POINTER(C.c_int64))[0]
+    if world > 1:
+        # one copy of the index per GPU: rank 0 fills the blob, a single NCCL broadcast over NVLink replicates it
+        nbytes = L.bwag_blob_bytes(i.bwt, l_pac)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            assert L.bwag_blob_fill(local_rank, blob.data_ptr(), i.bwt, l_pac, i.pac) == 0
+        torch.cuda.synchronize()
+        t0 = time.time()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            log("[bench] index blob %.2f GB broadcast over NCCL in %.3fs" % (nbytes / 1e9, time.time() - t0))
+        ctx = L.bwag_ctx_from_blob(local_rank, blob.data_ptr(), 0)
+        assert ctx, L.bwag_last_error()
+        L.bb_device_adopt(i.bwt, ctx)
+        idx.ctx = ctx
+        idx._blob = blob
+    else:
+        idx.attach()
+    if a.dense_sa:
+        idx.densify_sa(a.dense_sa)
+
+    opt = L.mem_opt_init()
+    opt.contents.n_threads = threads
+    batch = bwa_b200.ReadBatch(fq)
+    n_reads = batch.n
+
+    def step():
+        bwa_b200.mem_process_seqs(opt, idx, batch)
+        L.bb_batch_free_sam(batch.n, batch.seqs)   # release the SAM text like the reference's caller does (fastmap.c:114-119)
+
+    for _ in range(a.warmup):
+        step()
+    idx.stats(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    st = idx.stats()
+    k_ms = st["ms_smem"] + st["ms_sa"] + st["ms_extend"] + st["ms_global"]
+    vals = torch.tensor([dt, k_ms / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dt_max, k_max = float(vals[0]), float(vals[1])
+    total_reads = n_reads * a.steps * world
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        smem_gbs = st["occ_touches"] * 64 / (st["ms_smem"] * 1e-3) / 1e9 if st["ms_smem"] > 0 else 0.0
+        line = {
+            "metric": "reads_per_sec", "value": total_reads / k_max if k_max > 0 else None, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dt_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
+                       "l2": "inputs larger than L2 (index %.2f GB, reads %.0f MB per step)" % (os.path.getsize(fa + ".bwt") / 1e9 * 1.75, n_reads * a.read_len / 1e6),
+                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, extension and global-alignment kernels (inputs resident in HBM)",
+                       "dense_sa": a.dense_sa},
+            "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
+            "gpu_launches": st["n_launch"],
+            "clocks": clocks,
+            "roofline": {"kernel": "k_smem (SMEM seeding over the FM-index)", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": smem_gbs / hbm_peak if hbm_peak else None, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
+            "kernels_ms_per_step": {k: st[k] / a.steps for k in ("ms_smem", "ms_sa", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
+            "work_per_read": {"occ_touches": st["occ_touches"] / (n_reads * a.steps), "sa_touches": st["sa_touches"] / (n_reads * a.steps),
+                              "ext_cells": st["ext_cells"] / (n_reads * a.steps), "glb_cells": st["glb_cells"] / (n_reads * a.steps)},
+            "sw_gcups": {"extend": st["ext_cells"] / (st["ms_extend"] * 1e-3) / 1e9 if st["ms_extend"] > 0 else None,
+                         "global": st["glb_cells"] / (st["ms_global"] * 1e-3) / 1e9 if st["ms_global"] > 0 else None},
+        }
+        if world == 1:
+            try:
+                n_sample = min(a.reads, a.cpu_sample)
+                v, n = time_reference(fa, fq, n_sample, ncores)
+                line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                                        "sample": "first %d reads of the workload, oracle/_ref/bwa mem -t %d, rate from its own Processed-lines" % (n, ncores)}
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -243,6 +243,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 	CKP(cudaEventRecord(c->ev0, c->stream));
 	CKP(cudaMemcpyAsync(b->d_codes.p, codes, (size_t)b->total_bases, cudaMemcpyHostToDevice, c->stream));
 	CKP(cudaMemcpyAsync(b->d_off.p, off, sizeof(i64) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
+	c->st.h2d_bytes += (u64)b->total_bases + sizeof(i64) * ((u64)n + 1);
 	CKP(cudaEventRecord(c->ev1, c->stream));
 	CKP(cudaStreamSynchronize(c->stream));
 	{ float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->st.ms_h2d += ms; }
@@ -275,6 +276,8 @@ static int fetch_counters(bwag_ctx_t *c)
 	CK(cudaStreamSynchronize(c->stream));
 	return 0;
 }
+#define H2D(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (c)->stream)); (c)->st.h2d_bytes += (u64)(bytes); } while (0)
+#define D2H(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (c)->stream)); (c)->st.d2h_bytes += (u64)(bytes); } while (0)
 static double elapsed(bwag_ctx_t *c) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); return ms; }
 
 /* ------------------------------------------------------------------------------------------------ stage 1 */
@@ -344,11 +347,11 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	if (hbuf_reserve(&b->h_intv_beg, sizeof(i64) * (size_t)(n + 1)) || hbuf_reserve(&b->h_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 	    hbuf_reserve(&b->h_intv, 32 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_seed_beg, 8 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_rbeg, 8 * (size_t)(n_seeds + 1))) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	CK(cudaMemcpyAsync(b->h_intv_beg.p, b->d_intv_beg.p, sizeof(i64) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaMemcpyAsync(b->h_intv_n.p, b->d_intv_n.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-	if (n_intv) CK(cudaMemcpyAsync(b->h_intv.p, b->d_intv.p, 32 * (size_t)n_intv, cudaMemcpyDeviceToHost, c->stream));
-	if (n_intv) CK(cudaMemcpyAsync(b->h_seed_beg.p, b->d_seed_beg.p, 8 * (size_t)n_intv, cudaMemcpyDeviceToHost, c->stream));
-	if (n_seeds) CK(cudaMemcpyAsync(b->h_rbeg.p, b->d_rbeg.p, 8 * (size_t)n_seeds, cudaMemcpyDeviceToHost, c->stream));
+	D2H(c, b->h_intv_beg.p, b->d_intv_beg.p, sizeof(i64) * (size_t)n);
+	D2H(c, b->h_intv_n.p, b->d_intv_n.p, sizeof(int) * (size_t)n);
+	if (n_intv) D2H(c, b->h_intv.p, b->d_intv.p, 32 * (size_t)n_intv);
+	if (n_intv) D2H(c, b->h_seed_beg.p, b->d_seed_beg.p, 8 * (size_t)n_intv);
+	if (n_seeds) D2H(c, b->h_rbeg.p, b->d_rbeg.p, 8 * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_d2h += elapsed(c);
@@ -382,9 +385,9 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	    buf_reserve(&b->d_nregs, 4 * (size_t)(n + 1))) return 1;
 	if (reset_counters(c)) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	CK(cudaMemcpyAsync(b->d_chain_off.p, chain_off, 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
-	if (n_chains) CK(cudaMemcpyAsync(b->d_chains.p, chains, sizeof(bwag_xchain_t) * (size_t)n_chains, cudaMemcpyHostToDevice, c->stream));
-	if (n_seeds) CK(cudaMemcpyAsync(b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds, cudaMemcpyHostToDevice, c->stream));
+	H2D(c, b->d_chain_off.p, chain_off, 4 * (size_t)(n + 1));
+	if (n_chains) H2D(c, b->d_chains.p, chains, sizeof(bwag_xchain_t) * (size_t)n_chains);
+	if (n_seeds) H2D(c, b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_h2d += elapsed(c);
@@ -405,8 +408,8 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	c->st.ext_cells += c->h_cnt->ext_cells;
 	if (hbuf_reserve(&b->h_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) || hbuf_reserve(&b->h_nregs, 4 * (size_t)(n + 1))) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	if (n_seeds) CK(cudaMemcpyAsync(b->h_regs.p, b->d_regs.p, sizeof(bwag_xreg_t) * (size_t)n_seeds, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaMemcpyAsync(b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	if (n_seeds) D2H(c, b->h_regs.p, b->d_regs.p, sizeof(bwag_xreg_t) * (size_t)n_seeds);
+	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_d2h += elapsed(c);
@@ -452,7 +455,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	    buf_reserve(&c->s_wcig, n_warps * (size_t)cap_wcig * 4) || buf_reserve(&c->s_wmd, n_warps * (size_t)cap_wmd)) return 1;
 	if (buf_reserve(&b->d_tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	CK(cudaMemcpyAsync(b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks, cudaMemcpyHostToDevice, c->stream));
+	H2D(c, b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_h2d += elapsed(c);
@@ -485,9 +488,9 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	const i64 nc = (i64)c->h_cnt->n_cig, nm = (i64)c->h_cnt->n_md;
 	if (hbuf_reserve(&b->h_res, sizeof(bwag_gres_t) * (size_t)n_tasks) || hbuf_reserve(&b->h_cig, 4 * (size_t)(nc + 1)) || hbuf_reserve(&b->h_md, (size_t)nm + 16)) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	CK(cudaMemcpyAsync(b->h_res.p, b->d_res.p, sizeof(bwag_gres_t) * (size_t)n_tasks, cudaMemcpyDeviceToHost, c->stream));
-	if (nc) CK(cudaMemcpyAsync(b->h_cig.p, b->d_cig.p, 4 * (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
-	if (nm) CK(cudaMemcpyAsync(b->h_md.p, b->d_md.p, (size_t)nm, cudaMemcpyDeviceToHost, c->stream));
+	D2H(c, b->h_res.p, b->d_res.p, sizeof(bwag_gres_t) * (size_t)n_tasks);
+	if (nc) D2H(c, b->h_cig.p, b->d_cig.p, 4 * (size_t)nc);
+	if (nm) D2H(c, b->h_md.p, b->d_md.p, (size_t)nm);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_d2h += elapsed(c);

@@ -43,6 +43,17 @@ bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_
 	return ctx;
 }
 
+/* register a context created elsewhere (e.g. from an NCCL-broadcast blob) for this host index */
+void bb_device_adopt(const bwt_t *bwt, bwag_ctx_t *ctx)
+{
+	int i;
+	pthread_mutex_lock(&g_dev_mu);
+	for (i = 0; i < 8 && g_dev[i].ctx; ++i) {}
+	if (i == 8) bb_fatal("bb_device_adopt", "too many resident indexes");
+	g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
+	pthread_mutex_unlock(&g_dev_mu);
+}
+
 void bb_device_release(const bwt_t *bwt)
 {
 	int i;
@@ -536,4 +547,21 @@ mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *
 	gcache_free(&rs.gc);
 	free(s.seq);
 	return a;
+}
+
+/* release the SAM text of a batch the way the reference's caller does (fastmap.c:114-119), in one call */
+void bb_batch_free_sam(int n, bseq1_t *seqs)
+{
+	int i;
+	for (i = 0; i < n; ++i) { free(seqs[i].sam); seqs[i].sam = 0; }
+}
+
+/* total length of the SAM text of a batch; if dst != NULL the records are concatenated into it */
+int64_t bb_batch_cat_sam(int n, const bseq1_t *seqs, char *dst)
+{
+	int64_t l = 0;
+	int i;
+	for (i = 0; i < n; ++i)
+		if (seqs[i].sam) { size_t k = strlen(seqs[i].sam); if (dst) memcpy(dst + l, seqs[i].sam, k); l += (int64_t)k; }
+	return l;
 }

@@ -108,6 +108,7 @@ typedef struct {
 	double ms_smem, ms_sa, ms_extend, ms_global;   /* CUDA-event time of the kernels, accumulated */
 	double ms_h2d, ms_d2h;
 	uint64_t n_launch;         /* kernels launched */
+	uint64_t h2d_bytes, d2h_bytes;   /* bytes copied host->device / device->host by the stage calls */
 } bwag_stats_t;
 void bwag_stats_get(bwag_ctx_t *ctx, bwag_stats_t *s);
 void bwag_stats_reset(bwag_ctx_t *ctx);

@@ -1,0 +1,143 @@
+"""Parity of the CUDA path on a real B200, through the C ABI: SAM from libbwa_b200 / bwa-b200 must equal the
+unmodified reference binary (oracle/_ref/bwa mem) byte for byte; the seeding stage is additionally compared
+buffer by buffer with the CPU oracle through the same device-batch ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import bwa_b200
+from conftest import ORACLE_SO, ref_sam, run_sam, strip_pg
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("c1_se_10k", "c1", dict(tag="g10k", n=10000, seed=11), []),
+    ("c1_pe_5k", "c1", dict(tag="gpe", n=5000, seed=12, paired=True), []),
+    ("stress_se", "stress", dict(tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05), []),
+    ("stress_pe", "stress", dict(tag="gpe", n=3000, seed=4, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05), []),
+    ("two_1k", "two", dict(tag="g1k", n=200, length=1000, seed=10), []),
+    ("two_pacbio", "two", dict(tag="gpb", n=12, length=8000, seed=9, err=(0.02, 0.05, 0.03)), ["-x", "pacbio"]),
+    ("c1_len36", "c1", dict(tag="g36", n=2000, length=36, seed=21), []),
+    ("c1_len75", "c1", dict(tag="g75", n=2000, length=75, seed=22), []),
+    ("c1_len300", "c1", dict(tag="g300", n=1000, length=300, seed=23), []),
+    ("c1_opts", "c1", dict(tag="gopt", n=1500, seed=24), ["-a", "-Y", "-k", "17", "-A", "2", "-T", "50"]),
+]
+
+
+@pytest.mark.parametrize("name,ref,kw,extra", CASES, ids=[c[0] for c in CASES])
+def test_cli_sam_identical_to_reference(data, name, ref, kw, extra):
+    fa, fqs = data.reads(ref, **kw)
+    args = extra + ["-K", "100000000", "-t", "8", fa] + fqs
+    assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
+
+
+def test_edge_reads(data, tmp_path):
+    """Empty-ish and ragged input: reads shorter than the seed length, all-N reads, N runs, mixed lengths, lower case."""
+    fa = data.ref("c1")
+    import gen_data
+    contigs = gen_data.read_fasta(fa)
+    c = contigs[0]
+    recs = []
+    rng = np.random.default_rng(5)
+    for i, ln in enumerate([1, 5, 18, 19, 20, 33, 150, 151, 400, 2, 149]):
+        p = int(rng.integers(0, len(c) - ln))
+        recs.append((b"e%d" % i, c[p:p + ln].copy()))
+    recs.append((b"allN", np.frombuffer(b"N" * 100, dtype=np.uint8).copy()))
+    s = c[5000:5150].copy(); s[40:60] = ord("N"); recs.append((b"nrun", s))
+    recs.append((b"lower", np.frombuffer(c[9000:9150].tobytes().lower(), dtype=np.uint8).copy()))
+    recs.append((b"polyA", np.frombuffer(b"A" * 150, dtype=np.uint8).copy()))
+    fq = str(tmp_path / "edge.fq")
+    gen_data.write_fastq(fq, recs)
+    args = ["-K", "100000000", fa, fq]
+    assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
+
+
+def test_batching_and_threads_do_not_change_se_output(data):
+    fa, fqs = data.reads("c1", tag="g10k", n=10000, seed=11)
+    a = run_sam(bwa_b200.CLI_PATH, ["-K", "100000000", "-t", "8", fa] + fqs)
+    b = run_sam(bwa_b200.CLI_PATH, ["-K", "300000", "-t", "3", fa] + fqs)
+    assert a == b
+
+
+def test_library_call_and_dense_sa(data):
+    """mem_process_seqs through ctypes (host buffers in, SAM out); a denser on-device SA sample must not change a byte."""
+    fa, fqs = data.reads("stress", tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    want = b"\n".join(l for l in ref_sam(["-K", "100000000", fa] + fqs).split(b"\n") if not l.startswith(b"@"))
+    L = bwa_b200.lib()
+    idx = bwa_b200.Index(fa)
+    opt = L.mem_opt_init()
+    opt.contents.n_threads = 8
+    for dense in (0, 8, 2):
+        if dense:
+            idx.densify_sa(dense)
+        batch = bwa_b200.ReadBatch(fqs[0])
+        idx.stats(reset=True)
+        bwa_b200.mem_process_seqs(opt, idx, batch)
+        got = batch.sam().rstrip(b"\n")
+        st = idx.stats()
+        assert got == want, "dense=%d" % dense
+        assert st["occ_touches"] > 0 and st["ext_cells"] > 0 and st["n_launch"] >= 4
+    idx.close()
+
+
+class Intv(C.Structure):
+    _fields_ = [("x", C.c_uint64 * 3), ("info", C.c_uint64)]
+
+
+class SeedPar(C.Structure):
+    _fields_ = [("min_seed_len", C.c_int), ("split_len", C.c_int), ("split_width", C.c_int), ("max_occ", C.c_int), ("max_mem_intv", C.c_uint64)]
+
+
+class Seeds(C.Structure):
+    _fields_ = [("intv_beg", C.POINTER(C.c_int64)), ("intv_n", C.POINTER(C.c_int32)), ("intv", C.POINTER(Intv)), ("seed_beg", C.POINTER(C.c_int64)),
+                ("rbeg", C.POINTER(C.c_int64)), ("n_intv", C.c_int64), ("n_seeds", C.c_int64)]
+
+
+def _seed_stage(L, bwt, l_pac, pac, codes, off, par):
+    L.bwag_ctx_create.restype = C.c_void_p
+    L.bwag_ctx_create.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.bwag_batch_begin.restype = C.c_void_p
+    L.bwag_batch_begin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.bwag_seed.argtypes = [C.c_void_p, C.POINTER(SeedPar), C.POINTER(Seeds)]
+    L.bwag_batch_end.argtypes = [C.c_void_p]
+    L.bwag_ctx_destroy.argtypes = [C.c_void_p]
+    ctx = L.bwag_ctx_create(-1, bwt, l_pac, pac)
+    assert ctx
+    b = L.bwag_batch_begin(ctx, len(off) - 1, codes.ctypes.data, off.ctypes.data)
+    out = Seeds()
+    assert L.bwag_seed(b, C.byref(par), C.byref(out)) == 0
+    res = []
+    for r in range(len(off) - 1):
+        iv = []
+        for k in range(out.intv_beg[r], out.intv_beg[r] + out.intv_n[r]):
+            x = out.intv[k]
+            cnt = min(x.x[2], par.max_occ)
+            iv.append((x.x[0], x.x[1], x.x[2], x.info, tuple(out.rbeg[out.seed_beg[k] + c] for c in range(cnt))))
+        res.append(iv)
+    L.bwag_batch_end(b)
+    L.bwag_ctx_destroy(ctx)
+    return res
+
+
+def test_seed_stage_buffers_equal_oracle(data):
+    """bwag_seed of the CUDA library vs the CPU oracle: every interval (x0,x1,x2,info) and every suffix-array position."""
+    fa, fqs = data.reads("stress", tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    L = bwa_b200.lib()
+    O = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
+    idx = L.bwa_idx_load(fa.encode(), 7).contents
+    l_pac = C.cast(idx.bns, C.POINTER(C.c_int64))[0]
+    tab = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        tab[ch] = i; tab[ch + 32] = i
+    seqs = [l.strip() for i, l in enumerate(open(fqs[0], "rb")) if i % 4 == 1][:1500]
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    codes = tab[np.frombuffer(b"".join(seqs), dtype=np.uint8)].copy()
+    par = SeedPar(19, 28, 10, 500, 20)
+    got = _seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par)
+    want = _seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
+    assert got == want
+    assert sum(len(r) for r in want) > 5000
