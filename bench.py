@@ -46,11 +46,16 @@ def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0):
     if rank == 0 and not os.path.exists(done):
         t0 = time.time()
         contigs = gen_data.random_contigs(n_contigs, contig_len, 7)
-        gen_data.write_fasta(fa, contigs)
-        log("[bench] reference %d Mbp written in %.1fs" % (ref_mbp, time.time() - t0))
-        t0 = time.time()
-        build_index(fa)
-        log("[bench] index built in %.1fs" % (time.time() - t0))
+        if ref_mbp <= 60:
+            # small enough for the reference's own `bwa index` (about a minute at most)
+            gen_data.write_fasta(fa, contigs)
+            subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        else:
+            # `bwa index` needs hours at this size (bwa.1:767): same files from the GPU builder (bwa_b200/index_build.py,
+            # byte-identical to `bwa index` where both can run, see tests/test_gpu_parity.py::test_index_builder)
+            import bwa_b200.index_build as ib
+            ib.build_from_contigs(contigs, fa, verbose=True)
+        log("[bench] reference %d Mbp generated and indexed in %.1fs" % (ref_mbp, time.time() - t0))
         open(done, "w").write("ok")
     while not os.path.exists(done):
         time.sleep(0.5)
@@ -63,21 +68,6 @@ def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0):
         gen_data.write_fastq(fq, r1)
         log("[bench] %d reads written in %.1fs" % (n_reads, time.time() - t0))
     return fa, fq
-
-
-def build_index(fa):
-    """The reference's own `bwa index` (oracle/_ref) for sizes it finishes in about a minute; beyond that the
-    GPU index builder of this repo (same files, verified identical on small inputs)."""
-    size = os.path.getsize(fa)
-    try:
-        import bwa_b200.index_build as ib
-        have_gpu_builder = True
-    except Exception:
-        have_gpu_builder = False
-    if size > 60_000_000 and have_gpu_builder:
-        ib.build(fa)
-    else:
-        subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 class ClockSampler(threading.Thread):

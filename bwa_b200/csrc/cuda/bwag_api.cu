@@ -82,6 +82,7 @@ struct bwag_ctx {
 	/* scratch reused across batches */
 	DevBuf s_k1, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
 	int grid_k1, grid_k2, grid_k4, grid_k5;
+	struct bwag_batch *spare;   /* batch object (with its device and pinned buffers) kept for the next batch */
 };
 
 struct bwag_batch {
@@ -102,6 +103,7 @@ struct bwag_batch {
 	HostBuf h_res, h_cig, h_md;
 };
 
+static void batch_free(bwag_batch_t *b);
 static void free_dev(DevBuf *b) { if (b->p) cudaFree(b->p); b->p = 0; b->cap = 0; }
 static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->cap = 0; }
 
@@ -201,6 +203,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	free_dev(&c->s_k1); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
+	if (c->spare) { batch_free(c->spare); c->spare = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
@@ -235,8 +238,11 @@ extern "C" void bwag_stats_reset(bwag_ctx_t *c) { memset(&c->st, 0, sizeof(c->st
 
 extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *codes, const int64_t *off)
 {
-	bwag_batch_t *b = (bwag_batch_t *)calloc(1, sizeof(*b));
+	bwag_batch_t *b = c->spare;   /* buffers only grow: cudaMalloc/cudaMallocHost per batch would cost more than the kernels */
+	c->spare = 0;
+	if (!b) b = (bwag_batch_t *)calloc(1, sizeof(*b));
 	CKP(cudaSetDevice(c->device));
+	b->max_len = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
 	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
 	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { free(b); return 0; }
@@ -255,6 +261,12 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 	if (!b) return;
 	cudaSetDevice(b->ctx->device);
 	cudaStreamSynchronize(b->ctx->stream);
+	if (!b->ctx->spare) { b->ctx->spare = b; return; }
+	batch_free(b);
+}
+
+static void batch_free(bwag_batch_t *b)
+{
 	free_dev(&b->d_codes); free_dev(&b->d_off);
 	free_dev(&b->d_intv_beg); free_dev(&b->d_intv_n); free_dev(&b->d_intv); free_dev(&b->d_seed_beg); free_dev(&b->d_rbeg);
 	free_host(&b->h_intv_beg); free_host(&b->h_intv_n); free_host(&b->h_intv); free_host(&b->h_seed_beg); free_host(&b->h_rbeg);

@@ -21,6 +21,19 @@
 #include <math.h>
 #include "bb_host.h"
 
+/* phase timer: BWA_B200_PROFILE=1 prints the wall time of every phase of a batch to stderr */
+static int g_prof = -1;
+static double g_t_last;
+static void ph(const char *name)
+{
+	double t;
+	if (g_prof < 0) g_prof = getenv("BWA_B200_PROFILE") != 0;
+	if (!g_prof) return;
+	t = bb_realtime();
+	if (name) fprintf(stderr, "[prof] %-16s %9.2f ms\n", name, 1e3 * (t - g_t_last));
+	g_t_last = t;
+}
+
 /* ---------------------------------------------------------------- device residency */
 typedef struct { const bwt_t *bwt; bwag_ctx_t *ctx; } dev_slot_t;
 static dev_slot_t g_dev[8];
@@ -267,37 +280,74 @@ static void w_dedup(void *d, long i, int tid)
 }
 
 /* serve every outstanding alignment request of the batch with one device call; returns #requests */
+typedef struct { job_t *j; int64_t *off; bwag_gtask_t *tasks; const bwag_galn_t *out; } ground_t;
+
+static void w_gcount(void *d, long i, int tid)
+{
+	ground_t *g = d;
+	const bb_galn_v *m = &g->j->rs[i].gc.memo;
+	size_t k;
+	int c = 0;
+	(void)tid;
+	for (k = 0; k < m->n; ++k) c += !m->a[k].done;
+	g->off[i + 1] = c;
+}
+
+static void w_gfill(void *d, long i, int tid)
+{
+	ground_t *g = d;
+	const bb_galn_v *m = &g->j->rs[i].gc.memo;
+	bwag_gtask_t *x = g->tasks + g->off[i];
+	size_t k;
+	(void)tid;
+	if (g->off[i + 1] == g->off[i]) return;
+	for (k = 0; k < m->n; ++k) {
+		const bb_galn_t *e = &m->a[k];
+		if (e->done) continue;
+		x->rb = e->rb; x->re = e->re; x->read = (int32_t)i; x->qb = e->qb; x->qe = e->qe; x->w = e->w; x->truesc = e->truesc; x->mode = e->mode;
+		++x;
+	}
+}
+
+static void w_gstore(void *d, long i, int tid)
+{
+	ground_t *g = d;
+	bb_galn_v *m = &g->j->rs[i].gc.memo;
+	const bwag_gres_t *r = g->out->res + g->off[i];
+	size_t k;
+	(void)tid;
+	if (g->off[i + 1] == g->off[i]) return;
+	for (k = 0; k < m->n; ++k) {
+		bb_galn_t *e = &m->a[k];
+		if (e->done) continue;
+		e->score = r->score; e->n_cigar = r->n_cigar; e->NM = r->NM; e->l_md = r->l_md > 0 ? r->l_md : 1;
+		e->cigar = bb_malloc(4 * (size_t)r->n_cigar + e->l_md);
+		memcpy(e->cigar, g->out->cigar + r->cigar_off, 4 * (size_t)r->n_cigar);
+		if (r->l_md > 0) memcpy((char *)(e->cigar + r->n_cigar), g->out->md + r->md_off, r->l_md);
+		else *(char *)(e->cigar + r->n_cigar) = 0;
+		e->done = 1;
+		++r;
+	}
+}
+
 static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *swp)
 {
-	BB_VEC(bwag_gtask_t) tasks = {0, 0, 0};
+	ground_t g;
 	bwag_galn_t out;
-	int64_t i, t = 0;
-	size_t k;
-	for (i = 0; i < j->n; ++i)
-		for (k = 0; k < j->rs[i].gc.memo.n; ++k) {
-			const bb_galn_t *g = &j->rs[i].gc.memo.a[k];
-			bwag_gtask_t x;
-			if (g->done) continue;
-			x.rb = g->rb; x.re = g->re; x.read = (int32_t)i; x.qb = g->qb; x.qe = g->qe; x.w = g->w; x.truesc = g->truesc; x.mode = g->mode;
-			bb_vec_push(tasks, x);
-		}
-	if (tasks.n == 0) return 0;
-	if (bwag_global(batch, swp, (int)tasks.n, tasks.a, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
-	for (i = 0; i < j->n; ++i)
-		for (k = 0; k < j->rs[i].gc.memo.n; ++k) {
-			bb_galn_t *g = &j->rs[i].gc.memo.a[k];
-			const bwag_gres_t *r;
-			if (g->done) continue;
-			r = &out.res[t++];
-			g->score = r->score; g->n_cigar = r->n_cigar; g->NM = r->NM; g->l_md = r->l_md > 0 ? r->l_md : 1;
-			g->cigar = bb_malloc(4 * (size_t)r->n_cigar + g->l_md);
-			memcpy(g->cigar, out.cigar + r->cigar_off, 4 * (size_t)r->n_cigar);
-			if (r->l_md > 0) memcpy((char *)(g->cigar + r->n_cigar), out.md + r->md_off, r->l_md);
-			else *(char *)(g->cigar + r->n_cigar) = 0;
-			g->done = 1;
-		}
-	t = (int64_t)tasks.n;
-	free(tasks.a);
+	int64_t i, t;
+	int nt = j->opt->n_threads > 0 ? j->opt->n_threads : 1;
+	g.j = j; g.out = &out;
+	g.off = bb_malloc(sizeof(int64_t) * ((size_t)j->n + 1));
+	g.off[0] = 0;
+	bb_parallel_for(nt, w_gcount, &g, j->n);
+	for (i = 0; i < j->n; ++i) g.off[i + 1] += g.off[i];
+	t = g.off[j->n];
+	if (t == 0) { free(g.off); return 0; }
+	g.tasks = bb_malloc(sizeof(bwag_gtask_t) * (size_t)t);
+	bb_parallel_for(nt, w_gfill, &g, j->n);
+	if (bwag_global(batch, swp, (int)t, g.tasks, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
+	bb_parallel_for(nt, w_gstore, &g, j->n);
+	free(g.tasks); free(g.off);
 	return t;
 }
 
@@ -384,20 +434,25 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
 	j->off[n] = tot;
 	j->codes = bb_malloc((size_t)tot + 16);
+	ph(0);
 	bb_parallel_for(nt, w_encode, j, n);
+	ph("encode");
 
 	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
 	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
+	ph("batch_begin");
 	sp.min_seed_len = opt->min_seed_len;
 	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
 	sp.split_width = opt->split_width;
 	sp.max_occ = opt->max_occ;
 	sp.max_mem_intv = opt->max_mem_intv;
 	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
+	ph("seed_stage");
 
 	j->tls = bb_calloc(nt, sizeof(tls_t));
 	j->slice = bb_calloc((size_t)n + 1, sizeof(rslice_t));
 	bb_parallel_for(nt, w_chain, j, n);
+	ph("chain");
 
 	j->chain_off = bb_malloc(sizeof(int32_t) * ((size_t)n + 1));
 	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
@@ -420,14 +475,17 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	}
 	free(j->tls); j->tls = 0;
 	free(j->slice); j->slice = 0;
+	ph("flatten");
 
 	if (bwag_extend(batch, swp, j->chain_off, j->xchains, j->n_xseeds, j->xseeds, &j->xregs) != 0)
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
+	ph("extend_stage");
 
 	j->rs = bb_calloc((size_t)n + 1, sizeof(rstate_t));
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
 		int64_t left = 0;
 		bb_parallel_for(nt, w_dedup, j, n);
+		ph("dedup");
 		for (i = 0; i < n; ++i) left += !j->rs[i].dedup_done;
 		if (left == 0) break;
 		if (global_round(j, batch, swp) == 0) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
@@ -435,10 +493,16 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	return batch;
 }
 
+static void w_free(void *d, long i, int tid)
+{
+	job_t *j = d;
+	(void)tid;
+	free(j->rs[i].regs.a); gcache_free(&j->rs[i].gc);
+}
+
 static void job_free(job_t *j)
 {
-	int64_t i;
-	if (j->rs) for (i = 0; i < j->n; ++i) { free(j->rs[i].regs.a); gcache_free(&j->rs[i].gc); }
+	if (j->rs) bb_parallel_for(j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
 	free(j->rs); free(j->off); free(j->codes); free(j->chain_off); free(j->xchains); free(j->xseeds); free(j->chain_rid); free(j->chain_frac);
 }
 
@@ -475,12 +539,15 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	for (j.pass_dry = 1;; j.pass_dry = 0) { /* SAM: discover needed alignments, serve them on the device, write */
 		long i, left = 0;
 		bb_parallel_for(nt, w_sam, &j, n_units);
+		ph(j.pass_dry ? "sam_dry" : "sam_real");
 		for (i = 0; i < n; ++i) left += !j.rs[i].done;
 		if (left == 0) break;
 		if (global_round(&j, batch, &swp) == 0) bb_fatal("mem_process_seqs", "internal error: unfinished reads without requests");
+		ph("global_round");
 	}
 	bwag_batch_end(batch);
 	job_free(&j);
+	ph("cleanup");
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec\n", __func__, n, bb_cputime() - ctime, bb_realtime() - rtime);
 }

@@ -65,7 +65,7 @@ def test_batching_and_threads_do_not_change_se_output(data):
 def test_library_call_and_dense_sa(data):
     """mem_process_seqs through ctypes (host buffers in, SAM out); a denser on-device SA sample must not change a byte."""
     fa, fqs = data.reads("stress", tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05)
-    want = b"\n".join(l for l in ref_sam(["-K", "100000000", fa] + fqs).split(b"\n") if not l.startswith(b"@"))
+    want = b"\n".join(l for l in ref_sam(["-K", "100000000", fa] + fqs).split(b"\n") if not l.startswith(b"@")).rstrip(b"\n")
     L = bwa_b200.lib()
     idx = bwa_b200.Index(fa)
     opt = L.mem_opt_init()
@@ -141,3 +141,16 @@ def test_seed_stage_buffers_equal_oracle(data):
     want = _seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
     assert got == want
     assert sum(len(r) for r in want) > 5000
+
+
+def test_index_builder_identical_to_bwa_index(data, tmp_path):
+    """bwa_b200/index_build.py on the GPU writes the same five files as the reference's `bwa index`."""
+    import shutil
+    import bwa_b200.index_build as ib
+    for name in ("stress", "c1"):
+        fa = data.ref(name)
+        mine = str(tmp_path / (name + ".fa"))
+        shutil.copy(fa, mine)
+        ib.build(mine, verbose=False)
+        for ext in ("pac", "ann", "amb", "bwt", "sa"):
+            assert open(fa + "." + ext, "rb").read() == open(mine + "." + ext, "rb").read(), (name, ext)
