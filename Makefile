@@ -60,6 +60,6 @@ tests/_build/cusim_rt.o: tests/cusim/cusim.cpp tests/cusim/cusim.h
 	$(CXX) -O2 -g -std=c++17 -fPIC -Itests/cusim -c $< -o $@
 CUSIM_OBJ := $(patsubst $(CUDA)/%.cu,tests/_build/cusim_%.o,$(CUDA_SRC)) tests/_build/cusim_rt.o
 tests/_build/libbwa_b200_cusim.so: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_cli.o
-	$(CXX) -shared -o $@ $^ -lz -lm -lpthread
+	$(CXX) -shared -Wl,-Bsymbolic -o $@ $^ -lz -lm -lpthread
 tests/_build/bwa-b200-cusim: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_main.o
 	$(CXX) -o $@ build/host/bb_main.o $(HOST_OBJ) $(CUSIM_OBJ) -lz -lm -lpthread

@@ -63,7 +63,7 @@ def lib(path=None):
     p = path or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError("%s is missing: build it with `make` (nvcc, sm_100a); bwa_b200 has no CPU fallback" % p)
-    L = C.CDLL(p, mode=C.RTLD_GLOBAL if path is None else C.RTLD_LOCAL)
+    L = C.CDLL(p, mode=C.RTLD_LOCAL)
     L.mem_opt_init.restype = C.POINTER(MemOpt)
     L.bwa_idx_load.restype = C.POINTER(BwaIdx)
     L.bwa_idx_load.argtypes = [C.c_char_p, C.c_int]

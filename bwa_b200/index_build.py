@@ -15,6 +15,7 @@ checkpoints every 128 symbols are interleaved as in bwt_bwtupdate_core (bwtindex
 every 32nd row (bwt.c:62-84).  'N' bases become lrand48() draws with seed 11 (bntseq.c:266,295).
 """
 import os
+import sys
 import struct
 import time
 
@@ -154,7 +155,7 @@ def build_from_codes(codes_fwd, prefix, device="cuda", verbose=True):
         W[b:e] = (blk << sh).sum(dim=1)   # disjoint bit fields: the sum is the OR (wraps into the sign bit as intended)
         del blk
     if verbose:
-        print("[index_build] text of %d bases packed in %.1fs" % (n, time.time() - t0), flush=True)
+        print("[index_build] text of %d bases packed in %.1fs" % (n, time.time() - t0), file=sys.stderr, flush=True)
 
     # BWT rows: row 0 is the empty suffix ('$'), rows 1..n the sorted suffixes
     bwt_chars = torch.empty(n + 1, dtype=torch.uint8, device=dev)
@@ -203,7 +204,7 @@ def build_from_codes(codes_fwd, prefix, device="cuda", verbose=True):
         row += m
         del pos, prev, isz
         if verbose:
-            print("[index_build] bucket %d/%d done, %d rows, %.1fs" % (b + 1, nb, row, time.time() - t0), flush=True)
+            print("[index_build] bucket %d/%d done, %d rows, %.1fs" % (b + 1, nb, row, time.time() - t0), file=sys.stderr, flush=True)
     assert row == n + 1 and primary > 0
     del code_k, W
 
@@ -257,7 +258,7 @@ def build_from_codes(codes_fwd, prefix, device="cuda", verbose=True):
         f.write(struct.pack("<2Q", SA_INTV, n))
         f.write(sa[1:].tobytes())
     if verbose:
-        print("[index_build] %s.{bwt,sa} written, total %.1fs" % (prefix, time.time() - t0), flush=True)
+        print("[index_build] %s.{bwt,sa} written, total %.1fs" % (prefix, time.time() - t0), file=sys.stderr, flush=True)
 
 
 def _refine_ties(W, T, key, pos, n, torch, verbose):

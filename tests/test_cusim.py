@@ -17,3 +17,23 @@ def test_emulated_kernels_sam_vs_reference(data, name, ref, kw, extra):
     fa, fqs = data.reads(ref, **kw)
     args = extra + ["-K", "100000000", "-t", "2", fa] + fqs
     assert run_sam(CUSIMBIN, args) == ref_sam(args)
+
+
+def test_emulated_seed_stage_buffers_equal_oracle(data):
+    """bwag_seed of the emulated CUDA kernels vs the CPU oracle, buffer by buffer (intervals and SA positions)."""
+    import ctypes as C
+    import os
+    import bwa_b200
+    from conftest import ORACLE_SO, ROOT
+    from stage_abi import SeedPar, load_reads_as_codes, seed_stage
+    fa, fqs = data.reads("stress", tag="cs", n=120, seed=33, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    L = bwa_b200.lib()
+    idx = L.bwa_idx_load(fa.encode(), 7).contents
+    l_pac = C.cast(idx.bns, C.POINTER(C.c_int64))[0]
+    codes, off = load_reads_as_codes(fqs[0], 120)
+    par = SeedPar(19, 28, 10, 500, 20)
+    S = C.CDLL(os.path.join(ROOT, "tests/_build/libbwa_b200_cusim.so"), mode=C.RTLD_LOCAL)
+    O = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
+    got = seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par)
+    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
+    assert got == want and sum(len(r) for r in want) > 500

@@ -83,43 +83,7 @@ def test_library_call_and_dense_sa(data):
     idx.close()
 
 
-class Intv(C.Structure):
-    _fields_ = [("x", C.c_uint64 * 3), ("info", C.c_uint64)]
-
-
-class SeedPar(C.Structure):
-    _fields_ = [("min_seed_len", C.c_int), ("split_len", C.c_int), ("split_width", C.c_int), ("max_occ", C.c_int), ("max_mem_intv", C.c_uint64)]
-
-
-class Seeds(C.Structure):
-    _fields_ = [("intv_beg", C.POINTER(C.c_int64)), ("intv_n", C.POINTER(C.c_int32)), ("intv", C.POINTER(Intv)), ("seed_beg", C.POINTER(C.c_int64)),
-                ("rbeg", C.POINTER(C.c_int64)), ("n_intv", C.c_int64), ("n_seeds", C.c_int64)]
-
-
-def _seed_stage(L, bwt, l_pac, pac, codes, off, par):
-    L.bwag_ctx_create.restype = C.c_void_p
-    L.bwag_ctx_create.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
-    L.bwag_batch_begin.restype = C.c_void_p
-    L.bwag_batch_begin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-    L.bwag_seed.argtypes = [C.c_void_p, C.POINTER(SeedPar), C.POINTER(Seeds)]
-    L.bwag_batch_end.argtypes = [C.c_void_p]
-    L.bwag_ctx_destroy.argtypes = [C.c_void_p]
-    ctx = L.bwag_ctx_create(-1, bwt, l_pac, pac)
-    assert ctx
-    b = L.bwag_batch_begin(ctx, len(off) - 1, codes.ctypes.data, off.ctypes.data)
-    out = Seeds()
-    assert L.bwag_seed(b, C.byref(par), C.byref(out)) == 0
-    res = []
-    for r in range(len(off) - 1):
-        iv = []
-        for k in range(out.intv_beg[r], out.intv_beg[r] + out.intv_n[r]):
-            x = out.intv[k]
-            cnt = min(x.x[2], par.max_occ)
-            iv.append((x.x[0], x.x[1], x.x[2], x.info, tuple(out.rbeg[out.seed_beg[k] + c] for c in range(cnt))))
-        res.append(iv)
-    L.bwag_batch_end(b)
-    L.bwag_ctx_destroy(ctx)
-    return res
+from stage_abi import SeedPar, load_reads_as_codes, seed_stage
 
 
 def test_seed_stage_buffers_equal_oracle(data):
@@ -129,16 +93,10 @@ def test_seed_stage_buffers_equal_oracle(data):
     O = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
     idx = L.bwa_idx_load(fa.encode(), 7).contents
     l_pac = C.cast(idx.bns, C.POINTER(C.c_int64))[0]
-    tab = np.full(256, 4, dtype=np.uint8)
-    for i, ch in enumerate(b"ACGT"):
-        tab[ch] = i; tab[ch + 32] = i
-    seqs = [l.strip() for i, l in enumerate(open(fqs[0], "rb")) if i % 4 == 1][:1500]
-    off = np.zeros(len(seqs) + 1, dtype=np.int64)
-    off[1:] = np.cumsum([len(s) for s in seqs])
-    codes = tab[np.frombuffer(b"".join(seqs), dtype=np.uint8)].copy()
+    codes, off = load_reads_as_codes(fqs[0], 1500)
     par = SeedPar(19, 28, 10, 500, 20)
-    got = _seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par)
-    want = _seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
+    got = seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par)
+    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
     assert got == want
     assert sum(len(r) for r in want) > 5000
 
