@@ -19,7 +19,51 @@
 #include <pthread.h>
 #include <assert.h>
 #include <math.h>
+#include <malloc.h>
 #include "bb_host.h"
+
+/* ---------------------------------------------------------------- large host buffers
+ * A batch needs a few buffers of tens to hundreds of MB (codes, per-read state, extension work).  glibc
+ * serves those with mmap and returns them with munmap, i.e. every batch would page-fault them in again
+ * (with 100+ threads touching them at once, that costs more than the GPU stages).  Freed blocks are
+ * therefore parked here and handed out again; small allocations stay with malloc, whose arenas are told
+ * once not to trim (the same pages are recycled batch after batch). */
+typedef struct { void *p; size_t cap; } bigblk_t;
+static bigblk_t g_big[48];
+static pthread_mutex_t g_big_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_malloc_tuned;
+
+static void *big_alloc(size_t bytes)
+{
+	int i, best = -1;
+	void *p = 0;
+	pthread_mutex_lock(&g_big_mu);
+	if (!g_malloc_tuned) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20); g_malloc_tuned = 1; }
+	for (i = 0; i < 48; ++i)
+		if (g_big[i].p && g_big[i].cap >= bytes && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
+	if (best >= 0 && g_big[best].cap <= bytes * 4 + (64u << 20)) { p = g_big[best].p; g_big[best].p = 0; }
+	pthread_mutex_unlock(&g_big_mu);
+	if (!p) {
+		size_t cap = bytes + bytes / 8 + 4096;
+		size_t *q = bb_malloc(cap + 16);
+		q[0] = cap; q[1] = 0xB16B10C5u;
+		return q + 2;
+	}
+	return p;
+}
+
+static void big_free(void *p)
+{
+	size_t *q;
+	int i;
+	if (!p) return;
+	q = (size_t *)p - 2;
+	if (q[0] < (1u << 20)) { free(q); return; }
+	pthread_mutex_lock(&g_big_mu);
+	for (i = 0; i < 48; ++i) if (!g_big[i].p) { g_big[i].p = p; g_big[i].cap = q[0]; p = 0; break; }
+	pthread_mutex_unlock(&g_big_mu);
+	if (p) free(q);
+}
 
 /* phase timer: BWA_B200_PROFILE=1 prints the wall time of every phase of a batch to stderr */
 static int g_prof = -1;
@@ -259,6 +303,15 @@ static void load_raw_regs(job_t *j, long i, mem_alnreg_v *v)
 	v->n = (size_t)n;
 }
 
+static void w_zero_rs(void *d, long c, int tid)
+{
+	job_t *j = d;
+	long b = c * 4096, e = b + 4096 <= j->n ? b + 4096 : (long)j->n + 1;
+	(void)tid;
+	if (c == ((long)j->n + 4095) / 4096 - 1) e = (long)j->n + 1;
+	memset(j->rs + b, 0, (size_t)(e - b) * sizeof(rstate_t));
+}
+
 static void w_dedup(void *d, long i, int tid)
 {
 	job_t *j = d;
@@ -337,17 +390,17 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 	int64_t i, t;
 	int nt = j->opt->n_threads > 0 ? j->opt->n_threads : 1;
 	g.j = j; g.out = &out;
-	g.off = bb_malloc(sizeof(int64_t) * ((size_t)j->n + 1));
+	g.off = big_alloc(sizeof(int64_t) * ((size_t)j->n + 1));
 	g.off[0] = 0;
 	bb_parallel_for(nt, w_gcount, &g, j->n);
 	for (i = 0; i < j->n; ++i) g.off[i + 1] += g.off[i];
 	t = g.off[j->n];
-	if (t == 0) { free(g.off); return 0; }
-	g.tasks = bb_malloc(sizeof(bwag_gtask_t) * (size_t)t);
+	if (t == 0) { big_free(g.off); return 0; }
+	g.tasks = big_alloc(sizeof(bwag_gtask_t) * (size_t)t);
 	bb_parallel_for(nt, w_gfill, &g, j->n);
 	if (bwag_global(batch, swp, (int)t, g.tasks, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
 	bb_parallel_for(nt, w_gstore, &g, j->n);
-	free(g.tasks); free(g.off);
+	big_free(g.tasks); big_free(g.off);
 	return t;
 }
 
@@ -430,10 +483,10 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	int nt = opt->n_threads > 0 ? opt->n_threads : 1, t, n = j->n;
 	int64_t i, tot = 0, nc = 0, ns = 0;
 
-	j->off = bb_malloc(sizeof(int64_t) * ((size_t)n + 1));
+	j->off = big_alloc(sizeof(int64_t) * ((size_t)n + 1));
 	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
 	j->off[n] = tot;
-	j->codes = bb_malloc((size_t)tot + 16);
+	j->codes = big_alloc((size_t)tot + 16);
 	ph(0);
 	bb_parallel_for(nt, w_encode, j, n);
 	ph("encode");
@@ -450,17 +503,17 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	ph("seed_stage");
 
 	j->tls = bb_calloc(nt, sizeof(tls_t));
-	j->slice = bb_calloc((size_t)n + 1, sizeof(rslice_t));
+	j->slice = big_alloc(((size_t)n + 1) * sizeof(rslice_t));
 	bb_parallel_for(nt, w_chain, j, n);
 	ph("chain");
 
-	j->chain_off = bb_malloc(sizeof(int32_t) * ((size_t)n + 1));
+	j->chain_off = big_alloc(sizeof(int32_t) * ((size_t)n + 1));
 	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
 	j->n_xchains = nc; j->n_xseeds = ns;
-	j->xchains = bb_malloc(sizeof(bwag_xchain_t) * ((size_t)nc + 1));
-	j->xseeds = bb_malloc(sizeof(bwag_xseed_t) * ((size_t)ns + 1));
-	j->chain_rid = bb_malloc(sizeof(int) * ((size_t)nc + 1));
-	j->chain_frac = bb_malloc(sizeof(float) * ((size_t)nc + 1));
+	j->xchains = big_alloc(sizeof(bwag_xchain_t) * ((size_t)nc + 1));
+	j->xseeds = big_alloc(sizeof(bwag_xseed_t) * ((size_t)ns + 1));
+	j->chain_rid = big_alloc(sizeof(int) * ((size_t)nc + 1));
+	j->chain_frac = big_alloc(sizeof(float) * ((size_t)nc + 1));
 	for (i = 0, nc = ns = 0; i < n; ++i) {
 		j->chain_off[i] = (int32_t)nc;
 		if (j->slice[i].nc) j->xchains[nc].seed_off = (int32_t)ns; /* read's seed base, consumed by w_flatten */
@@ -474,14 +527,15 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		free(x->chains.a); free(x->xc.a); free(x->xs.a); free(x->c_rid.a); free(x->c_frac.a); free(x->srt.a);
 	}
 	free(j->tls); j->tls = 0;
-	free(j->slice); j->slice = 0;
+	big_free(j->slice); j->slice = 0;
 	ph("flatten");
 
 	if (bwag_extend(batch, swp, j->chain_off, j->xchains, j->n_xseeds, j->xseeds, &j->xregs) != 0)
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
 	ph("extend_stage");
 
-	j->rs = bb_calloc((size_t)n + 1, sizeof(rstate_t));
+	j->rs = big_alloc(((size_t)n + 1) * sizeof(rstate_t));
+	bb_parallel_for(nt, w_zero_rs, j, ((long)n + 4095) / 4096);
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
 		int64_t left = 0;
 		bb_parallel_for(nt, w_dedup, j, n);
@@ -503,7 +557,7 @@ static void w_free(void *d, long i, int tid)
 static void job_free(job_t *j)
 {
 	if (j->rs) bb_parallel_for(j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
-	free(j->rs); free(j->off); free(j->codes); free(j->chain_off); free(j->xchains); free(j->xseeds); free(j->chain_rid); free(j->chain_frac);
+	big_free(j->rs); big_free(j->off); big_free(j->codes); big_free(j->chain_off); big_free(j->xchains); big_free(j->xseeds); big_free(j->chain_rid); big_free(j->chain_frac);
 }
 
 void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
@@ -528,11 +582,11 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
 		else {
-			mem_alnreg_v *rv = bb_malloc(sizeof(mem_alnreg_v) * (size_t)n);
+			mem_alnreg_v *rv = big_alloc(sizeof(mem_alnreg_v) * (size_t)n);
 			int i;
 			for (i = 0; i < n; ++i) rv[i] = j.rs[i].regs;
 			mem_pestat(opt, bns->l_pac, n, rv, pes);
-			free(rv);
+			big_free(rv);
 		}
 		bb_parallel_for(nt, w_rescue, &j, n_units);
 	}
