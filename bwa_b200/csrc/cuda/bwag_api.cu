@@ -304,9 +304,9 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	SeedArgs a;
 	memset(&a, 0, sizeof(a));
 	for (int attempt = 0;; ++attempt) {
-		const int groups_per_block = K1_THREADS / 8;
+		const int groups_per_block = K1_THREADS;   /* one lane per read */
 		int grid = c->grid_k1;
-		size_t per_group = (size_t)(3 * cap_list + cap_mem) * 32;
+		size_t per_group = (size_t)(4 * cap_list + 2 * cap_mem) * 16;
 		{   /* keep the per-group scratch within ~6 GB: very long reads get fewer groups */
 			size_t budget = (size_t)6 << 30;
 			i64 max_groups = (i64)(budget / per_group);
@@ -329,8 +329,10 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		BWAG_LAUNCH(k_smem, grid, K1_THREADS, 0, c->stream, c->ix, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
+		BWAG_LAUNCH(k_seed_post, (n + K1B_THREADS - 1) / K1B_THREADS, K1B_THREADS, 0, c->stream, a);   /* harmless if K1 overflowed: the run is repeated */
+		CK(cudaGetLastError());
 		if (fetch_counters(c)) return 1;
-		c->st.ms_smem += elapsed(c); ++c->st.n_launch;
+		c->st.ms_smem += elapsed(c); c->st.n_launch += 2;
 		if (!(c->h_cnt->flags & 9u)) break;
 		if (attempt >= 6) return set_err("seeding: output pools keep overflowing (intervals %llu, seeds %llu)", (unsigned long long)c->h_cnt->n_intv, (unsigned long long)c->h_cnt->n_seeds);
 		if (c->h_cnt->flags & 1u) { /* pools too small: the counters say how much is needed */

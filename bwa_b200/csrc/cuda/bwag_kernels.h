@@ -4,6 +4,7 @@
 #include "bwag_dev.cuh"
 
 #define K1_THREADS 128
+#define K1B_THREADS 128
 #define K2_THREADS 128
 #define K4_THREADS 128
 #define K5_THREADS 128
@@ -56,6 +57,7 @@ extern "C" {
 #endif
 
 __global__ void k_smem(DevIndex ix, SeedArgs a);
+__global__ void k_seed_post(SeedArgs a);
 __global__ void k_sa(DevIndex ix, SaArgs a);
 __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
