@@ -34,7 +34,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0):
+def effective_cpus():
+    """CPUs this process may actually use: min(affinity mask, cgroup CPU quota).  GPU boxes of this pool show 128
+    logical CPUs but run the container under a CFS quota (cpu.max); oversubscribing the quota gets every thread throttled."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(round(int(q) / int(per)))))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            n = min(n, max(1, int(round(q / per))))
+    except Exception:
+        pass
+    return n
+
+
+def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0, paired=False):
     """Reference FASTA + index (once per box) and this rank's reads."""
     import gen_data
     import numpy as np
@@ -59,15 +80,18 @@ def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0):
         open(done, "w").write("ok")
     while not os.path.exists(done):
         time.sleep(0.5)
-    fq = os.path.join(workdir, "reads_%d_%d_r%d.fq" % (n_reads, read_len, rank))
-    if not os.path.exists(fq):
+    tag = os.path.join(workdir, "reads_%s%d_%d_r%d" % ("pe" if paired else "se", n_reads, read_len, rank))
+    fqs = [tag + "_1.fq", tag + "_2.fq"] if paired else [tag + ".fq"]
+    if not all(os.path.exists(f) for f in fqs):
         t0 = time.time()
         # reads are drawn without materialising the FASTA again: regenerate the contigs from the seed
         contigs = gen_data.random_contigs(n_contigs, contig_len, 7)
-        r1, _ = gen_data.gen_reads(contigs, n_reads, read_len, seed + rank)
-        gen_data.write_fastq(fq, r1)
+        r1, r2 = gen_data.gen_reads(contigs, n_reads // 2 if paired else n_reads, read_len, seed + rank, paired=paired)
+        gen_data.write_fastq(fqs[0], r1)
+        if paired:
+            gen_data.write_fastq(fqs[1], r2)
         log("[bench] %d reads written in %.1fs" % (n_reads, time.time() - t0))
-    return fa, fq
+    return fa, fqs
 
 
 class ClockSampler(threading.Thread):
@@ -101,17 +125,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference(fa, fq, n_sample, threads):
+def time_reference(fa, fqs, n_sample, threads):
     """`bwa mem -t threads` of the unmodified reference on the first n_sample reads; reads/s from its own
     '[M::mem_process_seqs] Processed N reads in X CPU sec, Y real sec' lines (excludes index load and I/O)."""
-    sample = fq + ".sample%d" % n_sample
-    if not os.path.exists(sample):
-        with open(fq, "rb") as f, open(sample, "wb") as o:
-            for i, line in enumerate(f):
-                if i >= 4 * n_sample:
-                    break
-                o.write(line)
-    r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa, sample], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    samples = []
+    per_file = n_sample // len(fqs)
+    for fq in fqs:
+        sample = fq + ".sample%d" % per_file
+        if not os.path.exists(sample):
+            with open(fq, "rb") as f, open(sample, "wb") as o:
+                for i, line in enumerate(f):
+                    if i >= 4 * per_file:
+                        break
+                    o.write(line)
+        samples.append(sample)
+    r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa] + samples, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     n, real = 0, 0.0
     for m in re.finditer(r"Processed (\d+) reads in ([\d.]+) CPU sec, ([\d.]+) real sec", r.stderr):
         n += int(m.group(1)); real += float(m.group(3))
@@ -129,6 +157,7 @@ def main():
     ap.add_argument("--ref-mbp", type=int, default=int(os.environ.get("BWA_B200_BENCH_REF_MBP", "3000")))
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BWA_B200_BENCH_READS", "1000000")))
     ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--layout", default=os.environ.get("BWA_B200_BENCH_LAYOUT", "pe"), choices=["pe", "se"], help="pe: 2x150 bp pairs (FR, insert N(400,50)); se: single-end")
     ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
     ap.add_argument("--cpu-sample", type=int, default=100000)
@@ -138,14 +167,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    ncores = os.cpu_count() or 1
+    ncores = effective_cpus()
     threads = a.threads or max(1, ncores // max(1, world))
-    workload = "%d synthetic %d-bp SE reads per GPU, 1%% error, vs %d Mbp uniform-random reference" % (a.reads, a.read_len, a.ref_mbp)
+    paired = a.layout == "pe"
+    workload = "%d synthetic %s reads per GPU per step (%s), 1%% error, vs %d Mbp uniform-random reference" % (
+        a.reads, "2x%d-bp PE" % a.read_len if paired else "%d-bp SE" % a.read_len, "%d pairs, FR, insert N(400,50)" % (a.reads // 2) if paired else "single-end", a.ref_mbp)
 
     if a.impl == "reference":
         if rank != 0:
             return
-        fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000)
+        fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, 0, paired)
         n_sample = min(a.reads, a.cpu_sample)
         vals = []
         for s in range(a.warmup + a.steps):
@@ -175,7 +206,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank)
+    fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank, paired)
     if world > 1:
         dist.barrier()
 
@@ -212,7 +243,9 @@ def main():
 
     opt = L.mem_opt_init()
     opt.contents.n_threads = threads
-    batch = bwa_b200.ReadBatch(fq)
+    batch = bwa_b200.ReadBatch(*fq)
+    if paired:
+        opt.contents.flag |= bwa_b200.MEM_F_PE
     n_reads = batch.n
 
     def step():

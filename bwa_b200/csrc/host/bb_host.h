@@ -80,6 +80,7 @@ typedef BB_VEC(bb_galn_t) bb_galn_v;
 typedef struct {
 	bb_galn_v memo;
 	int pending;     /* requests recorded in this pass */
+	bb_galn_t inl;   /* storage of the first entry: most reads need exactly one alignment */
 } bb_gcache_t;
 const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc);
 
@@ -97,6 +98,7 @@ typedef struct {
 	bb_gcache_t *gc;   /* of the read being formatted */
 	int dry;           /* pass that only discovers which alignments are needed: skip text */
 } bb_samctx_t;
+int bb_reg2aln_band(const mem_opt_t *opt, const mem_alnreg_t *ar);
 mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query, const mem_alnreg_t *ar);
 void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_t *s, int n, const mem_aln_t *list, int which, const mem_aln_t *m_);
 void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, const mem_aln_t *m);

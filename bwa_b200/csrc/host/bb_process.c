@@ -135,17 +135,23 @@ const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_
 	}
 	memset(&e, 0, sizeof(e));
 	e.mode = mode; e.qb = qb; e.qe = qe; e.rb = rb; e.re = re; e.w = w; e.truesc = truesc;
-	bb_vec_push(gc->memo, e);
+	if (gc->memo.a == 0) { gc->memo.a = &gc->inl; gc->memo.m = 1; gc->memo.n = 0; }
+	if (gc->memo.n == gc->memo.m) { /* leave the inline slot for the heap */
+		size_t m = gc->memo.m < 4 ? 4 : gc->memo.m << 1;
+		bb_galn_t *na = bb_malloc(m * sizeof(bb_galn_t));
+		memcpy(na, gc->memo.a, gc->memo.n * sizeof(bb_galn_t));
+		if (gc->memo.a != &gc->inl) free(gc->memo.a);
+		gc->memo.a = na; gc->memo.m = m;
+	}
+	gc->memo.a[gc->memo.n++] = e;
 	++gc->pending;
 	return 0;
 }
 
-static void gcache_free(bb_gcache_t *gc)
+static void gcache_free(bb_gcache_t *gc) /* CIGAR/MD bytes live in per-round blocks owned by the job */
 {
-	size_t i;
-	for (i = 0; i < gc->memo.n; ++i) free(gc->memo.a[i].cigar);
-	free(gc->memo.a);
-	memset(gc, 0, sizeof(*gc));
+	if (gc->memo.a != &gc->inl) free(gc->memo.a);
+	gc->memo.a = 0; gc->memo.n = gc->memo.m = 0;
 }
 
 /* ---------------------------------------------------------------- batch state */
@@ -195,6 +201,8 @@ typedef struct {
 	int64_t n_xchains, n_xseeds;
 	bwag_regs_t xregs;
 	int pass_dry;
+	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
+	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
 } job_t;
 
 static void w_encode(void *d, long i, int tid)
@@ -290,7 +298,8 @@ static void load_raw_regs(job_t *j, long i, mem_alnreg_v *v)
 	int k, n = c1 > c0 ? j->xregs.n_regs[i] : 0;
 	const bwag_xreg_t *x = c1 > c0 ? j->xregs.regs + j->xchains[c0].seed_off : 0;
 	v->n = 0;
-	bb_vec_reserve(*v, (size_t)n + 4);
+	if (j->reg_pool) { v->a = j->reg_pool + j->reg_off[i]; v->m = (size_t)n; }
+	else bb_vec_reserve(*v, (size_t)n + 4);
 	for (k = 0; k < n; ++k) {
 		mem_alnreg_t *a = &v->a[k];
 		memset(a, 0, sizeof(*a));
@@ -328,12 +337,16 @@ static void w_dedup(void *d, long i, int tid)
 	for (k = 0; k < r->regs.n; ++k) {
 		mem_alnreg_t *p = &r->regs.a[k];
 		if (p->rid >= 0 && j->bns->anns[p->rid].is_alt) p->is_alt = 1;
+		/* Every region that can reach the output (or an XA list) will need its CIGAR: ask for all of them now, so
+		 * that one device round serves the batch before the SAM pass (the K5 kernel is cheap; the host's time is not).
+		 * The SAM pass still recovers through the cache-miss path if it ever needs something else. */
+		bb_gcache_get(&r->gc, BWAG_G_REG2ALN, p->qb, p->qe, p->rb, p->re, bb_reg2aln_band(j->opt, p), p->truesc);
 	}
 	r->dedup_done = 1;
 }
 
 /* serve every outstanding alignment request of the batch with one device call; returns #requests */
-typedef struct { job_t *j; int64_t *off; bwag_gtask_t *tasks; const bwag_galn_t *out; } ground_t;
+typedef struct { job_t *j; int64_t *off; bwag_gtask_t *tasks; const bwag_galn_t *out; int64_t *boff; char *block; } ground_t;
 
 static void w_gcount(void *d, long i, int tid)
 {
@@ -367,6 +380,7 @@ static void w_gstore(void *d, long i, int tid)
 	ground_t *g = d;
 	bb_galn_v *m = &g->j->rs[i].gc.memo;
 	const bwag_gres_t *r = g->out->res + g->off[i];
+	const int64_t *bo = g->boff + g->off[i];
 	size_t k;
 	(void)tid;
 	if (g->off[i + 1] == g->off[i]) return;
@@ -374,7 +388,7 @@ static void w_gstore(void *d, long i, int tid)
 		bb_galn_t *e = &m->a[k];
 		if (e->done) continue;
 		e->score = r->score; e->n_cigar = r->n_cigar; e->NM = r->NM; e->l_md = r->l_md > 0 ? r->l_md : 1;
-		e->cigar = bb_malloc(4 * (size_t)r->n_cigar + e->l_md);
+		e->cigar = (uint32_t *)(g->block + *bo++);
 		memcpy(e->cigar, g->out->cigar + r->cigar_off, 4 * (size_t)r->n_cigar);
 		if (r->l_md > 0) memcpy((char *)(e->cigar + r->n_cigar), g->out->md + r->md_off, r->l_md);
 		else *(char *)(e->cigar + r->n_cigar) = 0;
@@ -399,8 +413,17 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 	g.tasks = big_alloc(sizeof(bwag_gtask_t) * (size_t)t);
 	bb_parallel_for(nt, w_gfill, &g, j->n);
 	if (bwag_global(batch, swp, (int)t, g.tasks, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
+	g.boff = big_alloc(sizeof(int64_t) * ((size_t)t + 1));
+	{
+		int64_t x, tot = 0;
+		for (x = 0; x < t; ++x) { g.boff[x] = tot; tot += ((int64_t)4 * out.res[x].n_cigar + (out.res[x].l_md > 0 ? out.res[x].l_md : 1) + 7) & ~(int64_t)7; }
+		g.boff[t] = tot;
+		if (j->n_blocks == 64) bb_fatal("mem_process_seqs", "too many device rounds in one batch");
+		g.block = big_alloc((size_t)tot + 8);
+		j->blocks[j->n_blocks++] = g.block;
+	}
 	bb_parallel_for(nt, w_gstore, &g, j->n);
-	big_free(g.tasks); big_free(g.off);
+	big_free(g.tasks); big_free(g.off); big_free(g.boff);
 	return t;
 }
 
@@ -414,13 +437,17 @@ static void w_rescue(void *d, long i, int tid)
 	j->rs[i << 1].regs = a[0]; j->rs[i << 1 | 1].regs = a[1];
 }
 
-static void copy_regs(mem_alnreg_v *dst, const mem_alnreg_v *src)
+#define STACK_REGS 8
+/* scratch copy of a read's regions: on the caller's stack when small, else on the heap (freed by drop_regs) */
+static void copy_regs(mem_alnreg_v *dst, const mem_alnreg_v *src, mem_alnreg_t *stack)
 {
 	dst->n = 0;
-	bb_vec_reserve(*dst, src->n + 1);
+	if (src->n <= STACK_REGS) { dst->a = stack; dst->m = STACK_REGS; }
+	else { dst->a = 0; dst->m = 0; bb_vec_reserve(*dst, src->n + 1); }
 	memcpy(dst->a, src->a, src->n * sizeof(mem_alnreg_t));
 	dst->n = src->n;
 }
+static void drop_regs(mem_alnreg_v *v, const mem_alnreg_t *stack) { if (v->a != stack) free(v->a); }
 
 /* worker2 of the reference (bwamem.c:1217-1233) for read / pair i, on a scratch copy of the regions */
 static void run_sam(job_t *j, long i, int dry)
@@ -429,18 +456,20 @@ static void run_sam(job_t *j, long i, int dry)
 	if (!(opt->flag & MEM_F_PE)) {
 		rstate_t *r = &j->rs[i];
 		mem_alnreg_v w = {0, 0, 0};
+		mem_alnreg_t st0[STACK_REGS];
 		bb_samctx_t sc = { opt, j->bns, j->pac, &r->gc, dry };
-		copy_regs(&w, &r->regs);
+		copy_regs(&w, &r->regs, st0);
 		bb_mark_primary_se(opt, (int)w.n, w.a, j->n_processed + i);
 		if (opt->flag & MEM_F_PRIMARY5) bb_reorder_primary5(opt->T, &w);
 		bb_reg2sam(&sc, &j->seqs[i], &w, 0, 0);
-		free(w.a);
+		drop_regs(&w, st0);
 	} else {
 		mem_alnreg_v w[2] = {{0, 0, 0}, {0, 0, 0}};
+		mem_alnreg_t st0[STACK_REGS], st1[STACK_REGS];
 		bb_samctx_t sc[2] = { { opt, j->bns, j->pac, &j->rs[i << 1].gc, dry }, { opt, j->bns, j->pac, &j->rs[i << 1 | 1].gc, dry } };
-		copy_regs(&w[0], &j->rs[i << 1].regs); copy_regs(&w[1], &j->rs[i << 1 | 1].regs);
+		copy_regs(&w[0], &j->rs[i << 1].regs, st0); copy_regs(&w[1], &j->rs[i << 1 | 1].regs, st1);
 		bb_sam_pe(sc, j->pes, (uint64_t)((j->n_processed >> 1) + i), &j->seqs[i << 1], w, 1);
-		free(w[0].a); free(w[1].a);
+		drop_regs(&w[0], st0); drop_regs(&w[1], st1);
 	}
 }
 
@@ -534,6 +563,12 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
 	ph("extend_stage");
 
+	if (!(opt->flag & MEM_F_PE)) { /* SE: region arrays never grow after this point -> one block for all reads */
+		int64_t tot_regs = 0;
+		j->reg_off = big_alloc(sizeof(int64_t) * ((size_t)n + 1));
+		for (i = 0; i < n; ++i) { j->reg_off[i] = tot_regs; tot_regs += j->chain_off[i + 1] > j->chain_off[i] ? j->xregs.n_regs[i] : 0; }
+		j->reg_pool = big_alloc(sizeof(mem_alnreg_t) * ((size_t)tot_regs + 1));
+	}
 	j->rs = big_alloc(((size_t)n + 1) * sizeof(rstate_t));
 	bb_parallel_for(nt, w_zero_rs, j, ((long)n + 4095) / 4096);
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
@@ -541,8 +576,9 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		bb_parallel_for(nt, w_dedup, j, n);
 		ph("dedup");
 		for (i = 0; i < n; ++i) left += !j->rs[i].dedup_done;
+		if (global_round(j, batch, swp) == 0 && left) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
+		ph("global_round");
 		if (left == 0) break;
-		if (global_round(j, batch, swp) == 0) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
 	}
 	return batch;
 }
@@ -551,12 +587,15 @@ static void w_free(void *d, long i, int tid)
 {
 	job_t *j = d;
 	(void)tid;
-	free(j->rs[i].regs.a); gcache_free(&j->rs[i].gc);
+	if (!j->reg_pool) free(j->rs[i].regs.a);
+	gcache_free(&j->rs[i].gc);
 }
 
 static void job_free(job_t *j)
 {
 	if (j->rs) bb_parallel_for(j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
+	{ int b; for (b = 0; b < j->n_blocks; ++b) big_free(j->blocks[b]); }
+	big_free(j->reg_pool); big_free(j->reg_off);
 	big_free(j->rs); big_free(j->off); big_free(j->codes); big_free(j->chain_off); big_free(j->xchains); big_free(j->xseeds); big_free(j->chain_rid); big_free(j->chain_frac);
 }
 
@@ -590,7 +629,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		}
 		bb_parallel_for(nt, w_rescue, &j, n_units);
 	}
-	for (j.pass_dry = 1;; j.pass_dry = 0) { /* SAM: discover needed alignments, serve them on the device, write */
+	for (j.pass_dry = 0;; j.pass_dry = 0) { /* SAM; a read that misses an alignment is retried after a device round */
 		long i, left = 0;
 		bb_parallel_for(nt, w_sam, &j, n_units);
 		ph(j.pass_dry ? "sam_dry" : "sam_real");
@@ -665,6 +704,7 @@ mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *
 		rs.gc.pending = 0;
 		a = bb_reg2aln(&sc, l_seq, s.seq, ar);
 	}
+	{ int b; for (b = 0; b < j.n_blocks; ++b) big_free(j.blocks[b]); }
 	gcache_free(&rs.gc);
 	free(s.seq);
 	return a;

@@ -30,13 +30,23 @@ static int cigar_ref_len(int n_cigar, const uint32_t *cigar)
 	return l;
 }
 
+/* starting band of the band-doubling loop of mem_reg2aln for region ar (bwamem.c:1138-1142) */
+int bb_reg2aln_band(const mem_opt_t *opt, const mem_alnreg_t *ar)
+{
+	int tmp = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
+	int w2 = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
+	w2 = w2 > tmp ? w2 : tmp;
+	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+	return w2;
+}
+
 /* bwamem.c:1119-1189 */
 mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query_, const mem_alnreg_t *ar)
 {
 	const mem_opt_t *opt = sc->opt;
 	const bntseq_t *bns = sc->bns;
 	mem_aln_t a;
-	int w2, tmp, qb, qe, is_rev, l_MD;
+	int w2, qb, qe, is_rev, l_MD;
 	int64_t pos, rb, re;
 	const bb_galn_t *g;
 	(void)query_;
@@ -48,10 +58,7 @@ mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query_, const mem
 	qb = ar->qb; qe = ar->qe; rb = ar->rb; re = ar->re;
 	a.mapq = ar->secondary < 0 ? bb_approx_mapq_se(opt, ar) : 0;
 	if (ar->secondary >= 0) a.flag |= 0x100;
-	tmp = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
-	w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
-	w2 = w2 > tmp ? w2 : tmp;
-	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+	w2 = bb_reg2aln_band(opt, ar);
 	/* the band-doubling loop (bwamem.c:1144-1152) runs on the device; w2 is its starting band */
 	g = bb_gcache_get(sc->gc, BWAG_G_REG2ALN, qb, qe, rb, re, w2, ar->truesc);
 	pos = bb_depos(bns, rb < bns->l_pac ? rb : re - 1, &is_rev);
@@ -240,6 +247,7 @@ char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const cha
 	int i, k, r, tot = 0, *cnt;
 	bb_str_t *aln, one = {0, 0, 0};
 	char **XA, *has_alt;
+	if (a->n <= 1) return 0;      /* a lone region has no parent: nothing to list (tot == 0 below) */
 	cnt = bb_calloc(a->n, sizeof(int));
 	has_alt = bb_calloc(a->n, 1);
 	for (i = 0; i < (int)a->n; ++i) {
@@ -281,6 +289,7 @@ void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, co
 	int l = 0;
 	char **XA = 0;
 	if (!(opt->flag & MEM_F_ALL)) XA = bb_gen_alt(sc, a, s->l_seq, s->seq);
+	if (!sc->dry) bb_str_need(&str, (size_t)s->l_seq * 2 + strlen(s->name) + 160);   /* one allocation for the common single-record case */
 	for (k = 0; k < a->n; ++k) {
 		mem_alnreg_t *p = &a->a[k];
 		mem_aln_t q;
