@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <pthread.h>
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
 
@@ -82,11 +83,15 @@ struct bwag_ctx {
 	/* scratch reused across batches */
 	DevBuf s_k1, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
 	int grid_k1, grid_k2, grid_k4, grid_k5;
-	struct bwag_batch *spare;   /* batch object (with its device and pinned buffers) kept for the next batch */
+	struct bwag_batch *spare[4]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
+	pthread_mutex_t mu;
+	struct bwag_ctx *parent;     /* set in the per-batch view of the context */
 };
 
 struct bwag_batch {
 	bwag_ctx_t *ctx;
+	bwag_ctx_t lc;               /* per-batch view of the context: own stream, events, counters, scratch, stats -> batches can overlap */
+	int lc_ready;
 	int n;
 	i64 total_bases;
 	int max_len;
@@ -179,6 +184,7 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
 	CKP(cudaMalloc((void **)&c->d_cnt, sizeof(Counters)));
 	CKP(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
+	pthread_mutex_init(&c->mu, 0);
 	if (pick_grid(c)) { free(c); return 0; }
 	return c;
 }
@@ -203,7 +209,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	free_dev(&c->s_k1); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
-	if (c->spare) { batch_free(c->spare); c->spare = 0; }
+	for (int i = 0; i < 4; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
@@ -231,21 +237,35 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 	return 0;
 }
 
-extern "C" void bwag_stats_get(bwag_ctx_t *c, bwag_stats_t *s) { *s = c->st; }
-extern "C" void bwag_stats_reset(bwag_ctx_t *c) { memset(&c->st, 0, sizeof(c->st)); }
+extern "C" void bwag_stats_get(bwag_ctx_t *c, bwag_stats_t *s) { pthread_mutex_lock(&c->mu); *s = c->st; pthread_mutex_unlock(&c->mu); }
+extern "C" void bwag_stats_reset(bwag_ctx_t *c) { pthread_mutex_lock(&c->mu); memset(&c->st, 0, sizeof(c->st)); pthread_mutex_unlock(&c->mu); }
 
 /* ------------------------------------------------------------------------------------------------ batch */
 
 extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *codes, const int64_t *off)
 {
-	bwag_batch_t *b = c->spare;   /* buffers only grow: cudaMalloc/cudaMallocHost per batch would cost more than the kernels */
-	c->spare = 0;
+	bwag_batch_t *b = 0;   /* buffers only grow: cudaMalloc/cudaMallocHost per batch would cost more than the kernels */
+	pthread_mutex_lock(&c->mu);
+	for (int i = 0; i < 4; ++i) if (c->spare[i]) { b = c->spare[i]; c->spare[i] = 0; break; }
+	pthread_mutex_unlock(&c->mu);
 	if (!b) b = (bwag_batch_t *)calloc(1, sizeof(*b));
 	CKP(cudaSetDevice(c->device));
+	if (!b->lc_ready) {    /* first use of this batch object: its own stream, events and counters */
+		memset(&b->lc, 0, sizeof(b->lc));
+		CKP(cudaStreamCreate(&b->lc.stream));
+		CKP(cudaEventCreate(&b->lc.ev0)); CKP(cudaEventCreate(&b->lc.ev1));
+		CKP(cudaMalloc((void **)&b->lc.d_cnt, sizeof(Counters)));
+		CKP(cudaMallocHost((void **)&b->lc.h_cnt, sizeof(Counters)));
+		b->lc_ready = 1;
+	}
+	b->lc.device = c->device; b->lc.n_sm = c->n_sm; b->lc.ix = c->ix; b->lc.parent = c;
+	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
+	memset(&b->lc.st, 0, sizeof(b->lc.st));
 	b->max_len = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
 	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
 	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { free(b); return 0; }
+	c = &b->lc;
 	CKP(cudaEventRecord(c->ev0, c->stream));
 	CKP(cudaMemcpyAsync(b->d_codes.p, codes, (size_t)b->total_bases, cudaMemcpyHostToDevice, c->stream));
 	CKP(cudaMemcpyAsync(b->d_off.p, off, sizeof(i64) * ((size_t)n + 1), cudaMemcpyHostToDevice, c->stream));
@@ -259,14 +279,29 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 extern "C" void bwag_batch_end(bwag_batch_t *b)
 {
 	if (!b) return;
-	cudaSetDevice(b->ctx->device);
-	cudaStreamSynchronize(b->ctx->stream);
-	if (!b->ctx->spare) { b->ctx->spare = b; return; }
-	batch_free(b);
+	bwag_ctx_t *c = b->ctx;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(b->lc.stream);
+	pthread_mutex_lock(&c->mu);
+	{   /* fold this batch's counters into the context */
+		bwag_stats_t *d = &c->st, *x = &b->lc.st;
+		d->occ_touches += x->occ_touches; d->sa_touches += x->sa_touches; d->sa_touches_algo += x->sa_touches_algo;
+		d->ext_cells += x->ext_cells; d->glb_cells += x->glb_cells;
+		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
+		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
+	}
+	for (int i = 0; i < 4; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
+	pthread_mutex_unlock(&c->mu);
+	if (b) batch_free(b);
 }
 
 static void batch_free(bwag_batch_t *b)
 {
+	if (b->lc_ready) {
+		free_dev(&b->lc.s_k1); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
+		cudaFree(b->lc.d_cnt); cudaFreeHost(b->lc.h_cnt);
+		cudaEventDestroy(b->lc.ev0); cudaEventDestroy(b->lc.ev1); cudaStreamDestroy(b->lc.stream);
+	}
 	free_dev(&b->d_codes); free_dev(&b->d_off);
 	free_dev(&b->d_intv_beg); free_dev(&b->d_intv_n); free_dev(&b->d_intv); free_dev(&b->d_seed_beg); free_dev(&b->d_rbeg);
 	free_host(&b->h_intv_beg); free_host(&b->h_intv_n); free_host(&b->h_intv); free_host(&b->h_seed_beg); free_host(&b->h_rbeg);
@@ -296,7 +331,7 @@ static double elapsed(bwag_ctx_t *c) { float ms = 0; cudaEventElapsedTime(&ms, c
 
 extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out)
 {
-	bwag_ctx_t *c = b->ctx;
+	bwag_ctx_t *c = &b->lc;
 	CK(cudaSetDevice(c->device));
 	const int n = b->n;
 	i64 cap_intv = (i64)n * 16 + b->total_bases / 8 + 1024, cap_seeds = (i64)n * 32 + b->total_bases / 4 + 4096;
@@ -379,7 +414,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int32_t *chain_off, const bwag_xchain_t *chains,
                            int64_t n_seeds, const bwag_xseed_t *seeds, bwag_regs_t *out)
 {
-	bwag_ctx_t *c = b->ctx;
+	bwag_ctx_t *c = &b->lc;
 	CK(cudaSetDevice(c->device));
 	const int n = b->n;
 	const i64 n_chains = chain_off[n];
@@ -435,7 +470,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 
 extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out)
 {
-	bwag_ctx_t *c = b->ctx;
+	bwag_ctx_t *c = &b->lc;
 	CK(cudaSetDevice(c->device));
 	if (n_tasks <= 0) { out->res = 0; out->cigar = 0; out->md = 0; return 0; }
 	i64 cap_z = 64, n_aln = 0;

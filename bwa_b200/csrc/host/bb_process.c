@@ -203,6 +203,9 @@ typedef struct {
 	int pass_dry;
 	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
+	int lane;                /* which host-thread pool / device batch object this chunk runs on */
+	bwag_batch_t *batch;
+	bwag_sw_par_t swp;
 } job_t;
 
 static void w_encode(void *d, long i, int tid)
@@ -406,12 +409,12 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 	g.j = j; g.out = &out;
 	g.off = big_alloc(sizeof(int64_t) * ((size_t)j->n + 1));
 	g.off[0] = 0;
-	bb_parallel_for(nt, w_gcount, &g, j->n);
+	bb_parallel_for_lane(j->lane, nt, w_gcount, &g, j->n);
 	for (i = 0; i < j->n; ++i) g.off[i + 1] += g.off[i];
 	t = g.off[j->n];
 	if (t == 0) { big_free(g.off); return 0; }
 	g.tasks = big_alloc(sizeof(bwag_gtask_t) * (size_t)t);
-	bb_parallel_for(nt, w_gfill, &g, j->n);
+	bb_parallel_for_lane(j->lane, nt, w_gfill, &g, j->n);
 	if (bwag_global(batch, swp, (int)t, g.tasks, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
 	g.boff = big_alloc(sizeof(int64_t) * ((size_t)t + 1));
 	{
@@ -422,7 +425,7 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 		g.block = big_alloc((size_t)tot + 8);
 		j->blocks[j->n_blocks++] = g.block;
 	}
-	bb_parallel_for(nt, w_gstore, &g, j->n);
+	bb_parallel_for_lane(j->lane, nt, w_gstore, &g, j->n);
 	big_free(g.tasks); big_free(g.off); big_free(g.boff);
 	return t;
 }
@@ -516,25 +519,24 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
 	j->off[n] = tot;
 	j->codes = big_alloc((size_t)tot + 16);
-	ph(0);
-	bb_parallel_for(nt, w_encode, j, n);
-	ph("encode");
+	bb_parallel_for_lane(j->lane, nt, w_encode, j, n);
+	if (j->lane == 0) ph("encode");
 
 	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
 	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
-	ph("batch_begin");
+	if (j->lane == 0) ph("batch_begin");
 	sp.min_seed_len = opt->min_seed_len;
 	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
 	sp.split_width = opt->split_width;
 	sp.max_occ = opt->max_occ;
 	sp.max_mem_intv = opt->max_mem_intv;
 	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
-	ph("seed_stage");
+	if (j->lane == 0) ph("seed_stage");
 
 	j->tls = bb_calloc(nt, sizeof(tls_t));
 	j->slice = big_alloc(((size_t)n + 1) * sizeof(rslice_t));
-	bb_parallel_for(nt, w_chain, j, n);
-	ph("chain");
+	bb_parallel_for_lane(j->lane, nt, w_chain, j, n);
+	if (j->lane == 0) ph("chain");
 
 	j->chain_off = big_alloc(sizeof(int32_t) * ((size_t)n + 1));
 	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
@@ -549,7 +551,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		nc += j->slice[i].nc; ns += j->slice[i].ns;
 	}
 	j->chain_off[n] = (int32_t)nc;
-	bb_parallel_for(nt, w_flatten, j, n);
+	bb_parallel_for_lane(j->lane, nt, w_flatten, j, n);
 	for (t = 0; t < nt; ++t) {
 		tls_t *x = &j->tls[t];
 		bb_chainer_free(x->chainer);
@@ -557,11 +559,11 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	}
 	free(j->tls); j->tls = 0;
 	big_free(j->slice); j->slice = 0;
-	ph("flatten");
+	if (j->lane == 0) ph("flatten");
 
 	if (bwag_extend(batch, swp, j->chain_off, j->xchains, j->n_xseeds, j->xseeds, &j->xregs) != 0)
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
-	ph("extend_stage");
+	if (j->lane == 0) ph("extend_stage");
 
 	if (!(opt->flag & MEM_F_PE)) { /* SE: region arrays never grow after this point -> one block for all reads */
 		int64_t tot_regs = 0;
@@ -570,14 +572,14 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		j->reg_pool = big_alloc(sizeof(mem_alnreg_t) * ((size_t)tot_regs + 1));
 	}
 	j->rs = big_alloc(((size_t)n + 1) * sizeof(rstate_t));
-	bb_parallel_for(nt, w_zero_rs, j, ((long)n + 4095) / 4096);
+	bb_parallel_for_lane(j->lane, nt, w_zero_rs, j, ((long)n + 4095) / 4096);
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
 		int64_t left = 0;
-		bb_parallel_for(nt, w_dedup, j, n);
-		ph("dedup");
+		bb_parallel_for_lane(j->lane, nt, w_dedup, j, n);
+		if (j->lane == 0) ph("dedup");
 		for (i = 0; i < n; ++i) left += !j->rs[i].dedup_done;
 		if (global_round(j, batch, swp) == 0 && left) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
-		ph("global_round");
+		if (j->lane == 0) ph("global_round");
 		if (left == 0) break;
 	}
 	return batch;
@@ -593,54 +595,118 @@ static void w_free(void *d, long i, int tid)
 
 static void job_free(job_t *j)
 {
-	if (j->rs) bb_parallel_for(j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
+	if (j->rs) bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
 	{ int b; for (b = 0; b < j->n_blocks; ++b) big_free(j->blocks[b]); }
 	big_free(j->reg_pool); big_free(j->reg_off);
 	big_free(j->rs); big_free(j->off); big_free(j->codes); big_free(j->chain_off); big_free(j->xchains); big_free(j->xseeds); big_free(j->chain_rid); big_free(j->chain_frac);
 }
 
+/* second half of a chunk: (PE: mate rescue,) SAM with as many device rounds as cache misses require */
+static void job_finish(job_t *j, bwag_ctx_t *ctx)
+{
+	const mem_opt_t *opt = j->opt;
+	int nt = opt->n_threads > 0 ? opt->n_threads : 1, pe = !!(opt->flag & MEM_F_PE);
+	long n_units = pe ? j->n >> 1 : j->n;
+	if (!j->batch) {
+		j->batch = bwag_batch_begin(ctx, j->n, j->codes, j->off);
+		if (!j->batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
+	}
+	if (pe) bb_parallel_for_lane(j->lane, nt, w_rescue, j, n_units);
+	for (j->pass_dry = 0;; j->pass_dry = 0) { /* SAM; a read that misses an alignment is retried after a device round */
+		long i, left = 0;
+		bb_parallel_for_lane(j->lane, nt, w_sam, j, n_units);
+		if (j->lane == 0) ph("sam");
+		for (i = 0; i < j->n; ++i) left += !j->rs[i].done;
+		if (left == 0) break;
+		if (global_round(j, j->batch, &j->swp) == 0) bb_fatal("mem_process_seqs", "internal error: unfinished reads without requests");
+		if (j->lane == 0) ph("global_round");
+	}
+	bwag_batch_end(j->batch); j->batch = 0;
+	job_free(j);
+	if (j->lane == 0) ph("cleanup");
+}
+
+typedef struct { job_t *jobs; int n_jobs; volatile int next; bwag_ctx_t *ctx; int phase, lane, pe; } lane_arg_t;
+
+static void *lane_main(void *a_)
+{
+	lane_arg_t *a = a_;
+	for (;;) {
+		int k = __sync_fetch_and_add(&a[-a->lane].next, 1);   /* the shared counter lives in lane 0's record */
+		job_t *j;
+		if (k >= a->n_jobs) break;
+		j = &a->jobs[k];
+		j->lane = a->lane;
+		if (a->phase == 0) {
+			j->batch = run_to_regs(j, a->ctx, &j->swp);
+			if (a->pe) { bwag_batch_end(j->batch); j->batch = 0; }   /* the insert-size model needs every chunk first */
+			else job_finish(j, a->ctx);
+		} else job_finish(j, a->ctx);
+	}
+	return 0;
+}
+
+static void run_lanes(job_t *jobs, int n_jobs, int n_lanes, bwag_ctx_t *ctx, int phase, int pe)
+{
+	lane_arg_t la[8];
+	pthread_t th[8];
+	int l;
+	for (l = 0; l < n_lanes; ++l) { la[l].jobs = jobs; la[l].n_jobs = n_jobs; la[l].next = 0; la[l].ctx = ctx; la[l].phase = phase; la[l].lane = l; la[l].pe = pe; }
+	for (l = 1; l < n_lanes; ++l) pthread_create(&th[l], 0, lane_main, &la[l]);
+	lane_main(&la[0]);
+	for (l = 1; l < n_lanes; ++l) pthread_join(th[l], 0);
+}
+
+/* The batch is cut into chunks that travel through the stages on `lanes` independent lanes (own CUDA stream and
+ * device buffers, own host-thread pool): while one chunk sits in a GPU stage the other runs a host phase, so
+ * kernels, PCIe copies and host work overlap.  BWA_B200_LANES / BWA_B200_CHUNK override the defaults. */
 void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                       int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	job_t j;
+	job_t *jobs;
 	mem_pestat_t pes[4];
-	bwag_sw_par_t swp;
 	bwag_ctx_t *ctx;
-	bwag_batch_t *batch;
 	double ctime = bb_cputime(), rtime = bb_realtime();
-	int nt = opt->n_threads > 0 ? opt->n_threads : 1, pe = !!(opt->flag & MEM_F_PE);
-	long n_units = pe ? n >> 1 : n;
+	int pe = !!(opt->flag & MEM_F_PE), n_lanes = 2, n_jobs, k;
+	long chunk = 1 << 18, start;
+	const char *e;
 
 	if (n <= 0) return;
-	memset(&j, 0, sizeof(j));
-	j.opt = opt; j.bwt = bwt; j.bns = bns; j.pac = pac; j.n_processed = n_processed; j.n = n; j.seqs = seqs; j.pes = pes;
-	sw_par_from_opt(opt, &swp);
+	if ((e = getenv("BWA_B200_LANES")) != 0) n_lanes = atoi(e);
+	if ((e = getenv("BWA_B200_CHUNK")) != 0) chunk = atol(e);
+	if (n_lanes < 1) n_lanes = 1;
+	if (n_lanes > 8) n_lanes = 8;
+	if (chunk < 2) chunk = 2;
+	chunk &= ~1L;
+	if (n <= chunk + chunk / 2) chunk = n;                 /* do not split off a small tail */
+	n_jobs = (int)((n + chunk - 1) / chunk);
+	if (n_lanes > n_jobs) n_lanes = n_jobs;
 	ctx = bb_device_attach(bwt, bns, pac);
-	batch = run_to_regs(&j, ctx, &swp);
-
+	jobs = bb_calloc((size_t)n_jobs, sizeof(job_t));
+	for (k = 0, start = 0; k < n_jobs; ++k, start += chunk) {
+		job_t *j = &jobs[k];
+		j->opt = opt; j->bwt = bwt; j->bns = bns; j->pac = pac; j->pes = pes;
+		j->n = (int)(start + chunk <= n ? chunk : n - start);
+		j->seqs = seqs + start;
+		j->n_processed = n_processed + start;
+		sw_par_from_opt(opt, &j->swp);
+	}
+	ph(0);
+	run_lanes(jobs, n_jobs, n_lanes, ctx, 0, pe);
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
 		else {
 			mem_alnreg_v *rv = big_alloc(sizeof(mem_alnreg_v) * (size_t)n);
 			int i;
-			for (i = 0; i < n; ++i) rv[i] = j.rs[i].regs;
+			for (k = 0, start = 0; k < n_jobs; ++k, start += chunk)
+				for (i = 0; i < jobs[k].n; ++i) rv[start + i] = jobs[k].rs[i].regs;
 			mem_pestat(opt, bns->l_pac, n, rv, pes);
 			big_free(rv);
 		}
-		bb_parallel_for(nt, w_rescue, &j, n_units);
+		ph("pestat");
+		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
 	}
-	for (j.pass_dry = 0;; j.pass_dry = 0) { /* SAM; a read that misses an alignment is retried after a device round */
-		long i, left = 0;
-		bb_parallel_for(nt, w_sam, &j, n_units);
-		ph(j.pass_dry ? "sam_dry" : "sam_real");
-		for (i = 0; i < n; ++i) left += !j.rs[i].done;
-		if (left == 0) break;
-		if (global_round(&j, batch, &swp) == 0) bb_fatal("mem_process_seqs", "internal error: unfinished reads without requests");
-		ph("global_round");
-	}
-	bwag_batch_end(batch);
-	job_free(&j);
-	ph("cleanup");
+	free(jobs);
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec\n", __func__, n, bb_cputime() - ctime, bb_realtime() - rtime);
 }

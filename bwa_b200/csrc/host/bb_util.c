@@ -78,6 +78,7 @@ typedef struct bb_pool {
 	void *data;
 	long n, chunk;
 	volatile long next;
+	int lane;
 	struct bb_pool *link;
 } bb_pool_t;
 typedef struct { bb_pool_t *p; int tid; } pool_arg_t;
@@ -113,15 +114,15 @@ static void *pool_worker(void *a_)
 static bb_pool_t *g_pools;
 static pthread_mutex_t g_pools_mu = PTHREAD_MUTEX_INITIALIZER;
 
-static bb_pool_t *pool_get(int nt)
+static bb_pool_t *pool_get(int nt, int lane)
 {
 	bb_pool_t *p;
 	int t;
 	pthread_mutex_lock(&g_pools_mu);
-	for (p = g_pools; p; p = p->link) if (p->nt == nt) break;
+	for (p = g_pools; p; p = p->link) if (p->nt == nt && p->lane == lane) break;
 	if (!p) {
 		p = bb_calloc(1, sizeof(*p));
-		p->nt = nt;
+		p->nt = nt; p->lane = lane;
 		pthread_mutex_init(&p->mu, 0); pthread_mutex_init(&p->job_mu, 0);
 		pthread_cond_init(&p->cv_go, 0); pthread_cond_init(&p->cv_done, 0);
 		p->th = bb_malloc(sizeof(pthread_t) * nt);
@@ -137,13 +138,16 @@ static bb_pool_t *pool_get(int nt)
 	return p;
 }
 
-void bb_parallel_for(int nt, void (*fn)(void *, long, int), void *data, long n)
+void bb_parallel_for(int nt, void (*fn)(void *, long, int), void *data, long n) { bb_parallel_for_lane(0, nt, fn, data, n); }
+
+/* independent pools per lane: two batches in flight run their host loops side by side */
+void bb_parallel_for_lane(int lane, int nt, void (*fn)(void *, long, int), void *data, long n)
 {
 	bb_pool_t *p;
 	if (n <= 0) return;
 	if (nt < 1) nt = 1;
 	if (nt == 1 || n == 1) { long i; for (i = 0; i < n; ++i) fn(data, i, 0); return; }
-	p = pool_get(nt);
+	p = pool_get(nt, lane);
 	pthread_mutex_lock(&p->job_mu);       /* one job at a time per pool */
 	p->fn = fn; p->data = data; p->n = n; p->next = 0;
 	p->chunk = n / (nt * 8L); if (p->chunk < 1) p->chunk = 1; if (p->chunk > 512) p->chunk = 512;
