@@ -269,7 +269,26 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
     st = idx.stats()
-    k_ms = st["ms_smem"] + st["ms_sa"] + st["ms_extend"] + st["ms_global"]
+    # Kernel-only figures (value, roofline): the timed region above overlaps several chunks on different streams, so
+    # per-kernel event times there include waiting for each other.  Two more passes with ONE lane and ONE chunk give
+    # each kernel the GPU alone ("timed in isolation", burst peak applies); they are not part of the e2e number.
+    pipe_cfg = "chunks of %s reads on %s lanes (streams)" % (os.environ.get("BWA_B200_CHUNK", "131072"), os.environ.get("BWA_B200_LANES", "3"))
+    user_env = {k: os.environ.get(k) for k in ("BWA_B200_LANES", "BWA_B200_CHUNK")}
+    os.environ["BWA_B200_LANES"] = "1"
+    os.environ["BWA_B200_CHUNK"] = str(1 << 30)
+    step()
+    idx.stats(reset=True)
+    KSTEPS = 2
+    for _ in range(KSTEPS):
+        step()
+    torch.cuda.synchronize()
+    ks = idx.stats()
+    for k, v in user_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_extend"] + ks["ms_global"]) / KSTEPS * a.steps
     vals = torch.tensor([dt, k_ms / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -283,13 +302,14 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        smem_gbs = st["occ_touches"] * 64 / (st["ms_smem"] * 1e-3) / 1e9 if st["ms_smem"] > 0 else 0.0
+        smem_gbs = ks["occ_touches"] * 64 / (ks["ms_smem"] * 1e-3) / 1e9 if ks["ms_smem"] > 0 else 0.0
         line = {
             "metric": "reads_per_sec", "value": total_reads / k_max if k_max > 0 else None, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dt_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
                        "l2": "inputs larger than L2 (index %.2f GB, reads %.0f MB per step)" % (os.path.getsize(fa + ".bwt") / 1e9 * 1.75, n_reads * a.read_len / 1e6),
-                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, extension and global-alignment kernels (inputs resident in HBM)",
+                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
+                       "pipeline": pipe_cfg,
                        "dense_sa": a.dense_sa},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],
@@ -298,11 +318,11 @@ def main():
                          "frac": smem_gbs / hbm_peak if hbm_peak else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
-            "kernels_ms_per_step": {k: st[k] / a.steps for k in ("ms_smem", "ms_sa", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
+            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
             "work_per_read": {"occ_touches": st["occ_touches"] / (n_reads * a.steps), "sa_touches": st["sa_touches"] / (n_reads * a.steps),
                               "ext_cells": st["ext_cells"] / (n_reads * a.steps), "glb_cells": st["glb_cells"] / (n_reads * a.steps)},
-            "sw_gcups": {"extend": st["ext_cells"] / (st["ms_extend"] * 1e-3) / 1e9 if st["ms_extend"] > 0 else None,
-                         "global": st["glb_cells"] / (st["ms_global"] * 1e-3) / 1e9 if st["ms_global"] > 0 else None},
+            "sw_gcups": {"extend": ks["ext_cells"] / (ks["ms_extend"] * 1e-3) / 1e9 if ks["ms_extend"] > 0 else None,
+                         "global": ks["glb_cells"] / (ks["ms_global"] * 1e-3) / 1e9 if ks["ms_global"] > 0 else None},
         }
         if world == 1:
             try:

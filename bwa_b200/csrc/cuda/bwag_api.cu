@@ -240,6 +240,14 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 extern "C" void bwag_stats_get(bwag_ctx_t *c, bwag_stats_t *s) { pthread_mutex_lock(&c->mu); *s = c->st; pthread_mutex_unlock(&c->mu); }
 extern "C" void bwag_stats_reset(bwag_ctx_t *c) { pthread_mutex_lock(&c->mu); memset(&c->st, 0, sizeof(c->st)); pthread_mutex_unlock(&c->mu); }
 
+extern "C" void *bwag_host_alloc(size_t bytes)
+{
+	void *p = 0;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return p;
+}
+extern "C" void bwag_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 /* ------------------------------------------------------------------------------------------------ batch */
 
 extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *codes, const int64_t *off)

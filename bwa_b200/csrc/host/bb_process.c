@@ -28,25 +28,30 @@
  * (with 100+ threads touching them at once, that costs more than the GPU stages).  Freed blocks are
  * therefore parked here and handed out again; small allocations stay with malloc, whose arenas are told
  * once not to trim (the same pages are recycled batch after batch). */
-typedef struct { void *p; size_t cap; } bigblk_t;
+typedef struct { void *p; size_t cap; int pinned; } bigblk_t;
 static bigblk_t g_big[48];
 static pthread_mutex_t g_big_mu = PTHREAD_MUTEX_INITIALIZER;
 static int g_malloc_tuned;
 
-static void *big_alloc(size_t bytes)
+static void *big_alloc_x(size_t bytes, int pinned);
+static void *big_alloc(size_t bytes) { return big_alloc_x(bytes, 0); }
+/* pinned: page-locked (bwag_host_alloc) for buffers the device stages read; cached the same way */
+static void *big_alloc_x(size_t bytes, int pinned)
 {
 	int i, best = -1;
 	void *p = 0;
 	pthread_mutex_lock(&g_big_mu);
 	if (!g_malloc_tuned) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20); g_malloc_tuned = 1; }
 	for (i = 0; i < 48; ++i)
-		if (g_big[i].p && g_big[i].cap >= bytes && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
+		if (g_big[i].p && g_big[i].pinned == pinned && g_big[i].cap >= bytes && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
 	if (best >= 0 && g_big[best].cap <= bytes * 4 + (64u << 20)) { p = g_big[best].p; g_big[best].p = 0; }
 	pthread_mutex_unlock(&g_big_mu);
 	if (!p) {
 		size_t cap = bytes + bytes / 8 + 4096;
-		size_t *q = bb_malloc(cap + 16);
-		q[0] = cap; q[1] = 0xB16B10C5u;
+		size_t *q = 0;
+		if (pinned && cap >= (1u << 20)) q = bwag_host_alloc(cap + 16);
+		if (q) q[1] = 1; else { q = bb_malloc(cap + 16); q[1] = 0; }
+		q[0] = cap;
 		return q + 2;
 	}
 	return p;
@@ -58,11 +63,11 @@ static void big_free(void *p)
 	int i;
 	if (!p) return;
 	q = (size_t *)p - 2;
-	if (q[0] < (1u << 20)) { free(q); return; }
+	if (q[0] < (1u << 20)) { if (q[1]) bwag_host_free(q); else free(q); return; }
 	pthread_mutex_lock(&g_big_mu);
-	for (i = 0; i < 48; ++i) if (!g_big[i].p) { g_big[i].p = p; g_big[i].cap = q[0]; p = 0; break; }
+	for (i = 0; i < 48; ++i) if (!g_big[i].p) { g_big[i].p = p; g_big[i].cap = q[0]; g_big[i].pinned = (int)q[1]; p = 0; break; }
 	pthread_mutex_unlock(&g_big_mu);
-	if (p) free(q);
+	if (p) { if (q[1]) bwag_host_free(q); else free(q); }
 }
 
 /* phase timer: BWA_B200_PROFILE=1 prints the wall time of every phase of a batch to stderr */
@@ -413,7 +418,7 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 	for (i = 0; i < j->n; ++i) g.off[i + 1] += g.off[i];
 	t = g.off[j->n];
 	if (t == 0) { big_free(g.off); return 0; }
-	g.tasks = big_alloc(sizeof(bwag_gtask_t) * (size_t)t);
+	g.tasks = big_alloc_x(sizeof(bwag_gtask_t) * (size_t)t, 1);
 	bb_parallel_for_lane(j->lane, nt, w_gfill, &g, j->n);
 	if (bwag_global(batch, swp, (int)t, g.tasks, &out) != 0) bb_fatal("mem_process_seqs", "global-alignment stage failed: %s", bwag_last_error());
 	g.boff = big_alloc(sizeof(int64_t) * ((size_t)t + 1));
@@ -515,10 +520,10 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	int nt = opt->n_threads > 0 ? opt->n_threads : 1, t, n = j->n;
 	int64_t i, tot = 0, nc = 0, ns = 0;
 
-	j->off = big_alloc(sizeof(int64_t) * ((size_t)n + 1));
+	j->off = big_alloc_x(sizeof(int64_t) * ((size_t)n + 1), 1);
 	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
 	j->off[n] = tot;
-	j->codes = big_alloc((size_t)tot + 16);
+	j->codes = big_alloc_x((size_t)tot + 16, 1);
 	bb_parallel_for_lane(j->lane, nt, w_encode, j, n);
 	if (j->lane == 0) ph("encode");
 
@@ -538,11 +543,11 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	bb_parallel_for_lane(j->lane, nt, w_chain, j, n);
 	if (j->lane == 0) ph("chain");
 
-	j->chain_off = big_alloc(sizeof(int32_t) * ((size_t)n + 1));
+	j->chain_off = big_alloc_x(sizeof(int32_t) * ((size_t)n + 1), 1);
 	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
 	j->n_xchains = nc; j->n_xseeds = ns;
-	j->xchains = big_alloc(sizeof(bwag_xchain_t) * ((size_t)nc + 1));
-	j->xseeds = big_alloc(sizeof(bwag_xseed_t) * ((size_t)ns + 1));
+	j->xchains = big_alloc_x(sizeof(bwag_xchain_t) * ((size_t)nc + 1), 1);
+	j->xseeds = big_alloc_x(sizeof(bwag_xseed_t) * ((size_t)ns + 1), 1);
 	j->chain_rid = big_alloc(sizeof(int) * ((size_t)nc + 1));
 	j->chain_frac = big_alloc(sizeof(float) * ((size_t)nc + 1));
 	for (i = 0, nc = ns = 0; i < n; ++i) {
@@ -667,8 +672,8 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	mem_pestat_t pes[4];
 	bwag_ctx_t *ctx;
 	double ctime = bb_cputime(), rtime = bb_realtime();
-	int pe = !!(opt->flag & MEM_F_PE), n_lanes = 2, n_jobs, k;
-	long chunk = 1 << 18, start;
+	int pe = !!(opt->flag & MEM_F_PE), n_lanes = 3, n_jobs, k;
+	long chunk = 1 << 17, start;
 	const char *e;
 
 	if (n <= 0) return;
@@ -777,10 +782,18 @@ mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *
 }
 
 /* release the SAM text of a batch the way the reference's caller does (fastmap.c:114-119), in one call */
+static void w_free_sam(void *d, long c, int tid)
+{
+	bseq1_t *seqs = d;
+	long i;
+	(void)tid;
+	for (i = c * 1024; i < (c + 1) * 1024; ++i) { free(seqs[i].sam); seqs[i].sam = 0; }
+}
 void bb_batch_free_sam(int n, bseq1_t *seqs)
 {
-	int i;
-	for (i = 0; i < n; ++i) { free(seqs[i].sam); seqs[i].sam = 0; }
+	int i, full = n / 1024;
+	bb_parallel_for(8, w_free_sam, seqs, full);   /* the records were allocated by many threads: free them in parallel too */
+	for (i = full * 1024; i < n; ++i) { free(seqs[i].sam); seqs[i].sam = 0; }
 }
 
 /* total length of the SAM text of a batch; if dst != NULL the records are concatenated into it */

@@ -39,6 +39,11 @@ void bwag_ctx_destroy(bwag_ctx_t *ctx);
 int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
 const char *bwag_last_error(void);
 
+/* Page-locked host memory for buffers that are handed to the stage calls (reads, extension work, tasks):
+ * copies from such memory are DMA transfers instead of staged driver copies.  Plain malloc memory works too. */
+void *bwag_host_alloc(size_t bytes);
+void bwag_host_free(void *p);
+
 /* ---- batch ------------------------------------------------------------------------------------ */
 /* codes: concatenated reads, one byte per base, values 0..4 (bwamem.c:1087-1088); off[n_reads+1]. */
 bwag_batch_t *bwag_batch_begin(bwag_ctx_t *ctx, int n_reads, const uint8_t *codes, const int64_t *off);

@@ -68,6 +68,8 @@ static void pfor(void (*fn)(void *, long), void *d, long n)
 	for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
 }
 
+void *bwag_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void bwag_host_free(void *p) { free(p); }
 const char *bwag_last_error(void) { return "oracle (CPU) stages"; }
 size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac) { (void)bwt; (void)l_pac; return 0; }
 int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac) { (void)device; (void)d_blob; (void)bwt; (void)l_pac; (void)pac; return 1; }
