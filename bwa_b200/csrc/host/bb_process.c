@@ -538,7 +538,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
 	if (j->lane == 0) ph("seed_stage");
 
-	j->tls = bb_calloc(nt, sizeof(tls_t));
+	j->tls = bb_calloc(bb_parallel_ids(), sizeof(tls_t));
 	j->slice = big_alloc(((size_t)n + 1) * sizeof(rslice_t));
 	bb_parallel_for_lane(j->lane, nt, w_chain, j, n);
 	if (j->lane == 0) ph("chain");
@@ -557,7 +557,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	}
 	j->chain_off[n] = (int32_t)nc;
 	bb_parallel_for_lane(j->lane, nt, w_flatten, j, n);
-	for (t = 0; t < nt; ++t) {
+	for (t = 0; t < bb_parallel_ids(); ++t) {
 		tls_t *x = &j->tls[t];
 		bb_chainer_free(x->chainer);
 		free(x->chains.a); free(x->xc.a); free(x->xs.a); free(x->c_rid.a); free(x->c_frac.a); free(x->srt.a);

@@ -63,101 +63,94 @@ BB_SORT_DEFINE(, bb_sort_u64, uint64_t, u64_lt)
 #define p64_lt(a, b) ((a).x < (b).x || ((a).x == (b).x && (a).y < (b).y))
 BB_SORT_DEFINE(, bb_sort_pair64, bb_pair64_t, p64_lt)
 
-/* ---- parallel for on a persistent pool of worker threads ----
- * Workers sleep on a condition variable between jobs; a job hands out dynamic chunks from one atomic
- * counter.  Pools are keyed by size and created on first use (a batch issues ~10 parallel loops, so
- * creating 100+ threads per loop would cost more than the loops themselves). */
-typedef struct bb_pool {
-	int nt;                       /* workers including the caller */
-	pthread_t *th;
-	pthread_mutex_t mu, job_mu;
-	pthread_cond_t cv_go, cv_done;
-	long gen;                     /* job generation */
-	int n_idle_done;              /* workers finished with the current job */
+/* ---- parallel loops on ONE shared pool of worker threads ----
+ * Several batches (lanes) are in flight at once and each issues parallel loops; if every lane had its own
+ * threads the process would oversubscribe the CPUs it is allowed to use (containers with a CFS quota then
+ * throttle ALL threads for the rest of the period).  So there is one pool of `nt` workers; a loop is a job
+ * record on a shared list, workers take chunks from any active job, and the caller works on its own job and
+ * waits for it.  Worker ids are 0..nt-1, the caller of lane L uses id BB_MAX_WORKERS+L (per-id scratch arrays
+ * are sized with bb_parallel_ids()). */
+#define BB_MAX_WORKERS 256
+#define BB_MAX_LANES 8
+typedef struct pjob {
 	void (*fn)(void *, long, int);
 	void *data;
-	long n, chunk;
-	volatile long next;
-	int lane;
-	struct bb_pool *link;
-} bb_pool_t;
-typedef struct { bb_pool_t *p; int tid; } pool_arg_t;
+	long n, chunk, n_chunks;
+	volatile long next, done;
+	volatile int refs;            /* workers currently holding this record */
+	struct pjob *link;
+} pjob_t;
 
-static void pool_run(bb_pool_t *p, int tid)
+static struct {
+	pthread_mutex_t mu;
+	pthread_cond_t cv_work, cv_done;
+	pjob_t *jobs;
+	int n_workers;
+	pthread_t th[BB_MAX_WORKERS];
+} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, {0} };
+
+int bb_parallel_ids(void) { return BB_MAX_WORKERS + BB_MAX_LANES; }
+
+static long job_run(pjob_t *j, int tid)   /* returns the number of chunks executed */
 {
+	long c = 0;
 	for (;;) {
-		long b = __sync_fetch_and_add(&p->next, p->chunk), e, i;
-		if (b >= p->n) break;
-		e = b + p->chunk < p->n ? b + p->chunk : p->n;
-		for (i = b; i < e; ++i) p->fn(p->data, i, tid);
+		long b = __sync_fetch_and_add(&j->next, j->chunk), e, i;
+		if (b >= j->n) break;
+		e = b + j->chunk < j->n ? b + j->chunk : j->n;
+		for (i = b; i < e; ++i) j->fn(j->data, i, tid);
+		++c;
 	}
+	return c;
 }
 
 static void *pool_worker(void *a_)
 {
-	pool_arg_t *a = a_;
-	bb_pool_t *p = a->p;
-	long seen = 0;
+	int tid = (int)(long)a_;
+	pthread_mutex_lock(&g_pool.mu);
 	for (;;) {
-		pthread_mutex_lock(&p->mu);
-		while (p->gen == seen) pthread_cond_wait(&p->cv_go, &p->mu);
-		seen = p->gen;
-		pthread_mutex_unlock(&p->mu);
-		pool_run(p, a->tid);
-		pthread_mutex_lock(&p->mu);
-		if (++p->n_idle_done == p->nt - 1) pthread_cond_signal(&p->cv_done);
-		pthread_mutex_unlock(&p->mu);
+		pjob_t *j;
+		long c;
+		for (j = g_pool.jobs; j; j = j->link) if (j->next < j->n) break;
+		if (!j) { pthread_cond_wait(&g_pool.cv_work, &g_pool.mu); continue; }
+		++j->refs;
+		pthread_mutex_unlock(&g_pool.mu);
+		c = job_run(j, tid);
+		pthread_mutex_lock(&g_pool.mu);
+		j->done += c; --j->refs;
+		if (j->done == j->n_chunks && j->refs == 0) pthread_cond_broadcast(&g_pool.cv_done);
 	}
 	return 0;
 }
 
-static bb_pool_t *g_pools;
-static pthread_mutex_t g_pools_mu = PTHREAD_MUTEX_INITIALIZER;
-
-static bb_pool_t *pool_get(int nt, int lane)
-{
-	bb_pool_t *p;
-	int t;
-	pthread_mutex_lock(&g_pools_mu);
-	for (p = g_pools; p; p = p->link) if (p->nt == nt && p->lane == lane) break;
-	if (!p) {
-		p = bb_calloc(1, sizeof(*p));
-		p->nt = nt; p->lane = lane;
-		pthread_mutex_init(&p->mu, 0); pthread_mutex_init(&p->job_mu, 0);
-		pthread_cond_init(&p->cv_go, 0); pthread_cond_init(&p->cv_done, 0);
-		p->th = bb_malloc(sizeof(pthread_t) * nt);
-		for (t = 1; t < nt; ++t) {
-			pool_arg_t *a = bb_malloc(sizeof(*a));
-			a->p = p; a->tid = t;
-			if (pthread_create(&p->th[t], 0, pool_worker, a) != 0) bb_fatal("bb_parallel_for", "pthread_create failed");
-			pthread_detach(p->th[t]);
-		}
-		p->link = g_pools; g_pools = p;
-	}
-	pthread_mutex_unlock(&g_pools_mu);
-	return p;
-}
-
 void bb_parallel_for(int nt, void (*fn)(void *, long, int), void *data, long n) { bb_parallel_for_lane(0, nt, fn, data, n); }
 
-/* independent pools per lane: two batches in flight run their host loops side by side */
 void bb_parallel_for_lane(int lane, int nt, void (*fn)(void *, long, int), void *data, long n)
 {
-	bb_pool_t *p;
+	pjob_t job, **pp;
+	long c;
 	if (n <= 0) return;
 	if (nt < 1) nt = 1;
-	if (nt == 1 || n == 1) { long i; for (i = 0; i < n; ++i) fn(data, i, 0); return; }
-	p = pool_get(nt, lane);
-	pthread_mutex_lock(&p->job_mu);       /* one job at a time per pool */
-	p->fn = fn; p->data = data; p->n = n; p->next = 0;
-	p->chunk = n / (nt * 8L); if (p->chunk < 1) p->chunk = 1; if (p->chunk > 512) p->chunk = 512;
-	pthread_mutex_lock(&p->mu);
-	p->n_idle_done = 0; ++p->gen;
-	pthread_cond_broadcast(&p->cv_go);
-	pthread_mutex_unlock(&p->mu);
-	pool_run(p, 0);
-	pthread_mutex_lock(&p->mu);
-	while (p->n_idle_done < p->nt - 1) pthread_cond_wait(&p->cv_done, &p->mu);
-	pthread_mutex_unlock(&p->mu);
-	pthread_mutex_unlock(&p->job_mu);
+	if (nt > BB_MAX_WORKERS) nt = BB_MAX_WORKERS;
+	if (lane < 0 || lane >= BB_MAX_LANES) lane = 0;
+	if (nt == 1 || n == 1) { long i; for (i = 0; i < n; ++i) fn(data, i, BB_MAX_WORKERS + lane); return; }
+	job.fn = fn; job.data = data; job.n = n; job.next = 0; job.done = 0; job.refs = 0;
+	job.chunk = n / (nt * 8L); if (job.chunk < 1) job.chunk = 1; if (job.chunk > 512) job.chunk = 512;
+	job.n_chunks = (n + job.chunk - 1) / job.chunk;
+	pthread_mutex_lock(&g_pool.mu);
+	while (g_pool.n_workers < nt - 1) {   /* the caller is the nt-th participant */
+		int t = g_pool.n_workers;
+		if (pthread_create(&g_pool.th[t], 0, pool_worker, (void *)(long)t) != 0) bb_fatal("bb_parallel_for", "pthread_create failed");
+		pthread_detach(g_pool.th[t]);
+		++g_pool.n_workers;
+	}
+	job.link = g_pool.jobs; g_pool.jobs = &job;
+	pthread_cond_broadcast(&g_pool.cv_work);
+	pthread_mutex_unlock(&g_pool.mu);
+	c = job_run(&job, BB_MAX_WORKERS + lane);
+	pthread_mutex_lock(&g_pool.mu);
+	job.done += c;
+	while (job.done < job.n_chunks || job.refs > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+	for (pp = &g_pool.jobs; *pp; pp = &(*pp)->link) if (*pp == &job) { *pp = job.link; break; }
+	pthread_mutex_unlock(&g_pool.mu);
 }
