@@ -84,6 +84,11 @@ typedef struct {
 } bb_gcache_t;
 const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc);
 
+/* a region array whose storage belongs to a batch-wide block: mem_alnreg_v.m carries this flag and the real
+ * capacity equals n; whoever needs to grow it must move it to the heap first (bb_regs_make_room) */
+#define BB_BORROWED ((size_t)1 << 62)
+void bb_regs_make_room(mem_alnreg_v *v);
+
 /* ---- regions (bb_reg.c) ---- */
 int bb_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, int l_query, int n, mem_alnreg_t *a);
 int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id);

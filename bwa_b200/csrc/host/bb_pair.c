@@ -152,7 +152,8 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 				b.csub = aln.score2;
 				b.secondary = -1;
 				b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
-				bb_vec_push(*ma, b);
+				bb_regs_make_room(ma);
+				ma->a[ma->n++] = b;
 				for (i = 0; i < (int)ma->n - 1; ++i)
 					if (ma->a[i].score < b.score) break;
 				tmp = i;
@@ -173,15 +174,19 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 	int i, n = 0;
 	size_t j;
 	mem_alnreg_v b[2];
+	mem_alnreg_t st[2][4];
 	if (opt->flag & MEM_F_NO_RESCUE) return 0;
 	memset(b, 0, sizeof(b));
-	for (i = 0; i < 2; ++i)
+	for (i = 0; i < 2; ++i) {
+		if (a[i].n <= 4) { b[i].a = st[i]; b[i].m = 4; }   /* anchors: copies, because a[] changes while we rescue */
 		for (j = 0; j < a[i].n; ++j)
 			if (a[i].a[j].score >= a[i].a[0].score - opt->pen_unpaired) bb_vec_push(b[i], a[i].a[j]);
+	}
 	for (i = 0; i < 2; ++i)
 		for (j = 0; j < b[i].n && (int)j < opt->max_matesw; ++j)
 			n += bb_matesw(opt, bns, pac, pes, &b[i].a[j], s[!i].l_seq, (uint8_t *)s[!i].seq, &a[!i]);
-	free(b[0].a); free(b[1].a);
+	if (b[0].a != st[0]) free(b[0].a);
+	if (b[1].a != st[1]) free(b[1].a);
 	return n;
 }
 
@@ -189,8 +194,10 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 static int pair_hits(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], mem_alnreg_v a[2], int id, int *sub, int *n_sub, int z[2], int n_pri[2])
 {
 	BB_VEC(bb_pair64_t) v = {0, 0, 0}, u = {0, 0, 0};
+	bb_pair64_t vst[16], ust[32];
 	int r, i, k, y[4], ret;
 	int64_t l_pac = bns->l_pac;
+	if (n_pri[0] + n_pri[1] <= 16) { v.a = vst; v.m = 16; }
 	for (r = 0; r < 2; ++r)
 		for (i = 0; i < n_pri[r]; ++i) {
 			bb_pair64_t key;
@@ -222,6 +229,8 @@ static int pair_hits(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat
 				if (q < 0) q = 0;
 				p.y = (uint64_t)k << 32 | i;
 				p.x = (uint64_t)q << 32 | (bb_mix64(p.y ^ id << 8) & 0xffffffffU);
+				if (u.a == 0 && u.n == 0) { u.a = ust; u.m = 32; }
+				if (u.a == ust && u.n == 32) { bb_pair64_t *h_ = bb_malloc(64 * sizeof(bb_pair64_t)); memcpy(h_, ust, sizeof(ust)); u.a = h_; u.m = 64; }
 				bb_vec_push(u, p);
 			}
 		}
@@ -240,7 +249,8 @@ static int pair_hits(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat
 		for (i = (int)u.n - 2, *n_sub = 0; i >= 0; --i)
 			if (*sub - (int)(u.a[i].x >> 32) <= tmp) ++*n_sub;
 	} else { ret = 0; *sub = 0; *n_sub = 0; }
-	free(u.a); free(v.a);
+	if (u.a != ust) free(u.a);
+	if (v.a != vst) free(v.a);
 	return ret;
 }
 

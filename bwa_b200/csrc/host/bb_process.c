@@ -306,7 +306,7 @@ static void load_raw_regs(job_t *j, long i, mem_alnreg_v *v)
 	int k, n = c1 > c0 ? j->xregs.n_regs[i] : 0;
 	const bwag_xreg_t *x = c1 > c0 ? j->xregs.regs + j->xchains[c0].seed_off : 0;
 	v->n = 0;
-	if (j->reg_pool) { v->a = j->reg_pool + j->reg_off[i]; v->m = (size_t)n; }
+	if (j->reg_pool) { v->a = j->reg_pool + j->reg_off[i]; v->m = (size_t)n | BB_BORROWED; }
 	else bb_vec_reserve(*v, (size_t)n + 4);
 	for (k = 0; k < n; ++k) {
 		mem_alnreg_t *a = &v->a[k];
@@ -570,7 +570,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
 	if (j->lane == 0) ph("extend_stage");
 
-	if (!(opt->flag & MEM_F_PE)) { /* SE: region arrays never grow after this point -> one block for all reads */
+	{ /* region arrays of all reads in one block; the rare array that must grow (mate rescue) moves to the heap */
 		int64_t tot_regs = 0;
 		j->reg_off = big_alloc(sizeof(int64_t) * ((size_t)n + 1));
 		for (i = 0; i < n; ++i) { j->reg_off[i] = tot_regs; tot_regs += j->chain_off[i + 1] > j->chain_off[i] ? j->xregs.n_regs[i] : 0; }
@@ -594,7 +594,7 @@ static void w_free(void *d, long i, int tid)
 {
 	job_t *j = d;
 	(void)tid;
-	if (!j->reg_pool) free(j->rs[i].regs.a);
+	if (!(j->rs[i].regs.m & BB_BORROWED)) free(j->rs[i].regs.a);
 	gcache_free(&j->rs[i].gc);
 }
 

@@ -100,6 +100,16 @@ int bb_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *
 	return m;
 }
 
+void bb_regs_make_room(mem_alnreg_v *v) /* room for one more region */
+{
+	if (v->m & BB_BORROWED) {
+		size_t cap = v->n + 4;
+		mem_alnreg_t *na = bb_malloc(cap * sizeof(mem_alnreg_t));
+		memcpy(na, v->a, v->n * sizeof(mem_alnreg_t));
+		v->a = na; v->m = cap;
+	} else bb_vec_reserve(*v, v->n + 1);
+}
+
 static void mark_core(const mem_opt_t *opt, int n, mem_alnreg_t *a, bb_int_v *z_)
 {
 	bb_int_v z = *z_;
@@ -133,9 +143,11 @@ static void mark_core(const mem_opt_t *opt, int n, mem_alnreg_t *a, bb_int_v *z_
 /* bwamem.c:547-584 */
 int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id)
 {
+	int zstack[32];
 	bb_int_v z = {0, 0, 0};
 	int i, n_pri = 0;
 	if (n == 0) return 0;
+	if (n <= 32) { z.a = zstack; z.m = 32; }   /* the usual case: no heap traffic */
 	for (i = 0; i < n; ++i) {
 		a[i].sub = a[i].alt_sc = 0; a[i].secondary = a[i].secondary_all = -1;
 		a[i].hash = bb_mix64((uint64_t)(id + i));
@@ -149,7 +161,7 @@ int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id)
 		if (!p->is_alt && p->secondary >= 0 && a[p->secondary].is_alt) p->alt_sc = a[p->secondary].score;
 	}
 	if (n_pri >= 0 && n_pri < n) {
-		bb_vec_reserve(z, (size_t)n);
+		if (z.a != zstack) bb_vec_reserve(z, (size_t)n);
 		if (n_pri > 0) sort_regs_alt_score_hash(n, a);
 		for (i = 0; i < n; ++i) z.a[a[i].secondary_all] = i;
 		for (i = 0; i < n; ++i) {
@@ -163,7 +175,7 @@ int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id)
 			mark_core(opt, n_pri, a, &z);
 		}
 	} else for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
-	free(z.a);
+	if (z.a != zstack) free(z.a);
 	return n_pri;
 }
 
