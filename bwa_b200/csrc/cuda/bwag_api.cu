@@ -39,7 +39,7 @@ static int set_err(const char *fmt, ...)
 
 /* device counters, mirrored in pinned host memory */
 struct Counters {
-	int next_read, next_task, pad0, pad1;
+	int next_read, next_task, max_rlen, pad1;
 	u64 next_seed;
 	u64 n_intv, n_seeds;
 	u64 occ_touches, sa_touches, ext_cells, glb_cells;
@@ -102,7 +102,11 @@ struct bwag_batch {
 	HostBuf h_intv_beg, h_intv_n, h_intv, h_seed_beg, h_rbeg;
 	/* stage 2 */
 	DevBuf d_chain_off, d_chains, d_seeds, d_regs, d_nregs;
-	HostBuf h_regs, h_nregs;
+	DevBuf d_chain_beg, d_chain_cnt, d_reg_base, d_chain_rid, d_chain_frac, d_cregs, d_creg_beg, d_ctg;
+	DevBuf s_bt, s_sn, s_ch, s_order, s_idx, s_keys;
+	HostBuf h_regs, h_nregs, h_cregs, h_creg_beg, h_tmp;
+	i64 n_intv, n_seeds;         /* pool sizes left in HBM by the last bwag_seed */
+	int seeded;
 	/* stage 3 */
 	DevBuf d_tasks, d_res, d_cig, d_md;
 	HostBuf h_res, h_cig, h_md;
@@ -269,7 +273,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 	b->lc.device = c->device; b->lc.n_sm = c->n_sm; b->lc.ix = c->ix; b->lc.parent = c;
 	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
 	memset(&b->lc.st, 0, sizeof(b->lc.st));
-	b->max_len = 0;
+	b->max_len = 0; b->seeded = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
 	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
 	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { free(b); return 0; }
@@ -295,7 +299,7 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		bwag_stats_t *d = &c->st, *x = &b->lc.st;
 		d->occ_touches += x->occ_touches; d->sa_touches += x->sa_touches; d->sa_touches_algo += x->sa_touches_algo;
 		d->ext_cells += x->ext_cells; d->glb_cells += x->glb_cells;
-		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
+		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
 	}
 	for (int i = 0; i < 4; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
@@ -314,7 +318,9 @@ static void batch_free(bwag_batch_t *b)
 	free_dev(&b->d_intv_beg); free_dev(&b->d_intv_n); free_dev(&b->d_intv); free_dev(&b->d_seed_beg); free_dev(&b->d_rbeg);
 	free_host(&b->h_intv_beg); free_host(&b->h_intv_n); free_host(&b->h_intv); free_host(&b->h_seed_beg); free_host(&b->h_rbeg);
 	free_dev(&b->d_chain_off); free_dev(&b->d_chains); free_dev(&b->d_seeds); free_dev(&b->d_regs); free_dev(&b->d_nregs);
-	free_host(&b->h_regs); free_host(&b->h_nregs);
+	free_dev(&b->d_chain_beg); free_dev(&b->d_chain_cnt); free_dev(&b->d_reg_base); free_dev(&b->d_chain_rid); free_dev(&b->d_chain_frac); free_dev(&b->d_cregs); free_dev(&b->d_creg_beg); free_dev(&b->d_ctg);
+	free_dev(&b->s_bt); free_dev(&b->s_sn); free_dev(&b->s_ch); free_dev(&b->s_order); free_dev(&b->s_idx); free_dev(&b->s_keys);
+	free_host(&b->h_regs); free_host(&b->h_nregs); free_host(&b->h_cregs); free_host(&b->h_creg_beg); free_host(&b->h_tmp);
 	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
 	free(b);
@@ -401,6 +407,8 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		c->st.ms_sa += elapsed(c); ++c->st.n_launch;
 		c->st.sa_touches += c->h_cnt->sa_touches;
 	}
+	b->n_intv = n_intv; b->n_seeds = n_seeds; b->seeded = 1;
+	if (!out) return 0;      /* results stay in HBM for bwag_chain_extend */
 	if (hbuf_reserve(&b->h_intv_beg, sizeof(i64) * (size_t)(n + 1)) || hbuf_reserve(&b->h_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 	    hbuf_reserve(&b->h_intv, 32 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_seed_beg, 8 * (size_t)(n_intv + 1)) || hbuf_reserve(&b->h_rbeg, 8 * (size_t)(n_seeds + 1))) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
@@ -440,9 +448,19 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	if (buf_reserve(&b->d_chain_off, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_chains, sizeof(bwag_xchain_t) * (size_t)(n_chains + 1)) ||
 	    buf_reserve(&b->d_seeds, sizeof(bwag_xseed_t) * (size_t)(n_seeds + 1)) || buf_reserve(&b->d_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) ||
 	    buf_reserve(&b->d_nregs, 4 * (size_t)(n + 1))) return 1;
+	if (buf_reserve(&b->d_chain_beg, 8 * (size_t)(n + 1)) || buf_reserve(&b->d_chain_cnt, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_reg_base, 8 * (size_t)(n + 1)) ||
+	    hbuf_reserve(&b->h_tmp, 20 * (size_t)(n + 1))) return 1;
+	i64 *h_cbeg = (i64 *)b->h_tmp.p, *h_rbase = h_cbeg + n + 1;
+	int *h_ccnt = (int *)(h_rbase + n + 1);
+	for (int r = 0; r < n; ++r) {   /* per read: its chains, and where its regions go (the slot range of its seeds) */
+		h_cbeg[r] = chain_off[r]; h_ccnt[r] = chain_off[r + 1] - chain_off[r];
+		h_rbase[r] = h_ccnt[r] ? chains[chain_off[r]].seed_off : 0;
+	}
 	if (reset_counters(c)) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	H2D(c, b->d_chain_off.p, chain_off, 4 * (size_t)(n + 1));
+	H2D(c, b->d_chain_beg.p, h_cbeg, 8 * (size_t)n);
+	H2D(c, b->d_reg_base.p, h_rbase, 8 * (size_t)n);
+	H2D(c, b->d_chain_cnt.p, h_ccnt, 4 * (size_t)n);
 	if (n_chains) H2D(c, b->d_chains.p, chains, sizeof(bwag_xchain_t) * (size_t)n_chains);
 	if (n_seeds) H2D(c, b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
@@ -451,7 +469,8 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	ExtArgs a;
 	memset(&a, 0, sizeof(a));
 	a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n; a.par = *par;
-	a.chain_off = (const int32_t *)b->d_chain_off.p; a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
+	a.chain_beg = (const i64 *)b->d_chain_beg.p; a.chain_cnt = (const int *)b->d_chain_cnt.p; a.reg_base = (const i64 *)b->d_reg_base.p;
+	a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
 	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
 	a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.cap_q = cap_q; a.cap_r = cap_r;
 	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
@@ -471,6 +490,104 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	CK(cudaStreamSynchronize(c->stream));
 	c->st.ms_d2h += elapsed(c);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->regs = (const bwag_xreg_t *)b->h_regs.p;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ stages 2a+2 fused */
+
+extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *par, const bwag_contigs_t *ctg, bwag_cregs_t *out)
+{
+	bwag_ctx_t *c = &b->lc;
+	CK(cudaSetDevice(c->device));
+	if (!b->seeded) return set_err("bwag_chain_extend needs a preceding bwag_seed on the same batch");
+	const int n = b->n;
+	const i64 ns = b->n_seeds;
+	if (ns >= ((i64)1 << 31)) return set_err("too many seeds in one batch for the 32-bit seed offsets; use smaller chunks");
+	/* contig table: offsets (i64), lengths (int), ALT flags (byte) in one device buffer */
+	const size_t ctg_bytes = (size_t)ctg->n_seqs * 13 + 64;
+	if (buf_reserve(&b->d_ctg, ctg_bytes) || hbuf_reserve(&b->h_tmp, ctg_bytes)) return 1;
+	{
+		char *h = (char *)b->h_tmp.p;
+		memcpy(h, ctg->offset, 8 * (size_t)ctg->n_seqs);
+		memcpy(h + 8 * (size_t)ctg->n_seqs, ctg->len, 4 * (size_t)ctg->n_seqs);
+		memcpy(h + 12 * (size_t)ctg->n_seqs, ctg->is_alt, (size_t)ctg->n_seqs);
+	}
+	if (buf_reserve(&b->s_bt, 88 * (size_t)(ns + 1)) || buf_reserve(&b->s_sn, 32 * (size_t)(ns + 1)) || buf_reserve(&b->s_ch, 48 * (size_t)(ns + 1)) ||
+	    buf_reserve(&b->s_order, 4 * (size_t)(ns + 1)) || buf_reserve(&b->s_idx, 4 * (size_t)(ns + 1)) || buf_reserve(&b->s_keys, 8 * (size_t)(ns + 1)) ||
+	    buf_reserve(&b->d_chains, sizeof(bwag_xchain_t) * (size_t)(ns + 1)) || buf_reserve(&b->d_seeds, sizeof(bwag_xseed_t) * (size_t)(ns + 1)) ||
+	    buf_reserve(&b->d_regs, sizeof(bwag_xreg_t) * (size_t)(ns + 1)) || buf_reserve(&b->d_chain_rid, 4 * (size_t)(ns + 1)) || buf_reserve(&b->d_chain_frac, 4 * (size_t)(ns + 1)) ||
+	    buf_reserve(&b->d_chain_beg, 8 * (size_t)(n + 1)) || buf_reserve(&b->d_chain_cnt, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_reg_base, 8 * (size_t)(n + 1)) ||
+	    buf_reserve(&b->d_nregs, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_creg_beg, 8 * (size_t)(n + 1))) return 1;
+	if (reset_counters(c)) return 1;
+	H2D(c, b->d_ctg.p, b->h_tmp.p, 13 * (size_t)ctg->n_seqs);
+	ChainArgs k;
+	memset(&k, 0, sizeof(k));
+	k.off = (const i64 *)b->d_off.p; k.n_reads = n;
+	k.intv_beg = (const i64 *)b->d_intv_beg.p; k.intv_n = (const int *)b->d_intv_n.p; k.intv = (const bwtintv_t *)b->d_intv.p;
+	k.seed_beg = (const i64 *)b->d_seed_beg.p; k.rbeg = (const i64 *)b->d_rbeg.p;
+	k.w = cp->w; k.max_chain_gap = cp->max_chain_gap; k.max_occ = cp->max_occ; k.min_seed_len = cp->min_seed_len; k.min_chain_weight = cp->min_chain_weight;
+	k.max_chain_extend = cp->max_chain_extend; k.mask_level = cp->mask_level; k.drop_ratio = cp->drop_ratio;
+	k.a = par->a; k.o_del = par->o_del; k.e_del = par->e_del; k.o_ins = par->o_ins; k.e_ins = par->e_ins;
+	k.l_pac = c->ix.l_pac; k.n_seqs = ctg->n_seqs;
+	k.ctg_off = (const i64 *)b->d_ctg.p; k.ctg_len = (const int *)((char *)b->d_ctg.p + 8 * (size_t)ctg->n_seqs); k.ctg_alt = (const uint8_t *)b->d_ctg.p + 12 * (size_t)ctg->n_seqs;
+	k.s_bt = b->s_bt.p; k.s_sn = b->s_sn.p; k.s_ch = b->s_ch.p; k.s_order = (int *)b->s_order.p; k.s_idx = (int *)b->s_idx.p; k.s_keys = (u64 *)b->s_keys.p;
+	k.xchains = (bwag_xchain_t *)b->d_chains.p; k.xseeds = (bwag_xseed_t *)b->d_seeds.p; k.chain_rid = (int *)b->d_chain_rid.p; k.chain_frac = (float *)b->d_chain_frac.p;
+	k.chain_beg = (i64 *)b->d_chain_beg.p; k.reg_base = (i64 *)b->d_reg_base.p; k.n_chains = (int *)b->d_chain_cnt.p;
+	k.max_rlen = &c->d_cnt->max_rlen;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	BWAG_LAUNCH(k_chain, (n + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, c->stream, k);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	if (fetch_counters(c)) return 1;
+	c->st.ms_chain += elapsed(c); ++c->st.n_launch;
+
+	/* extension over the chains that K3 left in HBM; K3 reported the longest reference window */
+	const int cap_q = (b->max_len + 3) & ~3;
+	const int cap_r = (c->h_cnt->max_rlen + 16 + 15) & ~15;
+	CK(cudaMemsetAsync(&c->d_cnt->next_read, 0, sizeof(int), c->stream));
+	int grid = c->grid_k4;
+	{
+		i64 need = ((i64)n + (K4_THREADS / 32) - 1) / (K4_THREADS / 32);
+		if (grid > need) grid = (int)(need > 0 ? need : 1);
+	}
+	const size_t n_warps = (size_t)grid * (K4_THREADS / 32);
+	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r)) return 1;
+	ExtArgs a;
+	memset(&a, 0, sizeof(a));
+	a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n; a.par = *par;
+	a.chain_beg = (const i64 *)b->d_chain_beg.p; a.chain_cnt = (const int *)b->d_chain_cnt.p; a.reg_base = (const i64 *)b->d_reg_base.p;
+	a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
+	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
+	a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.cap_q = cap_q; a.cap_r = cap_r;
+	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	/* dense copy of the regions (with contig id and repeat fraction of their chain) for the download */
+	RegCompactArgs rc;
+	rc.n_reads = n; rc.n_regs = (const int *)b->d_nregs.p; rc.regs = (const bwag_xreg_t *)b->d_regs.p; rc.reg_base = (const i64 *)b->d_reg_base.p;
+	rc.chain_beg = (const i64 *)b->d_chain_beg.p; rc.chain_rid = (const int *)b->d_chain_rid.p; rc.chain_frac = (const float *)b->d_chain_frac.p;
+	rc.out_beg = (i64 *)b->d_creg_beg.p; rc.total = &c->d_cnt->n_cig;
+	/* the number of regions is not known before K4 ran: size the dense array by the number of seeds (upper bound) */
+	if (buf_reserve(&b->d_cregs, sizeof(bwag_creg_t) * (size_t)(ns + 1))) return 1;
+	rc.out = (bwag_creg_t *)b->d_cregs.p;
+	BWAG_LAUNCH(k_regs_compact, (n + 127) / 128, 128, 0, c->stream, rc);
+	CK(cudaGetLastError());
+	if (fetch_counters(c)) return 1;
+	c->st.ms_extend += elapsed(c); c->st.n_launch += 2;
+	if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
+	c->st.ext_cells += c->h_cnt->ext_cells;
+	const i64 n_regs = (i64)c->h_cnt->n_cig;
+	if (hbuf_reserve(&b->h_cregs, sizeof(bwag_creg_t) * (size_t)(n_regs + 1)) || hbuf_reserve(&b->h_creg_beg, 8 * (size_t)(n + 1)) || hbuf_reserve(&b->h_nregs, 4 * (size_t)(n + 1))) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	if (n_regs) D2H(c, b->h_cregs.p, b->d_cregs.p, sizeof(bwag_creg_t) * (size_t)n_regs);
+	D2H(c, b->h_creg_beg.p, b->d_creg_beg.p, 8 * (size_t)n);
+	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.ms_d2h += elapsed(c);
+	out->n_regs = (const int32_t *)b->h_nregs.p; out->reg_beg = (const int64_t *)b->h_creg_beg.p; out->regs = (const bwag_creg_t *)b->h_cregs.p;
 	return 0;
 }
 

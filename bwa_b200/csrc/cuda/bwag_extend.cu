@@ -170,19 +170,19 @@ k_extend(DevIndex ix, ExtArgs a)
 		if (lane == 0) rid = atomicAdd(a.next_read, 1);
 		rid = __shfl_sync(FULL_MASK, rid, 0);
 		if (rid >= a.n_reads) break;
-		const int c0 = a.chain_off[rid], c1 = a.chain_off[rid + 1];
+		const i64 c0 = a.chain_beg[rid], c1 = c0 + a.chain_cnt[rid];
 		int n_regs = 0;
 		if (c1 > c0) {
 			const uint8_t *query = a.codes + a.off[rid];
 			const int l_query = (int)(a.off[rid + 1] - a.off[rid]);
-			bwag_xreg_t *regs = a.regs + a.chains[c0].seed_off;
+			bwag_xreg_t *regs = a.regs + a.reg_base[rid];
 			if (l_query > a.cap_q) { overflow = 1; if (lane == 0) a.n_regs[rid] = 0; continue; }
-			for (int c = c0; c < c1; ++c) {
+			for (i64 c = c0; c < c1; ++c) {
 				const bwag_xchain_t ch = a.chains[c];
 				bwag_xseed_t *seeds = const_cast<bwag_xseed_t *>(a.seeds) + ch.seed_off;
 				const i64 rmax0 = ch.rmax0, rmax1 = ch.rmax1;
 				const int rlen = (int)(rmax1 - rmax0);
-				if (rlen > a.cap_r) { overflow = 1; continue; }
+				if (rlen > a.cap_r) { if (lane == 0) printf("[k_extend] read %d chain %lld: window %lld..%lld (%d) > cap %d, n_seeds %d\n", rid, (long long)(c - c0), (long long)rmax0, (long long)rmax1, rlen, a.cap_r, ch.n_seeds); overflow = 1; continue; }
 				__syncwarp();
 				for (int x = lane; x < rlen; x += 32) rseq[x] = (uint8_t)bwag_ref_base(ix, rmax0 + x); /* bns_fetch_seq (bwamem.c:685) */
 				__syncwarp();
@@ -228,7 +228,7 @@ k_extend(DevIndex ix, ExtArgs a)
 					/* extend (bwamem.c:734-797) */
 					bwag_xreg_t reg;
 					int aw0 = p.w, aw1 = p.w;
-					reg.score = reg.truesc = -1; reg.chain = c - c0; reg.seedlen0 = s_len; reg.seedcov = 0; reg.w = 0;
+					reg.score = reg.truesc = -1; reg.chain = (int)(c - c0); reg.seedlen0 = s_len; reg.seedcov = 0; reg.w = 0;
 					if (s_qbeg) {   /* to the left: reversed query prefix against the reversed reference prefix */
 						int qle, tle, gtle, gscore, moff;
 						const int tl = (int)(s_rbeg - rmax0);

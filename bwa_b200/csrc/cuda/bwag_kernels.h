@@ -6,6 +6,7 @@
 #define K1_THREADS 128
 #define K1B_THREADS 128
 #define K2_THREADS 128
+#define K3_THREADS 128
 #define K4_THREADS 128
 #define K5_THREADS 128
 
@@ -27,10 +28,29 @@ struct SeedArgs {
 
 struct SaArgs { i64 *rbeg; i64 n; u64 *next; u64 *sa_touches; };
 
+/* one record per region for the download of the fused chain+extend path */
+struct ChainArgs {
+	const i64 *off; int n_reads;
+	const i64 *intv_beg; const int *intv_n; const bwtintv_t *intv; const i64 *seed_beg; const i64 *rbeg;
+	int w, max_chain_gap, max_occ, min_seed_len, min_chain_weight, max_chain_extend; float mask_level, drop_ratio;
+	int a, o_del, e_del, o_ins, e_ins;
+	i64 l_pac; int n_seqs; const i64 *ctg_off; const int *ctg_len; const uint8_t *ctg_alt;
+	void *s_bt, *s_sn, *s_ch; int *s_order, *s_idx; u64 *s_keys;     /* scratch, indexed by seed slot */
+	bwag_xchain_t *xchains; bwag_xseed_t *xseeds; int *chain_rid; float *chain_frac;   /* outputs, indexed by seed slot */
+	i64 *chain_beg, *reg_base; int *n_chains;                          /* per read */
+	int *max_rlen;                                                     /* longest reference window of any chain (sizes K4's scratch) */
+};
+
+struct RegCompactArgs {
+	int n_reads; const int *n_regs; const bwag_xreg_t *regs; const i64 *reg_base, *chain_beg; const int *chain_rid; const float *chain_frac;
+	i64 *out_beg; bwag_creg_t *out; u64 *total;
+};
+
 struct ExtArgs {
 	const uint8_t *codes; const i64 *off; int n_reads;
 	bwag_sw_par_t par;
-	const int32_t *chain_off; const bwag_xchain_t *chains; const bwag_xseed_t *seeds;
+	const i64 *chain_beg; const int *chain_cnt; const i64 *reg_base;   /* per read: its chains in chains[], where its regions go in regs[] */
+	const bwag_xchain_t *chains; const bwag_xseed_t *seeds;
 	bwag_xreg_t *regs; int32_t *n_regs;
 	/* per-warp scratch: H, E (int32 each, cap_q+2), reference window (cap_r bytes) */
 	int *eh; uint8_t *rseq; int cap_q, cap_r;
@@ -60,6 +80,8 @@ __global__ void k_smem(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);
 __global__ void k_sa(DevIndex ix, SaArgs a);
 __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
+__global__ void k_chain(ChainArgs a);
+__global__ void k_regs_compact(RegCompactArgs a);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
 

@@ -205,6 +205,7 @@ typedef struct {
 	float *chain_frac;
 	int64_t n_xchains, n_xseeds;
 	bwag_regs_t xregs;
+	bwag_cregs_t cregs; int have_cregs;   /* regions from the fused device chain+extend stage */
 	int pass_dry;
 	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
@@ -302,6 +303,24 @@ static void w_flatten(void *d, long i, int tid)
 /* regions of read i from the extension stage -> pristine mem_alnreg_t array */
 static void load_raw_regs(job_t *j, long i, mem_alnreg_v *v)
 {
+	if (j->have_cregs) {
+		const int n = j->cregs.n_regs[i];
+		const bwag_creg_t *x = j->cregs.regs + j->cregs.reg_beg[i];
+		int k;
+		v->n = 0;
+		if (j->reg_pool) { v->a = j->reg_pool + j->reg_off[i]; v->m = (size_t)n | BB_BORROWED; }
+		else bb_vec_reserve(*v, (size_t)n + 4);
+		for (k = 0; k < n; ++k) {
+			mem_alnreg_t *a = &v->a[k];
+			memset(a, 0, sizeof(*a));
+			a->rb = x[k].r.rb; a->re = x[k].r.re; a->qb = x[k].r.qb; a->qe = x[k].r.qe;
+			a->score = x[k].r.score; a->truesc = x[k].r.truesc; a->w = x[k].r.w;
+			a->seedcov = x[k].r.seedcov; a->seedlen0 = x[k].r.seedlen0;
+			a->rid = x[k].rid; a->frac_rep = x[k].frac_rep;
+		}
+		v->n = (size_t)n;
+		return;
+	}
 	int64_t c0 = j->chain_off[i], c1 = j->chain_off[i + 1];
 	int k, n = c1 > c0 ? j->xregs.n_regs[i] : 0;
 	const bwag_xreg_t *x = c1 > c0 ? j->xregs.regs + j->xchains[c0].seed_off : 0;
@@ -511,30 +530,12 @@ static void sw_par_from_opt(const mem_opt_t *opt, bwag_sw_par_t *p)
 	memcpy(p->mat, opt->mat, 25);
 }
 
-/* stages up to de-duplicated regions for all reads of the job (worker1 of the reference) */
-static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t *swp)
+/* host chaining path: download intervals and seeds, chain and filter on the host, upload the extension work */
+static void host_chain_extend(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *swp, const bwag_seed_par_t *sp_, int nt)
 {
-	const mem_opt_t *opt = j->opt;
-	bwag_batch_t *batch;
-	bwag_seed_par_t sp;
-	int nt = opt->n_threads > 0 ? opt->n_threads : 1, t, n = j->n;
-	int64_t i, tot = 0, nc = 0, ns = 0;
-
-	j->off = big_alloc_x(sizeof(int64_t) * ((size_t)n + 1), 1);
-	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
-	j->off[n] = tot;
-	j->codes = big_alloc_x((size_t)tot + 16, 1);
-	bb_parallel_for_lane(j->lane, nt, w_encode, j, n);
-	if (j->lane == 0) ph("encode");
-
-	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
-	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
-	if (j->lane == 0) ph("batch_begin");
-	sp.min_seed_len = opt->min_seed_len;
-	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
-	sp.split_width = opt->split_width;
-	sp.max_occ = opt->max_occ;
-	sp.max_mem_intv = opt->max_mem_intv;
+	const bwag_seed_par_t sp = *sp_;
+	int n = j->n, t;
+	int64_t i, nc = 0, ns = 0;
 	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
 	if (j->lane == 0) ph("seed_stage");
 
@@ -570,10 +571,67 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
 	if (j->lane == 0) ph("extend_stage");
 
+}
+
+/* stages up to de-duplicated regions for all reads of the job (worker1 of the reference) */
+static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t *swp)
+{
+	const mem_opt_t *opt = j->opt;
+	bwag_batch_t *batch;
+	bwag_seed_par_t sp;
+	int nt = opt->n_threads > 0 ? opt->n_threads : 1, n = j->n;
+	int64_t i, tot = 0;
+
+	j->off = big_alloc_x(sizeof(int64_t) * ((size_t)n + 1), 1);
+	for (i = 0; i < n; ++i) { j->off[i] = tot; tot += j->seqs[i].l_seq; }
+	j->off[n] = tot;
+	j->codes = big_alloc_x((size_t)tot + 16, 1);
+	bb_parallel_for_lane(j->lane, nt, w_encode, j, n);
+	if (j->lane == 0) ph("encode");
+
+	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
+	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
+	if (j->lane == 0) ph("batch_begin");
+	sp.min_seed_len = opt->min_seed_len;
+	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+	sp.split_width = opt->split_width;
+	sp.max_occ = opt->max_occ;
+	sp.max_mem_intv = opt->max_mem_intv;
+	{   /* chaining on the device when every read of the chunk is short enough that the seed-level SW filter
+	     * (mem_flt_chained_seeds, bwamem.c:626-628) is inactive; otherwise (or if the stage is not provided) on the host */
+		static volatile int no_dev_chain = 0;
+		int dev_chain = !no_dev_chain && !(getenv("BWA_B200_DEVICE_CHAIN") && atoi(getenv("BWA_B200_DEVICE_CHAIN")) == 0);
+		for (i = 0; i < n && dev_chain; ++i) {
+			int l = j->seqs[i].l_seq;
+			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l > 0 ? l : 1);
+			if (l > 0 && !(min_l > 0.05f * l)) dev_chain = 0;
+		}
+		if (dev_chain) {
+			bwag_chain_par_t cp;
+			bwag_contigs_t ctg;
+			int rc, c, n_seqs = j->bns->n_seqs;
+			int64_t *c_off = bb_malloc(sizeof(int64_t) * n_seqs);
+			int32_t *c_len = bb_malloc(sizeof(int32_t) * n_seqs);
+			uint8_t *c_alt = bb_malloc(n_seqs);
+			for (c = 0; c < n_seqs; ++c) { c_off[c] = j->bns->anns[c].offset; c_len[c] = j->bns->anns[c].len; c_alt[c] = !!j->bns->anns[c].is_alt; }
+			ctg.n_seqs = n_seqs; ctg.offset = c_off; ctg.len = c_len; ctg.is_alt = c_alt;
+			cp.w = opt->w; cp.max_chain_gap = opt->max_chain_gap; cp.max_occ = opt->max_occ; cp.min_seed_len = opt->min_seed_len;
+			cp.min_chain_weight = opt->min_chain_weight; cp.max_chain_extend = opt->max_chain_extend; cp.mask_level = opt->mask_level; cp.drop_ratio = opt->drop_ratio;
+			if (bwag_seed(batch, &sp, 0) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
+			if (j->lane == 0) ph("seed_stage");
+			rc = bwag_chain_extend(batch, &cp, swp, &ctg, &j->cregs);
+			free(c_off); free(c_len); free(c_alt);
+			if (rc == BWAG_UNSUPPORTED) { no_dev_chain = 1; dev_chain = 0; }
+			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
+			else { j->have_cregs = 1; if (j->lane == 0) ph("chain_extend"); }
+		}
+		if (!dev_chain) host_chain_extend(j, batch, swp, &sp, nt);
+	}
+
 	{ /* region arrays of all reads in one block; the rare array that must grow (mate rescue) moves to the heap */
 		int64_t tot_regs = 0;
 		j->reg_off = big_alloc(sizeof(int64_t) * ((size_t)n + 1));
-		for (i = 0; i < n; ++i) { j->reg_off[i] = tot_regs; tot_regs += j->chain_off[i + 1] > j->chain_off[i] ? j->xregs.n_regs[i] : 0; }
+		for (i = 0; i < n; ++i) { j->reg_off[i] = tot_regs; tot_regs += j->have_cregs ? j->cregs.n_regs[i] : (j->chain_off[i + 1] > j->chain_off[i] ? j->xregs.n_regs[i] : 0); }
 		j->reg_pool = big_alloc(sizeof(mem_alnreg_t) * ((size_t)tot_regs + 1));
 	}
 	j->rs = big_alloc(((size_t)n + 1) * sizeof(rstate_t));

@@ -67,7 +67,7 @@ typedef struct {
 	int64_t n_intv, n_seeds;   /* pool sizes (reads may sit in the pools in any order) */
 } bwag_seeds_t;
 
-int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out);
+int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out);   /* out == NULL: keep the results in HBM only */
 
 /* ---- stage 2: chain -> alignment regions (replaces the mem_chain2aln loop + ksw_extend2) ------ */
 typedef struct {
@@ -75,6 +75,7 @@ typedef struct {
 	int8_t mat[25];
 } bwag_sw_par_t;
 
+#define BWAG_UNSUPPORTED 77           /* returned by a stage an implementation does not provide */
 #define BWAG_XSEED_ZEROKEY 0x80000000u   /* the seed's sort key (score<<32|index) is 0, see bwamem.c:720 */
 typedef struct { int64_t rbeg; int32_t qbeg; uint32_t len; } bwag_xseed_t;  /* seeds of a chain in ks_introsort_64 order (bwamem.c:688-691) */
 typedef struct { int64_t rmax0, rmax1; int32_t seed_off, n_seeds; } bwag_xchain_t; /* rmax after bns_fetch_seq clamping (bwamem.c:668-685) */
@@ -88,6 +89,23 @@ typedef struct {
 int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par,
                 const int32_t *chain_off /* [n_reads+1] */, const bwag_xchain_t *chains,
                 int64_t n_seeds, const bwag_xseed_t *seeds, bwag_regs_t *out);
+
+/* ---- stages 2a+2: chaining on the device, fused with the extension (replaces mem_chain's chaining loop,
+ * mem_chain_flt and the mem_chain2aln loop: bwamem.c:299-334, 353-411, 658-812).  Requires a preceding
+ * bwag_seed(b, par, NULL) on the same batch (results stay in HBM).  Valid for reads for which
+ * mem_flt_chained_seeds is inactive (bwamem.c:626-628); the caller checks that. ------------------------ */
+typedef struct {
+	int w, max_chain_gap, max_occ, min_seed_len, min_chain_weight, max_chain_extend;
+	float mask_level, drop_ratio;
+} bwag_chain_par_t;
+typedef struct { int n_seqs; const int64_t *offset; const int32_t *len; const uint8_t *is_alt; } bwag_contigs_t;  /* bntann1_t columns (bntseq.h:41-50) */
+typedef struct { bwag_xreg_t r; int32_t rid; float frac_rep; } bwag_creg_t;   /* region + contig and repeat fraction of its chain */
+typedef struct {
+	const int32_t *n_regs;     /* [n_reads] */
+	const int64_t *reg_beg;    /* [n_reads] first region of each read in regs[] */
+	const bwag_creg_t *regs;
+} bwag_cregs_t;
+int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *sp, const bwag_contigs_t *ctg, bwag_cregs_t *out);
 
 /* ---- stage 3: banded global alignment -> CIGAR/NM/MD (replaces bwa_gen_cigar2 + ksw_global2) -- */
 #define BWAG_G_REG2ALN 0   /* the do-while of mem_reg2aln (bwamem.c:1144-1152): up to 3 band doublings, CIGAR+NM+MD */
@@ -114,6 +132,7 @@ typedef struct {
 	double ms_h2d, ms_d2h;
 	uint64_t n_launch;         /* kernels launched */
 	uint64_t h2d_bytes, d2h_bytes;   /* bytes copied host->device / device->host by the stage calls */
+	double ms_chain;           /* CUDA-event time of the chaining kernel */
 } bwag_stats_t;
 void bwag_stats_get(bwag_ctx_t *ctx, bwag_stats_t *s);
 void bwag_stats_reset(bwag_ctx_t *ctx);

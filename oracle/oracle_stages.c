@@ -153,6 +153,7 @@ int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds_t *out)
 	pfor(s2_seed, &s2, n_seeds);
 	for (i = 0; i < n_seeds; ++i) { b->ctx->st.sa_touches += steps[i]; b->ctx->st.sa_touches_algo += steps[i]; }
 	free(steps); free(s2.row); free(s1.per); free(s1.touch);
+	if (!out) return 0;
 	out->intv_beg = b->intv_off; out->intv_n = b->intv_n; out->intv = b->intv; out->seed_beg = b->seed_off; out->rbeg = b->rbeg; out->n_intv = n_intv; out->n_seeds = n_seeds;
 	return 0;
 }
@@ -189,6 +190,14 @@ int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int32_t *chain_
 	free(cells);
 	out->n_regs = b->n_regs; out->regs = b->regs;
 	return 0;
+}
+
+/* the oracle has no device-side chaining: the host glue then chains on the host (bb_chain.c), which is what the
+ * CPU tests of the host glue are about */
+int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *sp, const bwag_contigs_t *ctg, bwag_cregs_t *out)
+{
+	(void)b; (void)cp; (void)sp; (void)ctg; (void)out;
+	return BWAG_UNSUPPORTED;
 }
 
 /* ---------------------------------------------------------------- stage 3 */

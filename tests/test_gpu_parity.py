@@ -112,3 +112,13 @@ def test_index_builder_identical_to_bwa_index(data, tmp_path):
         ib.build(mine, verbose=False)
         for ext in ("pac", "ann", "amb", "bwt", "sa"):
             assert open(fa + "." + ext, "rb").read() == open(mine + "." + ext, "rb").read(), (name, ext)
+
+
+def test_host_chaining_path_still_identical(data, monkeypatch):
+    """BWA_B200_DEVICE_CHAIN=0 forces the host chaining path (the one long reads take); default is chaining on the device."""
+    monkeypatch.setenv("BWA_B200_DEVICE_CHAIN", "0")
+    for ref, kw in (("stress", dict(tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05)),
+                    ("stress", dict(tag="gpe", n=3000, seed=4, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05))):
+        fa, fqs = data.reads(ref, **kw)
+        args = ["-K", "100000000", "-t", "8", fa] + fqs
+        assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
