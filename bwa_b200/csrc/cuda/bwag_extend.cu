@@ -182,7 +182,7 @@ k_extend(DevIndex ix, ExtArgs a)
 				bwag_xseed_t *seeds = const_cast<bwag_xseed_t *>(a.seeds) + ch.seed_off;
 				const i64 rmax0 = ch.rmax0, rmax1 = ch.rmax1;
 				const int rlen = (int)(rmax1 - rmax0);
-				if (rlen > a.cap_r) { if (lane == 0) printf("[k_extend] read %d chain %lld: window %lld..%lld (%d) > cap %d, n_seeds %d\n", rid, (long long)(c - c0), (long long)rmax0, (long long)rmax1, rlen, a.cap_r, ch.n_seeds); overflow = 1; continue; }
+				if (rlen > a.cap_r) { overflow = 1; continue; }
 				__syncwarp();
 				for (int x = lane; x < rlen; x += 32) rseq[x] = (uint8_t)bwag_ref_base(ix, rmax0 + x); /* bns_fetch_seq (bwamem.c:685) */
 				__syncwarp();

@@ -229,18 +229,20 @@ k_smem(DevIndex ix, SeedArgs a)
 			const bool kv = k != (u64)-1, lv = l != (u64)-1;
 			const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
 			const bool same = kv && lv && (kp >> 7) == (lp >> 7);
-			uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0, c0 = b0, c1 = b0, c2 = b0, c3 = b0;
+			uint4 b0, b1, b2, b3;
 			if (lv) {
 				const uint4 *bl = ix.bwt + ((lp >> 7) << 2);
 				b0 = __ldg(bl); b1 = __ldg(bl + 1); b2 = __ldg(bl + 2); b3 = __ldg(bl + 3);
 			}
 			if (kv && !same) {
 				const uint4 *bk = ix.bwt + ((kp >> 7) << 2);
-				c0 = __ldg(bk); c1 = __ldg(bk + 1); c2 = __ldg(bk + 2); c3 = __ldg(bk + 3);
+				uint4 c0 = __ldg(bk), c1 = __ldg(bk + 1), c2 = __ldg(bk + 2), c3 = __ldg(bk + 3);
+				block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
 			}
-			if (same) { c0 = b0; c1 = b1; c2 = b2; c3 = b3; }   /* both ranks in one block: it was fetched once */
-			if (lv) block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
-			if (kv) block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
+			if (lv) {
+				block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
+				if (same) block_counts(b0, b1, b2, b3, (int)(kp & 127), tk);   /* both ranks in one block: it was fetched once */
+			}
 			touches += same ? 1 : 2;
 		}
 		const int cq = q[i];                               /* base to add: forward uses its complement (bwt.c:309), backward the base itself */

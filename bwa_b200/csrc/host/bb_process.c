@@ -29,7 +29,8 @@
  * therefore parked here and handed out again; small allocations stay with malloc, whose arenas are told
  * once not to trim (the same pages are recycled batch after batch). */
 typedef struct { void *p; size_t cap; int pinned; } bigblk_t;
-static bigblk_t g_big[48];
+#define N_BIG 256
+static bigblk_t g_big[N_BIG];
 static pthread_mutex_t g_big_mu = PTHREAD_MUTEX_INITIALIZER;
 static int g_malloc_tuned;
 
@@ -42,7 +43,7 @@ static void *big_alloc_x(size_t bytes, int pinned)
 	void *p = 0;
 	pthread_mutex_lock(&g_big_mu);
 	if (!g_malloc_tuned) { mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20); g_malloc_tuned = 1; }
-	for (i = 0; i < 48; ++i)
+	for (i = 0; i < N_BIG; ++i)
 		if (g_big[i].p && g_big[i].pinned == pinned && g_big[i].cap >= bytes && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
 	if (best >= 0 && g_big[best].cap <= bytes * 4 + (64u << 20)) { p = g_big[best].p; g_big[best].p = 0; }
 	pthread_mutex_unlock(&g_big_mu);
@@ -65,7 +66,7 @@ static void big_free(void *p)
 	q = (size_t *)p - 2;
 	if (q[0] < (1u << 20)) { if (q[1]) bwag_host_free(q); else free(q); return; }
 	pthread_mutex_lock(&g_big_mu);
-	for (i = 0; i < 48; ++i) if (!g_big[i].p) { g_big[i].p = p; g_big[i].cap = q[0]; g_big[i].pinned = (int)q[1]; p = 0; break; }
+	for (i = 0; i < N_BIG; ++i) if (!g_big[i].p) { g_big[i].p = p; g_big[i].cap = q[0]; g_big[i].pinned = (int)q[1]; p = 0; break; }
 	pthread_mutex_unlock(&g_big_mu);
 	if (p) { if (q[1]) bwag_host_free(q); else free(q); }
 }
@@ -82,6 +83,13 @@ static void ph(const char *name)
 	if (name) fprintf(stderr, "[prof] %-16s %9.2f ms\n", name, 1e3 * (t - g_t_last));
 	g_t_last = t;
 }
+
+/* BWA_B200_TRACE=1: one line per (lane, chunk, phase) with start/end in ms since the batch began */
+static int g_trace = -1;
+static double g_trace_t0;
+static double trace_now(void) { return 1e3 * (bb_realtime() - g_trace_t0); }
+#define PH(j, name) do { if ((j)->lane == 0) ph(name); if (g_trace > 0) { double t_ = trace_now(); fprintf(stderr, "[trace] lane %d chunk %d %-12s %8.1f -> %8.1f\n", (j)->lane, (j)->chunk_id, name, (j)->t_last, t_); (j)->t_last = t_; } } while (0)
+#define TRACE(j, name, t_start) do { if (g_trace > 0) fprintf(stderr, "[trace] lane %d chunk %d %-12s %8.1f -> %8.1f\n", (j)->lane, (j)->chunk_id, name, t_start, trace_now()); } while (0)
 
 /* ---------------------------------------------------------------- device residency */
 typedef struct { const bwt_t *bwt; bwag_ctx_t *ctx; } dev_slot_t;
@@ -209,7 +217,8 @@ typedef struct {
 	int pass_dry;
 	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
-	int lane;                /* which host-thread pool / device batch object this chunk runs on */
+	double t_last;
+	int lane, chunk_id;      /* which lane (device batch object) runs this chunk */
 	bwag_batch_t *batch;
 	bwag_sw_par_t swp;
 } job_t;
@@ -537,12 +546,12 @@ static void host_chain_extend(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t
 	int n = j->n, t;
 	int64_t i, nc = 0, ns = 0;
 	if (bwag_seed(batch, &sp, &j->seeds) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
-	if (j->lane == 0) ph("seed_stage");
+	PH(j, "seed_stage");
 
 	j->tls = bb_calloc(bb_parallel_ids(), sizeof(tls_t));
 	j->slice = big_alloc(((size_t)n + 1) * sizeof(rslice_t));
 	bb_parallel_for_lane(j->lane, nt, w_chain, j, n);
-	if (j->lane == 0) ph("chain");
+	PH(j, "chain");
 
 	j->chain_off = big_alloc_x(sizeof(int32_t) * ((size_t)n + 1), 1);
 	for (i = 0; i < n; ++i) { nc += j->slice[i].nc; ns += j->slice[i].ns; }
@@ -565,11 +574,11 @@ static void host_chain_extend(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t
 	}
 	free(j->tls); j->tls = 0;
 	big_free(j->slice); j->slice = 0;
-	if (j->lane == 0) ph("flatten");
+	PH(j, "flatten");
 
 	if (bwag_extend(batch, swp, j->chain_off, j->xchains, j->n_xseeds, j->xseeds, &j->xregs) != 0)
 		bb_fatal("mem_process_seqs", "extension stage failed: %s", bwag_last_error());
-	if (j->lane == 0) ph("extend_stage");
+	PH(j, "extend_stage");
 
 }
 
@@ -587,11 +596,11 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	j->off[n] = tot;
 	j->codes = big_alloc_x((size_t)tot + 16, 1);
 	bb_parallel_for_lane(j->lane, nt, w_encode, j, n);
-	if (j->lane == 0) ph("encode");
+	PH(j, "encode");
 
 	batch = bwag_batch_begin(ctx, n, j->codes, j->off);
 	if (!batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
-	if (j->lane == 0) ph("batch_begin");
+	PH(j, "batch_begin");
 	sp.min_seed_len = opt->min_seed_len;
 	sp.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
 	sp.split_width = opt->split_width;
@@ -618,12 +627,12 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 			cp.w = opt->w; cp.max_chain_gap = opt->max_chain_gap; cp.max_occ = opt->max_occ; cp.min_seed_len = opt->min_seed_len;
 			cp.min_chain_weight = opt->min_chain_weight; cp.max_chain_extend = opt->max_chain_extend; cp.mask_level = opt->mask_level; cp.drop_ratio = opt->drop_ratio;
 			if (bwag_seed(batch, &sp, 0) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
-			if (j->lane == 0) ph("seed_stage");
+			PH(j, "seed_stage");
 			rc = bwag_chain_extend(batch, &cp, swp, &ctg, &j->cregs);
 			free(c_off); free(c_len); free(c_alt);
 			if (rc == BWAG_UNSUPPORTED) { no_dev_chain = 1; dev_chain = 0; }
 			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
-			else { j->have_cregs = 1; if (j->lane == 0) ph("chain_extend"); }
+			else { j->have_cregs = 1; PH(j, "chain_extend"); }
 		}
 		if (!dev_chain) host_chain_extend(j, batch, swp, &sp, nt);
 	}
@@ -639,10 +648,10 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
 		int64_t left = 0;
 		bb_parallel_for_lane(j->lane, nt, w_dedup, j, n);
-		if (j->lane == 0) ph("dedup");
+		PH(j, "dedup");
 		for (i = 0; i < n; ++i) left += !j->rs[i].dedup_done;
 		if (global_round(j, batch, swp) == 0 && left) bb_fatal("mem_process_seqs", "internal error: pending reads without requests");
-		if (j->lane == 0) ph("global_round");
+		PH(j, "global_round");
 		if (left == 0) break;
 	}
 	return batch;
@@ -674,19 +683,19 @@ static void job_finish(job_t *j, bwag_ctx_t *ctx)
 		j->batch = bwag_batch_begin(ctx, j->n, j->codes, j->off);
 		if (!j->batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
 	}
-	if (pe) bb_parallel_for_lane(j->lane, nt, w_rescue, j, n_units);
+	if (pe) { bb_parallel_for_lane(j->lane, nt, w_rescue, j, n_units); PH(j, "rescue"); }
 	for (j->pass_dry = 0;; j->pass_dry = 0) { /* SAM; a read that misses an alignment is retried after a device round */
 		long i, left = 0;
 		bb_parallel_for_lane(j->lane, nt, w_sam, j, n_units);
-		if (j->lane == 0) ph("sam");
+		PH(j, "sam");
 		for (i = 0; i < j->n; ++i) left += !j->rs[i].done;
 		if (left == 0) break;
 		if (global_round(j, j->batch, &j->swp) == 0) bb_fatal("mem_process_seqs", "internal error: unfinished reads without requests");
-		if (j->lane == 0) ph("global_round");
+		PH(j, "global_round");
 	}
 	bwag_batch_end(j->batch); j->batch = 0;
 	job_free(j);
-	if (j->lane == 0) ph("cleanup");
+	PH(j, "cleanup");
 }
 
 typedef struct { job_t *jobs; int n_jobs; volatile int next; bwag_ctx_t *ctx; int phase, lane, pe; } lane_arg_t;
@@ -699,7 +708,8 @@ static void *lane_main(void *a_)
 		job_t *j;
 		if (k >= a->n_jobs) break;
 		j = &a->jobs[k];
-		j->lane = a->lane;
+		j->lane = a->lane; j->chunk_id = k;
+		if (g_trace > 0) j->t_last = trace_now();
 		if (a->phase == 0) {
 			j->batch = run_to_regs(j, a->ctx, &j->swp);
 			if (a->pe) { bwag_batch_end(j->batch); j->batch = 0; }   /* the insert-size model needs every chunk first */
@@ -755,6 +765,8 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		sw_par_from_opt(opt, &j->swp);
 	}
 	ph(0);
+	if (g_trace < 0) g_trace = getenv("BWA_B200_TRACE") ? atoi(getenv("BWA_B200_TRACE")) : 0;
+	g_trace_t0 = bb_realtime();
 	run_lanes(jobs, n_jobs, n_lanes, ctx, 0, pe);
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
@@ -767,9 +779,11 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 			big_free(rv);
 		}
 		ph("pestat");
+		if (g_trace > 0) fprintf(stderr, "[trace] pestat done %8.1f\n", trace_now());
 		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
 	}
 	free(jobs);
+	if (g_trace > 0) fprintf(stderr, "[trace] batch done %8.1f\n", trace_now());
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec\n", __func__, n, bb_cputime() - ctime, bb_realtime() - rtime);
 }
