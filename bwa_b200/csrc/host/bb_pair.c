@@ -39,24 +39,53 @@ static int best_overlapping_sub(const mem_opt_t *opt, const mem_alnreg_v *r) /* 
 	return j < r->n ? r->a[j].score : opt->min_seed_len * opt->a;
 }
 
+/* one pair's contribution to the insert-size model (the loop body of bwamem_pair.c:88-101): 0 if the pair is
+ * not a confident unique one, else (orientation+1) << 48 | distance.  Independent per pair, so the batch
+ * driver evaluates it in parallel while the chunks are still in flight. */
+uint64_t bb_pestat_pair(const mem_opt_t *opt, int64_t l_pac, const mem_alnreg_v *r0, const mem_alnreg_v *r1)
+{
+	int64_t is;
+	int dir;
+	if (r0->n == 0 || r1->n == 0) return 0;
+	if (best_overlapping_sub(opt, r0) > MIN_RATIO * r0->a[0].score) return 0;
+	if (best_overlapping_sub(opt, r1) > MIN_RATIO * r1->a[0].score) return 0;
+	if (r0->a[0].rid != r1->a[0].rid) return 0;
+	dir = infer_dir(l_pac, r0->a[0].rb, r1->a[0].rb, &is);
+	return is && is <= opt->max_ins ? (uint64_t)(dir + 1) << 48 | (uint64_t)is : 0;
+}
+
+/* ascending order of insert sizes; they are bounded by max_ins, so a counting pass replaces the comparison sort */
+static void sort_isizes(size_t n, uint64_t *q, int max_ins)
+{
+	size_t k, o = 0;
+	uint32_t *cnt;
+	int v;
+	if (n < 4096 || max_ins > 1 << 24) { bb_sort_u64(n, q); return; }
+	cnt = bb_calloc((size_t)max_ins + 1, sizeof(uint32_t));
+	for (k = 0; k < n; ++k) ++cnt[q[k]];
+	for (v = 0; v <= max_ins; ++v) { uint32_t c = cnt[v]; while (c--) q[o++] = (uint64_t)v; }
+	free(cnt);
+}
+
 void mem_pestat(const mem_opt_t *opt, int64_t l_pac, int n, const mem_alnreg_v *regs, mem_pestat_t pes[4])
 {
+	uint64_t *v = bb_malloc(sizeof(uint64_t) * ((size_t)(n >> 1) + 1));
+	int i;
+	for (i = 0; i < n >> 1; ++i) v[i] = bb_pestat_pair(opt, l_pac, &regs[i << 1], &regs[i << 1 | 1]);
+	bb_pestat_from_pairs(opt, n >> 1, v, pes);
+	free(v);
+}
+
+void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v, mem_pestat_t pes[4])
+{
 	BB_VEC(uint64_t) isize[4];
-	int i, d;
+	long i;
+	int d;
 	size_t max;
 	memset(pes, 0, 4 * sizeof(mem_pestat_t));
 	memset(isize, 0, sizeof(isize));
-	for (i = 0; i < n >> 1; ++i) {
-		const mem_alnreg_v *r0 = &regs[i << 1 | 0], *r1 = &regs[i << 1 | 1];
-		int64_t is;
-		int dir;
-		if (r0->n == 0 || r1->n == 0) continue;
-		if (best_overlapping_sub(opt, r0) > MIN_RATIO * r0->a[0].score) continue;
-		if (best_overlapping_sub(opt, r1) > MIN_RATIO * r1->a[0].score) continue;
-		if (r0->a[0].rid != r1->a[0].rid) continue;
-		dir = infer_dir(l_pac, r0->a[0].rb, r1->a[0].rb, &is);
-		if (is && is <= opt->max_ins) bb_vec_push(isize[dir], (uint64_t)is);
-	}
+	for (i = 0; i < n_pairs; ++i)
+		if (v[i]) bb_vec_push(isize[(v[i] >> 48) - 1], v[i] & 0xffffffffffffULL);
 	if (bwa_verbose >= 3) fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", __func__, (long)isize[0].n, (long)isize[1].n, (long)isize[2].n, (long)isize[3].n);
 	for (d = 0; d < 4; ++d) {
 		mem_pestat_t *r = &pes[d];
@@ -68,7 +97,7 @@ void mem_pestat(const mem_opt_t *opt, int64_t l_pac, int n, const mem_alnreg_v *
 			r->failed = 1;
 			continue;
 		} else fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", __func__, "FR"[d >> 1 & 1], "FR"[d & 1]);
-		bb_sort_u64(qn, q);
+		sort_isizes(qn, q, opt->max_ins);
 		p25 = (int)q[(int)(.25 * qn + .499)];
 		p50 = (int)q[(int)(.50 * qn + .499)];
 		p75 = (int)q[(int)(.75 * qn + .499)];

@@ -218,6 +218,7 @@ typedef struct {
 	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
 	double t_last;
+	uint64_t *pe_is;         /* PE: this chunk's slice of the per-pair insert-size candidates */
 	int lane, chunk_id;      /* which lane (device batch object) runs this chunk */
 	bwag_batch_t *batch;
 	bwag_sw_par_t swp;
@@ -657,6 +658,14 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	return batch;
 }
 
+static void w_pe_pairs(void *d, long c, int tid)   /* insert-size candidates of 1024 pairs */
+{
+	job_t *j = d;
+	long i, e = (c + 1) * 1024 < j->n >> 1 ? (c + 1) * 1024 : j->n >> 1;
+	(void)tid;
+	for (i = c * 1024; i < e; ++i) j->pe_is[i] = bb_pestat_pair(j->opt, j->bns->l_pac, &j->rs[i << 1].regs, &j->rs[i << 1 | 1].regs);
+}
+
 static void w_free(void *d, long i, int tid)
 {
 	job_t *j = d;
@@ -694,6 +703,7 @@ static void job_finish(job_t *j, bwag_ctx_t *ctx)
 		PH(j, "global_round");
 	}
 	bwag_batch_end(j->batch); j->batch = 0;
+	PH(j, "batch_end");
 	job_free(j);
 	PH(j, "cleanup");
 }
@@ -712,7 +722,10 @@ static void *lane_main(void *a_)
 		if (g_trace > 0) j->t_last = trace_now();
 		if (a->phase == 0) {
 			j->batch = run_to_regs(j, a->ctx, &j->swp);
-			if (a->pe) { bwag_batch_end(j->batch); j->batch = 0; }   /* the insert-size model needs every chunk first */
+			if (a->pe) {   /* the insert-size model needs every chunk first */
+				bwag_batch_end(j->batch); j->batch = 0;
+				if (j->pe_is) { bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_pe_pairs, j, ((j->n >> 1) + 1023) / 1024); PH(j, "pe_pairs"); }
+			}
 			else job_finish(j, a->ctx);
 		} else job_finish(j, a->ctx);
 	}
@@ -742,6 +755,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	double ctime = bb_cputime(), rtime = bb_realtime();
 	int pe = !!(opt->flag & MEM_F_PE), n_lanes = 3, n_jobs, k;
 	long chunk = 1 << 17, start;
+	uint64_t *pe_is = 0;
 	const char *e;
 
 	if (n <= 0) return;
@@ -764,6 +778,10 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		j->n_processed = n_processed + start;
 		sw_par_from_opt(opt, &j->swp);
 	}
+	if (pe && !pes0) {
+		pe_is = big_alloc(sizeof(uint64_t) * ((size_t)(n >> 1) + 1));
+		for (k = 0, start = 0; k < n_jobs; ++k, start += chunk) jobs[k].pe_is = pe_is + (start >> 1);
+	}
 	ph(0);
 	if (g_trace < 0) g_trace = getenv("BWA_B200_TRACE") ? atoi(getenv("BWA_B200_TRACE")) : 0;
 	g_trace_t0 = bb_realtime();
@@ -771,13 +789,9 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
 		else {
-			mem_alnreg_v *rv = big_alloc(sizeof(mem_alnreg_v) * (size_t)n);
-			int i;
-			for (k = 0, start = 0; k < n_jobs; ++k, start += chunk)
-				for (i = 0; i < jobs[k].n; ++i) rv[start + i] = jobs[k].rs[i].regs;
-			mem_pestat(opt, bns->l_pac, n, rv, pes);
-			big_free(rv);
+			bb_pestat_from_pairs(opt, n >> 1, pe_is, pes);
 		}
+		big_free(pe_is);
 		ph("pestat");
 		if (g_trace > 0) fprintf(stderr, "[trace] pestat done %8.1f\n", trace_now());
 		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
