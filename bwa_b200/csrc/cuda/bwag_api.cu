@@ -3,7 +3,7 @@
  * the work/time counters the roofline is computed from.
  *
  * HBM layout of the index blob (all offsets 256-byte aligned):
- *   [ header 256 B | Occ/BWT blocks (bwt_size*4 B) | sampled SA (n_sa*8 B) | pac (l_pac/4+1 B) ]
+ *   [ header 256 B | Occ/BWT blocks (bwt_size*4 B, symbols as bit planes) | sampled SA (n_sa*8 B) | pac (l_pac/4+1 B) ]
  * The blob is position independent (the header holds sizes, not pointers) so that it can be filled
  * on one GPU and broadcast to the others with a single collective.
  */
@@ -39,7 +39,7 @@ static int set_err(const char *fmt, ...)
 
 /* device counters, mirrored in pinned host memory */
 struct Counters {
-	int next_read, next_task, max_rlen, pad1;
+	int next_read, next_task, max_rlen, next_read3;
 	u64 next_seed;
 	u64 n_intv, n_seeds;
 	u64 occ_touches, sa_touches, ext_cells, glb_cells;
@@ -81,8 +81,8 @@ struct bwag_ctx {
 	bwag_stats_t st;
 	int sa_intv_disk;
 	/* scratch reused across batches */
-	DevBuf s_k1, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
-	int grid_k1, grid_k2, grid_k4, grid_k5;
+	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
+	int grid_k1, grid_k1f, grid_k2, grid_k4, grid_k5;
 	struct bwag_batch *spare[4]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
 	pthread_mutex_t mu;
 	struct bwag_ctx *parent;     /* set in the per-batch view of the context */
@@ -116,6 +116,8 @@ static void batch_free(bwag_batch_t *b);
 static void free_dev(DevBuf *b) { if (b->p) cudaFree(b->p); b->p = 0; b->cap = 0; }
 static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->cap = 0; }
 
+#define K1_SMEM_MAX (200 * 1024)
+
 /* ------------------------------------------------------------------------------------------------ index */
 
 extern "C" size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac)
@@ -142,7 +144,14 @@ extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_
 	h.total = h.off_pac + ALIGN256((size_t)l_pac / 4 + 1 + 64);
 	char *d = (char *)d_blob;
 	CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
+	CK(cudaMemset(d + h.off_bwt, 0, ALIGN256((size_t)bwt->bwt_size * 4 + 64)));
 	CK(cudaMemcpy(d + h.off_bwt, bwt->bwt, (size_t)bwt->bwt_size * 4, cudaMemcpyHostToDevice));
+	{   /* symbols -> bit planes, in place (layout: bwag_dev.cuh) */
+		const u64 n_blocks = ((u64)bwt->bwt_size * 4 + 63) / 64;
+		BWAG_LAUNCH(k_occ_planes, (int)((n_blocks + 255) / 256 < 65535 ? (n_blocks + 255) / 256 : 65535), 256, 0, 0, (uint4 *)(d + h.off_bwt), n_blocks);
+		CK(cudaGetLastError());
+		CK(cudaDeviceSynchronize());
+	}
 	CK(cudaMemcpy(d + h.off_sa, bwt->sa, (size_t)bwt->n_sa * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(d + h.off_pac, pac, (size_t)l_pac / 4 + 1, cudaMemcpyHostToDevice));
 	return 0;
@@ -152,13 +161,15 @@ static int pick_grid(bwag_ctx_t *c)
 {
 #ifdef BWAG_CUSIM
 	c->n_sm = 2;
-	c->grid_k1 = c->grid_k2 = c->grid_k4 = c->grid_k5 = 2;
+	c->grid_k1 = c->grid_k1f = c->grid_k2 = c->grid_k4 = c->grid_k5 = 2;
 #else
 	cudaDeviceProp prop;
 	int nb;
 	CK(cudaGetDeviceProperties(&prop, c->device));
 	c->n_sm = prop.multiProcessorCount;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, 0)); c->grid_k1 = c->n_sm * (nb > 0 ? nb : 1);
+	CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_MAX));
+	c->grid_k1 = 0;   /* depends on the shared read slots: chosen per launch */
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem_fwd, K1F_THREADS, 0)); c->grid_k1f = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
@@ -212,7 +223,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	free_dev(&c->s_k1); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
+	free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
 	for (int i = 0; i < 4; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
@@ -271,7 +282,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 		b->lc_ready = 1;
 	}
 	b->lc.device = c->device; b->lc.n_sm = c->n_sm; b->lc.ix = c->ix; b->lc.parent = c;
-	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
+	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k1f = c->grid_k1f; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
 	memset(&b->lc.st, 0, sizeof(b->lc.st));
 	b->max_len = 0; b->seeded = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
@@ -310,7 +321,7 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 static void batch_free(bwag_batch_t *b)
 {
 	if (b->lc_ready) {
-		free_dev(&b->lc.s_k1); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
+		free_dev(&b->lc.s_k1); free_dev(&b->lc.s_k1f); free_dev(&b->lc.s_n3); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
 		cudaFree(b->lc.d_cnt); cudaFreeHost(b->lc.h_cnt);
 		cudaEventDestroy(b->lc.ev0); cudaEventDestroy(b->lc.ev1); cudaStreamDestroy(b->lc.stream);
 	}
@@ -354,7 +365,20 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	memset(&a, 0, sizeof(a));
 	for (int attempt = 0;; ++attempt) {
 		const int groups_per_block = K1_THREADS;   /* one lane per read */
-		int grid = c->grid_k1;
+		/* shared memory of a block: the heads of both candidate lists + one read slot per lane (odd number of words) */
+		int qstride = (((b->max_len + 6) >> 2) | 1) << 2;
+		size_t smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16 + (size_t)K1_THREADS * qstride;
+#ifdef K1_NO_QSMEM
+		qstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16;
+#endif
+		if (smem > K1_SMEM_MAX) { qstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
+		int grid;
+#ifdef BWAG_CUSIM
+		grid = 2;
+#else
+		{ int nb; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, smem)); grid = c->n_sm * (nb > 0 ? nb : 1); }
+#endif
+		const int cap3 = b->max_len / (par->min_seed_len + 1) + 2;
 		size_t per_group = (size_t)(4 * cap_list + 2 * cap_mem) * 16;
 		{   /* keep the per-group scratch within ~6 GB: very long reads get fewer groups */
 			size_t budget = (size_t)6 << 30;
@@ -365,17 +389,26 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 			if (grid > need_groups) grid = (int)(need_groups > 0 ? need_groups : 1);
 		}
 		if (buf_reserve(&c->s_k1, per_group * (size_t)grid * groups_per_block)) return 1;
+		if (buf_reserve(&c->s_k1f, 32 * (size_t)cap3 * (size_t)n + 64) || buf_reserve(&c->s_n3, sizeof(int) * (size_t)(n + 1))) return 1;
 		if (buf_reserve(&b->d_intv_beg, sizeof(i64) * (size_t)(n + 1)) || buf_reserve(&b->d_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
 		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
 		a.min_seed_len = par->min_seed_len; a.split_len = par->split_len; a.split_width = par->split_width; a.max_occ = par->max_occ; a.max_mem_intv = par->max_mem_intv;
-		a.scratch = (Intv *)c->s_k1.p; a.cap_list = cap_list; a.cap_mem = cap_mem;
+		a.scratch = (Intv *)c->s_k1.p; a.cap_list = cap_list; a.cap_mem = cap_mem; a.qstride = qstride;
+		a.stage3 = (Intv *)c->s_k1f.p; a.cap3 = cap3; a.n3 = par->max_mem_intv ? (int *)c->s_n3.p : 0; a.next_read3 = &c->d_cnt->next_read3;
 		a.intv_beg = (i64 *)b->d_intv_beg.p; a.intv_n = (int *)b->d_intv_n.p; a.intv = (bwtintv_t *)b->d_intv.p; a.seed_beg = (i64 *)b->d_seed_beg.p; a.rbeg = (i64 *)b->d_rbeg.p;
 		a.cap_intv = cap_intv; a.cap_seeds = cap_seeds;
 		a.next_read = &c->d_cnt->next_read; a.n_intv = &c->d_cnt->n_intv; a.n_seeds = &c->d_cnt->n_seeds; a.occ_touches = &c->d_cnt->occ_touches; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
-		BWAG_LAUNCH(k_smem, grid, K1_THREADS, 0, c->stream, c->ix, a);
+		if (a.n3) {   /* third pass first: K1 appends its seeds to the read's list */
+			int g3 = c->grid_k1f;
+			if (g3 > (n + K1F_THREADS - 1) / K1F_THREADS) g3 = (n + K1F_THREADS - 1) / K1F_THREADS;
+			BWAG_LAUNCH(k_smem_fwd, g3, K1F_THREADS, 0, c->stream, c->ix, a);
+			CK(cudaGetLastError());
+			++c->st.n_launch;
+		}
+		BWAG_LAUNCH(k_smem, grid, K1_THREADS, smem, c->stream, c->ix, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		BWAG_LAUNCH(k_seed_post, (n + K1B_THREADS - 1) / K1B_THREADS, K1B_THREADS, 0, c->stream, a);   /* harmless if K1 overflowed: the run is repeated */

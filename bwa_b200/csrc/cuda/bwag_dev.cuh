@@ -1,10 +1,13 @@
 /* bwag_dev.cuh -- device-side view of the index, launch/portability macros, FM-index block arithmetic.
  *
- * Index layout in HBM (one blob, see bwag_api.cu): the reference's own structures, unchanged:
- *   - Occ/BWT blocks exactly as in bwt_t::bwt (bwt.h:74-82): one 64-byte block per 128 BWT symbols =
- *     4 x u64 cumulative counts (A,C,G,T; '$' excluded) followed by 8 x u32 words of 16 2-bit symbols,
- *     first symbol in the top bits.  64-byte aligned so a block is two 32-byte HBM sectors / four
- *     16-byte vector loads;
+ * Index layout in HBM (one blob, see bwag_api.cu):
+ *   - Occ/BWT blocks: one 64-byte block per 128 BWT symbols like bwt_t::bwt (bwt.h:74-82), with the same
+ *     4 x u64 cumulative counts (A,C,G,T; '$' excluded) in the first 32 bytes, but the 128 symbols stored
+ *     as two bit planes instead of the file's 2-bit packing (k_occ_planes converts in place after upload):
+ *     bytes 32-47 = bit 1 of every symbol, bytes 48-63 = bit 0, symbol p of the block at bit p&31 of
+ *     word p>>5 of its plane.  Ranks of all four symbols up to a position are then three masked popcounts
+ *     per 32 symbols with no data-dependent branch: popc(hi), popc(lo), popc(hi&lo) give T = both,
+ *     G = hi-only, C = lo-only, A = the rest.  64-byte aligned: a block is two 32-byte HBM sectors;
  *   - the sampled suffix array bwt_t::sa (every sa_intv-th row, sa[0] = -1), optionally re-sampled
  *     more densely on the device;
  *   - the 2-bit forward reference pac (4 bases per byte, first base in the top bits).
@@ -41,30 +44,36 @@ struct DevIndex {
 
 #define FULL_MASK 0xffffffffu
 
-/* number of symbols == c among the first n (1..16) symbols of a BWT word (symbol 0 in the top bits);
- * returns the four counts packed one per byte (A in bits 0-7 ... T in bits 24-31) */
-__device__ __forceinline__ u32 bwag_word_counts(u32 w, int n)
+/* low t bits set, t clamped to [0,32]: which symbols of a 32-symbol plane word lie in [0,pos] */
+__device__ __forceinline__ u32 bwag_plane_mask(int t) { return __funnelshift_lc(0xffffffffu, 0u, (u32)(t > 0 ? t : 0)); }
+
+/* ranks of all four symbols over positions [0,pos] of one Occ block given its four 16-byte quarters:
+ * cA = counts A,C ; cG = counts G,T ; ph, pl = the two bit planes (bwt_occ4, bwt.c:169-186) */
+__device__ __forceinline__ void bwag_block_counts(const uint4 &cA, const uint4 &cG, const uint4 &ph, const uint4 &pl, int pos, u64 out[4])
 {
-	u32 s = w >> ((16 - n) << 1);              /* drop the symbols after the n-th; zeros enter at the top */
-	u32 lo = s & 0x55555555u, hi = (s >> 1) & 0x55555555u;
-	u32 nT = __popc(hi & lo), nG = __popc(hi & ~lo), nC = __popc(~hi & lo & 0x55555555u);
-	u32 nA = (u32)n - nT - nG - nC;             /* everything else among the n real symbols */
-	return nA | nC << 8 | nG << 16 | nT << 24;
+	const int n = pos + 1;
+	const u32 m0 = bwag_plane_mask(n), m1 = bwag_plane_mask(n - 32), m2 = bwag_plane_mask(n - 64), m3 = bwag_plane_mask(n - 96);
+	const u32 h0 = ph.x & m0, h1 = ph.y & m1, h2 = ph.z & m2, h3 = ph.w & m3;
+	const u32 l0 = pl.x & m0, l1 = pl.y & m1, l2 = pl.z & m2, l3 = pl.w & m3;
+	const u32 nH = __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3);
+	const u32 nL = __popc(l0) + __popc(l1) + __popc(l2) + __popc(l3);
+	const u32 nT = __popc(h0 & l0) + __popc(h1 & l1) + __popc(h2 & l2) + __popc(h3 & l3);
+	out[0] = ((u64)cA.y << 32 | cA.x) + (u32)(n + nT - nH - nL);
+	out[1] = ((u64)cA.w << 32 | cA.z) + (nL - nT);
+	out[2] = ((u64)cG.y << 32 | cG.x) + (nH - nT);
+	out[3] = ((u64)cG.w << 32 | cG.z) + nT;
 }
 
-/* counts over symbols [0, pos] (pos in 0..127) of a block restricted to the four words held in v,
- * which are words 4*half .. 4*half+3 of the block's symbol area (half = 0 or 1) */
-__device__ __forceinline__ u32 bwag_quad_counts(uint4 v, int half, int pos)
+/* symbol at position pos of a block and the number of its occurrences in [0,pos] */
+__device__ __forceinline__ int bwag_block_symbol_rank(const uint4 &ph, const uint4 &pl, int pos, u32 *rank)
 {
-	int n = pos + 1 - (half << 6);              /* symbols of this 64-symbol half that count */
-	u32 r = 0;
-	if (n <= 0) return 0;
-	if (n > 64) n = 64;
-	r += bwag_word_counts(v.x, n >= 16 ? 16 : n);
-	if (n > 16) r += bwag_word_counts(v.y, n >= 32 ? 16 : n - 16);
-	if (n > 32) r += bwag_word_counts(v.z, n >= 48 ? 16 : n - 32);
-	if (n > 48) r += bwag_word_counts(v.w, n - 48);
-	return r;
+	const int w = pos >> 5, n = pos + 1;
+	const u32 hw = w == 0 ? ph.x : w == 1 ? ph.y : w == 2 ? ph.z : ph.w, lw = w == 0 ? pl.x : w == 1 ? pl.y : w == 2 ? pl.z : pl.w;
+	const int c = (int)(hw >> (pos & 31) & 1) << 1 | (int)(lw >> (pos & 31) & 1);
+	const u32 fh = (c & 2) ? 0u : 0xffffffffu, fl = (c & 1) ? 0u : 0xffffffffu;   /* flip a plane where the symbol's bit is 0 */
+	*rank = __popc((ph.x ^ fh) & (pl.x ^ fl) & bwag_plane_mask(n)) + __popc((ph.y ^ fh) & (pl.y ^ fl) & bwag_plane_mask(n - 32))
+	      + __popc((ph.z ^ fh) & (pl.z ^ fl) & bwag_plane_mask(n - 64)) + __popc((ph.w ^ fh) & (pl.w ^ fl) & bwag_plane_mask(n - 96));
+	return c;
 }
 
 __device__ __forceinline__ int bwag_pac_base(const uint8_t *pac, i64 k) { return pac[k >> 2] >> ((~k & 3) << 1) & 3; }

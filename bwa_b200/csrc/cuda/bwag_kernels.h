@@ -4,6 +4,11 @@
 #include "bwag_dev.cuh"
 
 #define K1_THREADS 128
+#define K1F_THREADS 128
+#ifndef K1_SLOTS
+#define K1_SLOTS 4
+#endif
+//       /* candidate-list entries per list kept in shared memory */
 #define K1B_THREADS 128
 #define K2_THREADS 128
 #define K3_THREADS 128
@@ -19,6 +24,8 @@ struct SeedArgs {
 	int min_seed_len, split_len, split_width, max_occ; u64 max_mem_intv;
 	/* per-group scratch */
 	Intv *scratch; int cap_list, cap_mem;
+	int qstride;                                   /* bytes of a lane's shared read slot (0: read the bases from global memory) */
+	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
 	i64 cap_intv, cap_seeds;
@@ -76,7 +83,9 @@ extern "C" {
 }
 #endif
 
+__global__ void k_occ_planes(uint4 *bwt, u64 n_blocks);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
+__global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);
 __global__ void k_sa(DevIndex ix, SaArgs a);
 __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);

@@ -3,9 +3,8 @@
  * K2 replaces bwt_sa/bwt_invPsi/bwt_occ (bwt.c:53-59,86-129): one lane per seed walks LF-steps until it
  * hits a sampled row.  Walk lengths are geometric (mean = sampling interval - 1), so lanes that finish
  * pull new seeds (ballot + one atomicAdd per warp): a warp keeps 32 independent 64-byte requests in
- * flight regardless of the spread.  Each step reads the 16-byte quarter holding the symbol, the 16 bytes
- * holding its cumulative count and, for positions in the second half, the first symbol quarter pair --
- * all inside one 64-byte Occ block, i.e. two HBM sectors per step.
+ * flight regardless of the spread.  Each step reads the 32-byte sector holding the block's two bit planes
+ * and the 16 bytes holding the symbol's cumulative count, i.e. both HBM sectors of one 64-byte Occ block.
  */
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
@@ -18,15 +17,11 @@ __device__ __forceinline__ u64 lf_step(const DevIndex &ix, u64 k)
 	if (k == ix.primary) return 0;
 	u64 kp = k - (k > ix.primary);                 /* row in the '$'-less BWT == what bwt_occ uses since k != primary */
 	const uint4 *blk = ix.bwt + ((kp >> 7) << 2);
-	int pos = (int)(kp & 127);
-	uint4 w = __ldg(blk + 2 + (pos >> 6));         /* the 64-symbol half holding kp */
-	u32 word = (pos >> 4 & 3) == 0 ? w.x : (pos >> 4 & 3) == 1 ? w.y : (pos >> 4 & 3) == 2 ? w.z : w.w;
-	int c = word >> ((~pos & 15) << 1) & 3;
-	uint4 cn = __ldg(blk + (c >> 1));
-	u64 n = (c & 1) ? ((u64)cn.w << 32 | cn.z) : ((u64)cn.y << 32 | cn.x);
-	u32 pc = bwag_quad_counts(w, pos >> 6, pos);
-	if (pos >= 64) pc += bwag_quad_counts(__ldg(blk + 2), 0, pos);
-	return ix.L2[c] + n + (pc >> (c << 3) & 0xff);
+	u32 pc;
+	const int c = bwag_block_symbol_rank(__ldg(blk + 2), __ldg(blk + 3), (int)(kp & 127), &pc);   /* the block's plane sector */
+	const uint4 cn = __ldg(blk + (c >> 1));                                                      /* and 16 bytes of its count sector */
+	const u64 n = (c & 1) ? ((u64)cn.w << 32 | cn.z) : ((u64)cn.y << 32 | cn.x);
+	return ix.L2[c] + n + pc;
 }
 
 __global__ void __launch_bounds__(K2_THREADS)
@@ -71,5 +66,32 @@ __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out)
 		u64 k = r << out_shift, steps = 0;
 		while (k & mask) { k = lf_step(ix, k); ++steps; }
 		out[r] = r == 0 ? (u64)-1 : steps + ix.sa[k >> ix.sa_shift];
+	}
+}
+
+/* convert the symbol area of every Occ block from the file's packing (8 words of 16 2-bit symbols, first
+ * symbol in the top bits) to the two bit planes described in bwag_dev.cuh; in place, one lane per block */
+__global__ void k_occ_planes(uint4 *bwt, u64 n_blocks)
+{
+	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) {
+		const uint4 w0 = bwt[b * 4 + 2], w1 = bwt[b * 4 + 3];
+		const u32 w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+		u32 hi[4], lo[4];
+#pragma unroll
+		for (int g = 0; g < 4; ++g) {           /* 32 symbols = two file words -> one word of each plane */
+			u32 h = 0, l = 0;
+#pragma unroll
+			for (int t = 0; t < 2; ++t) {
+				const u32 v = w[2 * g + t];
+#pragma unroll
+				for (int s = 0; s < 16; ++s) {
+					const u32 sym = v >> ((15 - s) << 1) & 3;
+					h |= (sym >> 1) << (16 * t + s); l |= (sym & 1) << (16 * t + s);
+				}
+			}
+			hi[g] = h; lo[g] = l;
+		}
+		bwt[b * 4 + 2] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+		bwt[b * 4 + 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 	}
 }

@@ -1,26 +1,29 @@
-/* bwag_smem.cu -- stage 1 kernels: SMEM seeding (K1) and its per-read epilogue (K1b).
+/* bwag_smem.cu -- stage 1 kernels: SMEM seeding (K1, K1f) and the per-read epilogue (K1b).
  *
- * K1 replaces mem_collect_intv (bwamem.c:140-188) and everything under it: bwt_smem1a (bwt.c:289-351),
+ * K1/K1f replace mem_collect_intv (bwamem.c:140-188) and everything under it: bwt_smem1a (bwt.c:289-351),
  * bwt_seed_strategy1 (bwt.c:358-379), bwt_extend (bwt.c:262-275), bwt_2occ4/bwt_occ4 (bwt.c:169-220).
  *
- * Mapping to the machine.  Per read the work is a chain of ~1000 dependent FM-index steps, each needing
- * one or two 64-byte Occ blocks at effectively random addresses of a multi-GB table.  Arithmetic per
- * step is a few dozen integer ops, so throughput = (independent steps in flight) / (HBM latency), and the
- * design goal is to keep as many independent 64-byte requests in flight per SM as registers allow while
- * spending as few issue slots per step as possible:
+ * Mapping to the machine.  Per read the work is a chain of ~800 dependent FM-index steps, each needing
+ * one or two 64-byte Occ blocks at effectively random addresses of a multi-GB table.  Throughput =
+ * (independent steps in flight) / (HBM latency + issue time of one step), so the design keeps as many
+ * independent 64-byte requests in flight per SM as registers allow and spends as few issue slots per
+ * step as possible:
  *   - ONE LANE PER READ.  A lane keeps the whole seeding state machine of its read in registers and
  *     fetches the blocks of its current bwt_extend itself (4 x LDG.128 per block; the two rank
  *     positions share a block in about half of the steps, which is then fetched once).  A warp thus has
  *     32 independent extensions = up to 64 blocks (128 HBM sectors) in flight per iteration, and no
  *     shuffles are needed to combine partial counts;
- *   - LOCK-STEP STATE MACHINES.  The three seeding passes of the 32 reads of a warp are in different
- *     phases, so each lane advances its own state machine (short, divergent) until it needs the next
- *     extension; then the whole warp meets at ONE converged load/popcount/select sequence.  Divergence
- *     is confined to the bookkeeping between memory phases;
+ *   - LOCK-STEP STATE MACHINES.  The reads of a warp are in different phases, so each lane advances its
+ *     own state machine (short, divergent) until it needs the next extension; then the whole warp meets
+ *     at ONE converged, branch-free load/popcount/select sequence (bit-plane blocks, bwag_dev.cuh);
+ *   - the third seeding pass (forward-only seeds, bwamem.c:170-185) does not depend on the first two, so
+ *     it is its own kernel K1f with a tenth of the state, three times the occupancy and no lists; it
+ *     leaves its intervals in a fixed-stride staging area that K1 appends to the read's list;
+ *   - the read's bases and the first K1_SLOTS entries of both candidate lists live in SHARED memory
+ *     (a lane's private slice, conflict-free stride); longer lists continue in a per-lane global array.
+ *     Entries are 16 bytes (three 35-bit interval fields + a 23-bit end position);
  *   - PERSISTENT LANES pull the next read from an atomic counter, so a warp stays full until the batch
  *     is exhausted regardless of read length or repeat content;
- *   - candidate lists are per-lane arrays in global memory holding 16-byte packed entries (three
- *     35-bit interval fields + a 23-bit end position): one vector load/store per entry, L1/L2 resident;
  *   - a finished read appends its (unsorted) interval list to the batch-wide pool with one atomicAdd;
  *     K1b (one lane per read) sorts each list by (start,end) -- ties are identical intervals -- sizes
  *     the seed pool and writes the BWT rows whose suffix-array values K2 resolves.
@@ -30,7 +33,7 @@
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
 
-enum { ST_IDLE = 0, ST_FWD, ST_BWD, ST_STR, ST_NONE };
+enum { ST_IDLE = 0, ST_FWD, ST_BWD, ST_NONE };
 
 struct Intv { u64 x0, x1, x2, info; };
 
@@ -50,74 +53,147 @@ __device__ __forceinline__ void st_intv(Intv *p, u64 x0, u64 x1, u64 x2, u64 inf
 
 /* candidate-list entry, 16 bytes: a = x0[35] | x2.lo[29] ; b = x1[35] | x2.hi[6] | end[23] */
 #define M35 ((u64)0x7ffffffffULL)
-__device__ __forceinline__ void st_ent(ulonglong2 *p, u64 x0, u64 x1, u64 x2, u32 end)
+__device__ __forceinline__ ulonglong2 pack_ent(u64 x0, u64 x1, u64 x2, u32 end)
 {
 	ulonglong2 v;
 	v.x = x0 | (x2 & 0x1fffffffULL) << 35;
 	v.y = x1 | (x2 >> 29 & 0x3f) << 35 | (u64)end << 41;
-	*p = v;
+	return v;
 }
-__device__ __forceinline__ void ld_ent(const ulonglong2 *p, u64 &x0, u64 &x1, u64 &x2, u32 &end)
+__device__ __forceinline__ void unpack_ent(ulonglong2 v, u64 &x0, u64 &x1, u64 &x2, u32 &end)
 {
-	ulonglong2 v = *p;
 	x0 = v.x & M35; x1 = v.y & M35;
 	x2 = v.x >> 35 | (v.y >> 35 & 0x3f) << 29;
 	end = (u32)(v.y >> 41);
 }
 
-/* symbol counts over positions [0,pos] of one Occ block given its four 16-byte quarters:
- * cA = counts A,C ; cG = counts G,T ; w0,w1 = the 128 symbols (bwt.h:74-82, bwt.c:169-186) */
-__device__ __forceinline__ void block_counts(const uint4 &cA, const uint4 &cG, const uint4 &w0, const uint4 &w1, int pos, u64 out[4])
-{
-	u64 nC = 0, nG = 0, nT = 0;
-	const u64 m5 = 0x5555555555555555ULL;
-#pragma unroll
-	for (int m = 0; m < 4; ++m) {
-		const u32 hiw = m == 0 ? w0.x : m == 1 ? w0.z : m == 2 ? w1.x : w1.z;
-		const u32 low = m == 0 ? w0.y : m == 1 ? w0.w : m == 2 ? w1.y : w1.w;
-		int n = pos + 1 - 32 * m;                 /* symbols of this 32-symbol chunk that count */
-		if (n > 0) {
-			u64 v = (u64)hiw << 32 | low;         /* symbol s of the chunk sits at bits 62-2s */
-			if (n < 32) v >>= (32 - n) << 1;      /* keep the first n symbols; zeros (= 'A') enter at the top */
-			u64 lo = v & m5, hi = (v >> 1) & m5;
-			nT += __popcll(hi & lo); nG += __popcll(hi & ~lo); nC += __popcll(~hi & lo & m5);
-		}
-	}
-	out[0] = ((u64)cA.y << 32 | cA.x) + (u64)(pos + 1) - nC - nG - nT;
-	out[1] = ((u64)cA.w << 32 | cA.z) + nC;
-	out[2] = ((u64)cG.y << 32 | cG.x) + nG;
-	out[3] = ((u64)cG.w << 32 | cG.z) + nT;
-}
-
 #define SEL4(c, a0, a1, a2, a3) ((c) == 0 ? (a0) : (c) == 1 ? (a1) : (c) == 2 ? (a2) : (a3))
 
+/* bwt_extend (bwt.c:262-275) of the interval (xs = the side being extended, xo = the other side, size e2) by
+ * symbol c: ranks of all four symbols at k = xs-1 and l = xs-1+e2, converged and branch-free across the warp */
+__device__ __forceinline__ void extend_step(const DevIndex &ix, u64 xs, u64 xo, u64 e2, int c, u64 &touches, u64 &o_s, u64 &o_o, u64 &o_x2)
+{
+	const u64 k = xs - 1, l = xs - 1 + e2;
+	u64 tk[4] = {0, 0, 0, 0}, tl[4] = {0, 0, 0, 0};
+	const bool kv = k != (u64)-1, lv = l != (u64)-1;
+	const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
+	const bool same = kv && lv && (kp >> 7) == (lp >> 7);
+	uint4 b0, b1, b2, b3, c0, c1, c2, c3;
+	b0 = b1 = b2 = b3 = c0 = c1 = c2 = c3 = make_uint4(0, 0, 0, 0);
+	if (lv) {
+		const uint4 *bl = ix.bwt + ((lp >> 7) << 2);
+		b0 = __ldg(bl); b1 = __ldg(bl + 1); b2 = __ldg(bl + 2); b3 = __ldg(bl + 3);
+	}
+	if (kv && !same) {
+		const uint4 *bk = ix.bwt + ((kp >> 7) << 2);
+		c0 = __ldg(bk); c1 = __ldg(bk + 1); c2 = __ldg(bk + 2); c3 = __ldg(bk + 3);
+	}
+	if (same) { c0 = b0; c1 = b1; c2 = b2; c3 = b3; }   /* both ranks in one block: it was fetched once */
+	if (lv) bwag_block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
+	if (kv) bwag_block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
+	touches += same ? 1 : 2;
+	const u64 x2_1 = tl[1] - tk[1], x2_2 = tl[2] - tk[2], x2_3 = tl[3] - tk[3];
+	o_x2 = SEL4(c, tl[0] - tk[0], x2_1, x2_2, x2_3);
+	o_s = SEL4(c, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1 + SEL4(c, tk[0], tk[1], tk[2], tk[3]);   /* new x[!is_back] */
+	o_o = xo + ((xs <= ix.primary && xs + e2 - 1 >= ix.primary) ? 1 : 0);                                 /* new x[is_back]: bwt.c:271-274 */
+	if (c < 3) o_o += x2_3;
+	if (c < 2) o_o += x2_2;
+	if (c < 1) o_o += x2_1;
+}
+
+#define INIT_INTV(c, X0, X1, X2) do { int c_ = (c); X0 = SEL4(c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1; X2 = SEL4(c_, ix.L2[1], ix.L2[2], ix.L2[3], ix.L2[4]) - SEL4(c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]); X1 = SEL4(3 - c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1; } while (0)
+
+/* ------------------------------------------------------------------------------------------------ K1f
+ * third pass (bwamem.c:170-185, bwt_seed_strategy1 bwt.c:358-379): from every start x extend forward until the
+ * interval is smaller than max_mem_intv and at least min_seed_len long; continue after the seed's end */
+__global__ void __launch_bounds__(K1F_THREADS)
+k_smem_fwd(DevIndex ix, SeedArgs a)
+{
+	int rid = -1, len = 0, x = 0, i = 0, n_out = 0;
+	bool in_seed = false, done = false;
+	const uint8_t *q = 0;
+	u64 ik0 = 0, ik1 = 0, ik2 = 0, touches = 0;
+	u32 overflow = 0;
+	Intv *out = 0;
+	for (;;) {
+		bool need = false;
+		for (;;) {
+			if (!in_seed) {
+				while (x < len && q[x] > 3) ++x;
+				if (x >= len) {             /* read finished (or none yet): fetch the next one */
+					if (done) break;
+					if (rid >= 0) a.n3[rid] = n_out;
+					rid = atomicAdd(a.next_read3, 1);
+					if (rid >= a.n_reads) { rid = -1; len = 0; x = 0; done = true; break; }
+					q = a.codes + a.off[rid]; len = (int)(a.off[rid + 1] - a.off[rid]);
+					out = a.stage3 + (i64)rid * a.cap3;
+					x = 0; n_out = 0;
+					continue;
+				}
+				INIT_INTV(q[x], ik0, ik1, ik2);
+				i = x + 1; in_seed = true;
+			}
+			if (i >= len) { x = len; in_seed = false; continue; }
+			if (q[i] > 3) { x = i + 1; in_seed = false; continue; }
+			need = true;
+			break;
+		}
+		if (__all_sync(FULL_MASK, done)) break;
+		if (!need) continue;
+		u64 o_s, o_o, o_x2;
+		extend_step(ix, ik1, ik0, ik2, 3 - q[i], touches, o_s, o_o, o_x2);
+		if (o_x2 < a.max_mem_intv && i - x >= a.min_seed_len) {     /* bwt.c:366-375 */
+			if (o_x2 > 0) {
+				if (n_out < a.cap3) { st_intv(out + n_out, o_o, o_s, o_x2, (u64)x << 32 | (u64)(i + 1)); ++n_out; } else overflow |= 8;
+			}
+			x = i + 1; in_seed = false;
+		} else { ik0 = o_o; ik1 = o_s; ik2 = o_x2; ++i; }
+	}
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(a.occ_touches, touches);
+	overflow = __reduce_or_sync(FULL_MASK, overflow);
+	if ((threadIdx.x & 31) == 0 && overflow) atomicOr(a.flags, overflow);
+}
+
+/* ------------------------------------------------------------------------------------------------ K1 */
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 1
+#define K1_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k_smem(DevIndex ix, SeedArgs a)
 {
+#ifdef BWAG_CUSIM
+	ulonglong2 *sl = reinterpret_cast<ulonglong2 *>(cusim_dyn_smem);
+#else
+	extern __shared__ ulonglong2 k1_dyn[];
+	ulonglong2 *sl = k1_dyn;
+#endif
+	/* shared: [2 lists][K1_SLOTS][K1_THREADS] entries, then K1_THREADS read slots of qstride bytes (odd word count) */
+	const uint8_t *sq = reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)threadIdx.x * a.qstride;
+	sl += threadIdx.x;
 	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-	/* per-lane scratch (units of 16 bytes): two candidate lists of cap_list packed entries, then the raw
-	 * results of the current bwt_smem1 call (cap_list x 32 B) and the read's interval list (cap_mem x 32 B) */
-	ulonglong2 *listA = reinterpret_cast<ulonglong2 *>(a.scratch) + tid * (i64)(4 * a.cap_list + 2 * a.cap_mem);
-	ulonglong2 *listB = listA + a.cap_list;
-	Intv *m1 = reinterpret_cast<Intv *>(listB + a.cap_list), *mem = m1 + a.cap_list;
-	const u64 L0 = ix.L2[0], L1 = ix.L2[1], L2_ = ix.L2[2], L3 = ix.L2[3], L4 = ix.L2[4];
+	/* per-lane global scratch (units of 16 bytes): the tails of the two candidate lists (cap_list entries each),
+	 * then the raw results of the current bwt_smem1 call (cap_list x 32 B) and the read's interval list (cap_mem x 32 B) */
+	ulonglong2 *gl = reinterpret_cast<ulonglong2 *>(a.scratch) + tid * (i64)(4 * a.cap_list + 2 * a.cap_mem);
+	Intv *m1 = reinterpret_cast<Intv *>(gl + 2 * a.cap_list), *mem = m1 + a.cap_list;
 
-	int rid = -1, len = 0, pass = 3, st = ST_IDLE, x = 0, k2 = 0, old_n = 0;
+	int rid = -1, len = 0, pass = 2, st = ST_IDLE, x = 0, k2 = 0, old_n = 0;
 	int sx = 0, min_intv = 1, i = 0, j = 0, n_prev = 0, n_curr = 0, rev_first = 0, mem_n = 0, m1_n = 0, last_start = 0, ret = 0;
+	int pl = 0;                    /* which list is `prev`; the other is `curr` */
 	const uint8_t *q = 0;
-	ulonglong2 *prev = listA, *curr = listB;
 	u64 ik0 = 0, ik1 = 0, ik2 = 0, curr_last_x2 = 0;
 	u32 ikend = 0, pend = 0;
 	u64 e0 = 0, e1 = 0, e2 = 0;
 	u64 touches = 0;
 	u32 overflow = 0;
 
-#define INIT_INTV(c, X0, X1, X2) do { int c_ = (c); X0 = SEL4(c_, L0, L1, L2_, L3) + 1; X2 = SEL4(c_, L1, L2_, L3, L4) - SEL4(c_, L0, L1, L2_, L3); X1 = SEL4(3 - c_, L0, L1, L2_, L3) + 1; } while (0)
+#define ENT_PTR(l, idx) ((idx) < K1_SLOTS ? sl + ((l) * K1_SLOTS + (idx)) * K1_THREADS : gl + (l) * a.cap_list + (idx))
+#define ENT_ST(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); const ulonglong2 v_ = pack_ent(X0, X1, X2, E); \
+		if (i_ < K1_SLOTS) sl[(l_ * K1_SLOTS + i_) * K1_THREADS] = v_; else gl[l_ * a.cap_list + i_] = v_; } while (0)
+#define ENT_LD(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); ulonglong2 v_; \
+		if (i_ < K1_SLOTS) v_ = sl[(l_ * K1_SLOTS + i_) * K1_THREADS]; else v_ = gl[l_ * a.cap_list + i_]; unpack_ent(v_, X0, X1, X2, E); } while (0)
 	/* forward sweep over: candidates are visited longest match first; the call returns the end of the longest match */
-#define TURN_AROUND() do { ret = (int)ikend; { ulonglong2 *t_ = prev; prev = curr; curr = t_; } n_prev = n_curr; n_curr = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; } while (0)
+#define TURN_AROUND() do { ret = (int)ikend; pl ^= 1; n_prev = n_curr; n_curr = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; } while (0)
 	/* bwt_smem1 returns (bwt.c:346-350 + bwamem.c:150-155): keep matches of at least min_seed_len, ascending start */
 #define CALL_DONE() do { \
 		for (int e_ = m1_n - 1; e_ >= 0; --e_) { \
@@ -149,29 +225,33 @@ k_smem(DevIndex ix, SeedArgs a)
 						sx = (s + e) >> 1; min_intv = (int)p.x2 + 1; found = true;
 						break;
 					}
-					if (!found) { pass = 2; x = 0; continue; }
-				} else if (pass == 2) {     /* third pass: forward-only seeds (bwamem.c:170-185) */
-					if (a.max_mem_intv == 0) { pass = 3; continue; }
-					while (x < len && q[x] > 3) ++x;
-					if (x >= len) { pass = 3; continue; }
-					INIT_INTV(q[x], ik0, ik1, ik2);
-					i = x + 1; st = ST_STR;
-					continue;
+					if (!found) { pass = 2; continue; }
 				} else {                    /* read finished (or none yet): hand over its intervals, fetch the next read */
 					if (rid >= 0) {
-						i64 base = (i64)atomicAdd(a.n_intv, (u64)mem_n);
-						a.intv_beg[rid] = base; a.intv_n[rid] = mem_n;
-						if (base + mem_n > a.cap_intv) overflow |= 1;
+						const int n3 = a.n3 ? a.n3[rid] : 0;                    /* the third pass's seeds (K1f) join the list */
+						const i64 base = (i64)atomicAdd(a.n_intv, (u64)(mem_n + n3));
+						a.intv_beg[rid] = base; a.intv_n[rid] = mem_n + n3;
+						if (base + mem_n + n3 > a.cap_intv) overflow |= 1;
 						else {
 							Intv *dst = reinterpret_cast<Intv *>(a.intv) + base;
+							const Intv *s3 = a.stage3 + (i64)rid * a.cap3;
 							for (int e = 0; e < mem_n; ++e) { Intv p = ld_intv(mem + e); st_intv(dst + e, p.x0, p.x1, p.x2, p.info); }
+							for (int e = 0; e < n3; ++e) { Intv p = ld_intv(s3 + e); st_intv(dst + mem_n + e, p.x0, p.x1, p.x2, p.info); }
 						}
 					}
 					rid = atomicAdd(a.next_read, 1);
 					if (rid >= a.n_reads) { rid = -1; st = ST_NONE; break; }
-					q = a.codes + a.off[rid]; len = (int)(a.off[rid + 1] - a.off[rid]);
+					const i64 o = a.off[rid];
+					len = (int)(a.off[rid + 1] - o);
 					pass = 0; x = 0; mem_n = 0;
-					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 3; }
+					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
+					if (a.qstride) {            /* the read moves to this lane's shared slot (whole aligned words) */
+						const u32 *g = reinterpret_cast<const u32 *>(a.codes + (o & ~(i64)3));
+						u32 *d = reinterpret_cast<u32 *>(const_cast<uint8_t *>(sq));
+						const int nw = ((int)(o & 3) + len + 3) >> 2;
+						for (int w = 0; w < nw; ++w) d[w] = g[w];
+						q = sq + (o & 3);
+					} else q = a.codes + o;
 					continue;
 				}
 				/* start bwt_smem1(sx, min_intv) (bwt.c:289-303) */
@@ -183,15 +263,9 @@ k_smem(DevIndex ix, SeedArgs a)
 			if (st == ST_FWD) {
 				if (i < len && q[i] < 4) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; break; }
 				/* end of read or ambiguous base: keep the current interval, then turn around (bwt.c:317-326) */
-				st_ent(curr + n_curr, ik0, ik1, ik2, ikend); ++n_curr;
+				ENT_ST(pl ^ 1, n_curr, ik0, ik1, ik2, ikend); ++n_curr;
 				TURN_AROUND();
 				continue;
-			}
-			if (st == ST_STR) {
-				if (i >= len) { x = len; st = ST_IDLE; continue; }
-				if (q[i] > 3) { x = i + 1; st = ST_IDLE; continue; }
-				e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0;
-				break;
 			}
 			if (st == ST_BWD) {
 				const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
@@ -199,19 +273,19 @@ k_smem(DevIndex ix, SeedArgs a)
 					/* nothing extends: only the longest candidate (first in visiting order) can be an SMEM (bwt.c:332-338) */
 					if (m1_n == 0 || i + 1 < last_start) {
 						u64 p0, p1, p2; u32 pe;
-						ld_ent(prev + (rev_first ? n_prev - 1 : 0), p0, p1, p2, pe);
+						ENT_LD(pl, rev_first ? n_prev - 1 : 0, p0, p1, p2, pe);
 						st_intv(m1 + m1_n, p0, p1, p2, (u64)(i + 1) << 32 | pe); ++m1_n; last_start = i + 1;
 					}
 					CALL_DONE();
 					continue;
 				}
 				if (j < n_prev) {
-					ld_ent(prev + (rev_first ? n_prev - 1 - j : j), e0, e1, e2, pend);
+					ENT_LD(pl, rev_first ? n_prev - 1 - j : j, e0, e1, e2, pend);
 					need = true; back = 1;
 					break;
 				}
 				if (n_curr == 0) { CALL_DONE(); continue; }
-				{ ulonglong2 *t_ = prev; prev = curr; curr = t_; }
+				pl ^= 1;
 				n_prev = n_curr; n_curr = 0; rev_first = 0; --i; j = 0;
 				continue;
 			}
@@ -221,45 +295,15 @@ k_smem(DevIndex ix, SeedArgs a)
 		if (__all_sync(FULL_MASK, st == ST_NONE)) break;
 		if (!need) continue;
 
-		/* ---- bwt_extend (bwt.c:262-275): ranks of all four symbols at k = xs-1 and l = xs-1+x2 ---- */
-		const u64 xs = back ? e0 : e1, xo = back ? e1 : e0;
-		const u64 k = xs - 1, l = xs - 1 + e2;
-		u64 tk[4] = {0, 0, 0, 0}, tl[4] = {0, 0, 0, 0};
-		{
-			const bool kv = k != (u64)-1, lv = l != (u64)-1;
-			const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
-			const bool same = kv && lv && (kp >> 7) == (lp >> 7);
-			uint4 b0, b1, b2, b3;
-			if (lv) {
-				const uint4 *bl = ix.bwt + ((lp >> 7) << 2);
-				b0 = __ldg(bl); b1 = __ldg(bl + 1); b2 = __ldg(bl + 2); b3 = __ldg(bl + 3);
-			}
-			if (kv && !same) {
-				const uint4 *bk = ix.bwt + ((kp >> 7) << 2);
-				uint4 c0 = __ldg(bk), c1 = __ldg(bk + 1), c2 = __ldg(bk + 2), c3 = __ldg(bk + 3);
-				block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
-			}
-			if (lv) {
-				block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
-				if (same) block_counts(b0, b1, b2, b3, (int)(kp & 127), tk);   /* both ranks in one block: it was fetched once */
-			}
-			touches += same ? 1 : 2;
-		}
 		const int cq = q[i];                               /* base to add: forward uses its complement (bwt.c:309), backward the base itself */
-		const int c = back ? cq : 3 - cq;
-		const u64 x2_0 = tl[0] - tk[0], x2_1 = tl[1] - tk[1], x2_2 = tl[2] - tk[2], x2_3 = tl[3] - tk[3];
-		const u64 o_x2 = SEL4(c, x2_0, x2_1, x2_2, x2_3);
-		const u64 o_s = SEL4(c, L0, L1, L2_, L3) + 1 + SEL4(c, tk[0], tk[1], tk[2], tk[3]);   /* new x[!is_back] */
-		u64 o_o = xo + ((xs <= ix.primary && xs + e2 - 1 >= ix.primary) ? 1 : 0);              /* new x[is_back]: bwt.c:271-274 */
-		if (c < 3) o_o += x2_3;
-		if (c < 2) o_o += x2_2;
-		if (c < 1) o_o += x2_1;
+		u64 o_s, o_o, o_x2;
+		extend_step(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, touches, o_s, o_o, o_x2);
 
 		/* ---- consume ---- */
 		if (st == ST_FWD) {                 /* bwt.c:307-316 */
 			bool stop = false;
 			if (o_x2 != ik2) {
-				if (n_curr < a.cap_list) { st_ent(curr + n_curr, ik0, ik1, ik2, ikend); ++n_curr; } else overflow |= 8;
+				if (n_curr < a.cap_list) { ENT_ST(pl ^ 1, n_curr, ik0, ik1, ik2, ikend); ++n_curr; } else overflow |= 8;
 				if (o_x2 < (u64)min_intv) stop = true;
 			}
 			if (stop) TURN_AROUND();
@@ -267,24 +311,17 @@ k_smem(DevIndex ix, SeedArgs a)
 				ik0 = o_o; ik1 = o_s; ik2 = o_x2; ikend = (u32)i + 1;
 				++i;
 				if (i == len) {             /* reached the end: the last interval is a candidate too (bwt.c:322) */
-					if (n_curr < a.cap_list) { st_ent(curr + n_curr, ik0, ik1, ik2, ikend); ++n_curr; } else overflow |= 8;
+					if (n_curr < a.cap_list) { ENT_ST(pl ^ 1, n_curr, ik0, ik1, ik2, ikend); ++n_curr; } else overflow |= 8;
 					TURN_AROUND();
 				}
 			}
-		} else if (st == ST_STR) {          /* bwt.c:366-375 */
-			if (o_x2 < a.max_mem_intv && i - x >= a.min_seed_len) {
-				if (o_x2 > 0) {
-					if (mem_n < a.cap_mem) { st_intv(mem + mem_n, o_o, o_s, o_x2, (u64)x << 32 | (u64)(i + 1)); ++mem_n; } else overflow |= 8;
-				}
-				x = i + 1; st = ST_IDLE;
-			} else { ik0 = o_o; ik1 = o_s; ik2 = o_x2; ++i; }
 		} else {                            /* ST_BWD, bwt.c:331-343 */
 			if (o_x2 < (u64)min_intv) {
 				if (n_curr == 0 && (m1_n == 0 || i + 1 < last_start)) {
 					st_intv(m1 + m1_n, e0, e1, e2, (u64)(i + 1) << 32 | pend); ++m1_n; last_start = i + 1;
 				}
 			} else if (n_curr == 0 || o_x2 != curr_last_x2) {
-				st_ent(curr + n_curr, o_s, o_o, o_x2, pend); ++n_curr; curr_last_x2 = o_x2;
+				ENT_ST(pl ^ 1, n_curr, o_s, o_o, o_x2, pend); ++n_curr; curr_last_x2 = o_x2;
 			}
 			++j;
 		}

@@ -122,6 +122,7 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= (x >> i & 1) << (31 - i); return r; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { uint64_t v = (uint64_t)hi << 32 | lo; return (unsigned)(v >> (s & 31)); }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) { uint64_t v = (uint64_t)hi << 32 | lo; if (s > 32) s = 32; return (unsigned)((v << s) >> 32); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { uint64_t v = (uint64_t)hi << 32 | lo; return (unsigned)((v << (s & 31)) >> 32); }
 static inline int __vimax3_s32(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 static inline int __vimin3_s32(int a, int b, int c) { return std::min(a, std::min(b, c)); }
