@@ -211,33 +211,19 @@ def main():
         dist.barrier()
 
     L = bwa_b200.lib()
-    idx = bwa_b200.Index(fa)
-    L.bwag_blob_bytes.restype = C.c_size_t
-    L.bwag_blob_bytes.argtypes = [C.c_void_p, C.c_int64]
-    L.bwag_blob_fill.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-    L.bwag_ctx_from_blob.restype = C.c_void_p
-    L.bwag_ctx_from_blob.argtypes = [C.c_int, C.c_void_p, C.c_int]
-    i = idx.p.contents
-    l_pac = C.cast(i.bns, C.POINTER(C.c_int64))[0]
     if world > 1:
-        # one copy of the index per GPU: rank 0 fills the blob, a single NCCL broadcast over NVLink replicates it
-        nbytes = L.bwag_blob_bytes(i.bwt, l_pac)
-        blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            assert L.bwag_blob_fill(local_rank, blob.data_ptr(), i.bwt, l_pac, i.pac) == 0
+        # one copy of the index per GPU: rank 0 loads it and fills the blob, a single NCCL broadcast over NVLink replicates it
+        from bwa_b200 import multi
         torch.cuda.synchronize()
         t0 = time.time()
-        dist.broadcast(blob, 0)
+        p, keep = multi.replicate_index(L, fa, rank, local_rank, dist, True)
         torch.cuda.synchronize()
         if rank == 0:
-            log("[bench] index blob %.2f GB broadcast over NCCL in %.3fs" % (nbytes / 1e9, time.time() - t0))
-        ctx = L.bwag_ctx_from_blob(local_rank, blob.data_ptr(), 0)
-        assert ctx, L.bwag_last_error()
-        L.bb_device_adopt(i.bwt, ctx)
-        idx.ctx = ctx
-        idx._blob = blob
+            log("[bench] index replicated to %d GPUs (fill + NCCL broadcast) in %.3fs" % (world, time.time() - t0))
+        idx = bwa_b200.Index.wrap(p, L, keep)
     else:
-        idx.attach()
+        idx = bwa_b200.Index(fa)
+    idx.attach()
     if a.dense_sa:
         idx.densify_sa(a.dense_sa)
 

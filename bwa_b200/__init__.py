@@ -103,6 +103,13 @@ class Index:
             raise RuntimeError("cannot load index %s" % prefix)
         self.ctx = None
 
+    @classmethod
+    def wrap(cls, p, library, keep=None):
+        """An index that is already loaded (and possibly resident, see multi.replicate_index)."""
+        self = cls.__new__(cls)
+        self.L, self.p, self.ctx, self._keep = library, p, None, keep
+        return self
+
     def attach(self):
         """Upload to the current CUDA device (no-op if already resident); returns the device context handle."""
         if self.ctx is None:

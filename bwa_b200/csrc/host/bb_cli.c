@@ -14,7 +14,7 @@
 
 #define BB_VERSION "0.7.19-r1273-b200"
 
-typedef struct { int n; bseq1_t *seqs; int last; } batch_t;
+typedef struct { int n; bseq1_t *seqs; int last; int skip; long no; } batch_t;   /* skip: another rank's batch (multi-GPU runs) */
 
 typedef struct { /* single-slot mailbox */
 	pthread_mutex_t mu;
@@ -52,7 +52,36 @@ typedef struct {
 	int copy_comment, chunk;
 	int64_t n_processed;
 	mbox_t to_align, to_write;
+	/* multi-GPU runs (bwa_b200/multi.py): batches are dealt round-robin, batch b belongs to rank b % world; every rank
+	 * parses the whole input so that batch boundaries -- and with them the per-batch insert-size model -- are those of
+	 * a single-GPU run.  shard_idx records "batch bytes" per written batch so that rank 0 can merge the parts in order */
+	int rank, world;
+	long n_batches;
+	FILE *shard_idx;
 } run_t;
+
+static bwaidx_t *g_cli_idx;   /* an index the caller already holds (and has made resident): used instead of loading */
+void bb_cli_set_index(bwaidx_t *idx) { g_cli_idx = idx; }
+
+static void free_reads(batch_t *b)
+{
+	int i;
+	for (i = 0; i < b->n; ++i) { bseq1_t *s = &b->seqs[i]; free(s->name); free(s->comment); free(s->seq); free(s->qual); free(s->sam); }
+	free(b->seqs); b->seqs = 0;
+}
+
+static void write_batch(run_t *r, batch_t *b)
+{
+	long bytes = 0;
+	int i;
+	for (i = 0; i < b->n; ++i) {
+		bseq1_t *s = &b->seqs[i];
+		if (!s->sam) continue;
+		if (fputs(s->sam, stdout) == EOF) bb_fatal("main_mem", "fail to write the SAM output");
+		if (r->shard_idx) bytes += (long)strlen(s->sam);
+	}
+	if (r->shard_idx) fprintf(r->shard_idx, "%ld %ld\n", b->no, bytes);
+}
 
 static void *reader_main(void *a)
 {
@@ -63,6 +92,8 @@ static void *reader_main(void *a)
 		int64_t size = 0;
 		b->seqs = bseq_read(r->chunk, &b->n, r->f1, r->f2);
 		if (!b->seqs) { free(b); mbox_put(&r->to_align, 0); return 0; }
+		b->no = r->n_batches++;
+		if (b->no % r->world != r->rank) { b->skip = 1; free_reads(b); mbox_put(&r->to_align, b); continue; }
 		if (!r->copy_comment)
 			for (i = 0; i < b->n; ++i) { free(b->seqs[i].comment); b->seqs[i].comment = 0; }
 		for (i = 0; i < b->n; ++i) size += b->seqs[i].l_seq;
@@ -76,13 +107,8 @@ static void *writer_main(void *a)
 	run_t *r = a;
 	batch_t *b;
 	while ((b = mbox_get(&r->to_write)) != 0) {
-		int i;
-		for (i = 0; i < b->n; ++i) {
-			bseq1_t *s = &b->seqs[i];
-			if (s->sam && fputs(s->sam, stdout) == EOF) bb_fatal("main_mem", "fail to write the SAM output");
-			free(s->name); free(s->comment); free(s->seq); free(s->qual); free(s->sam);
-		}
-		free(b->seqs); free(b);
+		if (!b->skip) { write_batch(r, b); free_reads(b); }
+		free(b);
 	}
 	return 0;
 }
@@ -91,6 +117,7 @@ static void align_batch(run_t *r, batch_t *b)
 {
 	const mem_opt_t *opt = r->opt;
 	const bwaidx_t *idx = r->idx;
+	if (b->skip) { r->n_processed += b->n; return; }
 	if (opt->flag & MEM_F_SMARTPE) { /* -p: split the batch into single-end and paired reads (fastmap.c:90-109) */
 		bseq1_t *sep[2];
 		int n_sep[2], i;
@@ -269,7 +296,15 @@ int main_mem(int argc, char *argv[])
 	} else scale_by_match_score(opt, &set);
 	bwa_fill_scmat(opt->a, opt->b, opt->mat);
 
-	if ((run.idx = bwa_idx_load(argv[optind], BWA_IDX_ALL)) == 0) return 1;
+	{   /* rank/world of a multi-GPU run, set by the launcher */
+		const char *e;
+		run.rank = (e = getenv("BWA_B200_RANK")) ? atoi(e) : 0;
+		run.world = (e = getenv("BWA_B200_WORLD")) ? atoi(e) : 1;
+		if (run.world < 1 || run.rank < 0 || run.rank >= run.world) bb_fatal("main_mem", "bad BWA_B200_RANK/BWA_B200_WORLD");
+		if ((e = getenv("BWA_B200_SHARD_IDX")) != 0 && (run.shard_idx = fopen(e, "w")) == 0) bb_fatal("main_mem", "fail to open '%s' for writing", e);
+	}
+	if (g_cli_idx) run.idx = g_cli_idx;
+	else if ((run.idx = bwa_idx_load(argv[optind], BWA_IDX_ALL)) == 0) return 1;
 	if (ignore_alt) for (i = 0; i < run.idx->bns->n_seqs; ++i) run.idx->bns->anns[i].is_alt = 0;
 	if ((run.f1 = bb_fq_open(argv[optind + 1])) == 0) {
 		if (bwa_verbose >= 1) fprintf(stderr, "[E::%s] fail to open file `%s'.\n", __func__, argv[optind + 1]);
@@ -287,7 +322,8 @@ int main_mem(int argc, char *argv[])
 		}
 	}
 	bb_device_attach(run.idx->bwt, run.idx->bns, run.idx->pac); /* fail early, before any output, if there is no GPU */
-	bwa_print_sam_hdr(run.idx->bns, hdr_line);
+	if (run.rank == 0) bwa_print_sam_hdr(run.idx->bns, hdr_line);
+	if (run.shard_idx) { fflush(stdout); fprintf(run.shard_idx, "-1 %ld\n", ftell(stdout)); }
 	run.chunk = fixed_chunk > 0 ? fixed_chunk : opt->chunk_size * opt->n_threads;
 
 	mbox_init(&run.to_align); mbox_init(&run.to_write);
@@ -297,14 +333,12 @@ int main_mem(int argc, char *argv[])
 			memset(&bb, 0, sizeof(bb));
 			bb.seqs = bseq_read(run.chunk, &bb.n, run.f1, run.f2);
 			if (!bb.seqs) break;
-			if (!run.copy_comment) for (i = 0; i < bb.n; ++i) { free(bb.seqs[i].comment); bb.seqs[i].comment = 0; }
+			bb.no = run.n_batches++;
+			bb.skip = bb.no % run.world != run.rank;
+			if (!bb.skip && !run.copy_comment) for (i = 0; i < bb.n; ++i) { free(bb.seqs[i].comment); bb.seqs[i].comment = 0; }
 			align_batch(&run, &bb);
-			for (i = 0; i < bb.n; ++i) {
-				bseq1_t *s = &bb.seqs[i];
-				if (s->sam) fputs(s->sam, stdout);
-				free(s->name); free(s->comment); free(s->seq); free(s->qual); free(s->sam);
-			}
-			free(bb.seqs);
+			if (!bb.skip) write_batch(&run, &bb);
+			free_reads(&bb);
 		}
 	} else {
 		pthread_create(&th_r, 0, reader_main, &run);
@@ -318,8 +352,9 @@ int main_mem(int argc, char *argv[])
 		pthread_join(th_w, 0);
 	}
 	fflush(stdout);
+	if (run.shard_idx) fclose(run.shard_idx);
 	free(hdr_line);
-	bwa_idx_destroy(run.idx);
+	if (run.idx != g_cli_idx) bwa_idx_destroy(run.idx);
 	bb_fq_close(run.f1);
 	bb_fq_close(run.f2);
 	free(opt);

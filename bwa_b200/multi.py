@@ -1,0 +1,188 @@
+"""Multi-GPU `mem`: one process per GPU (torch.distributed), reads dealt over the ranks, no hot-path collective.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        -m bwa_b200.multi [bwa mem options] -o out.sam ref.fa reads_1.fq [reads_2.fq]
+
+What is distributed:
+  - the index: rank 0 loads the files of `bwa index` and fills the device blob; ONE broadcast (NCCL over
+    NVLink) gives every GPU its copy; the other ranks only read .ann/.amb/.pac for the SAM text;
+  - the reads: every rank parses the input into the batches a single-GPU run would form (-K bases each) and
+    aligns batch b iff b % world == rank, so batch boundaries -- and the per-batch insert-size model of
+    paired-end data -- do not depend on the number of GPUs: the merged SAM is the single-GPU SAM;
+  - the output: each rank writes its batches to a part file, rank 0 merges the parts in batch order.
+The alignment itself is the C library's `main_mem` (bb_cli.c), unchanged; this module is only plumbing.
+With BWA_B200_LIB pointing at the CPU-emulated build (tests/_build/libbwa_b200_cusim.so) the same code runs
+on the gloo backend, which is how the N>1 logic is tested without GPUs.
+"""
+import ctypes as C
+import os
+import sys
+
+import bwa_b200
+
+BWA_IDX_BNS, BWA_IDX_PAC, BWA_IDX_ALL = 2, 4, 7
+
+
+def shard_of(batch_no, world):
+    """Rank that aligns batch `batch_no` (mirrors bb_cli.c)."""
+    return batch_no % world
+
+
+def _bind(L):
+    L.bwag_blob_bytes.restype = C.c_size_t
+    L.bwag_blob_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.bwag_blob_fill.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.bwag_ctx_from_blob.restype = C.c_void_p
+    L.bwag_ctx_from_blob.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    L.bb_device_adopt.argtypes = [C.c_void_p, C.c_void_p]
+    L.bb_cli_set_index.argtypes = [C.c_void_p]
+    L.bwa_idx_load.restype = C.POINTER(bwa_b200.BwaIdx)
+    L.bwa_idx_load.argtypes = [C.c_char_p, C.c_int]
+
+
+def replicate_index(L, prefix, rank, device, dist=None, on_gpu=True):
+    """Load the index on rank 0, broadcast its device blob, make it resident on every rank.
+
+    Returns (idx pointer, keep-alive objects).  `device` is the CUDA ordinal of this rank."""
+    import torch
+    _bind(L)
+    world = dist.get_world_size() if dist is not None else 1
+    idx = L.bwa_idx_load(prefix.encode(), BWA_IDX_ALL if rank == 0 else BWA_IDX_BNS | BWA_IDX_PAC)
+    if not idx:
+        raise RuntimeError("cannot load index %s" % prefix)
+    i = idx.contents
+    l_pac = C.cast(i.bns, C.POINTER(C.c_int64))[0]
+    keep = []
+    if world == 1:
+        L.bb_device_attach.restype = C.c_void_p
+        L.bb_device_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bb_device_attach(i.bwt, i.bns, i.pac)
+        return idx, keep
+    dev = torch.device("cuda", device) if on_gpu else torch.device("cpu")
+    nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        nbytes[0] = L.bwag_blob_bytes(i.bwt, l_pac)
+    dist.broadcast(nbytes, 0)
+    blob = torch.empty(int(nbytes[0]), dtype=torch.uint8, device=dev)
+    if rank == 0 and L.bwag_blob_fill(device, blob.data_ptr(), i.bwt, l_pac, i.pac) != 0:
+        raise RuntimeError(L.bwag_last_error().decode())
+    dist.broadcast(blob, 0)          # the only collective of a run
+    ctx = L.bwag_ctx_from_blob(device, blob.data_ptr(), 0)
+    if not ctx:
+        raise RuntimeError(L.bwag_last_error().decode())
+    if rank != 0:                    # no FM-index in host memory here: the host code only needs a key for the resident copy
+        key = C.create_string_buffer(256)
+        i.bwt = C.cast(key, C.c_void_p)
+        keep.append(key)
+    L.bb_device_adopt(i.bwt, ctx)
+    keep.append(blob)
+    return idx, keep
+
+
+def merge_parts(out_path, parts):
+    """parts: [(sam part file, its index file)] by rank; writes the header, then the batches in batch order."""
+    where = {}
+    hdr = 0
+    for r, (part, idxf) in enumerate(parts):
+        pos = 0
+        for line in open(idxf):
+            no, nbytes = (int(x) for x in line.split())
+            if no < 0:
+                if r == 0:
+                    hdr = nbytes
+                pos = nbytes
+            else:
+                where[no] = (r, pos, nbytes)
+                pos += nbytes
+    files = [open(p, "rb") for p, _ in parts]
+    with open(out_path, "wb") as out:
+        out.write(files[0].read(hdr))
+        for no in sorted(where):
+            r, pos, nbytes = where[no]
+            files[r].seek(pos)
+            left = nbytes
+            while left > 0:
+                buf = files[r].read(min(left, 1 << 24))
+                if not buf:
+                    raise RuntimeError("part file %s is shorter than its index says" % parts[r][0])
+                out.write(buf)
+                left -= len(buf)
+    for f in files:
+        f.close()
+    if sorted(where) != list(range(len(where))):
+        raise RuntimeError("batches missing from the parts: have %s" % sorted(where))
+
+
+def main(argv=None):
+    import torch
+    import torch.distributed as dist
+    argv = list(sys.argv[1:] if argv is None else argv)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    lib_path = os.environ.get("BWA_B200_LIB")
+    L = bwa_b200.lib(lib_path)
+    on_gpu = lib_path is None or "cusim" not in os.path.basename(lib_path)
+    if on_gpu:
+        if not torch.cuda.is_available():
+            raise SystemExit("bwa_b200.multi: no CUDA device; there is no CPU path")
+        torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl" if on_gpu else "gloo", **({"device_id": torch.device("cuda", local_rank)} if on_gpu else {}))
+    # the output file and the index prefix are the only arguments this launcher looks at
+    out = None
+    for k, a in enumerate(argv):
+        if a in ("-o", "-f") and k + 1 < len(argv):
+            out = argv[k + 1]
+    if out is None:
+        raise SystemExit("bwa_b200.multi: -o FILE is required (every rank writes a part of it)")
+    positional = _positionals(argv)
+    if len(positional) < 2:
+        raise SystemExit("usage: python -m bwa_b200.multi [bwa mem options] -o out.sam ref.fa reads_1.fq [reads_2.fq]")
+    idx, keep = replicate_index(L, positional[0], rank, local_rank if on_gpu else 0, dist if world > 1 else None, on_gpu)
+    part, part_idx = "%s.part%d" % (out, rank), "%s.part%d.idx" % (out, rank)
+    os.environ["BWA_B200_RANK"], os.environ["BWA_B200_WORLD"], os.environ["BWA_B200_SHARD_IDX"] = str(rank), str(world), part_idx
+    L.bb_cli_set_index(idx)
+    args = ["mem"] + [part if (k > 0 and argv[k - 1] in ("-o", "-f")) else a for k, a in enumerate(argv)]
+    arr = (C.c_char_p * (len(args) + 1))(*[a.encode() for a in args], None)
+    rc = L.main_mem(len(args), arr)
+    ok = torch.tensor([0 if rc == 0 else 1])
+    if world > 1:
+        if on_gpu:
+            ok = ok.cuda()
+        dist.all_reduce(ok)      # also the barrier before the merge
+    if int(ok[0]) != 0:
+        raise SystemExit("bwa_b200.multi: a rank failed")
+    if rank == 0:
+        parts = [("%s.part%d" % (out, r), "%s.part%d.idx" % (out, r)) for r in range(world)]
+        merge_parts(out, parts)
+        for p, q in parts:
+            os.remove(p)
+            os.remove(q)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _positionals(argv):
+    """Non-option arguments the way getopt sees them for bb_cli.c's option string."""
+    flags_with_arg = set("kcvsrtRABOEUwLdTQDmINofWxGhyKXHFz")   # the ':' options of bb_cli.c's getopt string
+    pos, k = [], 0
+    while k < len(argv):
+        a = argv[k]
+        if a == "--":
+            pos += argv[k + 1:]
+            break
+        if a.startswith("-") and len(a) > 1:
+            c = a[1]
+            if c in flags_with_arg and len(a) == 2:
+                k += 1
+        else:
+            pos.append(a)
+        k += 1
+    return pos
+
+
+if __name__ == "__main__":
+    sys.exit(main())

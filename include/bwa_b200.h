@@ -189,6 +189,10 @@ void mem_pestat(const mem_opt_t *opt, int64_t l_pac, int n, const mem_alnreg_v *
 
 /* command-line entry (fastmap.c:141 main_mem; main.c:87) */
 int main_mem(int argc, char *argv[]);
+/* extension for multi-GPU launchers (bwa_b200/multi.py): main_mem uses this index, which the caller has already made
+ * resident on the GPU (bb_device_adopt), instead of loading argv's prefix; with BWA_B200_RANK / BWA_B200_WORLD set it
+ * aligns only the batches b with b % world == rank */
+void bb_cli_set_index(bwaidx_t *idx);
 
 #ifdef __cplusplus
 }

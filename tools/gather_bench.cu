@@ -1,0 +1,57 @@
+// Random-gather ceiling of HBM for the FM-index access pattern: every lane reads whole 64-byte blocks (4 x LDG.128,
+// or 32-byte half blocks) at independent random addresses of a table much larger than L2.  This is what K1/K2 can at
+// best approach; a streaming-copy peak is not reachable with 64-byte random requests (one DRAM row activation each).
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gather_bench tools/gather_bench.cu && ./gather_bench [table GB]
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+template <int BYTES, int ILP>
+__global__ void k_gather(const uint4 *tab, u64 n_blocks, int iters, u64 *sink)
+{
+	u64 s = (u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+	u64 acc = 0;
+	for (int it = 0; it < iters; ++it) {
+		uint4 v[ILP][BYTES / 16];
+#pragma unroll
+		for (int u = 0; u < ILP; ++u) {
+			s = s * 6364136223846793005ull + 1442695040888963407ull;
+			const u64 b = (s >> 20) % n_blocks;
+#pragma unroll
+			for (int q = 0; q < BYTES / 16; ++q) v[u][q] = __ldg(tab + b * 4 + q);
+		}
+#pragma unroll
+		for (int u = 0; u < ILP; ++u)
+#pragma unroll
+			for (int q = 0; q < BYTES / 16; ++q) acc += v[u][q].x ^ v[u][q].w;
+		s ^= acc & 1;     // the next address depends on the data, like an FM-index walk
+	}
+	if (acc == 0x1234567) *sink = acc;
+}
+template <int BYTES, int ILP> void run(const uint4 *tab, u64 n_blocks, u64 *sink, int threads_per_sm_target)
+{
+	int dev, nsm; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+	const int block = 128, grid = nsm * threads_per_sm_target / block, iters = 2000 / ILP;
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	k_gather<BYTES, ILP><<<grid, block>>>(tab, n_blocks, iters / 4, sink);
+	cudaEventRecord(e0);
+	k_gather<BYTES, ILP><<<grid, block>>>(tab, n_blocks, iters, sink);
+	cudaEventRecord(e1); cudaEventSynchronize(e1);
+	float ms; cudaEventElapsedTime(&ms, e0, e1);
+	const double n = (double)grid * block * iters * ILP;
+	printf("bytes/request %3d  requests in flight/lane %d  lanes/SM %4d : %7.1f G requests/s  %7.1f GB/s\n", BYTES, ILP, threads_per_sm_target, n / ms / 1e6, n * BYTES / ms / 1e6);
+}
+int main(int argc, char **argv)
+{
+	const double gb = argc > 1 ? atof(argv[1]) : 6.0;
+	const u64 n_blocks = (u64)(gb * 1e9 / 64);
+	uint4 *tab; u64 *sink;
+	cudaMalloc(&tab, n_blocks * 64); cudaMalloc(&sink, 8);
+	cudaMemset(tab, 1, n_blocks * 64);
+	printf("table %.1f GB, dependent random requests\n", gb);
+	run<64, 1>(tab, n_blocks, sink, 640);  run<64, 1>(tab, n_blocks, sink, 1024); run<64, 1>(tab, n_blocks, sink, 2048);
+	run<64, 2>(tab, n_blocks, sink, 640);  run<64, 2>(tab, n_blocks, sink, 1024); run<64, 2>(tab, n_blocks, sink, 2048);
+	run<64, 4>(tab, n_blocks, sink, 1024); run<64, 4>(tab, n_blocks, sink, 2048);
+	run<32, 2>(tab, n_blocks, sink, 2048); run<32, 4>(tab, n_blocks, sink, 2048);
+	return 0;
+}
