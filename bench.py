@@ -125,7 +125,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference(fa, fqs, n_sample, threads):
+def time_reference(fa, fqs, n_sample, threads, keep_sam=False):
     """`bwa mem -t threads` of the unmodified reference on the first n_sample reads; reads/s from its own
     '[M::mem_process_seqs] Processed N reads in X CPU sec, Y real sec' lines (excludes index load and I/O)."""
     samples = []
@@ -139,7 +139,10 @@ def time_reference(fa, fqs, n_sample, threads):
                         break
                     o.write(line)
         samples.append(sample)
-    r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa] + samples, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    ref_out = samples[0] + ".ref.sam" if keep_sam else os.devnull
+    with open(ref_out, "wb") as so:
+        r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa] + samples, stdout=so, stderr=subprocess.PIPE, text=True)
+    time_reference.last = (samples, ref_out)
     n, real = 0, 0.0
     for m in re.finditer(r"Processed (\d+) reads in ([\d.]+) CPU sec, ([\d.]+) real sec", r.stderr):
         n += int(m.group(1)); real += float(m.group(3))
@@ -310,7 +313,7 @@ def main():
                        "l2": "inputs larger than L2 (index %.2f GB, reads %.0f MB per step)" % (os.path.getsize(fa + ".bwt") / 1e9 * 1.75, n_reads * a.read_len / 1e6),
                        "value_definition": "reads / summed CUDA-event time of the seeding, SA, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
                        "pipeline": pipe_cfg,
-                       "dense_sa": a.dense_sa},
+                       "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "8")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],
             "clocks": clocks,
@@ -327,9 +330,17 @@ def main():
         if world == 1:
             try:
                 n_sample = min(a.reads, a.cpu_sample)
-                v, n = time_reference(fa, fq, n_sample, ncores)
+                v, n = time_reference(fa, fq, n_sample, ncores, keep_sam=True)
                 line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
                                         "sample": "first %d reads of the workload, oracle/_ref/bwa mem -t %d, rate from its own Processed-lines" % (n, ncores)}
+                # the same sample through `bwa-b200 mem` on the full-size index: its SAM must equal the reference's byte for byte
+                samples, ref_out = time_reference.last
+                mine = samples[0] + ".b200.sam"
+                rc = bwa_b200.run_cli(["-t", str(threads), "-K", "100000000", fa] + samples, mine)
+                strip = lambda path: b"\n".join(l for l in open(path, "rb").read().split(b"\n") if not l.startswith(b"@PG"))
+                line["cpu_baseline"]["sam_identical_on_sample"] = bool(rc == 0 and strip(mine) == strip(ref_out))
+                for f in (mine, ref_out):
+                    os.remove(f)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
         print(json.dumps(line))

@@ -3,7 +3,7 @@
  * the work/time counters the roofline is computed from.
  *
  * HBM layout of the index blob (all offsets 256-byte aligned):
- *   [ header 256 B | Occ/BWT blocks (bwt_size*4 B, symbols as bit planes) | sampled SA (n_sa*8 B) | pac (l_pac/4+1 B) ]
+ *   [ header | Occ/BWT blocks (bwt_size*4 B, re-packed: 32 B per 64 symbols) | sampled SA (n_sa*8 B) | pac (l_pac/4+1 B) ]
  * The blob is position independent (the header holds sizes, not pointers) so that it can be filled
  * on one GPU and broadcast to the others with a single collective.
  */
@@ -20,8 +20,9 @@ struct BlobHeader {
 	u64 L2[5];
 	u64 sa_shift;
 	u64 off_bwt, off_sa, off_pac, total;
+	u64 sb[BWAG_MAX_SB][4];   /* counts before each 2^31-symbol superblock of the re-packed Occ table */
 };
-#define BLOB_MAGIC 0x3042574142323030ull
+#define BLOB_MAGIC 0x3142574142323030ull
 #define ALIGN256(x) (((x) + 255) & ~(size_t)255)
 
 static __thread char g_err[512];
@@ -138,6 +139,11 @@ extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_
 		if ((1 << s) != bwt->sa_intv) return set_err("suffix-array interval %d is not a power of two", bwt->sa_intv);
 		h.sa_shift = (u64)s;
 	}
+	if (bwt->seq_len >= (u64)BWAG_MAX_SB << BWAG_SB_SHIFT) return set_err("index too large: %llu BWT symbols", (unsigned long long)bwt->seq_len);
+	for (u64 s = 0; s << BWAG_SB_SHIFT < bwt->seq_len; ++s) {   /* counts before symbol s*2^31 = the count words of that file block */
+		const u64 *cnt = (const u64 *)(bwt->bwt + ((s << BWAG_SB_SHIFT) >> 7) * 16);
+		for (int k = 0; k < 4; ++k) h.sb[s][k] = cnt[k];
+	}
 	h.off_bwt = ALIGN256(sizeof(BlobHeader));
 	h.off_sa = h.off_bwt + ALIGN256((size_t)bwt->bwt_size * 4 + 64);
 	h.off_pac = h.off_sa + ALIGN256((size_t)bwt->n_sa * 8);
@@ -146,9 +152,13 @@ extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_
 	CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
 	CK(cudaMemset(d + h.off_bwt, 0, ALIGN256((size_t)bwt->bwt_size * 4 + 64)));
 	CK(cudaMemcpy(d + h.off_bwt, bwt->bwt, (size_t)bwt->bwt_size * 4, cudaMemcpyHostToDevice));
-	{   /* symbols -> bit planes, in place (layout: bwag_dev.cuh) */
+	{   /* file layout -> 32-byte blocks, in place (bwag_dev.cuh) */
 		const u64 n_blocks = ((u64)bwt->bwt_size * 4 + 63) / 64;
-		BWAG_LAUNCH(k_occ_planes, (int)((n_blocks + 255) / 256 < 65535 ? (n_blocks + 255) / 256 : 65535), 256, 0, 0, (uint4 *)(d + h.off_bwt), n_blocks);
+		DevIndex tmp;
+		memset(&tmp, 0, sizeof(tmp));
+		for (int s = 0; s < BWAG_MAX_SB; ++s)
+			for (int k = 0; k < 4; ++k) tmp.sb[s][k] = h.sb[s][k];
+		BWAG_LAUNCH(k_occ_pack, (int)((n_blocks + 255) / 256 < 65535 ? (n_blocks + 255) / 256 : 65535), 256, 0, 0, tmp, (uint4 *)(d + h.off_bwt), n_blocks);
 		CK(cudaGetLastError());
 		CK(cudaDeviceSynchronize());
 	}
@@ -194,6 +204,8 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	c->ix.pac = (const uint8_t *)(d + h.off_pac);
 	c->ix.primary = h.primary; c->ix.seq_len = h.seq_len; c->ix.n_sa = h.n_sa; c->ix.l_pac = (i64)h.l_pac; c->ix.sa_shift = (int)h.sa_shift;
 	for (int i = 0; i < 5; ++i) c->ix.L2[i] = h.L2[i];
+	for (int s = 0; s < BWAG_MAX_SB; ++s)
+		for (int k = 0; k < 4; ++k) c->ix.sb[s][k] = h.sb[s][k];
 	c->sa_intv_disk = 1 << h.sa_shift;
 	CKP(cudaStreamCreate(&c->stream));
 	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
@@ -241,6 +253,11 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 	if (s == c->ix.sa_shift) return 0;
 	CK(cudaSetDevice(c->device));
 	u64 n_out = (c->ix.seq_len + (u64)intv) / (u64)intv, *out = 0;
+	{   /* leave room for the batch buffers */
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		if ((double)n_out * 8 > 0.5 * (double)free_b) return set_err("not enough free device memory for a suffix-array sample of interval %d", intv);
+	}
 	CK(cudaMalloc((void **)&out, n_out * 8));
 	BWAG_LAUNCH(k_sa_densify, c->n_sm * 8, 256, 0, c->stream, c->ix, out, s, n_out);
 	CK(cudaGetLastError());

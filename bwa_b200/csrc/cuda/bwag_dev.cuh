@@ -1,15 +1,19 @@
 /* bwag_dev.cuh -- device-side view of the index, launch/portability macros, FM-index block arithmetic.
  *
  * Index layout in HBM (one blob, see bwag_api.cu):
- *   - Occ/BWT blocks: one 64-byte block per 128 BWT symbols like bwt_t::bwt (bwt.h:74-82), with the same
- *     4 x u64 cumulative counts (A,C,G,T; '$' excluded) in the first 32 bytes, but the 128 symbols stored
- *     as two bit planes instead of the file's 2-bit packing (k_occ_planes converts in place after upload):
- *     bytes 32-47 = bit 1 of every symbol, bytes 48-63 = bit 0, symbol p of the block at bit p&31 of
- *     word p>>5 of its plane.  Ranks of all four symbols up to a position are then three masked popcounts
- *     per 32 symbols with no data-dependent branch: popc(hi), popc(lo), popc(hi&lo) give T = both,
- *     G = hi-only, C = lo-only, A = the rest.  64-byte aligned: a block is two 32-byte HBM sectors;
- *   - the sampled suffix array bwt_t::sa (every sa_intv-th row, sa[0] = -1), optionally re-sampled
- *     more densely on the device;
+ *   - Occ/BWT blocks.  The index files hold one 64-byte block per 128 BWT symbols: 4 x u64 cumulative counts +
+ *     8 words of 16 2-bit symbols (bwt.h:74-82).  A rank query needs the counts AND the symbols, i.e. both
+ *     32-byte HBM sectors of such a block.  Random sectors are the scarce resource here, so
+ *     k_occ_pack re-packs the table in place after upload into one 32-BYTE block per 64 symbols:
+ *         bytes  0-15  four u32 counts of A,C,G,T before the block, relative to the block's 2^31-symbol superblock
+ *         bytes 16-23  bit 1 of each of the 64 symbols (symbol p at bit p)
+ *         bytes 24-31  bit 0 of each symbol
+ *     plus a table of absolute u64 counts per superblock that travels in the kernel arguments.  Same 0.5 byte
+ *     per symbol, but a rank now costs ONE sector, and the bit planes make the ranks of all four symbols six
+ *     masked popcounts with no data-dependent branch: popc(hi), popc(lo), popc(hi&lo) give T = both,
+ *     G = hi-only, C = lo-only, A = the rest;
+ *   - the sampled suffix array bwt_t::sa (every sa_intv-th row, sa[0] = -1), re-sampled more densely on the
+ *     device at load time;
  *   - the 2-bit forward reference pac (4 bases per byte, first base in the top bits).
  */
 #ifndef BWAG_DEV_CUH
@@ -31,8 +35,12 @@ typedef unsigned long long u64;
 typedef long long i64;
 typedef unsigned int u32;
 
+#define BWAG_SB_SHIFT 31     /* symbols per superblock = 2^31: block counts fit u32 */
+#define BWAG_MAX_SB 8
+
 struct DevIndex {
-	const uint4 *bwt;   /* 4 x uint4 per block */
+	const uint4 *bwt;   /* 2 x uint4 per 64-symbol block: {counts}, {plane hi (2 words), plane lo (2 words)} */
+	u64 sb[BWAG_MAX_SB][4];   /* counts of A,C,G,T before each superblock */
 	const u64 *sa;
 	const uint8_t *pac;
 	u64 primary, seq_len;
@@ -47,32 +55,31 @@ struct DevIndex {
 /* low t bits set, t clamped to [0,32]: which symbols of a 32-symbol plane word lie in [0,pos] */
 __device__ __forceinline__ u32 bwag_plane_mask(int t) { return __funnelshift_lc(0xffffffffu, 0u, (u32)(t > 0 ? t : 0)); }
 
-/* ranks of all four symbols over positions [0,pos] of one Occ block given its four 16-byte quarters:
- * cA = counts A,C ; cG = counts G,T ; ph, pl = the two bit planes (bwt_occ4, bwt.c:169-186) */
-__device__ __forceinline__ void bwag_block_counts(const uint4 &cA, const uint4 &cG, const uint4 &ph, const uint4 &pl, int pos, u64 out[4])
+/* ranks of all four symbols over positions [0,p] of the '$'-less BWT (bwt_occ4, bwt.c:169-186), given the two
+ * 16-byte halves of the block holding p: cn = relative counts, pl = {hi.lo32, hi.hi32, lo.lo32, lo.hi32} */
+__device__ __forceinline__ void bwag_block_counts(const DevIndex &ix, const uint4 &cn, const uint4 &pl, u64 p, u64 out[4])
 {
-	const int n = pos + 1;
-	const u32 m0 = bwag_plane_mask(n), m1 = bwag_plane_mask(n - 32), m2 = bwag_plane_mask(n - 64), m3 = bwag_plane_mask(n - 96);
-	const u32 h0 = ph.x & m0, h1 = ph.y & m1, h2 = ph.z & m2, h3 = ph.w & m3;
-	const u32 l0 = pl.x & m0, l1 = pl.y & m1, l2 = pl.z & m2, l3 = pl.w & m3;
-	const u32 nH = __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3);
-	const u32 nL = __popc(l0) + __popc(l1) + __popc(l2) + __popc(l3);
-	const u32 nT = __popc(h0 & l0) + __popc(h1 & l1) + __popc(h2 & l2) + __popc(h3 & l3);
-	out[0] = ((u64)cA.y << 32 | cA.x) + (u32)(n + nT - nH - nL);
-	out[1] = ((u64)cA.w << 32 | cA.z) + (nL - nT);
-	out[2] = ((u64)cG.y << 32 | cG.x) + (nH - nT);
-	out[3] = ((u64)cG.w << 32 | cG.z) + nT;
+	const int n = (int)(p & 63) + 1;
+	const int sbi = (int)(p >> BWAG_SB_SHIFT);
+	const u32 m0 = bwag_plane_mask(n), m1 = bwag_plane_mask(n - 32);
+	const u32 h0 = pl.x & m0, h1 = pl.y & m1, l0 = pl.z & m0, l1 = pl.w & m1;
+	const u32 nH = __popc(h0) + __popc(h1), nL = __popc(l0) + __popc(l1), nT = __popc(h0 & l0) + __popc(h1 & l1);
+	out[0] = ix.sb[sbi][0] + (u32)(cn.x + n + nT - nH - nL);
+	out[1] = ix.sb[sbi][1] + (u32)(cn.y + nL - nT);
+	out[2] = ix.sb[sbi][2] + (u32)(cn.z + nH - nT);
+	out[3] = ix.sb[sbi][3] + (u32)(cn.w + nT);
 }
 
-/* symbol at position pos of a block and the number of its occurrences in [0,pos] */
-__device__ __forceinline__ int bwag_block_symbol_rank(const uint4 &ph, const uint4 &pl, int pos, u32 *rank)
+/* symbol at position p and the number of its occurrences in [0,p], same inputs */
+__device__ __forceinline__ int bwag_block_symbol_rank(const DevIndex &ix, const uint4 &cn, const uint4 &pl, u64 p, u64 *rank)
 {
-	const int w = pos >> 5, n = pos + 1;
-	const u32 hw = w == 0 ? ph.x : w == 1 ? ph.y : w == 2 ? ph.z : ph.w, lw = w == 0 ? pl.x : w == 1 ? pl.y : w == 2 ? pl.z : pl.w;
+	const int pos = (int)(p & 63), n = pos + 1;
+	const u32 hw = pos < 32 ? pl.x : pl.y, lw = pos < 32 ? pl.z : pl.w;
 	const int c = (int)(hw >> (pos & 31) & 1) << 1 | (int)(lw >> (pos & 31) & 1);
 	const u32 fh = (c & 2) ? 0u : 0xffffffffu, fl = (c & 1) ? 0u : 0xffffffffu;   /* flip a plane where the symbol's bit is 0 */
-	*rank = __popc((ph.x ^ fh) & (pl.x ^ fl) & bwag_plane_mask(n)) + __popc((ph.y ^ fh) & (pl.y ^ fl) & bwag_plane_mask(n - 32))
-	      + __popc((ph.z ^ fh) & (pl.z ^ fl) & bwag_plane_mask(n - 64)) + __popc((ph.w ^ fh) & (pl.w ^ fl) & bwag_plane_mask(n - 96));
+	const u32 r = __popc((pl.x ^ fh) & (pl.z ^ fl) & bwag_plane_mask(n)) + __popc((pl.y ^ fh) & (pl.w ^ fl) & bwag_plane_mask(n - 32));
+	const u32 cc = c == 0 ? cn.x : c == 1 ? cn.y : c == 2 ? cn.z : cn.w;
+	*rank = ix.sb[p >> BWAG_SB_SHIFT][c] + (u32)(cc + r);
 	return c;
 }
 

@@ -83,7 +83,7 @@ extern "C" {
 }
 #endif
 
-__global__ void k_occ_planes(uint4 *bwt, u64 n_blocks);
+__global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
 __global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);

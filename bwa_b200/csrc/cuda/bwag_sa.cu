@@ -3,8 +3,7 @@
  * K2 replaces bwt_sa/bwt_invPsi/bwt_occ (bwt.c:53-59,86-129): one lane per seed walks LF-steps until it
  * hits a sampled row.  Walk lengths are geometric (mean = sampling interval - 1), so lanes that finish
  * pull new seeds (ballot + one atomicAdd per warp): a warp keeps 32 independent 64-byte requests in
- * flight regardless of the spread.  Each step reads the 32-byte sector holding the block's two bit planes
- * and the 16 bytes holding the symbol's cumulative count, i.e. both HBM sectors of one 64-byte Occ block.
+ * flight regardless of the spread.  Each step reads ONE 32-byte sector (the block's counts and bit planes).
  */
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
@@ -16,12 +15,10 @@ __device__ __forceinline__ u64 lf_step(const DevIndex &ix, u64 k)
 {
 	if (k == ix.primary) return 0;
 	u64 kp = k - (k > ix.primary);                 /* row in the '$'-less BWT == what bwt_occ uses since k != primary */
-	const uint4 *blk = ix.bwt + ((kp >> 7) << 2);
-	u32 pc;
-	const int c = bwag_block_symbol_rank(__ldg(blk + 2), __ldg(blk + 3), (int)(kp & 127), &pc);   /* the block's plane sector */
-	const uint4 cn = __ldg(blk + (c >> 1));                                                      /* and 16 bytes of its count sector */
-	const u64 n = (c & 1) ? ((u64)cn.w << 32 | cn.z) : ((u64)cn.y << 32 | cn.x);
-	return ix.L2[c] + n + pc;
+	const uint4 *blk = ix.bwt + ((kp >> 6) << 1);    /* one 32-byte sector: counts + bit planes of the 64 symbols around kp */
+	u64 rank;
+	const int c = bwag_block_symbol_rank(ix, __ldg(blk), __ldg(blk + 1), kp, &rank);
+	return ix.L2[c] + rank;
 }
 
 __global__ void __launch_bounds__(K2_THREADS)
@@ -69,29 +66,40 @@ __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out)
 	}
 }
 
-/* convert the symbol area of every Occ block from the file's packing (8 words of 16 2-bit symbols, first
- * symbol in the top bits) to the two bit planes described in bwag_dev.cuh; in place, one lane per block */
-__global__ void k_occ_planes(uint4 *bwt, u64 n_blocks)
+/* re-pack the Occ table in place from the file layout (64-byte block per 128 symbols: 4 x u64 counts, 8 words of
+ * 16 2-bit symbols, first symbol in the top bits) to two 32-byte blocks of 64 symbols each (bwag_dev.cuh); one
+ * lane per file block, which owns exactly the 64 bytes it rewrites */
+__global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks)
 {
 	for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) {
-		const uint4 w0 = bwt[b * 4 + 2], w1 = bwt[b * 4 + 3];
+		const uint4 c0 = bwt[b * 4], c1 = bwt[b * 4 + 1], w0 = bwt[b * 4 + 2], w1 = bwt[b * 4 + 3];
 		const u32 w[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
-		u32 hi[4], lo[4];
+		const int sbi = (int)((b << 7) >> BWAG_SB_SHIFT);
+		u32 cnt[4] = { (u32)(((u64)c0.y << 32 | c0.x) - ix.sb[sbi][0]), (u32)(((u64)c0.w << 32 | c0.z) - ix.sb[sbi][1]),
+		               (u32)(((u64)c1.y << 32 | c1.x) - ix.sb[sbi][2]), (u32)(((u64)c1.w << 32 | c1.z) - ix.sb[sbi][3]) };
+		uint4 out[4];
 #pragma unroll
-		for (int g = 0; g < 4; ++g) {           /* 32 symbols = two file words -> one word of each plane */
-			u32 h = 0, l = 0;
+		for (int half = 0; half < 2; ++half) {   /* 64 symbols = four file words -> two words of each plane */
+			u32 hi[2], lo[2];
 #pragma unroll
-			for (int t = 0; t < 2; ++t) {
-				const u32 v = w[2 * g + t];
+			for (int g = 0; g < 2; ++g) {
+				u32 h = 0, l = 0;
 #pragma unroll
-				for (int s = 0; s < 16; ++s) {
-					const u32 sym = v >> ((15 - s) << 1) & 3;
-					h |= (sym >> 1) << (16 * t + s); l |= (sym & 1) << (16 * t + s);
+				for (int t = 0; t < 2; ++t) {
+					const u32 v = w[4 * half + 2 * g + t];
+#pragma unroll
+					for (int s = 0; s < 16; ++s) {
+						const u32 sym = v >> ((15 - s) << 1) & 3;
+						h |= (sym >> 1) << (16 * t + s); l |= (sym & 1) << (16 * t + s);
+					}
 				}
+				hi[g] = h; lo[g] = l;
 			}
-			hi[g] = h; lo[g] = l;
+			out[2 * half] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+			out[2 * half + 1] = make_uint4(hi[0], hi[1], lo[0], lo[1]);
+			const u32 nH = __popc(hi[0]) + __popc(hi[1]), nL = __popc(lo[0]) + __popc(lo[1]), nT = __popc(hi[0] & lo[0]) + __popc(hi[1] & lo[1]);
+			cnt[0] += 64 + nT - nH - nL; cnt[1] += nL - nT; cnt[2] += nH - nT; cnt[3] += nT;
 		}
-		bwt[b * 4 + 2] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-		bwt[b * 4 + 3] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+		bwt[b * 4] = out[0]; bwt[b * 4 + 1] = out[1]; bwt[b * 4 + 2] = out[2]; bwt[b * 4 + 3] = out[3];
 	}
 }

@@ -9,10 +9,10 @@
  * independent 64-byte requests in flight per SM as registers allow and spends as few issue slots per
  * step as possible:
  *   - ONE LANE PER READ.  A lane keeps the whole seeding state machine of its read in registers and
- *     fetches the blocks of its current bwt_extend itself (4 x LDG.128 per block; the two rank
- *     positions share a block in about half of the steps, which is then fetched once).  A warp thus has
- *     32 independent extensions = up to 64 blocks (128 HBM sectors) in flight per iteration, and no
- *     shuffles are needed to combine partial counts;
+ *     fetches the blocks of its current bwt_extend itself (one 32-byte sector = 2 x LDG.128 per rank
+ *     position; positions that share a block fetch it once).  A warp thus has 32 independent
+ *     extensions = up to 64 sectors in flight per iteration, and no shuffles are needed to combine
+ *     partial counts;
  *   - LOCK-STEP STATE MACHINES.  The reads of a warp are in different phases, so each lane advances its
  *     own state machine (short, divergent) until it needs the next extension; then the whole warp meets
  *     at ONE converged, branch-free load/popcount/select sequence (bit-plane blocks, bwag_dev.cuh);
@@ -77,21 +77,21 @@ __device__ __forceinline__ void extend_step(const DevIndex &ix, u64 xs, u64 xo, 
 	u64 tk[4] = {0, 0, 0, 0}, tl[4] = {0, 0, 0, 0};
 	const bool kv = k != (u64)-1, lv = l != (u64)-1;
 	const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
-	const bool same = kv && lv && (kp >> 7) == (lp >> 7);
-	uint4 b0, b1, b2, b3, c0, c1, c2, c3;
-	b0 = b1 = b2 = b3 = c0 = c1 = c2 = c3 = make_uint4(0, 0, 0, 0);
+	const bool same = kv && lv && (kp >> 6) == (lp >> 6);
+	uint4 b0, b1, c0, c1;
+	b0 = b1 = c0 = c1 = make_uint4(0, 0, 0, 0);
 	if (lv) {
-		const uint4 *bl = ix.bwt + ((lp >> 7) << 2);
-		b0 = __ldg(bl); b1 = __ldg(bl + 1); b2 = __ldg(bl + 2); b3 = __ldg(bl + 3);
+		const uint4 *bl = ix.bwt + ((lp >> 6) << 1);
+		b0 = __ldg(bl); b1 = __ldg(bl + 1);
 	}
 	if (kv && !same) {
-		const uint4 *bk = ix.bwt + ((kp >> 7) << 2);
-		c0 = __ldg(bk); c1 = __ldg(bk + 1); c2 = __ldg(bk + 2); c3 = __ldg(bk + 3);
+		const uint4 *bk = ix.bwt + ((kp >> 6) << 1);
+		c0 = __ldg(bk); c1 = __ldg(bk + 1);
 	}
-	if (same) { c0 = b0; c1 = b1; c2 = b2; c3 = b3; }   /* both ranks in one block: it was fetched once */
-	if (lv) bwag_block_counts(b0, b1, b2, b3, (int)(lp & 127), tl);
-	if (kv) bwag_block_counts(c0, c1, c2, c3, (int)(kp & 127), tk);
-	touches += same ? 1 : 2;
+	if (same) { c0 = b0; c1 = b1; }   /* both ranks in one block: it was fetched once */
+	if (lv) bwag_block_counts(ix, b0, b1, lp, tl);
+	if (kv) bwag_block_counts(ix, c0, c1, kp, tk);
+	touches += (kv && lv && (kp >> 7) == (lp >> 7)) ? 1 : 2;   /* as the reference counts them: its blocks hold 128 symbols (bwt.c:194-197) */
 	const u64 x2_1 = tl[1] - tk[1], x2_2 = tl[2] - tk[2], x2_3 = tl[3] - tk[3];
 	o_x2 = SEL4(c, tl[0] - tk[0], x2_1, x2_2, x2_3);
 	o_s = SEL4(c, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1 + SEL4(c, tk[0], tk[1], tk[2], tk[3]);   /* new x[!is_back] */

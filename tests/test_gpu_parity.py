@@ -68,6 +68,11 @@ def test_library_call_and_dense_sa(data):
     want = b"\n".join(l for l in ref_sam(["-K", "100000000", fa] + fqs).split(b"\n") if not l.startswith(b"@")).rstrip(b"\n")
     L = bwa_b200.lib()
     idx = bwa_b200.Index(fa)
+    os.environ["BWA_B200_SA_INTV"] = "32"      # first pass on the sample of the index files, then denser ones
+    try:
+        idx.attach()
+    finally:
+        del os.environ["BWA_B200_SA_INTV"]
     opt = L.mem_opt_init()
     opt.contents.n_threads = 8
     for dense in (0, 8, 2):
