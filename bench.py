@@ -291,7 +291,7 @@ def main():
             os.environ.pop(k, None)
         else:
             os.environ[k] = v
-    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_extend"] + ks["ms_global"]) / KSTEPS * a.steps
+    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_chain"] + ks["ms_extend"] + ks["ms_global"]) / KSTEPS * a.steps
     vals = torch.tensor([dt, k_ms / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -311,7 +311,7 @@ def main():
             "ms_per_step": 1e3 * dt_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
                        "l2": "inputs larger than L2 (index %.2f GB, reads %.0f MB per step)" % (os.path.getsize(fa + ".bwt") / 1e9 * 1.75, n_reads * a.read_len / 1e6),
-                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
+                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
                        "pipeline": pipe_cfg,
                        "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "8")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
@@ -321,7 +321,7 @@ def main():
                          "frac": smem_gbs / hbm_peak if hbm_peak else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
-            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
+            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
             "work_per_read": {"occ_touches": st["occ_touches"] / (n_reads * a.steps), "sa_touches": st["sa_touches"] / (n_reads * a.steps),
                               "ext_cells": st["ext_cells"] / (n_reads * a.steps), "glb_cells": st["glb_cells"] / (n_reads * a.steps)},
             "sw_gcups": {"extend": ks["ext_cells"] / (ks["ms_extend"] * 1e-3) / 1e9 if ks["ms_extend"] > 0 else None,
@@ -336,7 +336,7 @@ def main():
                 # the same sample through `bwa-b200 mem` on the full-size index: its SAM must equal the reference's byte for byte
                 samples, ref_out = time_reference.last
                 mine = samples[0] + ".b200.sam"
-                rc = bwa_b200.run_cli(["-t", str(threads), "-K", "100000000", fa] + samples, mine)
+                rc = bwa_b200.run_cli(["mem", "-t", str(threads), "-K", "100000000", fa] + samples, mine)
                 strip = lambda path: b"\n".join(l for l in open(path, "rb").read().split(b"\n") if not l.startswith(b"@PG"))
                 line["cpu_baseline"]["sam_identical_on_sample"] = bool(rc == 0 and strip(mine) == strip(ref_out))
                 for f in (mine, ref_out):

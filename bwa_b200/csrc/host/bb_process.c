@@ -795,6 +795,15 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		pe_is = big_alloc(sizeof(uint64_t) * ((size_t)(n >> 1) + 1));
 		for (k = 0, start = 0; k < n_jobs; ++k, start += chunk) jobs[k].pe_is = pe_is + (start >> 1);
 	}
+	{
+		static int named;
+		if (!named) {
+			named = 1;
+			bb_parallel_name(w_encode, "encode"); bb_parallel_name(w_chain, "chain"); bb_parallel_name(w_flatten, "flatten"); bb_parallel_name(w_zero_rs, "zero_rs");
+			bb_parallel_name(w_dedup, "dedup"); bb_parallel_name(w_gcount, "g_count"); bb_parallel_name(w_gfill, "g_fill"); bb_parallel_name(w_gstore, "g_store");
+			bb_parallel_name(w_rescue, "rescue"); bb_parallel_name(w_sam, "sam"); bb_parallel_name(w_free, "free"); bb_parallel_name(w_pe_pairs, "pe_pairs");
+		}
+	}
 	ph(0);
 	if (g_trace < 0) g_trace = getenv("BWA_B200_TRACE") ? atoi(getenv("BWA_B200_TRACE")) : 0;
 	g_trace_t0 = bb_realtime();
@@ -810,6 +819,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
 	}
 	free(jobs);
+	bb_parallel_report();
 	if (g_trace > 0) fprintf(stderr, "[trace] batch done %8.1f\n", trace_now());
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec\n", __func__, n, bb_cputime() - ctime, bb_realtime() - rtime);

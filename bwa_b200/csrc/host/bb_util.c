@@ -1,6 +1,7 @@
 /* bb_util.c -- fatal errors, checked allocation, timers, thread helpers, plain-key sorts. */
 #include <stdarg.h>
 #include <pthread.h>
+#include <time.h>
 #include <sys/time.h>
 #include <sys/resource.h>
 #include <limits.h>
@@ -91,16 +92,51 @@ static struct {
 
 int bb_parallel_ids(void) { return BB_MAX_WORKERS + BB_MAX_LANES; }
 
+/* BWA_B200_PROFILE: thread-CPU seconds per loop body, printed by bb_parallel_report() */
+static struct { void (*fn)(void *, long, int); const char *name; double cpu; long calls; } g_pstat[32];
+static int g_pstat_on = -1;
+static pthread_mutex_t g_pstat_mu = PTHREAD_MUTEX_INITIALIZER;
+static double thread_cpu(void) { struct timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+static void pstat_add(void (*fn)(void *, long, int), double dt, long items)
+{
+	int i;
+	pthread_mutex_lock(&g_pstat_mu);
+	for (i = 0; i < 32 && g_pstat[i].fn && g_pstat[i].fn != fn; ++i) {}
+	if (i < 32) { g_pstat[i].fn = fn; g_pstat[i].cpu += dt; g_pstat[i].calls += items; }
+	pthread_mutex_unlock(&g_pstat_mu);
+}
+void bb_parallel_name(void (*fn)(void *, long, int), const char *name)
+{
+	int i;
+	pthread_mutex_lock(&g_pstat_mu);
+	for (i = 0; i < 32 && g_pstat[i].fn && g_pstat[i].fn != fn; ++i) {}
+	if (i < 32) { g_pstat[i].fn = fn; g_pstat[i].name = name; }
+	pthread_mutex_unlock(&g_pstat_mu);
+}
+void bb_parallel_report(void)
+{
+	int i;
+	if (g_pstat_on <= 0) return;
+	for (i = 0; i < 32 && g_pstat[i].fn; ++i) {
+		fprintf(stderr, "[prof] loop %-14s %8.3f CPU-s %10ld items\n", g_pstat[i].name ? g_pstat[i].name : "?", g_pstat[i].cpu, g_pstat[i].calls);
+		g_pstat[i].cpu = 0; g_pstat[i].calls = 0;
+	}
+}
+
 static long job_run(pjob_t *j, int tid)   /* returns the number of chunks executed */
 {
-	long c = 0;
+	long c = 0, items = 0;
+	double t0 = 0;
+	if (g_pstat_on < 0) g_pstat_on = getenv("BWA_B200_PROFILE") != 0;
+	if (g_pstat_on) t0 = thread_cpu();
 	for (;;) {
 		long b = __sync_fetch_and_add(&j->next, j->chunk), e, i;
 		if (b >= j->n) break;
 		e = b + j->chunk < j->n ? b + j->chunk : j->n;
 		for (i = b; i < e; ++i) j->fn(j->data, i, tid);
-		++c;
+		++c; items += e - b;
 	}
+	if (g_pstat_on && items) pstat_add(j->fn, thread_cpu() - t0, items);
 	return c;
 }
 

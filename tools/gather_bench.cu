@@ -16,7 +16,7 @@ __global__ void k_gather(const uint4 *tab, u64 n_blocks, int iters, u64 *sink)
 #pragma unroll
 		for (int u = 0; u < ILP; ++u) {
 			s = s * 6364136223846793005ull + 1442695040888963407ull;
-			const u64 b = (s >> 20) % n_blocks;
+			const u64 b = (s >> 20) & (n_blocks - 1);     /* n_blocks is a power of two */
 #pragma unroll
 			for (int q = 0; q < BYTES / 16; ++q) v[u][q] = __ldg(tab + b * 4 + q);
 		}
@@ -43,15 +43,20 @@ template <int BYTES, int ILP> void run(const uint4 *tab, u64 n_blocks, u64 *sink
 }
 int main(int argc, char **argv)
 {
-	const double gb = argc > 1 ? atof(argv[1]) : 6.0;
-	const u64 n_blocks = (u64)(gb * 1e9 / 64);
 	uint4 *tab; u64 *sink;
-	cudaMalloc(&tab, n_blocks * 64); cudaMalloc(&sink, 8);
-	cudaMemset(tab, 1, n_blocks * 64);
-	printf("table %.1f GB, dependent random requests\n", gb);
-	run<64, 1>(tab, n_blocks, sink, 640);  run<64, 1>(tab, n_blocks, sink, 1024); run<64, 1>(tab, n_blocks, sink, 2048);
-	run<64, 2>(tab, n_blocks, sink, 640);  run<64, 2>(tab, n_blocks, sink, 1024); run<64, 2>(tab, n_blocks, sink, 2048);
-	run<64, 4>(tab, n_blocks, sink, 1024); run<64, 4>(tab, n_blocks, sink, 2048);
-	run<32, 2>(tab, n_blocks, sink, 2048); run<32, 4>(tab, n_blocks, sink, 2048);
+	const u64 max_blocks = (u64)1 << 27;          /* 8 GiB of 64-byte blocks */
+	cudaMalloc(&tab, max_blocks * 64); cudaMalloc(&sink, 8);
+	cudaMemset(tab, 1, max_blocks * 64);
+	(void)argc; (void)argv;
+	for (u64 n_blocks = (u64)1 << 22; n_blocks <= max_blocks; n_blocks <<= 1) {   /* 256 MiB .. 8 GiB */
+		if (n_blocks != (u64)1 << 22 && n_blocks != (u64)1 << 24 && n_blocks != (u64)1 << 26 && n_blocks != max_blocks) continue;
+		printf("table %.2f GiB, dependent random requests\n", n_blocks * 64.0 / (1 << 30));
+		run<64, 1>(tab, n_blocks, sink, 640);  run<64, 1>(tab, n_blocks, sink, 2048);
+		run<64, 2>(tab, n_blocks, sink, 640);  run<64, 2>(tab, n_blocks, sink, 2048);
+		run<64, 4>(tab, n_blocks, sink, 2048);
+		run<32, 1>(tab, n_blocks, sink, 640);  run<32, 1>(tab, n_blocks, sink, 2048);
+		run<32, 2>(tab, n_blocks, sink, 640);  run<32, 2>(tab, n_blocks, sink, 2048);
+		run<32, 4>(tab, n_blocks, sink, 2048);
+	}
 	return 0;
 }
