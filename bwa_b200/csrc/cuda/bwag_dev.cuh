@@ -52,6 +52,19 @@ struct DevIndex {
 
 #define FULL_MASK 0xffffffffu
 
+/* one 32-byte Occ block with ONE 256-bit load (LDG.E.256, sm_100+): the table is far larger than the TLB reach, and
+ * what limits random access to it is the number of translated load-lane accesses, not bytes (tools/gather_bench.cu:
+ * 2 x 128-bit loads per block run at half the block rate of 1 x 256-bit) */
+__device__ __forceinline__ void bwag_ld_block(const uint4 *p, uint4 &cn, uint4 &pl)
+{
+#ifdef BWAG_CUSIM
+	cn = p[0]; pl = p[1];
+#else
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(cn.x), "=r"(cn.y), "=r"(cn.z), "=r"(cn.w), "=r"(pl.x), "=r"(pl.y), "=r"(pl.z), "=r"(pl.w) : "l"(p));
+#endif
+}
+
 /* low t bits set, t clamped to [0,32]: which symbols of a 32-symbol plane word lie in [0,pos] */
 __device__ __forceinline__ u32 bwag_plane_mask(int t) { return __funnelshift_lc(0xffffffffu, 0u, (u32)(t > 0 ? t : 0)); }
 

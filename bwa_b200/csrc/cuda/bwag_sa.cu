@@ -17,7 +17,9 @@ __device__ __forceinline__ u64 lf_step(const DevIndex &ix, u64 k)
 	u64 kp = k - (k > ix.primary);                 /* row in the '$'-less BWT == what bwt_occ uses since k != primary */
 	const uint4 *blk = ix.bwt + ((kp >> 6) << 1);    /* one 32-byte sector: counts + bit planes of the 64 symbols around kp */
 	u64 rank;
-	const int c = bwag_block_symbol_rank(ix, __ldg(blk), __ldg(blk + 1), kp, &rank);
+	uint4 cn, pl;
+	bwag_ld_block(blk, cn, pl);
+	const int c = bwag_block_symbol_rank(ix, cn, pl, kp, &rank);
 	return ix.L2[c] + rank;
 }
 

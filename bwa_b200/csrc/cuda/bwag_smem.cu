@@ -9,7 +9,7 @@
  * independent 64-byte requests in flight per SM as registers allow and spends as few issue slots per
  * step as possible:
  *   - ONE LANE PER READ.  A lane keeps the whole seeding state machine of its read in registers and
- *     fetches the blocks of its current bwt_extend itself (one 32-byte sector = 2 x LDG.128 per rank
+ *     fetches the blocks of its current bwt_extend itself (one 32-byte sector = one LDG.256 per rank
  *     position; positions that share a block fetch it once).  A warp thus has 32 independent
  *     extensions = up to 64 sectors in flight per iteration, and no shuffles are needed to combine
  *     partial counts;
@@ -81,12 +81,10 @@ __device__ __forceinline__ void extend_step(const DevIndex &ix, u64 xs, u64 xo, 
 	uint4 b0, b1, c0, c1;
 	b0 = b1 = c0 = c1 = make_uint4(0, 0, 0, 0);
 	if (lv) {
-		const uint4 *bl = ix.bwt + ((lp >> 6) << 1);
-		b0 = __ldg(bl); b1 = __ldg(bl + 1);
+		bwag_ld_block(ix.bwt + ((lp >> 6) << 1), b0, b1);
 	}
 	if (kv && !same) {
-		const uint4 *bk = ix.bwt + ((kp >> 6) << 1);
-		c0 = __ldg(bk); c1 = __ldg(bk + 1);
+		bwag_ld_block(ix.bwt + ((kp >> 6) << 1), c0, c1);
 	}
 	if (same) { c0 = b0; c1 = b1; }   /* both ranks in one block: it was fetched once */
 	if (lv) bwag_block_counts(ix, b0, b1, lp, tl);
