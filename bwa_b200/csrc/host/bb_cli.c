@@ -14,7 +14,7 @@
 
 #define BB_VERSION "0.7.19-r1273-b200"
 
-typedef struct { int n; bseq1_t *seqs; int last; int skip; long no; } batch_t;   /* skip: another rank's batch (multi-GPU runs) */
+typedef struct { int n; bseq1_t *seqs; int last; int skip; long no; int64_t n_before; } batch_t;   /* skip: another rank's batch (multi-GPU runs) */
 
 typedef struct { /* single-slot mailbox */
 	pthread_mutex_t mu;
@@ -44,6 +44,36 @@ static batch_t *mbox_get(mbox_t *m)
 	return b;
 }
 
+/* finished batches wait here until it is their turn to be written (several batches are aligned at a time) */
+#define RO_SLOTS 8
+typedef struct {
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	batch_t *slot[RO_SLOTS];
+	long next_write, total;   /* total < 0 until the reader has seen the end of the input */
+} reorder_t;
+static void ro_init(reorder_t *o) { pthread_mutex_init(&o->mu, 0); pthread_cond_init(&o->cv, 0); memset(o->slot, 0, sizeof(o->slot)); o->next_write = 0; o->total = -1; }
+static void ro_post(reorder_t *o, batch_t *b)
+{
+	pthread_mutex_lock(&o->mu);
+	while (b->no - o->next_write >= RO_SLOTS) pthread_cond_wait(&o->cv, &o->mu);
+	o->slot[b->no % RO_SLOTS] = b;
+	pthread_cond_broadcast(&o->cv);
+	pthread_mutex_unlock(&o->mu);
+}
+static void ro_finish(reorder_t *o, long total) { pthread_mutex_lock(&o->mu); o->total = total; pthread_cond_broadcast(&o->cv); pthread_mutex_unlock(&o->mu); }
+static batch_t *ro_next(reorder_t *o)   /* the batch with the next number, or NULL when all have been written */
+{
+	batch_t *b;
+	pthread_mutex_lock(&o->mu);
+	while (!o->slot[o->next_write % RO_SLOTS] && !(o->total >= 0 && o->next_write >= o->total)) pthread_cond_wait(&o->cv, &o->mu);
+	b = o->slot[o->next_write % RO_SLOTS];
+	o->slot[o->next_write % RO_SLOTS] = 0;
+	if (b) { ++o->next_write; pthread_cond_broadcast(&o->cv); }
+	pthread_mutex_unlock(&o->mu);
+	return b;
+}
+
 typedef struct {
 	bb_fq_t *f1, *f2;
 	mem_opt_t *opt;
@@ -51,7 +81,8 @@ typedef struct {
 	bwaidx_t *idx;
 	int copy_comment, chunk;
 	int64_t n_processed;
-	mbox_t to_align, to_write;
+	mbox_t to_align;
+	reorder_t done;
 	/* multi-GPU runs (bwa_b200/multi.py): batches are dealt round-robin, batch b belongs to rank b % world; every rank
 	 * parses the whole input so that batch boundaries -- and with them the per-batch insert-size model -- are those of
 	 * a single-GPU run.  shard_idx records "batch bytes" per written batch so that rank 0 can merge the parts in order */
@@ -91,8 +122,9 @@ static void *reader_main(void *a)
 		int i;
 		int64_t size = 0;
 		b->seqs = bseq_read(r->chunk, &b->n, r->f1, r->f2);
-		if (!b->seqs) { free(b); mbox_put(&r->to_align, 0); return 0; }
+		if (!b->seqs) { free(b); ro_finish(&r->done, r->n_batches); mbox_put(&r->to_align, 0); return 0; }
 		b->no = r->n_batches++;
+		b->n_before = r->n_processed; r->n_processed += b->n;
 		if (b->no % r->world != r->rank) { b->skip = 1; free_reads(b); mbox_put(&r->to_align, b); continue; }
 		if (!r->copy_comment)
 			for (i = 0; i < b->n; ++i) { free(b->seqs[i].comment); b->seqs[i].comment = 0; }
@@ -106,7 +138,7 @@ static void *writer_main(void *a)
 {
 	run_t *r = a;
 	batch_t *b;
-	while ((b = mbox_get(&r->to_write)) != 0) {
+	while ((b = ro_next(&r->done)) != 0) {
 		if (!b->skip) { write_batch(r, b); free_reads(b); }
 		free(b);
 	}
@@ -117,7 +149,7 @@ static void align_batch(run_t *r, batch_t *b)
 {
 	const mem_opt_t *opt = r->opt;
 	const bwaidx_t *idx = r->idx;
-	if (b->skip) { r->n_processed += b->n; return; }
+	if (b->skip) return;
 	if (opt->flag & MEM_F_SMARTPE) { /* -p: split the batch into single-end and paired reads (fastmap.c:90-109) */
 		bseq1_t *sep[2];
 		int n_sep[2], i;
@@ -126,17 +158,27 @@ static void align_batch(run_t *r, batch_t *b)
 		if (bwa_verbose >= 3) fprintf(stderr, "[M::%s] %d single-end sequences; %d paired-end sequences\n", "process", n_sep[0], n_sep[1]);
 		if (n_sep[0]) {
 			tmp.flag &= ~MEM_F_PE;
-			mem_process_seqs(&tmp, idx->bwt, idx->bns, idx->pac, r->n_processed, n_sep[0], sep[0], 0);
+			mem_process_seqs(&tmp, idx->bwt, idx->bns, idx->pac, b->n_before, n_sep[0], sep[0], 0);
 			for (i = 0; i < n_sep[0]; ++i) b->seqs[sep[0][i].id].sam = sep[0][i].sam;
 		}
 		if (n_sep[1]) {
 			tmp.flag |= MEM_F_PE;
-			mem_process_seqs(&tmp, idx->bwt, idx->bns, idx->pac, r->n_processed + n_sep[0], n_sep[1], sep[1], r->pes0);
+			mem_process_seqs(&tmp, idx->bwt, idx->bns, idx->pac, b->n_before + n_sep[0], n_sep[1], sep[1], r->pes0);
 			for (i = 0; i < n_sep[1]; ++i) b->seqs[sep[1][i].id].sam = sep[1][i].sam;
 		}
 		free(sep[0]); free(sep[1]);
-	} else mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, r->n_processed, b->n, b->seqs, r->pes0);
-	r->n_processed += b->n;
+	} else mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, b->n_before, b->n, b->seqs, r->pes0);
+}
+
+static void *aligner_main(void *a)
+{
+	run_t *r = a;
+	batch_t *b;
+	while ((b = mbox_get(&r->to_align)) != 0) {
+		align_batch(r, b);
+		ro_post(&r->done, b);
+	}
+	return 0;
 }
 
 static void scale_by_match_score(mem_opt_t *opt, const mem_opt_t *set) /* -A scales what the user left alone (fastmap.c:125-139) */
@@ -184,7 +226,6 @@ int main_mem(int argc, char *argv[])
 	mem_pestat_t pes[4];
 	run_t run;
 	pthread_t th_r, th_w;
-	batch_t *b;
 
 	memset(&run, 0, sizeof(run));
 	memset(pes, 0, sizeof(pes));
@@ -326,7 +367,7 @@ int main_mem(int argc, char *argv[])
 	if (run.shard_idx) { fflush(stdout); fprintf(run.shard_idx, "-1 %ld\n", ftell(stdout)); }
 	run.chunk = fixed_chunk > 0 ? fixed_chunk : opt->chunk_size * opt->n_threads;
 
-	mbox_init(&run.to_align); mbox_init(&run.to_write);
+	mbox_init(&run.to_align); ro_init(&run.done);
 	if (no_mt_io) {
 		for (;;) {
 			batch_t bb;
@@ -334,6 +375,7 @@ int main_mem(int argc, char *argv[])
 			bb.seqs = bseq_read(run.chunk, &bb.n, run.f1, run.f2);
 			if (!bb.seqs) break;
 			bb.no = run.n_batches++;
+			bb.n_before = run.n_processed; run.n_processed += bb.n;
 			bb.skip = bb.no % run.world != run.rank;
 			if (!bb.skip && !run.copy_comment) for (i = 0; i < bb.n; ++i) { free(bb.seqs[i].comment); bb.seqs[i].comment = 0; }
 			align_batch(&run, &bb);
@@ -343,11 +385,18 @@ int main_mem(int argc, char *argv[])
 	} else {
 		pthread_create(&th_r, 0, reader_main, &run);
 		pthread_create(&th_w, 0, writer_main, &run);
-		while ((b = mbox_get(&run.to_align)) != 0) {
-			align_batch(&run, b);
-			mbox_put(&run.to_write, b);
+		/* BWA_B200_INFLIGHT batches are aligned at a time (default 2): while one is in its host-only phases
+		 * (pairing, SAM text) the GPU works on the next; the writer restores the input order */
+		{
+			const char *e = getenv("BWA_B200_INFLIGHT");
+			int n_al = e ? atoi(e) : 2, t;
+			pthread_t th_a[4];
+			if (n_al < 1) n_al = 1;
+			if (n_al > 4) n_al = 4;
+			for (t = 1; t < n_al; ++t) pthread_create(&th_a[t], 0, aligner_main, &run);
+			aligner_main(&run);
+			for (t = 1; t < n_al; ++t) pthread_join(th_a[t], 0);
 		}
-		mbox_put(&run.to_write, 0);
 		pthread_join(th_r, 0);
 		pthread_join(th_w, 0);
 	}

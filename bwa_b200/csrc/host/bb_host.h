@@ -80,6 +80,7 @@ typedef BB_VEC(bb_galn_t) bb_galn_v;
 typedef struct {
 	bb_galn_v memo;
 	int pending;     /* requests recorded in this pass */
+	int in_arena;    /* memo.a lives in the batch's bump arena (nothing to free) */
 	bb_galn_t inl;   /* storage of the first entry: most reads need exactly one alignment */
 } bb_gcache_t;
 const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc);

@@ -147,6 +147,36 @@ void bb_device_release(const bwt_t *bwt)
 }
 
 /* ---------------------------------------------------------------- alignment cache */
+/* Caches that outgrow their inline slot take their array from a per-thread bump arena of the chunk being processed:
+ * a million small mallocs released later by other threads cost more than the alignments they describe. */
+typedef struct memo_blk { struct memo_blk *next; size_t used, cap; } memo_blk_t;
+typedef struct { memo_blk_t *head; } memo_arena_t;
+static __thread memo_arena_t *tl_memo;
+static void *memo_alloc(size_t bytes)
+{
+	memo_arena_t *ar = tl_memo;
+	memo_blk_t *b;
+	void *p;
+	if (!ar) return 0;
+	bytes = (bytes + 15) & ~(size_t)15;
+	b = ar->head;
+	if (!b || b->used + bytes > b->cap) {
+		size_t cap = bytes > (1u << 18) ? bytes : (1u << 18);
+		b = bb_malloc(sizeof(memo_blk_t) + cap);
+		b->next = ar->head; b->used = 0; b->cap = cap;
+		ar->head = b;
+	}
+	p = (char *)(b + 1) + b->used;
+	b->used += bytes;
+	return p;
+}
+static void memo_arenas_free(memo_arena_t *ars, int n)
+{
+	int i;
+	if (!ars) return;
+	for (i = 0; i < n; ++i) { memo_blk_t *b = ars[i].head, *nx; for (; b; b = nx) { nx = b->next; free(b); } }
+	free(ars);
+}
 const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_t rb, int64_t re, int w, int truesc)
 {
 	size_t i;
@@ -164,10 +194,12 @@ const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_
 	if (gc->memo.a == 0) { gc->memo.a = &gc->inl; gc->memo.m = 1; gc->memo.n = 0; }
 	if (gc->memo.n == gc->memo.m) { /* leave the inline slot for the heap */
 		size_t m = gc->memo.m < 4 ? 4 : gc->memo.m << 1;
-		bb_galn_t *na = bb_malloc(m * sizeof(bb_galn_t));
+		bb_galn_t *na = memo_alloc(m * sizeof(bb_galn_t));
+		int arena = na != 0;
+		if (!na) na = bb_malloc(m * sizeof(bb_galn_t));
 		memcpy(na, gc->memo.a, gc->memo.n * sizeof(bb_galn_t));
-		if (gc->memo.a != &gc->inl) free(gc->memo.a);
-		gc->memo.a = na; gc->memo.m = m;
+		if (gc->memo.a != &gc->inl && !gc->in_arena) free(gc->memo.a);
+		gc->memo.a = na; gc->memo.m = m; gc->in_arena = arena;
 	}
 	gc->memo.a[gc->memo.n++] = e;
 	++gc->pending;
@@ -176,8 +208,8 @@ const bb_galn_t *bb_gcache_get(bb_gcache_t *gc, int mode, int qb, int qe, int64_
 
 static void gcache_free(bb_gcache_t *gc) /* CIGAR/MD bytes live in per-round blocks owned by the job */
 {
-	if (gc->memo.a != &gc->inl) free(gc->memo.a);
-	gc->memo.a = 0; gc->memo.n = gc->memo.m = 0;
+	if (gc->memo.a != &gc->inl && !gc->in_arena) free(gc->memo.a);
+	gc->memo.a = 0; gc->memo.n = gc->memo.m = 0; gc->in_arena = 0;
 }
 
 /* ---------------------------------------------------------------- batch state */
@@ -231,6 +263,7 @@ typedef struct {
 	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
 	double t_last;
+	memo_arena_t *arenas;    /* one bump arena per parallel id for the alignment caches of this chunk */
 	uint64_t *pe_is;         /* PE: this chunk's slice of the per-pair insert-size candidates */
 	int lane, chunk_id;      /* which lane (device batch object) runs this chunk */
 	bwag_batch_t *batch;
@@ -377,8 +410,8 @@ static void w_dedup(void *d, long i, int tid)
 	rstate_t *r = &j->rs[i];
 	int n;
 	size_t k;
-	(void)tid;
 	if (r->dedup_done) return;
+	tl_memo = j->arenas ? &j->arenas[tid] : 0;
 	load_raw_regs(j, i, &r->regs);
 	r->gc.pending = 0;
 	n = bb_sort_dedup_patch(j->opt, j->bns, &r->gc, j->seqs[i].l_seq, (int)r->regs.n, r->regs.a);
@@ -481,10 +514,11 @@ static void w_rescue(void *d, long i, int tid)
 {
 	job_t *j = d;
 	mem_alnreg_v a[2];
-	(void)tid;
+	tl_memo = j->arenas ? &j->arenas[tid] : 0;
 	a[0] = j->rs[i << 1].regs; a[1] = j->rs[i << 1 | 1].regs;
 	bb_rescue_pe(j->opt, j->bns, j->pac, j->pes, &j->seqs[i << 1], a);
 	j->rs[i << 1].regs = a[0]; j->rs[i << 1 | 1].regs = a[1];
+	tl_memo = 0;
 }
 
 #define STACK_REGS 8
@@ -529,8 +563,8 @@ static void w_sam(void *d, long i, int tid)
 	int pe = !!(j->opt->flag & MEM_F_PE);
 	rstate_t *r0 = pe ? &j->rs[i << 1] : &j->rs[i], *r1 = pe ? &j->rs[i << 1 | 1] : 0;
 	int dry = j->pass_dry;
-	(void)tid;
 	if (r0->done) return;
+	tl_memo = j->arenas ? &j->arenas[tid] : 0;
 	for (;;) {
 		r0->gc.pending = 0; if (r1) r1->gc.pending = 0;
 		run_sam(j, i, dry);
@@ -658,6 +692,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 		j->reg_pool = big_alloc(sizeof(mem_alnreg_t) * ((size_t)tot_regs + 1));
 	}
 	j->rs = big_alloc(((size_t)n + 1) * sizeof(rstate_t));
+	j->arenas = bb_calloc(bb_parallel_ids(), sizeof(memo_arena_t));
 	bb_parallel_for_lane(j->lane, nt, w_zero_rs, j, ((long)n + 4095) / 4096);
 	for (;;) { /* de-duplicate; repeat for reads whose merge test needed a device alignment */
 		int64_t left = 0;
@@ -690,6 +725,7 @@ static void w_free(void *d, long i, int tid)
 static void job_free(job_t *j)
 {
 	if (j->rs) bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
+	memo_arenas_free(j->arenas, bb_parallel_ids()); j->arenas = 0;
 	{ int b; for (b = 0; b < j->n_blocks; ++b) big_free(j->blocks[b]); }
 	big_free(j->reg_pool); big_free(j->reg_off);
 	big_free(j->rs); big_free(j->off); big_free(j->codes); big_free(j->chain_off); big_free(j->xchains); big_free(j->xseeds); big_free(j->chain_rid); big_free(j->chain_frac);
@@ -869,6 +905,7 @@ mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *
 	int k;
 	const bwt_t *bwt = any_resident_bwt(pac);
 	if (!bwt) bb_fatal("mem_reg2aln", "no index resident on the GPU; call mem_align1/mem_process_seqs first");
+	tl_memo = 0;
 	memset(&j, 0, sizeof(j)); memset(&s, 0, sizeof(s)); memset(&rs, 0, sizeof(rs));
 	s.l_seq = l_seq; s.seq = bb_malloc((size_t)l_seq + 1);
 	for (k = 0; k < l_seq; ++k) { unsigned char c = (unsigned char)seq[k]; c = c < 5 ? c : bb_nt4_table[c]; s.seq[k] = (char)(c > 4 ? 4 : c); }

@@ -37,3 +37,13 @@ def test_emulated_seed_stage_buffers_equal_oracle(data):
     got = seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par)
     want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
     assert got == want and sum(len(r) for r in want) > 500
+
+
+def test_batches_in_flight_keep_order_and_content(data, monkeypatch):
+    """Several batches aligned at a time (BWA_B200_INFLIGHT): the writer restores input order; PE statistics stay per batch."""
+    fa, fqs = data.reads("stress", tag="cspe", n=60, seed=34, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    args = ["-K", "3000", "-t", "2", fa] + fqs        # ~10 pairs per batch
+    want = ref_sam(args)
+    for inflight in ("1", "3"):
+        monkeypatch.setenv("BWA_B200_INFLIGHT", inflight)
+        assert run_sam(CUSIMBIN, args) == want
