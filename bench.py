@@ -154,7 +154,7 @@ def time_reference(fa, fqs, n_sample, threads, keep_sam=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-mbp", type=int, default=int(os.environ.get("BWA_B200_BENCH_REF_MBP", "3000")))
@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
     ap.add_argument("--cpu-sample", type=int, default=100000)
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BWA_B200_INFLIGHT", "2")), help="mem_process_seqs calls issued at a time (host threads), as bwa-b200 mem does")
     ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
     a = ap.parse_args()
 
@@ -232,7 +233,9 @@ def main():
 
     opt = L.mem_opt_init()
     opt.contents.n_threads = threads
-    batch = bwa_b200.ReadBatch(*fq)
+    inflight = max(1, min(4, a.inflight))
+    batches = [bwa_b200.ReadBatch(*fq) for _ in range(inflight)]     # one host copy of the step's reads per call in flight
+    batch = batches[0]
     if paired:
         opt.contents.flag |= bwa_b200.MEM_F_PE
     n_reads = batch.n
@@ -246,14 +249,37 @@ def main():
         while held:
             L.bb_batch_free_detached(batch.n, held.pop())
 
-    def step():
-        bwa_b200.mem_process_seqs(opt, idx, batch)
+    def step(b=None):
+        b = b or batch
+        bwa_b200.mem_process_seqs(opt, idx, b)
         # the SAM text is in host memory now; its release (what fastmap.c:114-119 does after printing) is kept out of the timed region
-        held.append(L.bb_batch_detach_sam(batch.n, batch.seqs))
+        held.append(L.bb_batch_detach_sam(b.n, b.seqs))
 
-    for _ in range(a.warmup):
-        step()
-        release()
+    def run_steps(n_steps):
+        """n_steps calls of mem_process_seqs, `inflight` at a time from as many host threads (ctypes drops the GIL),
+        the way the command line keeps two batches in flight (bb_cli.c)."""
+        if inflight == 1:
+            for _ in range(n_steps):
+                step()
+            return
+        todo = list(range(n_steps))
+        lock = threading.Lock()
+
+        def work(w):
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    todo.pop()
+                step(batches[w])
+        ths = [threading.Thread(target=work, args=(w,)) for w in range(inflight)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    run_steps(a.warmup)
+    release()
     idx.stats(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -261,8 +287,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step()
+    run_steps(a.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -312,7 +337,7 @@ def main():
             "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
                        "l2": "inputs larger than L2 (index %.2f GB, reads %.0f MB per step)" % (os.path.getsize(fa + ".bwt") / 1e9 * 1.75, n_reads * a.read_len / 1e6),
                        "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
-                       "pipeline": pipe_cfg,
+                       "pipeline": pipe_cfg + ", %d mem_process_seqs calls in flight" % inflight,
                        "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "8")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],
