@@ -298,7 +298,8 @@ def main():
     # Kernel-only figures (value, roofline): the timed region above overlaps several chunks on different streams, so
     # per-kernel event times there include waiting for each other.  Two more passes with ONE lane and ONE chunk give
     # each kernel the GPU alone ("timed in isolation", burst peak applies); they are not part of the e2e number.
-    pipe_cfg = "chunks of %s reads on %s lanes (streams)" % (os.environ.get("BWA_B200_CHUNK", "131072"), os.environ.get("BWA_B200_LANES", "3"))
+    pipe_cfg = "chunks of %s reads on %s lanes (streams) per call" % (os.environ.get("BWA_B200_CHUNK", "262144" if paired else "131072"),
+                                                                          os.environ.get("BWA_B200_LANES", "2" if inflight > 1 else "3"))
     user_env = {k: os.environ.get(k) for k in ("BWA_B200_LANES", "BWA_B200_CHUNK")}
     os.environ["BWA_B200_LANES"] = "1"
     os.environ["BWA_B200_CHUNK"] = str(1 << 30)

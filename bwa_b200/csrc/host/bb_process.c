@@ -802,12 +802,15 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	mem_pestat_t pes[4];
 	bwag_ctx_t *ctx;
 	double ctime = bb_cputime(), rtime = bb_realtime();
-	int pe = !!(opt->flag & MEM_F_PE), n_lanes = 3, n_jobs, k;
-	long chunk = 1 << 17, start;
+	static volatile int n_calls;   /* mem_process_seqs calls in flight (the command line keeps two) */
+	int pe = !!(opt->flag & MEM_F_PE), n_lanes, n_jobs, k;
+	long chunk = pe ? 1 << 18 : 1 << 17, start;
 	uint64_t *pe_is = 0;
 	const char *e;
 
 	if (n <= 0) return;
+	/* lanes of all calls share one GPU and one pool of host threads: about four in total is the sweet spot (tools/sweep_lanes.sh) */
+	n_lanes = __sync_add_and_fetch(&n_calls, 1) >= 2 ? 2 : 3;
 	if ((e = getenv("BWA_B200_LANES")) != 0) n_lanes = atoi(e);
 	if ((e = getenv("BWA_B200_CHUNK")) != 0) chunk = atol(e);
 	if (n_lanes < 1) n_lanes = 1;
@@ -855,6 +858,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
 	}
 	free(jobs);
+	__sync_sub_and_fetch(&n_calls, 1);
 	bb_parallel_report();
 	if (g_trace > 0) fprintf(stderr, "[trace] batch done %8.1f\n", trace_now());
 	if (bwa_verbose >= 3)

@@ -1,11 +1,10 @@
 #!/bin/bash
-# e2e vs (lanes, host threads) on the GPU box; assumes the 3 Gbp workload already exists in /tmp/bwa_b200_bench
-cd /root/repo
-for layout in se pe; do
- for cfg in "2 16" "3 16" "4 16" "3 12" "4 20"; do
+# e2e throughput vs (calls in flight, lanes per call, chunk size) on the GPU box
+cd /root/repo; mkdir -p gpurun_out
+python bench.py --layout se --steps 1 --warmup 1 --cpu-sample 2000 > /dev/null 2>&1
+for layout in pe se; do
+for cfg in "1 3 131072" "2 2 131072" "2 2 65536" "3 2 131072" "2 1 262144" "4 1 131072" "3 1 131072" "2 2 262144"; do
   set -- $cfg
-  BWA_B200_LANES=$1 timeout 600 python bench.py --layout $layout --threads $2 --steps 4 --warmup 2 --cpu-sample 2000 > /tmp/sw.json 2> /tmp/sw.err
-  python -c "import json; d=json.load(open('/tmp/sw.json')); print('$layout lanes $1 threads $2: e2e', round(d['e2e']['value']), 'ms/step', round(d['ms_per_step'],1))"
-  grep Processed /tmp/sw.err | tail -7 | head -4 | sed 's/.*in \([0-9.]*\) CPU sec, \([0-9.]*\) real.*/\1cpu \2real/' | tr '\n' ' '; echo
- done
-done
+  BWA_B200_LANES=$2 BWA_B200_CHUNK=$3 python bench.py --layout $layout --inflight $1 --steps 8 --warmup 3 --cpu-sample 2000 > /tmp/s.json 2>/dev/null
+  python -c "import json; d=json.load(open('/tmp/s.json')); print('$layout inflight $1 lanes $2 chunk $3: e2e %.0f reads/s, %.1f ms/step' % (d['e2e']['value'], d['ms_per_step']))"
+done; done
