@@ -77,7 +77,7 @@ struct bwag_ctx {
 	DevIndex ix;
 	u64 *dense_sa;
 	cudaStream_t stream;
-	cudaEvent_t ev0, ev1;
+	cudaEvent_t ev0, ev1, ev_wait;
 	Counters *d_cnt, *h_cnt;
 	bwag_stats_t st;
 	int sa_intv_disk;
@@ -118,6 +118,7 @@ static void free_dev(DevBuf *b) { if (b->p) cudaFree(b->p); b->p = 0; b->cap = 0
 static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->cap = 0; }
 
 #define K1_SMEM_MAX (200 * 1024)
+#define K4_SMEM_MAX (96 * 1024)
 
 /* ------------------------------------------------------------------------------------------------ index */
 
@@ -182,6 +183,7 @@ static int pick_grid(bwag_ctx_t *c)
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem_fwd, K1F_THREADS, 0)); c->grid_k1f = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
+	CK(cudaFuncSetAttribute(k_extend_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
 #endif
 	return 0;
@@ -209,6 +211,7 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	c->sa_intv_disk = 1 << h.sa_shift;
 	CKP(cudaStreamCreate(&c->stream));
 	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
+	CKP(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
 	CKP(cudaMalloc((void **)&c->d_cnt, sizeof(Counters)));
 	CKP(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
 	pthread_mutex_init(&c->mu, 0);
@@ -240,7 +243,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
-	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_wait);
 	cudaStreamDestroy(c->stream);
 	free(c);
 }
@@ -294,6 +297,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 		memset(&b->lc, 0, sizeof(b->lc));
 		CKP(cudaStreamCreate(&b->lc.stream));
 		CKP(cudaEventCreate(&b->lc.ev0)); CKP(cudaEventCreate(&b->lc.ev1));
+		CKP(cudaEventCreateWithFlags(&b->lc.ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
 		CKP(cudaMalloc((void **)&b->lc.d_cnt, sizeof(Counters)));
 		CKP(cudaMallocHost((void **)&b->lc.h_cnt, sizeof(Counters)));
 		b->lc_ready = 1;
@@ -340,7 +344,7 @@ static void batch_free(bwag_batch_t *b)
 	if (b->lc_ready) {
 		free_dev(&b->lc.s_k1); free_dev(&b->lc.s_k1f); free_dev(&b->lc.s_n3); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
 		cudaFree(b->lc.d_cnt); cudaFreeHost(b->lc.h_cnt);
-		cudaEventDestroy(b->lc.ev0); cudaEventDestroy(b->lc.ev1); cudaStreamDestroy(b->lc.stream);
+		cudaEventDestroy(b->lc.ev0); cudaEventDestroy(b->lc.ev1); cudaEventDestroy(b->lc.ev_wait); cudaStreamDestroy(b->lc.stream);
 	}
 	free_dev(&b->d_codes); free_dev(&b->d_off);
 	free_dev(&b->d_intv_beg); free_dev(&b->d_intv_n); free_dev(&b->d_intv); free_dev(&b->d_seed_beg); free_dev(&b->d_rbeg);
@@ -359,10 +363,19 @@ static int reset_counters(bwag_ctx_t *c)
 	CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
 	return 0;
 }
+/* wait for the context's stream WITHOUT spinning: several lanes wait at the same time and the host threads are
+ * needed for the host phases of other chunks (a spinning cudaStreamSynchronize burns a core per waiting lane) */
+static cudaError_t stream_wait(bwag_ctx_t *c)
+{
+	cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+	if (e != cudaSuccess) return e;
+	return cudaEventSynchronize(c->ev_wait);
+}
+
 static int fetch_counters(bwag_ctx_t *c)
 {
 	CK(cudaMemcpyAsync(c->h_cnt, c->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	return 0;
 }
 #define H2D(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (c)->stream)); (c)->st.h2d_bytes += (u64)(bytes); } while (0)
@@ -468,7 +481,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	if (n_intv) D2H(c, b->h_seed_beg.p, b->d_seed_beg.p, 8 * (size_t)n_intv);
 	if (n_seeds) D2H(c, b->h_rbeg.p, b->d_rbeg.p, 8 * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);
 	out->intv_beg = (const int64_t *)b->h_intv_beg.p; out->intv_n = (const int32_t *)b->h_intv_n.p; out->intv = (const bwtintv_t *)b->h_intv.p;
 	out->seed_beg = (const int64_t *)b->h_seed_beg.p; out->rbeg = (const int64_t *)b->h_rbeg.p; out->n_intv = n_intv; out->n_seeds = n_seeds;
@@ -476,6 +489,32 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 }
 
 /* ------------------------------------------------------------------------------------------------ stage 2 */
+
+/* K4 with its per-warp scratch in shared memory when that fits, else in global memory; n_units = reads to process */
+static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
+{
+	const int wpb = K4_THREADS / 32;
+	int per_warp = (8 * (a.cap_q + 2) + a.cap_r + a.cap_q + 15) & ~15;
+	size_t smem = (size_t)per_warp * wpb;
+	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX;
+#ifndef BWAG_CUSIM
+	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
+#endif
+	i64 need = ((i64)n_units + wpb - 1) / wpb;
+	if (grid > need) grid = (int)(need > 0 ? need : 1);
+	if (!use_sm) {
+		const size_t n_warps = (size_t)grid * wpb;
+		if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(a.cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)a.cap_r)) return 1;
+		a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.smem_per_warp = 0;
+		BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
+	} else {
+		a.eh = 0; a.rseq = 0; a.smem_per_warp = per_warp;
+		BWAG_LAUNCH(k_extend_sm, grid, K4_THREADS, smem, c->stream, c->ix, a);
+	}
+	CK(cudaGetLastError());
+	return 0;
+}
+
 
 extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int32_t *chain_off, const bwag_xchain_t *chains,
                            int64_t n_seeds, const bwag_xseed_t *seeds, bwag_regs_t *out)
@@ -493,8 +532,6 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 		i64 need = ((i64)n + (K4_THREADS / 32) - 1) / (K4_THREADS / 32);
 		if (grid > need) grid = (int)(need > 0 ? need : 1);
 	}
-	const size_t n_warps = (size_t)grid * (K4_THREADS / 32);
-	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r)) return 1;
 	if (buf_reserve(&b->d_chain_off, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_chains, sizeof(bwag_xchain_t) * (size_t)(n_chains + 1)) ||
 	    buf_reserve(&b->d_seeds, sizeof(bwag_xseed_t) * (size_t)(n_seeds + 1)) || buf_reserve(&b->d_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) ||
 	    buf_reserve(&b->d_nregs, 4 * (size_t)(n + 1))) return 1;
@@ -514,7 +551,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	if (n_chains) H2D(c, b->d_chains.p, chains, sizeof(bwag_xchain_t) * (size_t)n_chains);
 	if (n_seeds) H2D(c, b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_h2d += elapsed(c);
 	ExtArgs a;
 	memset(&a, 0, sizeof(a));
@@ -522,11 +559,10 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	a.chain_beg = (const i64 *)b->d_chain_beg.p; a.chain_cnt = (const int *)b->d_chain_cnt.p; a.reg_base = (const i64 *)b->d_reg_base.p;
 	a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
 	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
-	a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.cap_q = cap_q; a.cap_r = cap_r;
+	a.cap_q = cap_q; a.cap_r = cap_r;
 	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
-	CK(cudaGetLastError());
+	if (launch_extend(c, a, n)) return 1;
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (fetch_counters(c)) return 1;
 	c->st.ms_extend += elapsed(c); ++c->st.n_launch;
@@ -537,7 +573,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	if (n_seeds) D2H(c, b->h_regs.p, b->d_regs.p, sizeof(bwag_xreg_t) * (size_t)n_seeds);
 	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->regs = (const bwag_xreg_t *)b->h_regs.p;
 	return 0;
@@ -600,19 +636,16 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 		i64 need = ((i64)n + (K4_THREADS / 32) - 1) / (K4_THREADS / 32);
 		if (grid > need) grid = (int)(need > 0 ? need : 1);
 	}
-	const size_t n_warps = (size_t)grid * (K4_THREADS / 32);
-	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r)) return 1;
 	ExtArgs a;
 	memset(&a, 0, sizeof(a));
 	a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n; a.par = *par;
 	a.chain_beg = (const i64 *)b->d_chain_beg.p; a.chain_cnt = (const int *)b->d_chain_cnt.p; a.reg_base = (const i64 *)b->d_reg_base.p;
 	a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
 	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
-	a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.cap_q = cap_q; a.cap_r = cap_r;
+	a.cap_q = cap_q; a.cap_r = cap_r;
 	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
-	CK(cudaGetLastError());
+	if (launch_extend(c, a, n)) return 1;
 	CK(cudaEventRecord(c->ev1, c->stream));
 	/* dense copy of the regions (with contig id and repeat fraction of their chain) for the download */
 	RegCompactArgs rc;
@@ -635,7 +668,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	D2H(c, b->h_creg_beg.p, b->d_creg_beg.p, 8 * (size_t)n);
 	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->reg_beg = (const int64_t *)b->h_creg_beg.p; out->regs = (const bwag_creg_t *)b->h_cregs.p;
 	return 0;
@@ -681,7 +714,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	CK(cudaEventRecord(c->ev0, c->stream));
 	H2D(c, b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_h2d += elapsed(c);
 	i64 cap_cig = n_aln * 6 + 1024, cap_md = n_aln * 24 + 4096;   /* typical short-read sizes; grown on demand */
 	for (int attempt = 0;; ++attempt) {
@@ -716,7 +749,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	if (nc) D2H(c, b->h_cig.p, b->d_cig.p, 4 * (size_t)nc);
 	if (nm) D2H(c, b->h_md.p, b->d_md.p, (size_t)nm);
 	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
+	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);
 	out->res = (const bwag_gres_t *)b->h_res.p; out->cigar = (const uint32_t *)b->h_cig.p; out->md = (const char *)b->h_md.p;
 	return 0;

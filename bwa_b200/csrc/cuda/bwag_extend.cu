@@ -40,7 +40,7 @@ __device__ __forceinline__ int dev_cal_max_gap(const bwag_sw_par_t &p, int qlen)
 /* Banded extension of query q[0..qlen) (q[j] = qp[j*qs]) against target t[0..tlen) (t[i] = tp[i*ts])
  * starting from score h0; exact restatement of ksw_extend2 (ksw.c:416-515) with lanes across columns.
  * H, E: per-warp int arrays of at least qlen+1 entries.  All lanes return the same values. */
-__device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, int tlen, const uint8_t *tp, int ts,
+__device__ __forceinline__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, int tlen, const uint8_t *tp, int ts,
                                const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                                int *H, int *E, int *qle, int *tle, int *gtle, int *gscore_, int *max_off_, u64 *cells)
 {
@@ -63,8 +63,8 @@ __device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, in
 	max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
 	beg = 0; end = qlen;
 	for (int i = 0; i < tlen; ++i) {
-		const int8_t *srow = mat + tp[(i64)i * ts] * 5;
-		int m = 0, mj = -1, nz_min = 0x7fffffff, nz_max = -1;
+		const int8_t *srow = mat + tp[i * ts] * 5;
+		int m = 0, mj = -1, nz_min = 0x7fffffff, nz_max = -1;   /* nz_*: warp-uniform, from ballots */
 		if (beg < i - w) beg = i - w;
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
@@ -78,7 +78,7 @@ __device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, in
 			int M = 0, e = 0, t, s, f, h, hp;
 			if (act) {
 				M = H[j]; e = E[j];
-				M = M ? M + srow[qp[(i64)j * qs]] : 0;
+				M = M ? M + srow[qp[j * qs]] : 0;
 			}
 			t = M - oe_ins; t = t > 0 ? t : 0;        /* what this column offers to F of the columns on its right */
 			if (!act) t = 0;
@@ -105,12 +105,17 @@ __device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, in
 				carry_f = s31 > cf ? s31 : cf; if (carry_f < 0) carry_f = 0;
 				carry_h = __shfl_sync(FULL_MASK, h, la);
 			}
+			bool nz = false;
 			if (act) {
 				int te = M - oe_del; te = te > 0 ? te : 0;
 				e -= e_del; e = e > te ? e : te;
 				H[j] = hp; E[j] = e;
 				if (h >= m) { m = h; mj = j; }         /* a lane's columns ascend, so ties keep the larger j (ksw.c:473-474) */
-				if (hp != 0 || e != 0) { if (j < nz_min) nz_min = j; nz_max = j; }
+				nz = hp != 0 || e != 0;
+			}
+			{   /* first and last column whose stored cell is non-zero: chunks ascend, so the first ballot with a bit set holds the minimum */
+				const u32 bal = __ballot_sync(FULL_MASK, nz);
+				if (bal) { if (nz_min == 0x7fffffff) nz_min = j0 + __ffs(bal) - 1; nz_max = j0 + 31 - __clz(bal); }
 			}
 		}
 		const int h1 = carry_h;                        /* H(i, end-1), or the first-column value if the row was empty */
@@ -119,8 +124,6 @@ __device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, in
 			int ma = warp_max(m);
 			mj = warp_max(m == ma ? mj : -1);
 			m = ma;
-			nz_min = warp_min(nz_min);
-			nz_max = warp_max(nz_max);
 		}
 		if ((end > beg ? end : beg) == qlen) {         /* ksw.c:486-489: ties go to the later row */
 			max_ie = gscore > h1 ? max_ie : i;
@@ -151,13 +154,30 @@ __device__ int warp_ksw_extend(int lane, int qlen, const uint8_t *qp, int qs, in
 	return max;
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
-k_extend(DevIndex ix, ExtArgs a)
+/* SM: the per-warp scratch (H/E rows, reference window, a copy of the read) lives in shared memory -- 32-bit
+ * addressing and no L1 round trips in the row loop; chosen by the host whenever it fits (short reads) */
+template <bool SM>
+__device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a)
 {
 	const int lane = threadIdx.x & 31;
 	const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	int *H = a.eh + wid * (i64)(2 * (a.cap_q + 2)), *E = H + a.cap_q + 2;
-	uint8_t *rseq = a.rseq + wid * (i64)a.cap_r;
+	int *H, *E;
+	uint8_t *rseq, *qcopy = 0;
+	if (SM) {
+#ifdef BWAG_CUSIM
+		unsigned char *dyn = cusim_dyn_smem;
+#else
+		extern __shared__ int4 k4_dyn[];
+		unsigned char *dyn = reinterpret_cast<unsigned char *>(k4_dyn);
+#endif
+		unsigned char *mine = dyn + (size_t)(threadIdx.x >> 5) * a.smem_per_warp;
+		H = reinterpret_cast<int *>(mine); E = H + a.cap_q + 2;
+		rseq = reinterpret_cast<uint8_t *>(E + a.cap_q + 2);
+		qcopy = rseq + a.cap_r;
+	} else {
+		H = a.eh + wid * (i64)(2 * (a.cap_q + 2)); E = H + a.cap_q + 2;
+		rseq = a.rseq + wid * (i64)a.cap_r;
+	}
 	const bwag_sw_par_t &p = a.par;
 	__shared__ int8_t s_mat[32];
 	if (threadIdx.x < 25) s_mat[threadIdx.x] = p.mat[threadIdx.x];
@@ -177,6 +197,12 @@ k_extend(DevIndex ix, ExtArgs a)
 			const int l_query = (int)(a.off[rid + 1] - a.off[rid]);
 			bwag_xreg_t *regs = a.regs + a.reg_base[rid];
 			if (l_query > a.cap_q) { overflow = 1; if (lane == 0) a.n_regs[rid] = 0; continue; }
+			if (SM) {
+				__syncwarp();
+				for (int x = lane; x < l_query; x += 32) qcopy[x] = query[x];
+				__syncwarp();
+				query = qcopy;
+			}
 			for (i64 c = c0; c < c1; ++c) {
 				const bwag_xchain_t ch = a.chains[c];
 				bwag_xseed_t *seeds = const_cast<bwag_xseed_t *>(a.seeds) + ch.seed_off;
@@ -277,3 +303,6 @@ k_extend(DevIndex ix, ExtArgs a)
 	if (lane == 0 && cells) atomicAdd(a.cells, cells);
 	if (overflow && lane == 0) atomicOr(a.flags, 2u);
 }
+
+__global__ void __launch_bounds__(K4_THREADS) k_extend(DevIndex ix, ExtArgs a) { extend_body<false>(ix, a); }
+__global__ void __launch_bounds__(K4_THREADS) k_extend_sm(DevIndex ix, ExtArgs a) { extend_body<true>(ix, a); }

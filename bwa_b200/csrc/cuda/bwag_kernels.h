@@ -61,6 +61,7 @@ struct ExtArgs {
 	bwag_xreg_t *regs; int32_t *n_regs;
 	/* per-warp scratch: H, E (int32 each, cap_q+2), reference window (cap_r bytes) */
 	int *eh; uint8_t *rseq; int cap_q, cap_r;
+	int smem_per_warp;   /* k_extend_sm: bytes of shared scratch per warp = 8*(cap_q+2) + cap_r + cap_q, rounded up to 16 */
 	int *next_read; u64 *cells; u32 *flags;
 };
 
@@ -92,6 +93,7 @@ __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
 __global__ void k_chain(ChainArgs a);
 __global__ void k_regs_compact(RegCompactArgs a);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
+__global__ void k_extend_sm(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
 
 #endif

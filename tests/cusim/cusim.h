@@ -170,6 +170,8 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return cu
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 0; return cudaSuccess; }
+enum { cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned f) { (void)f; *e = 0; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0) { (void)e; (void)s; return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { (void)e; return cudaSuccess; }
