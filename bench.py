@@ -151,6 +151,42 @@ def time_reference(fa, fqs, n_sample, threads, keep_sam=False):
     return n / real, n
 
 
+def supervise(argv):
+    """Single-GPU runs happen in a child process under a watchdog: a GPU job that stops making progress must not take the
+    whole benchmark with it.  The child prints the JSON line; if it hangs it is killed and the run is repeated once in the
+    most conservative configuration (one call in flight), which is recorded in the line."""
+    limit = int(os.environ.get("BWA_B200_BENCH_TIMEOUT", "1200"))
+    for attempt in (0, 1):
+        env = dict(os.environ)
+        extra = []
+        if attempt == 1:
+            env["BWA_B200_INFLIGHT"] = "1"
+            extra = ["--inflight", "1"]
+        p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--worker"] + list(argv) + extra, stdout=subprocess.PIPE, env=env, start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=limit)
+        except subprocess.TimeoutExpired:
+            log("[bench] attempt %d made no progress for %d s: killing it" % (attempt, limit))
+            try:
+                os.killpg(p.pid, 9)
+            except Exception:
+                p.kill()
+            p.communicate()
+            continue
+        text = out.decode()
+        if p.returncode == 0 and attempt == 1:
+            try:
+                line = json.loads(text.strip().splitlines()[-1])
+                line["config"]["watchdog"] = "first attempt hung and was killed; this is the repeat with one call in flight"
+                text = json.dumps(line) + "\n"
+            except Exception:
+                pass
+        sys.stdout.write(text)
+        sys.stdout.flush()
+        return p.returncode
+    return 3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,8 +201,12 @@ def main():
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
     ap.add_argument("--cpu-sample", type=int, default=100000)
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("BWA_B200_INFLIGHT", "2")), help="mem_process_seqs calls issued at a time (host threads), as bwa-b200 mem does")
+    ap.add_argument("--worker", action="store_true", help="(internal) run the measurement in this process; without it a parent process supervises the run")
     ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
     a = ap.parse_args()
+
+    if a.impl == "b200" and not a.worker and "RANK" not in os.environ:
+        return supervise(sys.argv[1:])
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -375,4 +415,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main() or 0)

@@ -172,12 +172,12 @@ def mem_process_seqs(opt, index, batch, n_processed=0):
     index.L.mem_process_seqs(opt, i.bwt, i.bns, i.pac, n_processed, batch.n, batch.seqs, None)
 
 
-def run_cli(args, stdout_path, stderr_path=None, binary=None):
+def run_cli(args, stdout_path, stderr_path=None, binary=None, timeout=None):
     """Run `bwa-b200 mem ...` as a process."""
     with open(stdout_path, "wb") as so:
         se = open(stderr_path, "wb") if stderr_path else subprocess.DEVNULL
         try:
-            return subprocess.call([binary or CLI_PATH] + list(args), stdout=so, stderr=se)
+            return subprocess.call([binary or CLI_PATH] + list(args), stdout=so, stderr=se, timeout=timeout)
         finally:
             if stderr_path:
                 se.close()

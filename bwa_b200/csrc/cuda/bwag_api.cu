@@ -84,7 +84,8 @@ struct bwag_ctx {
 	/* scratch reused across batches */
 	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
 	int grid_k1, grid_k1f, grid_k2, grid_k4, grid_k5;
-	struct bwag_batch *spare[4]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
+#define N_SPARE 12
+	struct bwag_batch *spare[N_SPARE]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
 	pthread_mutex_t mu;
 	struct bwag_ctx *parent;     /* set in the per-batch view of the context */
 };
@@ -239,7 +240,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
-	for (int i = 0; i < 4; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
+	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
@@ -289,7 +290,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 {
 	bwag_batch_t *b = 0;   /* buffers only grow: cudaMalloc/cudaMallocHost per batch would cost more than the kernels */
 	pthread_mutex_lock(&c->mu);
-	for (int i = 0; i < 4; ++i) if (c->spare[i]) { b = c->spare[i]; c->spare[i] = 0; break; }
+	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { b = c->spare[i]; c->spare[i] = 0; break; }
 	pthread_mutex_unlock(&c->mu);
 	if (!b) b = (bwag_batch_t *)calloc(1, sizeof(*b));
 	CKP(cudaSetDevice(c->device));
@@ -334,7 +335,7 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
 	}
-	for (int i = 0; i < 4; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
+	for (int i = 0; i < N_SPARE; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
 	pthread_mutex_unlock(&c->mu);
 	if (b) batch_free(b);
 }
@@ -363,10 +364,13 @@ static int reset_counters(bwag_ctx_t *c)
 	CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
 	return 0;
 }
-/* wait for the context's stream WITHOUT spinning: several lanes wait at the same time and the host threads are
- * needed for the host phases of other chunks (a spinning cudaStreamSynchronize burns a core per waiting lane) */
+/* wait for the context's stream.  Default: cudaStreamSynchronize (the runtime spins: lowest latency, one core per
+ * waiting lane); optionally without spinning */
 static cudaError_t stream_wait(bwag_ctx_t *c)
 {
+	static int mode = -1;   /* BWA_B200_SYNC=block: sleep on a blocking event (saves the cores of waiting lanes, adds wake-up latency to every stage) */
+	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = e && strcmp(e, "block") == 0; }
+	if (!mode) return cudaStreamSynchronize(c->stream);
 	cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
 	if (e != cudaSuccess) return e;
 	return cudaEventSynchronize(c->ev_wait);

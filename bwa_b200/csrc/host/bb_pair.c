@@ -86,17 +86,17 @@ void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v,
 	memset(isize, 0, sizeof(isize));
 	for (i = 0; i < n_pairs; ++i)
 		if (v[i]) bb_vec_push(isize[(v[i] >> 48) - 1], v[i] & 0xffffffffffffULL);
-	if (bwa_verbose >= 3) fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", __func__, (long)isize[0].n, (long)isize[1].n, (long)isize[2].n, (long)isize[3].n);
+	if (bwa_verbose >= 3) fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", "mem_pestat", (long)isize[0].n, (long)isize[1].n, (long)isize[2].n, (long)isize[3].n);
 	for (d = 0; d < 4; ++d) {
 		mem_pestat_t *r = &pes[d];
 		uint64_t *q = isize[d].a;
 		size_t qn = isize[d].n, k;
 		int p25, p50, p75, x;
 		if (qn < MIN_DIR_CNT) {
-			fprintf(stderr, "[M::%s] skip orientation %c%c as there are not enough pairs\n", __func__, "FR"[d >> 1 & 1], "FR"[d & 1]);
+			fprintf(stderr, "[M::%s] skip orientation %c%c as there are not enough pairs\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
 			r->failed = 1;
 			continue;
-		} else fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", __func__, "FR"[d >> 1 & 1], "FR"[d & 1]);
+		} else fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
 		sort_isizes(qn, q, opt->max_ins);
 		p25 = (int)q[(int)(.25 * qn + .499)];
 		p50 = (int)q[(int)(.50 * qn + .499)];
@@ -104,27 +104,27 @@ void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v,
 		r->low = (int)(p25 - OUTLIER_BOUND * (p75 - p25) + .499);
 		if (r->low < 1) r->low = 1;
 		r->high = (int)(p75 + OUTLIER_BOUND * (p75 - p25) + .499);
-		fprintf(stderr, "[M::%s] (25, 50, 75) percentile: (%d, %d, %d)\n", __func__, p25, p50, p75);
-		fprintf(stderr, "[M::%s] low and high boundaries for computing mean and std.dev: (%d, %d)\n", __func__, r->low, r->high);
+		fprintf(stderr, "[M::%s] (25, 50, 75) percentile: (%d, %d, %d)\n", "mem_pestat", p25, p50, p75);
+		fprintf(stderr, "[M::%s] low and high boundaries for computing mean and std.dev: (%d, %d)\n", "mem_pestat", r->low, r->high);
 		for (k = 0, x = 0, r->avg = 0; k < qn; ++k)
 			if (q[k] >= (uint64_t)r->low && q[k] <= (uint64_t)r->high) { r->avg += q[k]; ++x; }
 		r->avg /= x;
 		for (k = 0, r->std = 0; k < qn; ++k)
 			if (q[k] >= (uint64_t)r->low && q[k] <= (uint64_t)r->high) r->std += (q[k] - r->avg) * (q[k] - r->avg);
 		r->std = sqrt(r->std / x);
-		fprintf(stderr, "[M::%s] mean and std.dev: (%.2f, %.2f)\n", __func__, r->avg, r->std);
+		fprintf(stderr, "[M::%s] mean and std.dev: (%.2f, %.2f)\n", "mem_pestat", r->avg, r->std);
 		r->low = (int)(p25 - MAPPING_BOUND * (p75 - p25) + .499);
 		r->high = (int)(p75 + MAPPING_BOUND * (p75 - p25) + .499);
 		if (r->low > r->avg - MAX_STDDEV * r->std) r->low = (int)(r->avg - MAX_STDDEV * r->std + .499);
 		if (r->high < r->avg + MAX_STDDEV * r->std) r->high = (int)(r->avg + MAX_STDDEV * r->std + .499);
 		if (r->low < 1) r->low = 1;
-		fprintf(stderr, "[M::%s] low and high boundaries for proper pairs: (%d, %d)\n", __func__, r->low, r->high);
+		fprintf(stderr, "[M::%s] low and high boundaries for proper pairs: (%d, %d)\n", "mem_pestat", r->low, r->high);
 	}
 	for (d = 0, max = 0; d < 4; ++d) if (isize[d].n > max) max = isize[d].n;
 	for (d = 0; d < 4; ++d)
 		if (pes[d].failed == 0 && isize[d].n < max * MIN_DIR_RATIO) {
 			pes[d].failed = 1;
-			fprintf(stderr, "[M::%s] skip orientation %c%c\n", __func__, "FR"[d >> 1 & 1], "FR"[d & 1]);
+			fprintf(stderr, "[M::%s] skip orientation %c%c\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
 		}
 	for (d = 0; d < 4; ++d) free(isize[d].a);
 }

@@ -46,7 +46,7 @@ def ref_sam(args):
 
 
 def run_sam(binary, args):
-    r = subprocess.run([binary, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([binary, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     return strip_pg(r.stdout)
 
