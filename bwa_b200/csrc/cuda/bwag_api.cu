@@ -185,6 +185,7 @@ static int pick_grid(bwag_ctx_t *c)
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaFuncSetAttribute(k_extend_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
+	CK(cudaFuncSetAttribute(k_global_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
 #endif
 	return 0;
@@ -500,7 +501,7 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	const int wpb = K4_THREADS / 32;
 	int per_warp = (8 * (a.cap_q + 2) + a.cap_r + a.cap_q + 15) & ~15;
 	size_t smem = (size_t)per_warp * wpb;
-	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX;
+	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K4_SM") && atoi(getenv("BWA_B200_K4_SM")) == 0);
 #ifndef BWAG_CUSIM
 	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
 #endif
@@ -703,6 +704,13 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	/* one task's CIGAR has at most lq+rlen ops, its MD at most 3 characters per reference base */
 	const int cap_wcig = cap_q + cap_r + 4, cap_wmd = 3 * cap_r + cap_q + 16;
 	int grid = c->grid_k5;
+	/* H/E rows and the sequences in shared memory when a block's share fits (BWA_B200_K5_SM=0 keeps them in global memory) */
+	const int k5_per_warp = (8 * (cap_q + 2) + cap_r + cap_q + 2 + 15) & ~15;
+	const size_t k5_smem = (size_t)k5_per_warp * (K5_THREADS / 32);
+	int k5_sm = k5_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K5_SM") && atoi(getenv("BWA_B200_K5_SM")) == 0);
+#ifndef BWAG_CUSIM
+	if (k5_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global_sm, K5_THREADS, k5_smem)); if (nb < 2) k5_sm = 0; else grid = c->n_sm * nb; }
+#endif
 	{
 		i64 need = ((i64)n_tasks + (K5_THREADS / 32) - 1) / (K5_THREADS / 32);
 		if (grid > need) grid = (int)(need > 0 ? need : 1);
@@ -735,7 +743,9 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 		a.next_task = &c->d_cnt->next_task; a.cells = &c->d_cnt->glb_cells; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
-		BWAG_LAUNCH(k_global, grid, K5_THREADS, 0, c->stream, c->ix, a);
+		a.smem_per_warp = k5_sm ? k5_per_warp : 0;
+		if (k5_sm) BWAG_LAUNCH(k_global_sm, grid, K5_THREADS, k5_smem, c->stream, c->ix, a);
+		else BWAG_LAUNCH(k_global, grid, K5_THREADS, 0, c->stream, c->ix, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;

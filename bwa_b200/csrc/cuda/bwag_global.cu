@@ -20,7 +20,7 @@
 
 /* Banded global alignment score of q[0..qlen) vs t[0..tlen), band w; z != 0: record directions
  * (n_col bytes per row).  Restatement of ksw_global2 (ksw.c:552-611), lanes across columns. */
-__device__ int warp_ksw_global(int lane, int qlen, const uint8_t *q, int tlen, const uint8_t *t, const int8_t *mat,
+__device__ __forceinline__ int warp_ksw_global(int lane, int qlen, const uint8_t *q, int tlen, const uint8_t *t, const int8_t *mat,
                                int o_del, int e_del, int o_ins, int e_ins, int w, int *H, int *E, uint8_t *z, int n_col, u64 *cells)
 {
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
@@ -95,13 +95,30 @@ __device__ __forceinline__ int md_put_num(char *md, int l, int v)
 	return l;
 }
 
-__global__ void __launch_bounds__(K5_THREADS)
-k_global(DevIndex ix, GlbArgs a)
+/* SM: H/E rows and the two sequences of the task in shared memory (short reads); the backtrack matrix, the CIGAR and
+ * the MD staging stay in the warp's global scratch */
+template <bool SM>
+__device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a)
 {
 	const int lane = threadIdx.x & 31;
 	const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	int *H = a.eh + wid * (i64)(2 * (a.cap_q + 2)), *E = H + a.cap_q + 2;
-	uint8_t *rseq = a.rseq + wid * (i64)a.cap_r, *qseq = a.qseq + wid * (i64)(a.cap_q + 2), *z = a.z + wid * a.cap_z;
+	int *H, *E;
+	uint8_t *rseq, *qseq, *z = a.z + wid * a.cap_z;
+	if (SM) {
+#ifdef BWAG_CUSIM
+		unsigned char *dyn = cusim_dyn_smem;
+#else
+		extern __shared__ int4 k5_dyn[];
+		unsigned char *dyn = reinterpret_cast<unsigned char *>(k5_dyn);
+#endif
+		unsigned char *mine = dyn + (size_t)(threadIdx.x >> 5) * a.smem_per_warp;
+		H = reinterpret_cast<int *>(mine); E = H + a.cap_q + 2;
+		rseq = reinterpret_cast<uint8_t *>(E + a.cap_q + 2);
+		qseq = rseq + a.cap_r;
+	} else {
+		H = a.eh + wid * (i64)(2 * (a.cap_q + 2)); E = H + a.cap_q + 2;
+		rseq = a.rseq + wid * (i64)a.cap_r; qseq = a.qseq + wid * (i64)(a.cap_q + 2);
+	}
 	const bwag_sw_par_t &p = a.par;
 	__shared__ int8_t s_mat[32];
 	if (threadIdx.x < 25) s_mat[threadIdx.x] = p.mat[threadIdx.x];
@@ -243,3 +260,6 @@ k_global(DevIndex ix, GlbArgs a)
 	if (lane == 0 && cells) atomicAdd(a.cells, cells);
 	if (overflow && lane == 0) atomicOr(a.flags, (u32)overflow);
 }
+
+__global__ void __launch_bounds__(K5_THREADS) k_global(DevIndex ix, GlbArgs a) { global_body<false>(ix, a); }
+__global__ void __launch_bounds__(K5_THREADS) k_global_sm(DevIndex ix, GlbArgs a) { global_body<true>(ix, a); }

@@ -74,6 +74,7 @@ struct GlbArgs {
 	u32 *w_cig; char *w_md; int cap_wcig, cap_wmd;   /* per-warp staging of one task's CIGAR / MD */
 	int *eh; uint8_t *rseq; uint8_t *qseq; uint8_t *z;   /* per-warp scratch: H/E rows, reference, query, backtrack matrix */
 	int cap_q, cap_r; i64 cap_z;
+	int smem_per_warp;   /* k_global_sm: 8*(cap_q+2) + cap_r + cap_q + 2, rounded up to 16 */
 	int *next_task; u64 *cells; u32 *flags;
 };
 
@@ -95,5 +96,6 @@ __global__ void k_regs_compact(RegCompactArgs a);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
+__global__ void k_global_sm(DevIndex ix, GlbArgs a);
 
 #endif
