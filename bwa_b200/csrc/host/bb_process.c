@@ -771,8 +771,8 @@ static void *lane_main(void *a_)
 		if (g_trace > 0) j->t_last = trace_now();
 		if (a->phase == 0) {
 			j->batch = run_to_regs(j, a->ctx, &j->swp);
-			if (a->pe) {   /* the insert-size model needs every chunk first */
-				bwag_batch_end(j->batch); j->batch = 0;
+			if (a->pe) {   /* the insert-size model needs every chunk first; with few chunks each keeps its device batch (reads resident) for the second phase */
+				if (a->n_jobs > 6) { bwag_batch_end(j->batch); j->batch = 0; }
 				if (j->pe_is) { bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_pe_pairs, j, ((j->n >> 1) + 1023) / 1024); PH(j, "pe_pairs"); }
 			}
 			else job_finish(j, a->ctx);
