@@ -118,6 +118,9 @@ static void batch_free(bwag_batch_t *b);
 static void free_dev(DevBuf *b) { if (b->p) cudaFree(b->p); b->p = 0; b->cap = 0; }
 static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->cap = 0; }
 
+#ifndef BWAG_L2_FETCH_DEFAULT
+#define BWAG_L2_FETCH_DEFAULT 0   /* 0: leave the device's setting */
+#endif
 #define K1_SMEM_MAX (200 * 1024)
 #define K4_SMEM_MAX (96 * 1024)
 
@@ -200,6 +203,12 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	CKP(cudaSetDevice(device));
 	CKP(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
 	if (h.magic != BLOB_MAGIC) { set_err("index blob has a bad magic number"); return 0; }
+	{   /* the hot tables are read one random 32-byte sector at a time: ask L2 not to fetch the neighbouring sector as well
+	     * (BWA_B200_L2_FETCH=32|64|128; a hint the hardware may ignore) */
+		const char *e = getenv("BWA_B200_L2_FETCH");
+		int g = e ? atoi(e) : BWAG_L2_FETCH_DEFAULT;
+		if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+	}
 	bwag_ctx_t *c = (bwag_ctx_t *)calloc(1, sizeof(*c));
 	c->device = device; c->own_blob = own_blob; c->blob = d_blob;
 	char *d = (char *)d_blob;

@@ -184,6 +184,8 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t e) { (void)e; return "cusim"; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) { (void)d; memset(p, 0, sizeof(*p)); p->multiProcessorCount = 2; p->totalGlobalMem = (size_t)8 << 30; strcpy(p->name, "cusim"); p->major = 10; p->sharedMemPerBlockOptin = 227 << 10; return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute a, int v) { (void)f; (void)a; (void)v; return cudaSuccess; }
+enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit l, size_t v) { (void)l; (void)v; return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = (size_t)8 << 30; *tot = (size_t)8 << 30; return cudaSuccess; }
 
 #endif
