@@ -155,7 +155,7 @@ def supervise(argv):
     """Single-GPU runs happen in a child process under a watchdog: a GPU job that stops making progress must not take the
     whole benchmark with it.  The child prints the JSON line; if it hangs it is killed and the run is repeated once in the
     most conservative configuration (one call in flight), which is recorded in the line."""
-    limit = int(os.environ.get("BWA_B200_BENCH_TIMEOUT", "1200"))
+    limit = int(os.environ.get("BWA_B200_BENCH_TIMEOUT", "600"))
     for attempt in (0, 1):
         env = dict(os.environ)
         extra = []
@@ -244,6 +244,11 @@ def main():
     import torch.distributed as dist
     import ctypes as C
     import bwa_b200
+
+    # hard deadline for this process: a GPU job that stops making progress becomes a failed run, not a hung box
+    deadline = threading.Timer(float(os.environ.get("BWA_B200_BENCH_DEADLINE", "1500")), lambda: (log("[bench] deadline exceeded: giving up"), os._exit(4)))
+    deadline.daemon = True
+    deadline.start()
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU baseline)")
