@@ -29,7 +29,7 @@ k_sa(DevIndex ix, SaArgs a)
 	const int lane = threadIdx.x & 31;
 	const u64 mask = ((u64)1 << ix.sa_shift) - 1;
 	i64 idx = -1;
-	u64 k = 0, steps = 0, touches = 0, algo = 0;
+	u64 k = 0, steps = 0, touches = 0;
 	for (;;) {
 		/* refill idle lanes: one atomicAdd per warp for all of them */
 		bool idle = idx < 0;
@@ -50,8 +50,6 @@ k_sa(DevIndex ix, SaArgs a)
 				a.rbeg[idx] = (i64)(steps + ix.sa[k >> ix.sa_shift]);
 				idx = -1;
 			} else { k = lf_step(ix, k); ++steps; ++touches; }
-			/* what the walk would have cost with the on-disk sample (every 32nd row): counted separately */
-			(void)algo;
 		}
 	}
 	if (touches) atomicAdd(a.sa_touches, touches);

@@ -125,7 +125,7 @@ int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bw
 typedef struct {
 	uint64_t occ_touches;      /* 64-byte Occ blocks touched by bwt_extend (1 or 2 per call, bwt.c:194-197) */
 	uint64_t sa_touches;       /* 64-byte blocks touched by LF steps in bwt_sa */
-	uint64_t sa_touches_algo;  /* same, had the walk used the on-disk sa_intv=32 sample */
+	uint64_t sa_touches_algo;  /* reserved (LF steps the files' sa_intv=32 sample would have needed); not filled yet, reads 0 */
 	uint64_t ext_cells;        /* sum over ksw_extend2 rows of (end-beg) */
 	uint64_t glb_cells;        /* sum over ksw_global2 rows of (end-beg) */
 	double ms_smem, ms_sa, ms_extend, ms_global;   /* CUDA-event time of the kernels, accumulated */
