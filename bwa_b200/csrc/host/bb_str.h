@@ -12,6 +12,7 @@ static inline void bb_str_need(bb_str_t *s, size_t extra)
 	size_t need = s->l + extra + 1;
 	if (need > s->m) {
 		size_t m = s->m ? s->m : 64;
+		if (s->m == 0 && need > 64) m = (need + 31) & ~(size_t)31;   /* a caller's up-front estimate is taken as it is */
 		while (m < need) m <<= 1;
 		s->s = bb_realloc(s->s, m);
 		s->m = m;
