@@ -2,6 +2,7 @@
 #   make            -> bwa_b200/libbwa_b200.so (host glue in C + sm_100a CUDA kernels) and bwa_b200/bwa-b200 (CLI)
 #   make oracle     -> oracle/_build/liboracle.so, oracle/_ref/* (needs /root/reference or a prebuilt _ref)
 #   make testbin    -> tests/_build/bwa-b200-oracle : host glue linked against the CPU oracle stages (TEST ONLY)
+#   make tsan       -> tests/_build/bwa-b200-tsan : the same host glue + oracle stages under ThreadSanitizer (TEST ONLY)
 #   make cusim      -> tests/_build/libbwa_b200_cusim.so : the CUDA kernels compiled for the CPU SIMT emulator (TEST ONLY)
 NVCC  ?= /usr/local/cuda/bin/nvcc
 CC    ?= gcc
@@ -45,9 +46,16 @@ tests/_build/bwa-b200-oracle: $(HOST_OBJ) build/host/bb_main.o oracle/oracle_fm.
 	@mkdir -p tests/_build
 	$(CC) $(CFLAGS) -O3 -Ioracle -o $@ build/host/bb_main.o $(HOST_OBJ) oracle/oracle_fm.c oracle/oracle_sw.c oracle/oracle_stages.c -lz -lm -lpthread
 
+# host pipeline under ThreadSanitizer over the CPU oracle stages (TEST ONLY): make tsan
+TSAN_CC ?= $(shell test -x /usr/bin/gcc && echo /usr/bin/gcc || echo $(CC))   # a compiler whose installation ships libtsan
+tsan: tests/_build/bwa-b200-tsan
+tests/_build/bwa-b200-tsan: $(HOST_SRC) $(HOST)/bb_cli.c $(wildcard $(HOST)/*.h) $(wildcard include/*.h) oracle/oracle_fm.c oracle/oracle_sw.c oracle/oracle_stages.c
+	@mkdir -p tests/_build
+	$(TSAN_CC) -fsanitize=thread -O1 -g -Wall -Wno-unused-function -Iinclude -I$(HOST) -Ioracle -pthread -DBB_MAIN -o $@ $(HOST_SRC) $(HOST)/bb_cli.c oracle/oracle_fm.c oracle/oracle_sw.c oracle/oracle_stages.c -lz -lm -lpthread
+
 clean:
 	rm -rf build bwa_b200/libbwa_b200.so bwa_b200/bwa-b200 tests/_build
-.PHONY: all oracle testbin clean
+.PHONY: all oracle testbin tsan clean
 
 # CUDA kernels compiled for the CPU SIMT emulator (tests/cusim): TEST ONLY, checks kernel logic without a GPU
 CUSIM_FLAGS := -O2 -g -std=c++17 -fPIC -x c++ -include tests/cusim/cusim.h -DBWAG_CUSIM -Iinclude -I$(CUDA) -Itests/cusim -Wall -Wno-unused-function -Wno-unknown-pragmas -Wno-unused-variable

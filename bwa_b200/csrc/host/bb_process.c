@@ -77,8 +77,7 @@ static double g_t_last;
 static void ph(const char *name)
 {
 	double t;
-	if (g_prof < 0) g_prof = getenv("BWA_B200_PROFILE") != 0;
-	if (!g_prof) return;
+	if (g_prof <= 0) return;     /* set once by diag_init(); the timer is only meaningful with one call in flight */
 	t = bb_realtime();
 	if (name) fprintf(stderr, "[prof] %-16s %9.2f ms\n", name, 1e3 * (t - g_t_last));
 	g_t_last = t;
@@ -656,8 +655,8 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	sp.max_mem_intv = opt->max_mem_intv;
 	{   /* chaining on the device when every read of the chunk is short enough that the seed-level SW filter
 	     * (mem_flt_chained_seeds, bwamem.c:626-628) is inactive; otherwise (or if the stage is not provided) on the host */
-		static volatile int no_dev_chain = 0;
-		int dev_chain = !no_dev_chain && !(getenv("BWA_B200_DEVICE_CHAIN") && atoi(getenv("BWA_B200_DEVICE_CHAIN")) == 0);
+		static int no_dev_chain = 0;   /* set once if the stage library has no device chaining (the CPU oracle of the tests) */
+		int dev_chain = !__atomic_load_n(&no_dev_chain, __ATOMIC_RELAXED) && !(getenv("BWA_B200_DEVICE_CHAIN") && atoi(getenv("BWA_B200_DEVICE_CHAIN")) == 0);
 		for (i = 0; i < n && dev_chain; ++i) {
 			int l = j->seqs[i].l_seq;
 			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l > 0 ? l : 1);
@@ -678,7 +677,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 			PH(j, "seed_stage");
 			rc = bwag_chain_extend(batch, &cp, swp, &ctg, &j->cregs);
 			free(c_off); free(c_len); free(c_alt);
-			if (rc == BWAG_UNSUPPORTED) { no_dev_chain = 1; dev_chain = 0; }
+			if (rc == BWAG_UNSUPPORTED) { __atomic_store_n(&no_dev_chain, 1, __ATOMIC_RELAXED); dev_chain = 0; }
 			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
 			else { j->have_cregs = 1; PH(j, "chain_extend"); }
 		}
@@ -755,6 +754,19 @@ static void job_finish(job_t *j, bwag_ctx_t *ctx)
 	PH(j, "batch_end");
 	job_free(j);
 	PH(j, "cleanup");
+}
+
+static void w_encode(void *, long, int); static void w_chain(void *, long, int); static void w_flatten(void *, long, int); static void w_zero_rs(void *, long, int);
+static void w_dedup(void *, long, int); static void w_gcount(void *, long, int); static void w_gfill(void *, long, int); static void w_gstore(void *, long, int);
+static void w_rescue(void *, long, int); static void w_sam(void *, long, int); static void w_free(void *, long, int); static void w_pe_pairs(void *, long, int);
+static pthread_once_t g_diag_once = PTHREAD_ONCE_INIT;
+static void diag_init(void)   /* diagnostics switches are read once per process */
+{
+	g_prof = getenv("BWA_B200_PROFILE") != 0;
+	g_trace = getenv("BWA_B200_TRACE") ? atoi(getenv("BWA_B200_TRACE")) : 0;
+	bb_parallel_name(w_encode, "encode"); bb_parallel_name(w_chain, "chain"); bb_parallel_name(w_flatten, "flatten"); bb_parallel_name(w_zero_rs, "zero_rs");
+	bb_parallel_name(w_dedup, "dedup"); bb_parallel_name(w_gcount, "g_count"); bb_parallel_name(w_gfill, "g_fill"); bb_parallel_name(w_gstore, "g_store");
+	bb_parallel_name(w_rescue, "rescue"); bb_parallel_name(w_sam, "sam"); bb_parallel_name(w_free, "free"); bb_parallel_name(w_pe_pairs, "pe_pairs");
 }
 
 typedef struct { job_t *jobs; int n_jobs; volatile int next; bwag_ctx_t *ctx; int phase, lane, pe; } lane_arg_t;
@@ -834,18 +846,9 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		pe_is = big_alloc(sizeof(uint64_t) * ((size_t)(n >> 1) + 1));
 		for (k = 0, start = 0; k < n_jobs; ++k, start += chunk) jobs[k].pe_is = pe_is + (start >> 1);
 	}
-	{
-		static int named;
-		if (!named) {
-			named = 1;
-			bb_parallel_name(w_encode, "encode"); bb_parallel_name(w_chain, "chain"); bb_parallel_name(w_flatten, "flatten"); bb_parallel_name(w_zero_rs, "zero_rs");
-			bb_parallel_name(w_dedup, "dedup"); bb_parallel_name(w_gcount, "g_count"); bb_parallel_name(w_gfill, "g_fill"); bb_parallel_name(w_gstore, "g_store");
-			bb_parallel_name(w_rescue, "rescue"); bb_parallel_name(w_sam, "sam"); bb_parallel_name(w_free, "free"); bb_parallel_name(w_pe_pairs, "pe_pairs");
-		}
-	}
+	pthread_once(&g_diag_once, diag_init);
 	ph(0);
-	if (g_trace < 0) g_trace = getenv("BWA_B200_TRACE") ? atoi(getenv("BWA_B200_TRACE")) : 0;
-	g_trace_t0 = bb_realtime();
+	if (g_trace > 0) g_trace_t0 = bb_realtime();
 	run_lanes(jobs, n_jobs, n_lanes, ctx, 0, pe);
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));

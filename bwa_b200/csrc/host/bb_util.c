@@ -116,7 +116,7 @@ void bb_parallel_name(void (*fn)(void *, long, int), const char *name)
 void bb_parallel_report(void)
 {
 	int i;
-	if (g_pstat_on <= 0) return;
+	if (__atomic_load_n(&g_pstat_on, __ATOMIC_RELAXED) <= 0) return;
 	for (i = 0; i < 32 && g_pstat[i].fn; ++i) {
 		fprintf(stderr, "[prof] loop %-14s %8.3f CPU-s %10ld items\n", g_pstat[i].name ? g_pstat[i].name : "?", g_pstat[i].cpu, g_pstat[i].calls);
 		g_pstat[i].cpu = 0; g_pstat[i].calls = 0;
@@ -127,8 +127,9 @@ static long job_run(pjob_t *j, int tid)   /* returns the number of chunks execut
 {
 	long c = 0, items = 0;
 	double t0 = 0;
-	if (g_pstat_on < 0) g_pstat_on = getenv("BWA_B200_PROFILE") != 0;
-	if (g_pstat_on) t0 = thread_cpu();
+	int prof = __atomic_load_n(&g_pstat_on, __ATOMIC_RELAXED);
+	if (prof < 0) { prof = getenv("BWA_B200_PROFILE") != 0; __atomic_store_n(&g_pstat_on, prof, __ATOMIC_RELAXED); }
+	if (prof) t0 = thread_cpu();
 	for (;;) {
 		long b = __sync_fetch_and_add(&j->next, j->chunk), e, i;
 		if (b >= j->n) break;
@@ -136,7 +137,7 @@ static long job_run(pjob_t *j, int tid)   /* returns the number of chunks execut
 		for (i = b; i < e; ++i) j->fn(j->data, i, tid);
 		++c; items += e - b;
 	}
-	if (g_pstat_on && items) pstat_add(j->fn, thread_cpu() - t0, items);
+	if (prof && items) pstat_add(j->fn, thread_cpu() - t0, items);
 	return c;
 }
 
@@ -147,7 +148,7 @@ static void *pool_worker(void *a_)
 	for (;;) {
 		pjob_t *j;
 		long c;
-		for (j = g_pool.jobs; j; j = j->link) if (j->next < j->n) break;
+		for (j = g_pool.jobs; j; j = j->link) if (__atomic_load_n(&j->next, __ATOMIC_RELAXED) < j->n) break;
 		if (!j) { pthread_cond_wait(&g_pool.cv_work, &g_pool.mu); continue; }
 		++j->refs;
 		pthread_mutex_unlock(&g_pool.mu);
