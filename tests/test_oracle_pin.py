@@ -90,6 +90,15 @@ def test_local_golden(built):
     assert n == 400
 
 
+def test_local_golden_scalar_specification(built):
+    """the same vectors through the lane-by-lane scalar version of the routine (the specification of the SSE2 one)"""
+    import subprocess
+    import sys
+    code = "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_oracle_pin as t; t.test_local_golden(None)" % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BWA_B200_SCALAR_SW="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+
+
 class Intv(C.Structure):
     _fields_ = [("x0", C.c_uint64), ("x1", C.c_uint64), ("x2", C.c_uint64), ("info", C.c_uint64)]
 
