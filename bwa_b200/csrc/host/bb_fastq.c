@@ -4,7 +4,16 @@
  */
 #include <zlib.h>
 #include <ctype.h>
+#include <pthread.h>
 #include "bb_host.h"
+
+/* Parsing runs ahead of the consumer in one background thread per file (started by the first bseq_read on the
+ * file): the two files of a paired-end run are parsed concurrently, and both overlap whatever the caller does
+ * between two bseq_read calls.  Records travel in blocks through a small bounded queue. */
+#define BLK_RECS 512
+#define MAX_BLOCKS 64            /* at most this many parsed blocks wait per file */
+typedef struct { char *name, *comment, *seq, *qual; int l_seq; } fq_rec_t;
+typedef struct fq_blk { struct fq_blk *next; int n, status; fq_rec_t r[BLK_RECS]; } fq_blk_t;   /* status: 0, or the parser's end code (-1 EOF, -2 truncated) after the n records */
 
 struct bb_fq {
 	gzFile fp;
@@ -12,6 +21,14 @@ struct bb_fq {
 	int beg, end, eof;
 	int pending_hdr;          /* header character already consumed ('>' or '@'), or 0 */
 	bb_str_t name, comment, seq, qual;
+	/* producer/consumer state */
+	pthread_t th;
+	int started, stop, n_queued;
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	fq_blk_t *head, *tail;    /* parsed blocks not yet taken by the consumer */
+	fq_blk_t *cur;            /* block the consumer is reading */
+	int cur_pos, end_status;  /* end_status != 0: the stream has ended with that code */
 };
 
 #define FQ_BUFSZ (1 << 20)
@@ -26,9 +43,26 @@ bb_fq_t *bb_fq_open(const char *fn)
 	return f;
 }
 
+static void blk_free(fq_blk_t *b, int from)
+{
+	int i;
+	for (i = from; i < b->n; ++i) { free(b->r[i].name); free(b->r[i].comment); free(b->r[i].seq); free(b->r[i].qual); }
+	free(b);
+}
+
 void bb_fq_close(bb_fq_t *f)
 {
 	if (!f) return;
+	if (f->started) {
+		pthread_mutex_lock(&f->mu);
+		f->stop = 1;
+		pthread_cond_broadcast(&f->cv);
+		pthread_mutex_unlock(&f->mu);
+		pthread_join(f->th, 0);
+		while (f->head) { fq_blk_t *b = f->head; f->head = b->next; blk_free(b, 0); }
+		if (f->cur) blk_free(f->cur, f->cur_pos);
+		pthread_mutex_destroy(&f->mu); pthread_cond_destroy(&f->cv);
+	}
 	gzclose(f->fp);
 	free(f->buf); free(f->name.s); free(f->comment.s); free(f->seq.s); free(f->qual.s);
 	free(f);
@@ -112,7 +146,7 @@ static char *dup_str(const bb_str_t *s, int dup_empty)
 	return p;
 }
 
-static void take_record(bb_fq_t *f, bseq1_t *s, int id)
+static void take_record(bb_fq_t *f, fq_rec_t *s)
 {
 	if (f->name.l > 2 && f->name.s[f->name.l - 2] == '/' && isdigit((unsigned char)f->name.s[f->name.l - 1])) { f->name.l -= 2; f->name.s[f->name.l] = 0; }
 	s->name = dup_str(&f->name, 1);
@@ -120,8 +154,64 @@ static void take_record(bb_fq_t *f, bseq1_t *s, int id)
 	s->seq = dup_str(&f->seq, 1);
 	s->qual = dup_str(&f->qual, 0);
 	s->l_seq = (int)f->seq.l;
-	s->sam = 0;
-	s->id = id;
+}
+
+static void *producer_main(void *a)
+{
+	bb_fq_t *f = a;
+	for (;;) {
+		fq_blk_t *b = bb_malloc(sizeof(*b));
+		int st = 0;
+		b->next = 0; b->n = 0; b->status = 0;
+		while (b->n < BLK_RECS) {
+			st = fq_next(f);
+			if (st < 0) break;
+			take_record(f, &b->r[b->n++]);
+		}
+		if (st < 0) b->status = st;
+		pthread_mutex_lock(&f->mu);
+		while (f->n_queued >= MAX_BLOCKS && !f->stop) pthread_cond_wait(&f->cv, &f->mu);
+		if (f->stop) { pthread_mutex_unlock(&f->mu); blk_free(b, 0); return 0; }
+		if (f->tail) f->tail->next = b; else f->head = b;
+		f->tail = b; ++f->n_queued;
+		pthread_cond_broadcast(&f->cv);
+		pthread_mutex_unlock(&f->mu);
+		if (st < 0) return 0;
+	}
+}
+
+/* next parsed record of the file: 1 and *r filled (ownership of the strings moves to the caller), or the parser's end code */
+static int next_record(bb_fq_t *f, fq_rec_t *r)
+{
+	if (f->end_status) return f->end_status;
+	if (!f->started) {
+		pthread_mutex_init(&f->mu, 0); pthread_cond_init(&f->cv, 0);
+		f->started = 1;
+		if (pthread_create(&f->th, 0, producer_main, f) != 0) bb_fatal("bseq_read", "pthread_create failed");
+	}
+	for (;;) {
+		fq_blk_t *b = f->cur;
+		if (b && f->cur_pos < b->n) { *r = b->r[f->cur_pos++]; return 1; }
+		if (b) {
+			int st = b->status;
+			free(b); f->cur = 0;
+			if (st) { f->end_status = st; return st; }
+		}
+		pthread_mutex_lock(&f->mu);
+		while (!f->head) pthread_cond_wait(&f->cv, &f->mu);
+		b = f->head; f->head = b->next;
+		if (!f->head) f->tail = 0;
+		--f->n_queued;
+		pthread_cond_broadcast(&f->cv);
+		pthread_mutex_unlock(&f->mu);
+		f->cur = b; f->cur_pos = 0;
+	}
+}
+
+static void put_record(bseq1_t *s, const fq_rec_t *r, int id)
+{
+	s->name = r->name; s->comment = r->comment; s->seq = r->seq; s->qual = r->qual;
+	s->l_seq = r->l_seq; s->sam = 0; s->id = id;
 }
 
 bseq1_t *bseq_read(int chunk_size, int *n_, void *ks1_, void *ks2_)
@@ -129,17 +219,22 @@ bseq1_t *bseq_read(int chunk_size, int *n_, void *ks1_, void *ks2_)
 	bb_fq_t *f1 = ks1_, *f2 = ks2_;
 	int size = 0, m = 0, n = 0;
 	bseq1_t *seqs = 0;
-	while (fq_next(f1) >= 0) {
-		if (f2 && fq_next(f2) < 0) {
+	fq_rec_t r1, r2;
+	while (next_record(f1, &r1) >= 0) {
+		if (f2 && next_record(f2, &r2) < 0) {
 			fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", __func__);
+			free(r1.name); free(r1.comment); free(r1.seq); free(r1.qual);
 			break;
 		}
 		if (n + 2 > m) { m = m ? m << 1 : 256; seqs = bb_realloc(seqs, (size_t)m * sizeof(bseq1_t)); }
-		take_record(f1, &seqs[n], n); size += seqs[n++].l_seq;
-		if (f2) { take_record(f2, &seqs[n], n); size += seqs[n++].l_seq; }
+		put_record(&seqs[n], &r1, n); size += seqs[n++].l_seq;
+		if (f2) { put_record(&seqs[n], &r2, n); size += seqs[n++].l_seq; }
 		if (size >= chunk_size && (n & 1) == 0) break;
 	}
-	if (size == 0 && f2 && fq_next(f2) >= 0) fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", __func__);
+	if (size == 0 && f2 && next_record(f2, &r2) >= 0) {
+		fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", __func__);
+		free(r2.name); free(r2.comment); free(r2.seq); free(r2.qual);
+	}
 	*n_ = n;
 	return seqs;
 }
