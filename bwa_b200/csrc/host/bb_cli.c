@@ -94,10 +94,16 @@ typedef struct {
 static bwaidx_t *g_cli_idx;   /* an index the caller already holds (and has made resident): used instead of loading */
 void bb_cli_set_index(bwaidx_t *idx) { g_cli_idx = idx; }
 
-static void free_reads(batch_t *b)
+static void w_free_reads(void *d, long c, int tid)   /* 1024 reads per item */
 {
-	int i;
-	for (i = 0; i < b->n; ++i) { bseq1_t *s = &b->seqs[i]; free(s->name); free(s->comment); free(s->seq); free(s->qual); free(s->sam); }
+	batch_t *b = d;
+	long i, e = (c + 1) * 1024 < b->n ? (c + 1) * 1024 : b->n;
+	(void)tid;
+	for (i = c * 1024; i < e; ++i) { bseq1_t *s = &b->seqs[i]; free(s->name); free(s->comment); free(s->seq); free(s->qual); free(s->sam); }
+}
+static void free_reads(batch_t *b)   /* five strings per read, allocated by many threads: released by several threads as well */
+{
+	if (b->seqs) bb_parallel_for(b->n >= 8192 ? 4 : 1, w_free_reads, b, ((long)b->n + 1023) / 1024);
 	free(b->seqs); b->seqs = 0;
 }
 
