@@ -155,7 +155,7 @@ def supervise(argv):
     """Single-GPU runs happen in a child process under a watchdog: a GPU job that stops making progress must not take the
     whole benchmark with it.  The child prints the JSON line; if it hangs it is killed and the run is repeated once in the
     most conservative configuration (one call in flight), which is recorded in the line."""
-    limit = int(os.environ.get("BWA_B200_BENCH_TIMEOUT", "600"))
+    limit = int(os.environ.get("BWA_B200_BENCH_TIMEOUT", "900"))
     for attempt in (0, 1):
         env = dict(os.environ)
         extra = []
