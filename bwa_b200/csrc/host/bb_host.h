@@ -106,6 +106,8 @@ typedef struct {
 } bb_samctx_t;
 int bb_reg2aln_band(const mem_opt_t *opt, const mem_alnreg_t *ar);
 mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query, const mem_alnreg_t *ar);
+void bb_codes_to_text(char *dst, const uint8_t *codes, int n, int rev);   /* SEQ column: "ACGTN" / reverse complement */
+void bb_copy_text(char *dst, const char *src, int n, int rev);             /* QUAL column: copy / reverse */
 void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_t *s, int n, const mem_aln_t *list, int which, const mem_aln_t *m_);
 void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, const mem_aln_t *m);
 char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const char *query);

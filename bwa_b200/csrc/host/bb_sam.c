@@ -117,6 +117,55 @@ static void put_cigar(const mem_opt_t *opt, const mem_aln_t *p, bb_str_t *str, i
 	} else bb_putc(str, '*');
 }
 
+/* SEQ and QUAL columns: codes 0..4 -> "ACGTN" (reverse strand: complement, right to left), quality copied or reversed.
+ * 16 bases per step with byte shuffles where the CPU has SSSE3 (checked once at run time), else byte by byte. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <tmmintrin.h>
+__attribute__((target("ssse3"))) static void codes_to_text_ssse3(char *dst, const uint8_t *c, int n, int rev)
+{
+	const __m128i fwd = _mm_setr_epi8('A', 'C', 'G', 'T', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N');
+	const __m128i cmp = _mm_setr_epi8('T', 'G', 'C', 'A', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N');
+	const __m128i flip = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+	int i = 0;
+	if (!rev) {
+		for (; i + 16 <= n; i += 16) _mm_storeu_si128((__m128i *)(dst + i), _mm_shuffle_epi8(fwd, _mm_loadu_si128((const __m128i *)(c + i))));
+		for (; i < n; ++i) dst[i] = "ACGTN"[c[i] > 4 ? 4 : c[i]];
+	} else {
+		for (; i + 16 <= n; i += 16)   /* the 16 codes that end at n-i, emitted in reverse order */
+			_mm_storeu_si128((__m128i *)(dst + i), _mm_shuffle_epi8(cmp, _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(c + n - i - 16)), flip)));
+		for (; i < n; ++i) { uint8_t v = c[n - 1 - i]; dst[i] = "TGCAN"[v > 4 ? 4 : v]; }
+	}
+}
+__attribute__((target("ssse3"))) static void reverse_text_ssse3(char *dst, const char *src, int n)
+{
+	const __m128i flip = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+	int i = 0;
+	for (; i + 16 <= n; i += 16) _mm_storeu_si128((__m128i *)(dst + i), _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(src + n - i - 16)), flip));
+	for (; i < n; ++i) dst[i] = src[n - 1 - i];
+}
+static int have_ssse3(void) { static int v = -1; int x = __atomic_load_n(&v, __ATOMIC_RELAXED); if (x < 0) { x = __builtin_cpu_supports("ssse3") ? 1 : 0; __atomic_store_n(&v, x, __ATOMIC_RELAXED); } return x; }
+#else
+static int have_ssse3(void) { return 0; }
+static void codes_to_text_ssse3(char *dst, const uint8_t *c, int n, int rev) { (void)dst; (void)c; (void)n; (void)rev; }
+static void reverse_text_ssse3(char *dst, const char *src, int n) { (void)dst; (void)src; (void)n; }
+#endif
+
+void bb_codes_to_text(char *dst, const uint8_t *codes, int n, int rev)
+{
+	int i;
+	if (have_ssse3()) { codes_to_text_ssse3(dst, codes, n, rev); return; }
+	if (!rev) for (i = 0; i < n; ++i) dst[i] = "ACGTN"[codes[i] > 4 ? 4 : codes[i]];
+	else for (i = 0; i < n; ++i) { uint8_t v = codes[n - 1 - i]; dst[i] = "TGCAN"[v > 4 ? 4 : v]; }
+}
+
+void bb_copy_text(char *dst, const char *src, int n, int rev)
+{
+	int i;
+	if (!rev) { memcpy(dst, src, (size_t)n); return; }
+	if (have_ssse3()) { reverse_text_ssse3(dst, src, n); return; }
+	for (i = 0; i < n; ++i) dst[i] = src[n - 1 - i];
+}
+
 /* bwamem.c:851-976 */
 void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_t *s, int n, const mem_aln_t *list, int which, const mem_aln_t *m_)
 {
@@ -169,17 +218,11 @@ void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_
 			}
 		}
 		bb_str_need(str, (size_t)(qe - qb) * 2 + 4);
-		if (!p->is_rev) {
-			for (i = qb; i < qe; ++i) str->s[str->l++] = "ACGTN"[(int)s->seq[i]];
-			str->s[str->l++] = '\t';
-			if (s->qual) { for (i = qb; i < qe; ++i) str->s[str->l++] = s->qual[i]; }
-			else str->s[str->l++] = '*';
-		} else {
-			for (i = qe - 1; i >= qb; --i) str->s[str->l++] = "TGCAN"[(int)s->seq[i]];
-			str->s[str->l++] = '\t';
-			if (s->qual) { for (i = qe - 1; i >= qb; --i) str->s[str->l++] = s->qual[i]; }
-			else str->s[str->l++] = '*';
-		}
+		bb_codes_to_text(str->s + str->l, (const uint8_t *)s->seq + qb, qe - qb, p->is_rev);
+		str->l += (size_t)(qe - qb);
+		str->s[str->l++] = '\t';
+		if (s->qual) { bb_copy_text(str->s + str->l, s->qual + qb, qe - qb, p->is_rev); str->l += (size_t)(qe - qb); }
+		else str->s[str->l++] = '*';
 		str->s[str->l] = 0;
 	}
 
