@@ -103,7 +103,15 @@ typedef struct {
 	const uint8_t *pac;
 	bb_gcache_t *gc;   /* of the read being formatted */
 	int dry;           /* pass that only discovers which alignments are needed: skip text */
+	/* optional bump area (the caller's stack) for the CIGAR+MD copies bb_reg2aln hands out: most records need ~40 bytes
+	 * for a few hundred nanoseconds, not a malloc/free pair.  bb_cigar_free() releases only what did not fit. */
+	uint32_t *scratch;
+	int scratch_cap, scratch_used;   /* in 32-bit words */
 } bb_samctx_t;
+static inline void bb_cigar_free(const bb_samctx_t *sc, uint32_t *cigar)
+{
+	if (cigar && !(sc->scratch && cigar >= sc->scratch && cigar < sc->scratch + sc->scratch_cap)) free(cigar);
+}
 int bb_reg2aln_band(const mem_opt_t *opt, const mem_alnreg_t *ar);
 mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query, const mem_alnreg_t *ar);
 void bb_codes_to_text(char *dst, const uint8_t *codes, int n, int rev);   /* SEQ column: "ACGTN" / reverse complement */

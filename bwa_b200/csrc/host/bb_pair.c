@@ -373,7 +373,7 @@ int bb_sam_pe(bb_samctx_t sc[2], const mem_pestat_t pes[4], uint64_t id, bseq1_t
 			if (strcmp(s[0].name, s[1].name) != 0) bb_fatal("mem_sam_pe", "paired reads have different names: \"%s\", \"%s\"\n", s[0].name, s[1].name);
 		}
 		for (i = 0; i < 2; ++i) {
-			free(h[i].cigar); free(g[i].cigar);
+			bb_cigar_free(&sc[i], h[i].cigar); bb_cigar_free(&sc[i], g[i].cigar);
 			if (XA[i] == 0) continue;
 			for (j = 0; j < (int)a[i].n; ++j) free(XA[i][j]);
 			free(XA[i]);
@@ -399,6 +399,6 @@ no_pairing:
 	bb_reg2sam(&sc[0], &s[0], &a[0], 0x41 | extra_flag, &h[1]);
 	bb_reg2sam(&sc[1], &s[1], &a[1], 0x81 | extra_flag, &h[0]);
 	if (!dry && strcmp(s[0].name, s[1].name) != 0) bb_fatal("mem_sam_pe", "paired reads have different names: \"%s\", \"%s\"\n", s[0].name, s[1].name);
-	free(h[0].cigar); free(h[1].cigar);
+	bb_cigar_free(&sc[0], h[0].cigar); bb_cigar_free(&sc[1], h[1].cigar);
 	return 0;
 }

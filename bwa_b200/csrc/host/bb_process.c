@@ -540,7 +540,8 @@ static void run_sam(job_t *j, long i, int dry)
 		rstate_t *r = &j->rs[i];
 		mem_alnreg_v w = {0, 0, 0};
 		mem_alnreg_t st0[STACK_REGS];
-		bb_samctx_t sc = { opt, j->bns, j->pac, &r->gc, dry };
+		uint32_t cg[128];
+		bb_samctx_t sc = { opt, j->bns, j->pac, &r->gc, dry, cg, 128, 0 };
 		copy_regs(&w, &r->regs, st0);
 		bb_mark_primary_se(opt, (int)w.n, w.a, j->n_processed + i);
 		if (opt->flag & MEM_F_PRIMARY5) bb_reorder_primary5(opt->T, &w);
@@ -549,7 +550,8 @@ static void run_sam(job_t *j, long i, int dry)
 	} else {
 		mem_alnreg_v w[2] = {{0, 0, 0}, {0, 0, 0}};
 		mem_alnreg_t st0[STACK_REGS], st1[STACK_REGS];
-		bb_samctx_t sc[2] = { { opt, j->bns, j->pac, &j->rs[i << 1].gc, dry }, { opt, j->bns, j->pac, &j->rs[i << 1 | 1].gc, dry } };
+		uint32_t cg[2][128];
+		bb_samctx_t sc[2] = { { opt, j->bns, j->pac, &j->rs[i << 1].gc, dry, cg[0], 128, 0 }, { opt, j->bns, j->pac, &j->rs[i << 1 | 1].gc, dry, cg[1], 128, 0 } };
 		copy_regs(&w[0], &j->rs[i << 1].regs, st0); copy_regs(&w[1], &j->rs[i << 1 | 1].regs, st1);
 		bb_sam_pe(sc, j->pes, (uint64_t)((j->n_processed >> 1) + i), &j->seqs[i << 1], w, 1);
 		drop_regs(&w[0], st0); drop_regs(&w[1], st1);

@@ -66,7 +66,11 @@ mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query_, const mem
 	if (g) {
 		l_MD = g->l_md;
 		a.n_cigar = g->n_cigar;
-		a.cigar = bb_malloc(4 * (size_t)(g->n_cigar + 2) + l_MD);
+		{
+			const int words = g->n_cigar + 2 + ((l_MD + 3) >> 2);
+			if (sc->scratch && sc->scratch_used + words <= sc->scratch_cap) { a.cigar = sc->scratch + sc->scratch_used; sc->scratch_used += words; }
+			else a.cigar = bb_malloc(4 * (size_t)words);
+		}
 		memcpy(a.cigar, g->cigar, 4 * (size_t)g->n_cigar + l_MD);
 		a.NM = g->NM;
 		if (a.n_cigar > 0) { /* drop a leading or trailing deletion */
@@ -304,7 +308,7 @@ char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const cha
 		if ((r = xa_parent(opt->XA_drop_ratio, a->a, i)) < 0) continue;
 		if (cnt[r] > opt->max_XA_hits_alt || (!has_alt[r] && cnt[r] > opt->max_XA_hits)) continue;
 		t = bb_reg2aln(sc, l_query, query, &a->a[i]);
-		if (sc->dry) { free(t.cigar); continue; }
+		if (sc->dry) { bb_cigar_free(sc, t.cigar); continue; }
 		one.l = 0;
 		bb_puts(&one, bns->anns[t.rid].name);
 		bb_putc(&one, ','); bb_putc(&one, "+-"[t.is_rev]); bb_putl(&one, t.pos + 1);
@@ -313,7 +317,7 @@ char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const cha
 		bb_putc(&one, ','); bb_putl(&one, t.NM);
 		if (opt->flag & MEM_F_XB) { bb_putc(&one, ','); bb_putl(&one, t.score); bb_putc(&one, ','); bb_putl(&one, t.mapq); }
 		bb_putc(&one, ';');
-		free(t.cigar);
+		bb_cigar_free(sc, t.cigar);
 		bb_putsn(&aln[r], one.s, one.l);
 	}
 	XA = bb_calloc(a->n, sizeof(char *));
@@ -356,7 +360,7 @@ void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, co
 		} else for (k = 0; k < aa.n; ++k) bb_aln2sam(opt, sc->bns, &str, s, (int)aa.n, aa.a, (int)k, m);
 		s->sam = str.s;
 	}
-	for (k = 0; k < aa.n; ++k) free(aa.a[k].cigar);
+	for (k = 0; k < aa.n; ++k) bb_cigar_free(sc, aa.a[k].cigar);
 	free(aa.a);
 	if (XA) { for (k = 0; k < a->n; ++k) free(XA[k]); free(XA); }
 }
