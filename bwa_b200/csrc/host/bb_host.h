@@ -114,6 +114,7 @@ static inline void bb_cigar_free(const bb_samctx_t *sc, uint32_t *cigar)
 }
 int bb_reg2aln_band(const mem_opt_t *opt, const mem_alnreg_t *ar);
 mem_aln_t bb_reg2aln(bb_samctx_t *sc, int l_query, const char *query, const mem_alnreg_t *ar);
+void bb_encode_bases(char *seq, uint8_t *dst, int n);   /* ASCII (or codes) -> codes 0..5 in place, 0..4 into dst */
 void bb_codes_to_text(char *dst, const uint8_t *codes, int n, int rev);   /* SEQ column: "ACGTN" / reverse complement */
 void bb_copy_text(char *dst, const char *src, int n, int rev);             /* QUAL column: copy / reverse */
 void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_t *s, int n, const mem_aln_t *list, int which, const mem_aln_t *m_);

@@ -21,6 +21,9 @@
 #include <math.h>
 #include <malloc.h>
 #include "bb_host.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 /* ---------------------------------------------------------------- large host buffers
  * A batch needs a few buffers of tens to hundreds of MB (codes, per-read state, extension work).  glibc
@@ -269,19 +272,43 @@ typedef struct {
 	bwag_sw_par_t swp;
 } job_t;
 
+/* Bases to codes, in place (the caller's buffer, bwamem.c:1087: seq[i] < 4 ? seq[i] : nst_nt4_table[seq[i]]) and into the
+ * device staging buffer (codes above 4 -- the table's '-' -> 5 -- become 4 there: every kernel treats > 3 as N).
+ * 16 bases per step with SSE2 compares where available; the scalar loop is the specification (tests/test_cabi.py). */
+void bb_encode_bases(char *seq, uint8_t *dst, int n)
+{
+	int k = 0;
+#if defined(__SSE2__)
+	const __m128i c3 = _mm_set1_epi8(3), c4 = _mm_set1_epi8(4), c5 = _mm_set1_epi8(5), fold = _mm_set1_epi8((char)0xDF), zero = _mm_setzero_si128();
+	const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T'), cD = _mm_set1_epi8('-');
+	const __m128i one = _mm_set1_epi8(1), two = _mm_set1_epi8(2);
+	for (; k + 16 <= n; k += 16) {
+		const __m128i v = _mm_loadu_si128((const __m128i *)(seq + k));
+		const __m128i small = _mm_cmpeq_epi8(_mm_subs_epu8(v, c3), zero);      /* already a code 0..3 */
+		const __m128i u = _mm_and_si128(v, fold);
+		const __m128i isA = _mm_cmpeq_epi8(u, cA), isC = _mm_cmpeq_epi8(u, cC), isG = _mm_cmpeq_epi8(u, cG), isT = _mm_cmpeq_epi8(u, cT);
+		const __m128i acgt = _mm_or_si128(_mm_or_si128(isA, isC), _mm_or_si128(isG, isT));
+		const __m128i code = _mm_or_si128(_mm_and_si128(isC, one), _mm_or_si128(_mm_and_si128(isG, two), _mm_and_si128(isT, c3)));
+		const __m128i other = _mm_or_si128(_mm_and_si128(_mm_cmpeq_epi8(v, cD), c5), _mm_andnot_si128(_mm_cmpeq_epi8(v, cD), c4));
+		__m128i r = _mm_or_si128(_mm_and_si128(acgt, code), _mm_andnot_si128(acgt, other));
+		r = _mm_or_si128(_mm_and_si128(small, v), _mm_andnot_si128(small, r));
+		_mm_storeu_si128((__m128i *)(seq + k), r);
+		_mm_storeu_si128((__m128i *)(dst + k), _mm_min_epu8(r, c4));
+	}
+#endif
+	for (; k < n; ++k) {
+		unsigned char c = (unsigned char)seq[k];
+		c = c < 4 ? c : bb_nt4_table[c];
+		seq[k] = (char)c;
+		dst[k] = c > 4 ? 4 : c;
+	}
+}
+
 static void w_encode(void *d, long i, int tid)
 {
 	job_t *j = d;
-	bseq1_t *s = &j->seqs[i];
-	uint8_t *dst = j->codes + j->off[i];
-	int k;
 	(void)tid;
-	for (k = 0; k < s->l_seq; ++k) {
-		unsigned char c = (unsigned char)s->seq[k];
-		c = c < 4 ? c : bb_nt4_table[c];
-		s->seq[k] = (char)c;
-		dst[k] = c > 4 ? 4 : c; /* the reference table maps '-' to 5; every kernel treats >3 as N */
-	}
+	bb_encode_bases(j->seqs[i].seq, j->codes + j->off[i], j->seqs[i].l_seq);
 }
 
 static void w_chain(void *d, long i, int tid)

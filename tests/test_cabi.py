@@ -54,3 +54,22 @@ def test_fails_loudly_without_gpu(built, data):
     assert r.returncode != 0
     assert b"no CUDA device" in r.stderr or b"cuda" in r.stderr.lower()
     assert not r.stdout.strip(), "nothing may be written before the GPU check"
+
+
+def test_base_encoding_vector_path_equals_table():
+    """bb_encode_bases (SSE2, 16 bases per step) against the table it restates (bwamem.c:1087, nst_nt4_table), incl.
+    already-encoded input, lower case, '-', arbitrary bytes, and lengths around the vector width."""
+    import ctypes as C
+    import random
+    import bwa_b200
+    L = bwa_b200.lib()
+    tab = (C.c_ubyte * 256).in_dll(L, "bb_nt4_table")
+    rng = random.Random(1)
+    for n in [0, 1, 15, 16, 17, 31, 32, 33, 150, 251] * 20:
+        src = bytes(rng.choice([rng.randrange(256), rng.choice(b"ACGTNacgtn-")]) for _ in range(n))
+        buf = C.create_string_buffer(src, n + 1)
+        dst = (C.c_ubyte * (n + 1))()
+        L.bb_encode_bases(buf, dst, n)
+        want = [c if c < 4 else tab[c] for c in src]
+        assert list(buf.raw[:n]) == want
+        assert list(dst[:n]) == [min(c, 4) for c in want]
