@@ -12,6 +12,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <pthread.h>
+#include <sched.h>
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
 
@@ -378,9 +379,17 @@ static int reset_counters(bwag_ctx_t *c)
  * waiting lane); optionally without spinning */
 static cudaError_t stream_wait(bwag_ctx_t *c)
 {
-	static int mode = -1;   /* BWA_B200_SYNC=block: sleep on a blocking event (saves the cores of waiting lanes, adds wake-up latency to every stage) */
-	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = e && strcmp(e, "block") == 0; }
-	if (!mode) return cudaStreamSynchronize(c->stream);
+	static int mode = -1;   /* BWA_B200_SYNC=block: sleep on a blocking event (saves the cores of waiting lanes, adds wake-up latency to every
+	                         * stage); =yield: poll the stream and give the core away between polls (for boxes with fewer CPUs than threads) */
+	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = !e ? 0 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "yield") == 0 ? 2 : 0; }
+	if (mode == 0) return cudaStreamSynchronize(c->stream);
+	if (mode == 2) {
+		for (;;) {
+			cudaError_t q = cudaStreamQuery(c->stream);
+			if (q != cudaErrorNotReady) return q;
+			sched_yield();
+		}
+	}
 	cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
 	if (e != cudaSuccess) return e;
 	return cudaEventSynchronize(c->ev_wait);

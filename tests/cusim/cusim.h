@@ -150,7 +150,7 @@ static inline int atomicCAS(int *p, int c, int v) { return __sync_val_compare_an
 typedef int cudaError_t;
 typedef struct cusim_stream *cudaStream_t;
 typedef struct cusim_event *cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100, cudaErrorNotReady = 600 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaHostAllocDefault = 0, cudaEventDefault = 0, cudaStreamNonBlocking = 1 };
 struct cudaDeviceProp { int multiProcessorCount; size_t totalGlobalMem; char name[256]; int major, minor; size_t sharedMemPerBlockOptin; };
@@ -174,6 +174,7 @@ enum { cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned f) { (void)f; *e = 0; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0) { (void)e; (void)s; return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t s) { (void)s; return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { (void)e; return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { (void)a; (void)b; *ms = 0.f; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
