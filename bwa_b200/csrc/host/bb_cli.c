@@ -226,7 +226,7 @@ static void usage(const mem_opt_t *opt)
 int main_mem(int argc, char *argv[])
 {
 	mem_opt_t *opt, set;
-	int c, i, ignore_alt = 0, no_mt_io = 0, fixed_chunk = -1;
+	int c, i, ignore_alt = 0, no_mt_io = 0, fixed_chunk = -1, t_given = 0;
 	char *p, *rg_line = 0, *hdr_line = 0;
 	const char *mode = 0;
 	mem_pestat_t pes[4];
@@ -248,7 +248,7 @@ int main_mem(int argc, char *argv[])
 		case 'B': opt->b = atoi(optarg); set.b = 1; break;
 		case 'T': opt->T = atoi(optarg); set.T = 1; break;
 		case 'U': opt->pen_unpaired = atoi(optarg); set.pen_unpaired = 1; break;
-		case 't': opt->n_threads = atoi(optarg); if (opt->n_threads < 1) opt->n_threads = 1; break;
+		case 't': opt->n_threads = atoi(optarg); if (opt->n_threads < 1) opt->n_threads = 1; t_given = 1; break;
 		case 'P': opt->flag |= MEM_F_NOPAIRING; break;
 		case 'a': opt->flag |= MEM_F_ALL; break;
 		case 'p': opt->flag |= MEM_F_PE | MEM_F_SMARTPE; break;
@@ -372,6 +372,9 @@ int main_mem(int argc, char *argv[])
 	if (run.rank == 0) bwa_print_sam_hdr(run.idx->bns, hdr_line);
 	if (run.shard_idx) { fflush(stdout); fprintf(run.shard_idx, "-1 %ld\n", ftell(stdout)); }
 	run.chunk = fixed_chunk > 0 ? fixed_chunk : opt->chunk_size * opt->n_threads;
+	/* Without -t the reference runs one thread and forms batches of chunk_size bases; the batches stay exactly those (so
+	 * the output is `bwa mem`'s), but the host phases between the GPU stages use the CPUs the process is allowed. */
+	if (!t_given) opt->n_threads = bb_effective_cpus();
 
 	mbox_init(&run.to_align); ro_init(&run.done);
 	if (no_mt_io) {

@@ -1,6 +1,9 @@
+#define _GNU_SOURCE
 /* bb_util.c -- fatal errors, checked allocation, timers, thread helpers, plain-key sorts. */
 #include <stdarg.h>
 #include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
 #include <time.h>
 #include <sys/time.h>
 #include <sys/resource.h>
@@ -89,6 +92,30 @@ static struct {
 	int n_workers;
 	pthread_t th[BB_MAX_WORKERS];
 } g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, {0} };
+
+/* CPUs this process may really use: the affinity mask, capped by a cgroup CPU quota (containers) */
+int bb_effective_cpus(void)
+{
+	int n = 0;
+	FILE *f;
+	cpu_set_t set;
+	if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+	if (n < 1) n = (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (n < 1) n = 1;
+	if ((f = fopen("/sys/fs/cgroup/cpu.max", "r")) != 0) {          /* cgroup v2: "<quota|max> <period>" */
+		char q[32]; long period = 0;
+		if (fscanf(f, "%31s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) { long c = (atol(q) + period - 1) / period; if (c >= 1 && c < n) n = (int)c; }
+		fclose(f);
+	} else if ((f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) != 0) {   /* cgroup v1 */
+		long quota = -1, period = 0;
+		FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+		if (fscanf(f, "%ld", &quota) != 1) quota = -1;
+		if (g) { if (fscanf(g, "%ld", &period) != 1) period = 0; fclose(g); }
+		if (quota > 0 && period > 0) { long c = (quota + period - 1) / period; if (c >= 1 && c < n) n = (int)c; }
+		fclose(f);
+	}
+	return n;
+}
 
 int bb_parallel_ids(void) { return BB_MAX_WORKERS + BB_MAX_LANES; }
 

@@ -43,6 +43,7 @@ static inline uint64_t bb_mix64(uint64_t k)
 /* parallel-for over [0,n) on nt threads; fn(data, i, tid).  Same contract as kt_for (kthread.c:49-61). */
 void bb_parallel_for(int nt, void (*fn)(void *, long, int), void *data, long n);
 void bb_parallel_for_lane(int lane, int nt, void (*fn)(void *, long, int), void *data, long n);
+int bb_effective_cpus(void);   /* affinity mask capped by a cgroup CPU quota */
 int bb_parallel_ids(void);
 void bb_parallel_name(void (*fn)(void *, long, int), const char *name);   /* label a loop body for BWA_B200_PROFILE */
 void bb_parallel_report(void);   /* upper bound (exclusive) of the thread ids passed to loop bodies */

@@ -47,3 +47,9 @@ def test_batches_in_flight_keep_order_and_content(data, monkeypatch):
     for inflight in ("1", "3"):
         monkeypatch.setenv("BWA_B200_INFLIGHT", inflight)
         assert run_sam(CUSIMBIN, args) == want
+
+
+def test_default_thread_count_keeps_reference_batches(data):
+    """No -t: the batches are the reference's (chunk_size x 1 thread), only the host worker count differs; same SAM."""
+    fa, fqs = data.reads("stress", tag="cspe", n=60, seed=34, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    assert run_sam(CUSIMBIN, [fa] + fqs) == ref_sam([fa] + fqs)
