@@ -189,6 +189,7 @@ static int pick_grid(bwag_ctx_t *c)
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaFuncSetAttribute(k_extend_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
+	CK(cudaFuncSetAttribute(k_extend_sm_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaFuncSetAttribute(k_global_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
 #endif
@@ -520,8 +521,10 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	int per_warp = (8 * (a.cap_q + 2) + a.cap_r + a.cap_q + 15) & ~15;
 	size_t smem = (size_t)per_warp * wpb;
 	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K4_SM") && atoi(getenv("BWA_B200_K4_SM")) == 0);
+	/* the leaner row sweep needs non-negative insertion penalties (every real scoring scheme); BWA_B200_K4_FAST=0 forces the general one */
+	const int fast = a.par.e_ins >= 0 && a.par.o_ins + a.par.e_ins >= 0 && !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
 #ifndef BWAG_CUSIM
-	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
+	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast ? k_extend_sm_fast : k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
 #endif
 	i64 need = ((i64)n_units + wpb - 1) / wpb;
 	if (grid > need) grid = (int)(need > 0 ? need : 1);
@@ -529,10 +532,12 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 		const size_t n_warps = (size_t)grid * wpb;
 		if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(a.cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)a.cap_r)) return 1;
 		a.eh = (int *)c->s_eh.p; a.rseq = (uint8_t *)c->s_rseq.p; a.smem_per_warp = 0;
-		BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
+		if (fast) BWAG_LAUNCH(k_extend_fast, grid, K4_THREADS, 0, c->stream, c->ix, a);
+		else BWAG_LAUNCH(k_extend, grid, K4_THREADS, 0, c->stream, c->ix, a);
 	} else {
 		a.eh = 0; a.rseq = 0; a.smem_per_warp = per_warp;
-		BWAG_LAUNCH(k_extend_sm, grid, K4_THREADS, smem, c->stream, c->ix, a);
+		if (fast) BWAG_LAUNCH(k_extend_sm_fast, grid, K4_THREADS, smem, c->stream, c->ix, a);
+		else BWAG_LAUNCH(k_extend_sm, grid, K4_THREADS, smem, c->stream, c->ix, a);
 	}
 	CK(cudaGetLastError());
 	return 0;

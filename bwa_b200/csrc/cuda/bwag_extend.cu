@@ -22,9 +22,13 @@
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
 
+#ifndef K4_MINB
+#define K4_MINB 6   /* resident blocks per SM the lean kernels are compiled for (80 registers, as the first formulation) */
+#endif
 #define XSEED_DEAD 0x40000000u    /* set on a seed of the device copy when its extension was skipped (srt[k]=0, bwamem.c:727) */
 #define XSEED_LEN(x) ((int)((x) & 0x3fffffffu))
 
+__device__ __forceinline__ int imax2(int a, int b) { return a > b ? a : b; }
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(FULL_MASK, v); }
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(FULL_MASK, v); }
 
@@ -154,9 +158,158 @@ __device__ __forceinline__ int warp_ksw_extend(int lane, int qlen, const uint8_t
 	return max;
 }
 
+/* Scratch accessors of the lean row sweep.  Addresses are byte addresses.  PtrAcc: ordinary pointers (global scratch, and
+ * every variant under the CPU emulator).  SmemAcc: 32-bit shared-window addresses with explicit ld/st.shared -- the
+ * compiler otherwise re-derives the window base of every scratch array (S2UR CgaCtaId + 4 uniform ops) inside the row
+ * loop.  All accesses are volatile asm, so they keep their program order among themselves and around __syncwarp(). */
+struct PtrAcc {
+	typedef unsigned char *addr;
+	static __device__ __forceinline__ addr make(const void *p) { return (addr)const_cast<void *>(p); }
+	static __device__ __forceinline__ int2 ld_he(addr a) { return *reinterpret_cast<const int2 *>(a); }
+	static __device__ __forceinline__ void st_he(addr a, int h, int e) { *reinterpret_cast<int2 *>(a) = make_int2(h, e); }
+	static __device__ __forceinline__ int ld_u8(addr a) { return *a; }
+	static __device__ __forceinline__ int ld_s8(addr a) { return *reinterpret_cast<const int8_t *>(a); }
+	static __device__ __forceinline__ void st_u8(addr a, int v) { *a = (unsigned char)v; }
+};
+#ifdef BWAG_CUSIM
+typedef PtrAcc SmemAcc;
+#define BWAG_KEEP(x) do { } while (0)
+#else
+struct SmemAcc {
+	typedef u32 addr;
+	static __device__ __forceinline__ addr make(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+	static __device__ __forceinline__ int2 ld_he(addr a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+	static __device__ __forceinline__ void st_he(addr a, int h, int e) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(h), "r"(e)); }
+	static __device__ __forceinline__ int ld_u8(addr a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+	static __device__ __forceinline__ int ld_s8(addr a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+	static __device__ __forceinline__ void st_u8(addr a, int v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+};
+#define BWAG_KEEP(x) asm volatile("" : "+r"(x))   /* the value stays in its register: no re-derivation inside the loops */
+#endif
+
+/* The same extension for sane gap penalties (e_ins >= 0, o_ins + e_ins >= 0 -- every real scoring scheme), about half
+ * the instructions per 32-column chunk:
+ *   - H and E of a column sit side by side (one 64-bit load and store per cell);
+ *   - no divergent code in the chunk: idle lanes of the last chunk load a clamped column and are masked by selects;
+ *   - the F scan runs in slanted coordinates (value + column*e_ins), which makes it a plain max scan: one SHFL + one
+ *     max per step, no decay constants, and no lane guards (a lane below the shuffle distance gets its own value back);
+ *   - the F value entering the chunk is folded into lane 0's offer before the scan (max(t0, carry - e_ins)), so the
+ *     scan result IS F of the next column and F of the next chunk's first column is its lane-31 value;
+ *   - first / last non-zero stored cell are tracked per lane and reduced once per row.
+ * q[j] = byte at qa + j*QS, t[i] = byte at ta + i*TS, H/E pair of column j at he + 8*j, mat[k] at ma + k.
+ * Results are identical to warp_ksw_extend (and ksw_extend2) under the stated condition. */
+template <class A, class AM, int QS, int TS>
+__device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename A::addr qa, int tlen, typename A::addr ta,
+                               typename AM::addr ma, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                               typename A::addr he, int *qle, int *tle, int *gtle, int *gscore_, int *max_off_, u64 *cells)
+{
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	int max, max_i, max_j, max_ie, gscore, max_off, beg, end;
+	{   /* first row (ksw.c:431-433) */
+		int H1 = h0 > oe_ins ? h0 - oe_ins : 0, maxsc = 0;
+		for (int j = lane; j <= qlen; j += 32) {
+			int v = j == 0 ? h0 : H1 - (j - 1) * e_ins;
+			A::st_he(he + 8 * j, v > 0 ? v : 0, 0);
+		}
+		for (int k = 0; k < 25; ++k) { int v = AM::ld_s8(ma + k); maxsc = maxsc > v ? maxsc : v; }
+		int max_ins = (int)((double)(qlen * maxsc + end_bonus - o_ins) / e_ins + 1.); max_ins = max_ins > 1 ? max_ins : 1;
+		w = w < max_ins ? w : max_ins;
+		int max_del = (int)((double)(qlen * maxsc + end_bonus - o_del) / e_del + 1.); max_del = max_del > 1 ? max_del : 1;
+		w = w < max_del ? w : max_del;
+	}
+	__syncwarp();
+	max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+	beg = 0; end = qlen;
+	const int ne1 = -e_ins, noe_ins = -oe_ins, noe_del = -oe_del, ne_del = -e_del;
+	const bool lane0 = lane == 0;
+	const int le = lane * e_ins;
+	for (int i = 0; i < tlen; ++i) {
+		const typename AM::addr srow = ma + A::ld_u8(ta + i * TS) * 5;
+		int m = 0, mj = -1, jmin = 0x7fffffff, jmax = -1;   /* per lane; reduced after the row */
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		int carry_h = 0;             /* H(i, j-1) entering the chunk; first column: ksw.c:456-459 */
+		if (beg == 0) { carry_h = h0 - (o_del + e_del * (i + 1)); if (carry_h < 0) carry_h = 0; }
+		int carry_f = 0;             /* F(i, j0) entering the chunk */
+		if (end > beg) *cells += (u64)(end - beg);
+		for (int j0 = beg; j0 < end; j0 += 32) {
+			const int j = j0 + lane;
+			const bool act = j < end;
+			const int jc = act ? j : end - 1;                  /* idle lanes re-read the last column; their results are masked */
+			const int2 c = A::ld_he(he + 8 * jc);
+			const int sc = AM::ld_s8(srow + A::ld_u8(qa + jc * QS));
+			const int M = (act && c.x != 0) ? c.x + sc : 0;
+			int t = __viaddmax_s32(M, noe_ins, 0);             /* what this column offers to F on its right; 0 for idle lanes */
+			if (lane0) t = __viaddmax_s32(carry_f, ne1, t);
+			/* inclusive max-plus scan in slanted coordinates: s[l] = max_{k<=l} (t[k] + k*e_ins) = F(i, j0+l+1) + l*e_ins, so
+			 * the steps need no decay constants (and no lane guards: a lane below the distance gets its own value back) */
+			int s = t + le;
+			s = imax2(s, __shfl_up_sync(FULL_MASK, s, 1));
+			s = imax2(s, __shfl_up_sync(FULL_MASK, s, 2));
+			s = imax2(s, __shfl_up_sync(FULL_MASK, s, 4));
+			s = imax2(s, __shfl_up_sync(FULL_MASK, s, 8));
+			s = imax2(s, __shfl_up_sync(FULL_MASK, s, 16));
+			int f = __shfl_up_sync(FULL_MASK, s, 1) - le + e_ins;
+			if (lane0) f = carry_f;
+			carry_f = __shfl_sync(FULL_MASK, s, 31) - 31 * e_ins;
+			int h = __vimax3_s32(M, c.y, f);
+			if (!act) h = 0;
+			int hp = __shfl_up_sync(FULL_MASK, h, 1);
+			if (lane0) hp = carry_h;
+			{
+				int la = end - 1 - j0; la = la < 31 ? la : 31;
+				carry_h = __shfl_sync(FULL_MASK, h, la);           /* H of the chunk's last active column */
+			}
+			const int e = __vimax3_s32(c.y + ne_del, M + noe_del, 0);
+			if (act) A::st_he(he + 8 * j, hp, e);
+			if (act && h >= m) mj = j;                         /* a lane's columns ascend, so ties keep the larger j (ksw.c:473-474) */
+			m = m > h ? m : h;
+			if (act && (hp | e) != 0) { jmax = j; jmin = jmin < j ? jmin : j; }
+		}
+		const int h1 = carry_h;                        /* H(i, end-1), or the first-column value if the row was empty */
+		if (lane0) A::st_he(he + 8 * end, h1, 0);
+		{
+			int ma_ = warp_max(m);
+			mj = warp_max(m == ma_ ? mj : -1);
+			m = ma_;
+		}
+		if ((end > beg ? end : beg) == qlen) {         /* ksw.c:486-489: ties go to the later row */
+			max_ie = gscore > h1 ? max_ie : i;
+			gscore = gscore > h1 ? gscore : h1;
+		}
+		if (m == 0) break;
+		if (m > max) {
+			int d = mj - i;
+			max = m; max_i = i; max_j = mj;
+			d = d < 0 ? -d : d;
+			max_off = max_off > d ? max_off : d;
+		} else if (zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break; }
+		}
+		{   /* next band: first non-zero cell .. last non-zero cell + 2 (ksw.c:501-505; index `end` included) */
+			const int nz_min = warp_min(jmin), nz_max = warp_max(jmax);
+			int nb = nz_min == 0x7fffffff ? end : nz_min;
+			int jl = nz_max;
+			if (h1 != 0) jl = end;
+			if (jl < 0) jl = nb - 1;
+			beg = nb;
+			end = jl + 2 < qlen ? jl + 2 : qlen;
+		}
+		__syncwarp();
+	}
+	__syncwarp();
+	*qle = max_j + 1; *tle = max_i + 1; *gtle = max_ie + 1; *gscore_ = gscore; *max_off_ = max_off;
+	return max;
+}
+
 /* SM: the per-warp scratch (H/E rows, reference window, a copy of the read) lives in shared memory -- 32-bit
  * addressing and no L1 round trips in the row loop; chosen by the host whenever it fits (short reads) */
-template <bool SM>
+template <bool C, class X, class Y> struct SelT { typedef X type; };
+template <class X, class Y> struct SelT<false, X, Y> { typedef Y type; };
+
+template <bool SM, bool SANE>
 __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a)
 {
 	const int lane = threadIdx.x & 31;
@@ -178,10 +331,15 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 		H = a.eh + wid * (i64)(2 * (a.cap_q + 2)); E = H + a.cap_q + 2;
 		rseq = a.rseq + wid * (i64)a.cap_r;
 	}
+	typedef typename SelT<SM, SmemAcc, PtrAcc>::type A;   /* how the lean sweep reaches the scratch; the matrix is always shared */
+	typename A::addr he_a = A::make(H), rs_a = A::make(rseq), q_a = A::make(qcopy);
+	if constexpr (SM && SANE) { BWAG_KEEP(he_a); BWAG_KEEP(rs_a); BWAG_KEEP(q_a); }
 	const bwag_sw_par_t &p = a.par;
 	__shared__ int8_t s_mat[32];
 	if (threadIdx.x < 25) s_mat[threadIdx.x] = p.mat[threadIdx.x];
 	__syncthreads();
+	typename SmemAcc::addr mat_a = SmemAcc::make(s_mat);
+	if constexpr (SANE) BWAG_KEEP(mat_a);
 	u64 cells = 0;
 	int overflow = 0;
 
@@ -199,10 +357,11 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 			if (l_query > a.cap_q) { overflow = 1; if (lane == 0) a.n_regs[rid] = 0; continue; }
 			if (SM) {
 				__syncwarp();
-				for (int x = lane; x < l_query; x += 32) qcopy[x] = query[x];
+				if (SANE) { for (int x = lane; x < l_query; x += 32) A::st_u8(q_a + x, query[x]); }
+				else { for (int x = lane; x < l_query; x += 32) qcopy[x] = query[x]; }
 				__syncwarp();
 				query = qcopy;
-			}
+			} else if (SANE) q_a = A::make(query);
 			for (i64 c = c0; c < c1; ++c) {
 				const bwag_xchain_t ch = a.chains[c];
 				bwag_xseed_t *seeds = const_cast<bwag_xseed_t *>(a.seeds) + ch.seed_off;
@@ -210,7 +369,8 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 				const int rlen = (int)(rmax1 - rmax0);
 				if (rlen > a.cap_r) { overflow = 1; continue; }
 				__syncwarp();
-				for (int x = lane; x < rlen; x += 32) rseq[x] = (uint8_t)bwag_ref_base(ix, rmax0 + x); /* bns_fetch_seq (bwamem.c:685) */
+				if (SANE) { for (int x = lane; x < rlen; x += 32) A::st_u8(rs_a + x, bwag_ref_base(ix, rmax0 + x)); }   /* bns_fetch_seq (bwamem.c:685) */
+				else { for (int x = lane; x < rlen; x += 32) rseq[x] = (uint8_t)bwag_ref_base(ix, rmax0 + x); }
 				__syncwarp();
 				for (int k = ch.n_seeds - 1; k >= 0; --k) {
 					const i64 s_rbeg = seeds[k].rbeg;
@@ -261,7 +421,9 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 						for (int it = 0; it < 2; ++it) {
 							int prev = reg.score;
 							aw0 = p.w << it;
-							reg.score = warp_ksw_extend(lane, s_qbeg, query + s_qbeg - 1, -1, tl, rseq + tl - 1, -1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, -1, -1>(lane, s_qbeg, q_a + (s_qbeg - 1), tl, rs_a + (tl - 1), mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							                            aw0, p.pen_clip5, p.zdrop, s_len * p.a, he_a, &qle, &tle, &gtle, &gscore, &moff, &cells);
+							else reg.score = warp_ksw_extend(lane, s_qbeg, query + s_qbeg - 1, -1, tl, rseq + tl - 1, -1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw0, p.pen_clip5, p.zdrop, s_len * p.a, H, E, &qle, &tle, &gtle, &gscore, &moff, &cells);
 							if (reg.score == prev || moff < (aw0 >> 1) + (aw0 >> 2)) break;
 						}
@@ -275,7 +437,9 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 						for (int it = 0; it < 2; ++it) {
 							int prev = reg.score;
 							aw1 = p.w << it;
-							reg.score = warp_ksw_extend(lane, l_query - qe, query + qe, 1, (int)(rmax1 - rmax0 - re), rseq + re, 1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, 1, 1>(lane, l_query - qe, q_a + qe, (int)(rmax1 - rmax0 - re), rs_a + (int)re, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							                            aw1, p.pen_clip3, p.zdrop, sc0, he_a, &qle, &tle, &gtle, &gscore, &moff, &cells);
+							else reg.score = warp_ksw_extend(lane, l_query - qe, query + qe, 1, (int)(rmax1 - rmax0 - re), rseq + re, 1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw1, p.pen_clip3, p.zdrop, sc0, H, E, &qle, &tle, &gtle, &gscore, &moff, &cells);
 							if (reg.score == prev || moff < (aw1 >> 1) + (aw1 >> 2)) break;
 						}
@@ -304,5 +468,8 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 	if (overflow && lane == 0) atomicOr(a.flags, 2u);
 }
 
-__global__ void __launch_bounds__(K4_THREADS) k_extend(DevIndex ix, ExtArgs a) { extend_body<false>(ix, a); }
-__global__ void __launch_bounds__(K4_THREADS) k_extend_sm(DevIndex ix, ExtArgs a) { extend_body<true>(ix, a); }
+/* k_extend*: any penalties (the first formulation); k_extend*_fast: e_ins >= 0 and o_ins + e_ins >= 0, chosen by the host */
+__global__ void __launch_bounds__(K4_THREADS) k_extend(DevIndex ix, ExtArgs a) { extend_body<false, false>(ix, a); }
+__global__ void __launch_bounds__(K4_THREADS) k_extend_sm(DevIndex ix, ExtArgs a) { extend_body<true, false>(ix, a); }
+__global__ void __launch_bounds__(K4_THREADS, K4_MINB) k_extend_fast(DevIndex ix, ExtArgs a) { extend_body<false, true>(ix, a); }
+__global__ void __launch_bounds__(K4_THREADS, K4_MINB) k_extend_sm_fast(DevIndex ix, ExtArgs a) { extend_body<true, true>(ix, a); }

@@ -95,6 +95,8 @@ __global__ void k_chain(ChainArgs a);
 __global__ void k_regs_compact(RegCompactArgs a);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm(DevIndex ix, ExtArgs a);
+__global__ void k_extend_fast(DevIndex ix, ExtArgs a);
+__global__ void k_extend_sm_fast(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
 __global__ void k_global_sm(DevIndex ix, GlbArgs a);
 
