@@ -104,4 +104,33 @@ __device__ __forceinline__ int bwag_ref_base(const DevIndex &ix, i64 p)
 	return p < ix.l_pac ? bwag_pac_base(ix.pac, p) : 3 - bwag_pac_base(ix.pac, (ix.l_pac << 1) - 1 - p);
 }
 
+/* Scratch accessors of the lean row sweeps (K4, K5).  Addresses are byte addresses.  PtrAcc: ordinary pointers (global scratch, and
+ * every variant under the CPU emulator).  SmemAcc: 32-bit shared-window addresses with explicit ld/st.shared -- the
+ * compiler otherwise re-derives the window base of every scratch array (S2UR CgaCtaId + 4 uniform ops) inside the row
+ * loop.  All accesses are volatile asm, so they keep their program order among themselves and around __syncwarp(). */
+struct PtrAcc {
+	typedef unsigned char *addr;
+	static __device__ __forceinline__ addr make(const void *p) { return (addr)const_cast<void *>(p); }
+	static __device__ __forceinline__ int2 ld_he(addr a) { return *reinterpret_cast<const int2 *>(a); }
+	static __device__ __forceinline__ void st_he(addr a, int h, int e) { *reinterpret_cast<int2 *>(a) = make_int2(h, e); }
+	static __device__ __forceinline__ int ld_u8(addr a) { return *a; }
+	static __device__ __forceinline__ int ld_s8(addr a) { return *reinterpret_cast<const int8_t *>(a); }
+	static __device__ __forceinline__ void st_u8(addr a, int v) { *a = (unsigned char)v; }
+};
+#ifdef BWAG_CUSIM
+typedef PtrAcc SmemAcc;
+#define BWAG_KEEP(x) do { } while (0)
+#else
+struct SmemAcc {
+	typedef u32 addr;
+	static __device__ __forceinline__ addr make(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+	static __device__ __forceinline__ int2 ld_he(addr a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+	static __device__ __forceinline__ void st_he(addr a, int h, int e) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(h), "r"(e)); }
+	static __device__ __forceinline__ int ld_u8(addr a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+	static __device__ __forceinline__ int ld_s8(addr a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+	static __device__ __forceinline__ void st_u8(addr a, int v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+};
+#define BWAG_KEEP(x) asm volatile("" : "+r"(x))   /* the value stays in its register: no re-derivation inside the loops */
+#endif
+
 #endif

@@ -80,6 +80,68 @@ __device__ __forceinline__ int warp_ksw_global(int lane, int qlen, const uint8_t
 	return H[qlen];
 }
 
+/* The same sweep with about 40 % fewer instructions per 32-column chunk (see warp_ksw_extend_fast, bwag_extend.cu):
+ * H/E side by side (64-bit accesses), no divergent code in the chunk (idle lanes load a clamped column and are masked),
+ * F scanned in slanted coordinates (value + column*e_ins: a plain max scan without decay constants or lane guards) with
+ * the F entering the chunk folded into lane 0's offer.  The direction bits still compare against lane 0's own offer.
+ * q[j] at qa + j, t[i] at ta + i, the H/E pair of column j at he + 8*j, mat[k] at ma + k.  Exact for any penalties. */
+template <class A, class AM>
+__device__ __forceinline__ int warp_ksw_global_fast(int lane, int qlen, typename A::addr qa, int tlen, typename A::addr ta, typename AM::addr ma,
+                               int o_del, int e_del, int o_ins, int e_ins, int w, typename A::addr he, uint8_t *z, int n_col, u64 *cells)
+{
+	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+	for (int j = lane; j <= qlen; j += 32) A::st_he(he + 8 * j, j == 0 ? 0 : (j <= w ? -(o_ins + e_ins * j) : NEG_INF), NEG_INF);
+	__syncwarp();
+	const bool lane0 = lane == 0;
+	const int le = lane * e_ins;
+	for (int i = 0; i < tlen; ++i) {
+		const typename AM::addr srow = ma + A::ld_u8(ta + i) * 5;
+		const int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+		int carry_h = beg == 0 ? -(o_del + e_del * (i + 1)) : NEG_INF;
+		int carry_f = NEG_INF;
+		uint8_t *zi = z ? z + (i64)i * n_col - beg : 0;
+		if (end > beg) *cells += (u64)(end - beg);
+		for (int j0 = beg; j0 < end; j0 += 32) {
+			const int j = j0 + lane;
+			const bool act = j < end;
+			const int jc = act ? j : end - 1;
+			const int2 c = A::ld_he(he + 8 * jc);
+			const int m = c.x + AM::ld_s8(srow + A::ld_u8(qa + jc));
+			const int tt = act ? m - oe_ins : -0x7f000000;     /* idle lanes (only at the end of the last chunk) must not feed the scan */
+			int s = tt;
+			if (lane0) s = __viaddmax_s32(carry_f, -e_ins, s);
+			s += le;
+			{ const int v = __shfl_up_sync(FULL_MASK, s, 1); s = s > v ? s : v; }
+			{ const int v = __shfl_up_sync(FULL_MASK, s, 2); s = s > v ? s : v; }
+			{ const int v = __shfl_up_sync(FULL_MASK, s, 4); s = s > v ? s : v; }
+			{ const int v = __shfl_up_sync(FULL_MASK, s, 8); s = s > v ? s : v; }
+			{ const int v = __shfl_up_sync(FULL_MASK, s, 16); s = s > v ? s : v; }
+			int f = __shfl_up_sync(FULL_MASK, s, 1) - le + e_ins;    /* F(i, j) = the scan value of the column on the left */
+			if (lane0) f = carry_f;
+			carry_f = __shfl_sync(FULL_MASK, s, 31) - 31 * e_ins;
+			int d = m >= c.y ? 0 : 1, h = m >= c.y ? m : c.y;
+			d = h >= f ? d : 2; h = h >= f ? h : f;
+			if (!act) h = NEG_INF;
+			int hp = __shfl_up_sync(FULL_MASK, h, 1);
+			if (lane0) hp = carry_h;
+			{
+				int la = end - 1 - j0; la = la < 31 ? la : 31;
+				carry_h = __shfl_sync(FULL_MASK, h, la);
+			}
+			const int te = m - oe_del, ed = c.y - e_del;
+			d |= ed > te ? 1 << 2 : 0;
+			d |= (f - e_ins) > tt ? 2 << 4 : 0;
+			if (act) {
+				A::st_he(he + 8 * j, hp, ed > te ? ed : te);
+				if (zi) zi[j] = (uint8_t)d;
+			}
+		}
+		if (lane0) A::st_he(he + 8 * end, carry_h, NEG_INF);
+		__syncwarp();
+	}
+	return A::ld_he(he + 8 * qlen).x;
+}
+
 __device__ __forceinline__ void cig_push(u32 *cig, int *n, int op, int len)
 {
 	if (*n && (cig[*n - 1] & 0xf) == (u32)op) cig[*n - 1] += (u32)len << 4;
@@ -97,7 +159,10 @@ __device__ __forceinline__ int md_put_num(char *md, int l, int v)
 
 /* SM: H/E rows and the two sequences of the task in shared memory (short reads); the backtrack matrix, the CIGAR and
  * the MD staging stay in the warp's global scratch */
-template <bool SM>
+template <bool C, class X, class Y> struct SelG { typedef X type; };
+template <class X, class Y> struct SelG<false, X, Y> { typedef Y type; };
+
+template <bool SM, bool FAST>
 __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a)
 {
 	const int lane = threadIdx.x & 31;
@@ -119,10 +184,15 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 		H = a.eh + wid * (i64)(2 * (a.cap_q + 2)); E = H + a.cap_q + 2;
 		rseq = a.rseq + wid * (i64)a.cap_r; qseq = a.qseq + wid * (i64)(a.cap_q + 2);
 	}
+	typedef typename SelG<SM, SmemAcc, PtrAcc>::type A;   /* how the lean sweep reaches H/E and the sequences; the matrix is always shared */
+	typename A::addr he_a = A::make(H), rs_a = A::make(rseq), q_a = A::make(qseq);
+	if constexpr (SM && FAST) { BWAG_KEEP(he_a); BWAG_KEEP(rs_a); BWAG_KEEP(q_a); }
 	const bwag_sw_par_t &p = a.par;
 	__shared__ int8_t s_mat[32];
 	if (threadIdx.x < 25) s_mat[threadIdx.x] = p.mat[threadIdx.x];
 	__syncthreads();
+	typename SmemAcc::addr mat_a = SmemAcc::make(s_mat);
+	if constexpr (FAST) BWAG_KEEP(mat_a);
 	u64 cells = 0;
 	int overflow = 0;
 
@@ -170,7 +240,8 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 					w = w > min_w ? w : min_w;
 					const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
 					if (want && (i64)n_col * rlen > a.cap_z) { overflow |= 4; score = 0; break; }
-					score = warp_ksw_global(lane, lq, qseq, rlen, rseq, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, H, E, want ? z : 0, n_col, &cells);
+					if constexpr (FAST) score = warp_ksw_global_fast<A, SmemAcc>(lane, lq, q_a, rlen, rs_a, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins, w, he_a, want ? z : 0, n_col, &cells);
+					else score = warp_ksw_global(lane, lq, qseq, rlen, rseq, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, H, E, want ? z : 0, n_col, &cells);
 					if (want) {
 						if (lane == 0) {        /* backtrack (ksw.c:613-627) */
 							int i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1, which = 0, n = 0;
@@ -261,5 +332,11 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 	if (overflow && lane == 0) atomicOr(a.flags, (u32)overflow);
 }
 
-__global__ void __launch_bounds__(K5_THREADS) k_global(DevIndex ix, GlbArgs a) { global_body<false>(ix, a); }
-__global__ void __launch_bounds__(K5_THREADS) k_global_sm(DevIndex ix, GlbArgs a) { global_body<true>(ix, a); }
+#ifndef K5_MINB
+#define K5_MINB 6
+#endif
+/* k_global*: the first formulation of the sweep (BWA_B200_K5_FAST=0); k_global*_fast: the lean one, the default */
+__global__ void __launch_bounds__(K5_THREADS) k_global(DevIndex ix, GlbArgs a) { global_body<false, false>(ix, a); }
+__global__ void __launch_bounds__(K5_THREADS) k_global_sm(DevIndex ix, GlbArgs a) { global_body<true, false>(ix, a); }
+__global__ void __launch_bounds__(K5_THREADS, K5_MINB) k_global_fast(DevIndex ix, GlbArgs a) { global_body<false, true>(ix, a); }
+__global__ void __launch_bounds__(K5_THREADS, K5_MINB) k_global_sm_fast(DevIndex ix, GlbArgs a) { global_body<true, true>(ix, a); }

@@ -99,5 +99,7 @@ __global__ void k_extend_fast(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm_fast(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
 __global__ void k_global_sm(DevIndex ix, GlbArgs a);
+__global__ void k_global_fast(DevIndex ix, GlbArgs a);
+__global__ void k_global_sm_fast(DevIndex ix, GlbArgs a);
 
 #endif

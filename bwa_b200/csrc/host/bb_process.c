@@ -262,7 +262,8 @@ typedef struct {
 	bwag_regs_t xregs;
 	bwag_cregs_t cregs; int have_cregs;   /* regions from the fused device chain+extend stage */
 	int pass_dry;
-	void *blocks[64]; int n_blocks;   /* CIGAR/MD storage of each device round */
+	void **blocks; int n_blocks, m_blocks;   /* CIGAR/MD storage of each device round (a read whose regions merge one after
+	                                          * the other, bwamem.c:463-515, can need one round per merge: no fixed bound) */
 	mem_alnreg_t *reg_pool; int64_t *reg_off;   /* SE: regions of all reads in one block */
 	double t_last;
 	memo_arena_t *arenas;    /* one bump arena per parallel id for the alignment caches of this chunk */
@@ -527,7 +528,7 @@ static int64_t global_round(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t *
 		int64_t x, tot = 0;
 		for (x = 0; x < t; ++x) { g.boff[x] = tot; tot += ((int64_t)4 * out.res[x].n_cigar + (out.res[x].l_md > 0 ? out.res[x].l_md : 1) + 7) & ~(int64_t)7; }
 		g.boff[t] = tot;
-		if (j->n_blocks == 64) bb_fatal("mem_process_seqs", "too many device rounds in one batch");
+		if (j->n_blocks == j->m_blocks) { j->m_blocks = j->m_blocks ? j->m_blocks << 1 : 16; j->blocks = bb_realloc(j->blocks, sizeof(void *) * (size_t)j->m_blocks); }
 		g.block = big_alloc((size_t)tot + 8);
 		j->blocks[j->n_blocks++] = g.block;
 	}
@@ -754,7 +755,7 @@ static void job_free(job_t *j)
 {
 	if (j->rs) bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_free, j, j->n);
 	memo_arenas_free(j->arenas, bb_parallel_ids()); j->arenas = 0;
-	{ int b; for (b = 0; b < j->n_blocks; ++b) big_free(j->blocks[b]); }
+	{ int b; for (b = 0; b < j->n_blocks; ++b) big_free(j->blocks[b]); free(j->blocks); j->blocks = 0; j->n_blocks = j->m_blocks = 0; }
 	big_free(j->reg_pool); big_free(j->reg_off);
 	big_free(j->rs); big_free(j->off); big_free(j->codes); big_free(j->chain_off); big_free(j->xchains); big_free(j->xseeds); big_free(j->chain_rid); big_free(j->chain_frac);
 }
@@ -957,7 +958,7 @@ mem_aln_t mem_reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *
 		rs.gc.pending = 0;
 		a = bb_reg2aln(&sc, l_seq, s.seq, ar);
 	}
-	{ int b; for (b = 0; b < j.n_blocks; ++b) big_free(j.blocks[b]); }
+	{ int b; for (b = 0; b < j.n_blocks; ++b) big_free(j.blocks[b]); free(j.blocks); }
 	gcache_free(&rs.gc);
 	free(s.seq);
 	return a;

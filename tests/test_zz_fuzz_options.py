@@ -2,6 +2,7 @@
 output options, presets, read lengths 36-400, error rates, chimeras, batch sizes.  The CPU half runs the CUDA
 kernels in the SIMT emulator, the GPU half the real ones; both must reproduce the reference SAM byte for byte
 (or fail with the same exit status on an option set the reference rejects)."""
+import os
 import subprocess
 
 import pytest
@@ -10,8 +11,11 @@ import bwa_b200
 from conftest import CUSIMBIN, REF_BWA, strip_pg
 from fuzz_cases import command
 
-CPU_CASES = list(range(0, 10))
-GPU_CASES = list(range(0, 24))
+# BWA_B200_FUZZ_FROM/TO widen the emulated sweep (e.g. 10..300 after a kernel change); the default keeps the CPU suite short
+CPU_CASES = list(range(int(os.environ.get("BWA_B200_FUZZ_FROM", "0")), int(os.environ.get("BWA_B200_FUZZ_TO", "10"))))
+REGRESSIONS = [114]   # 114: a tandem-repeat read whose regions merge one by one (146 device rounds in one batch)
+CPU_CASES += [k for k in REGRESSIONS if k not in CPU_CASES]
+GPU_CASES = list(range(0, 24)) + [114]
 
 
 def _both(binary, args):
