@@ -53,3 +53,17 @@ def test_default_thread_count_keeps_reference_batches(data):
     """No -t: the batches are the reference's (chunk_size x 1 thread), only the host worker count differs; same SAM."""
     fa, fqs = data.reads("stress", tag="cspe", n=60, seed=34, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
     assert run_sam(CUSIMBIN, [fa] + fqs) == ref_sam([fa] + fqs)
+
+
+@pytest.mark.parametrize("env", [{"BWA_B200_K4_SM": "0", "BWA_B200_K5_SM": "0"}, {"BWA_B200_K4_FAST": "0", "BWA_B200_K5_FAST": "0"},
+                                 {"BWA_B200_K4_SM": "0", "BWA_B200_K5_SM": "0", "BWA_B200_K4_FAST": "0", "BWA_B200_K5_FAST": "0"}],
+                         ids=["global_scratch", "first_sweep", "global_scratch_first_sweep"])
+def test_emulated_kernel_variants(data, monkeypatch, env):
+    """K4/K5 exist in four variants each (scratch in shared or global memory x lean or first row sweep); the default
+    run covers shared+lean, this one the others."""
+    fa, fqs = data.reads("stress", tag="cspe", n=60, seed=34, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    args = ["-K", "100000000", "-t", "2", fa] + fqs
+    want = ref_sam(args)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert run_sam(CUSIMBIN, args) == want

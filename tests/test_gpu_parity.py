@@ -127,3 +127,17 @@ def test_host_chaining_path_still_identical(data, monkeypatch):
         fa, fqs = data.reads(ref, **kw)
         args = ["-K", "100000000", "-t", "8", fa] + fqs
         assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
+
+
+@pytest.mark.parametrize("env", [{"BWA_B200_K4_SM": "0", "BWA_B200_K5_SM": "0"}, {"BWA_B200_K4_FAST": "0", "BWA_B200_K5_FAST": "0"},
+                                 {"BWA_B200_K4_SM": "0", "BWA_B200_K5_SM": "0", "BWA_B200_K4_FAST": "0", "BWA_B200_K5_FAST": "0"}],
+                         ids=["global_scratch", "first_sweep", "global_scratch_first_sweep"])
+def test_kernel_variants(data, monkeypatch, env):
+    """K4/K5 exist in four variants each (scratch in shared or global memory x lean or first row sweep); the other
+    tests run shared+lean for short reads and global+lean for long ones, this one the remaining combinations."""
+    fa, fqs = data.reads("stress", tag="gpe", n=3000, seed=4, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    args = ["-K", "100000000", "-t", "4", fa] + fqs
+    want = ref_sam(args)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    assert run_sam(bwa_b200.CLI_PATH, args) == want
