@@ -77,6 +77,7 @@ struct bwag_ctx {
 	void *blob;
 	DevIndex ix;
 	u64 *dense_sa;
+	ulonglong2 *ktab;            /* short-string table (bwag_ctx_build_ktab) */
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1, ev_wait;
 	Counters *d_cnt, *h_cnt;
@@ -123,6 +124,11 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #define BWAG_L2_FETCH_DEFAULT 0   /* 0: leave the device's setting */
 #endif
 #define K1_SMEM_MAX (200 * 1024)
+#ifdef BWAG_CUSIM
+#define BWAG_KTAB_MAX_AUTO 5     /* the emulator builds the table one fiber per entry: keep it small */
+#else
+#define BWAG_KTAB_MAX_AUTO 12
+#endif
 #define K4_SMEM_MAX (96 * 1024)
 
 /* ------------------------------------------------------------------------------------------------ index */
@@ -255,6 +261,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
 	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
+	if (c->ktab) cudaFree(c->ktab);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_wait);
@@ -282,6 +289,48 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	c->dense_sa = out;
 	c->ix.sa = out; c->ix.sa_shift = s; c->ix.n_sa = n_out;
+	++c->st.n_launch;
+	return 0;
+}
+
+/* bi-intervals of all strings of 1..K bases (bwag_smem.cu); K = 0 picks a depth from the index size, K < 0 removes the table */
+extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
+{
+	CK(cudaSetDevice(c->device));
+	if (K == 0) {   /* deep enough that the deepest level still has a few occurrences per string, at most 12 (358 MB) */
+		int lg = 0;
+		while (lg < 31 && ((u64)1 << (2 * (lg + 1))) <= c->ix.seq_len) ++lg;   /* floor(log4(seq_len)) */
+		K = lg - 2;
+		if (K > BWAG_KTAB_MAX_AUTO) K = BWAG_KTAB_MAX_AUTO;
+	}
+	if (K > 14) K = 14;
+	if (K < 2) {
+		CK(cudaStreamSynchronize(c->stream));
+		if (c->ktab) { cudaFree(c->ktab); c->ktab = 0; }
+		c->ix.ktab = 0; c->ix.ktab_k = 0;
+		return 0;
+	}
+	if (c->ktab && c->ix.ktab_k == K) return 0;
+	const u64 total = (((u64)1 << (2 * (K + 1))) - 4) / 3;
+	ulonglong2 *tab = 0;
+	{
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		if ((double)total * 16 > 0.25 * (double)free_b) return set_err("not enough free device memory for a short-string table of depth %d", K);
+	}
+	CK(cudaMalloc((void **)&tab, (total + 2) * 16));
+	CK(cudaMemsetAsync(tab, 0, (total + 2) * 16, c->stream));
+	DevIndex plain = c->ix;
+	plain.ktab = 0; plain.ktab_k = 0;
+	{
+		u64 nb = (total + 255) / 256;
+		BWAG_LAUNCH(k_ktab_build, (int)(nb < (u64)c->n_sm * 32 ? nb : (u64)c->n_sm * 32), 256, 0, c->stream, plain, tab, K);
+	}
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->ktab) cudaFree(c->ktab);
+	c->ktab = tab;
+	c->ix.ktab = tab; c->ix.ktab_k = K;
 	++c->st.n_launch;
 	return 0;
 }
@@ -348,6 +397,9 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
 	}
+	if (getenv("BWA_B200_PROFILE"))   /* with the host's phase timer: the work counters of this batch */
+		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu\n", b->n,
+		        (unsigned long long)b->lc.st.occ_touches, (unsigned long long)b->lc.st.sa_touches, (unsigned long long)b->lc.st.ext_cells, (unsigned long long)b->lc.st.glb_cells);
 	for (int i = 0; i < N_SPARE; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
 	pthread_mutex_unlock(&c->mu);
 	if (b) batch_free(b);
@@ -422,11 +474,13 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		const int groups_per_block = K1_THREADS;   /* one lane per read */
 		/* shared memory of a block: the heads of both candidate lists + one read slot per lane (odd number of words) */
 		int qstride = (((b->max_len + 6) >> 2) | 1) << 2;
-		size_t smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16 + (size_t)K1_THREADS * qstride;
+		/* + a 2-bit packed copy of each read (the keys of the short-string table): 16 bases per word, one spare word, odd word count */
+		int pstride = c->ix.ktab_k ? ((((b->max_len + 15) >> 4) + 1) | 1) << 2 : 0;
+		size_t smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16 + (size_t)K1_THREADS * (qstride + pstride);
 #ifdef K1_NO_QSMEM
-		qstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16;
+		qstride = 0; pstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16;
 #endif
-		if (smem > K1_SMEM_MAX) { qstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
+		if (smem > K1_SMEM_MAX) { qstride = 0; pstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
 		int grid;
 #ifdef BWAG_CUSIM
 		grid = 2;
@@ -449,7 +503,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
 		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
 		a.min_seed_len = par->min_seed_len; a.split_len = par->split_len; a.split_width = par->split_width; a.max_occ = par->max_occ; a.max_mem_intv = par->max_mem_intv;
-		a.scratch = (Intv *)c->s_k1.p; a.cap_list = cap_list; a.cap_mem = cap_mem; a.qstride = qstride;
+		a.scratch = (Intv *)c->s_k1.p; a.cap_list = cap_list; a.cap_mem = cap_mem; a.qstride = qstride; a.pstride = pstride;
 		a.stage3 = (Intv *)c->s_k1f.p; a.cap3 = cap3; a.n3 = par->max_mem_intv ? (int *)c->s_n3.p : 0; a.next_read3 = &c->d_cnt->next_read3;
 		a.intv_beg = (i64 *)b->d_intv_beg.p; a.intv_n = (int *)b->d_intv_n.p; a.intv = (bwtintv_t *)b->d_intv.p; a.seed_beg = (i64 *)b->d_seed_beg.p; a.rbeg = (i64 *)b->d_rbeg.p;
 		a.cap_intv = cap_intv; a.cap_seeds = cap_seeds;
@@ -522,8 +576,9 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	int per_warp = (8 * (a.cap_q + 2) + a.cap_r + a.cap_q + 15) & ~15;
 	size_t smem = (size_t)per_warp * wpb;
 	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K4_SM") && atoi(getenv("BWA_B200_K4_SM")) == 0);
-	/* the leaner row sweep needs non-negative insertion penalties (every real scoring scheme); BWA_B200_K4_FAST=0 forces the general one */
-	const int fast = a.par.e_ins >= 0 && a.par.o_ins + a.par.e_ins >= 0 && !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
+	/* the leaner row sweep (and its row cut-off) needs non-negative gap penalties (every real scoring scheme); BWA_B200_K4_FAST=0 forces the general one */
+	const int fast = a.par.e_ins >= 0 && a.par.o_ins + a.par.e_ins >= 0 && a.par.e_del >= 0 && a.par.o_del + a.par.e_del >= 0 &&
+	                 !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
 #ifndef BWAG_CUSIM
 	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast ? k_extend_sm_fast : k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
 #endif

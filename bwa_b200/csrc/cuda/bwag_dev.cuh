@@ -48,6 +48,9 @@ struct DevIndex {
 	u64 n_sa;
 	i64 l_pac;
 	int sa_shift;       /* log2(sampling interval of sa[]) */
+	/* bi-intervals of all strings of 1..ktab_k bases (bwag_smem.cu), 16 bytes each in 32-byte aligned pairs; 0 = none */
+	const ulonglong2 *ktab;
+	int ktab_k;
 };
 
 #define FULL_MASK 0xffffffffu

@@ -166,18 +166,21 @@ __device__ __forceinline__ int warp_ksw_extend(int lane, int qlen, const uint8_t
  *     max per step, no decay constants, and no lane guards (a lane below the shuffle distance gets its own value back);
  *   - the F value entering the chunk is folded into lane 0's offer before the scan (max(t0, carry - e_ins)), so the
  *     scan result IS F of the next column and F of the next chunk's first column is its lane-31 value;
- *   - first / last non-zero stored cell are tracked per lane and reduced once per row.
+ *   - first / last non-zero stored cell are tracked per lane and reduced once per row;
+ *   - CUT: the sweep stops at the first row after which no output can change (see the comment at the cut-off); the
+ *     reference would go on to tlen = qlen + max_gap rows, i.e. about twice as many for a read that matches to its end.
+ *     Needs non-negative deletion penalties as well.  `cells` then counts the cells actually computed.
  * q[j] = byte at qa + j*QS, t[i] = byte at ta + i*TS, H/E pair of column j at he + 8*j, mat[k] at ma + k.
  * Results are identical to warp_ksw_extend (and ksw_extend2) under the stated condition. */
-template <class A, class AM, int QS, int TS>
+template <class A, class AM, int QS, int TS, bool CUT>
 __device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename A::addr qa, int tlen, typename A::addr ta,
                                typename AM::addr ma, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                                typename A::addr he, int *qle, int *tle, int *gtle, int *gscore_, int *max_off_, u64 *cells)
 {
 	const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-	int max, max_i, max_j, max_ie, gscore, max_off, beg, end;
+	int max, max_i, max_j, max_ie, gscore, max_off, beg, end, maxsc = 0;
 	{   /* first row (ksw.c:431-433) */
-		int H1 = h0 > oe_ins ? h0 - oe_ins : 0, maxsc = 0;
+		int H1 = h0 > oe_ins ? h0 - oe_ins : 0;
 		for (int j = lane; j <= qlen; j += 32) {
 			int v = j == 0 ? h0 : H1 - (j - 1) * e_ins;
 			A::st_he(he + 8 * j, v > 0 ? v : 0, 0);
@@ -194,9 +197,10 @@ __device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename
 	const int ne1 = -e_ins, noe_ins = -oe_ins, noe_del = -oe_del, ne_del = -e_del;
 	const bool lane0 = lane == 0;
 	const int le = lane * e_ins;
+	const int pot0 = maxsc * (qlen - 1);            /* potential of a cell: its score + maxsc * (columns to its right) */
 	for (int i = 0; i < tlen; ++i) {
 		const typename AM::addr srow = ma + A::ld_u8(ta + i * TS) * 5;
-		int m = 0, mj = -1, jmin = 0x7fffffff, jmax = -1;   /* per lane; reduced after the row */
+		int m = 0, mj = -1, jmin = 0x7fffffff, jmax = -1, phi = 0;   /* per lane; reduced after the row */
 		if (beg < i - w) beg = i - w;
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
@@ -236,6 +240,7 @@ __device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename
 			if (act) A::st_he(he + 8 * j, hp, e);
 			if (act && h >= m) mj = j;                         /* a lane's columns ascend, so ties keep the larger j (ksw.c:473-474) */
 			m = m > h ? m : h;
+			phi = __viaddmax_s32(h, pot0 - maxsc * j, phi);
 			if (act && (hp | e) != 0) { jmax = j; jmin = jmin < j ? jmin : j; }
 		}
 		const int h1 = carry_h;                        /* H(i, end-1), or the first-column value if the row was empty */
@@ -250,6 +255,7 @@ __device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename
 			gscore = gscore > h1 ? gscore : h1;
 		}
 		if (m == 0) break;
+		const bool falling = m <= max, to_end = end == qlen && end > beg;
 		if (m > max) {
 			int d = mj - i;
 			max = m; max_i = i; max_j = mj;
@@ -267,6 +273,19 @@ __device__ __forceinline__ int warp_ksw_extend_fast(int lane, int qlen, typename
 			if (jl < 0) jl = nb - 1;
 			beg = nb;
 			end = jl + 2 < qlen ? jl + 2 : qlen;
+		}
+		if (CUT && falling && to_end) {
+			/* Row cut-off.  ksw_extend2 keeps sweeping rows until tlen, Z-drop or an all-zero row, but once no cell can
+			 * reach the best score again the outputs are final.  A cell's potential = score + maxsc * (columns to its
+			 * right) bounds every score reachable from it (a diagonal step gains at most maxsc and uses up a column; E and
+			 * F only lose: penalties are non-negative here; zero cells do not propagate, ksw.c:465).  This row covered
+			 * every column from beg to the query's end, so all stored cells the later rows can read (fresh or stale) stem
+			 * from it: every future score is <= max(phi over the row, the first-column entry below).  No future row maximum
+			 * can exceed `max` (strictly needed: ksw.c:490) and no future H(i, qlen-1) can reach `gscore` (ties go to the
+			 * later row, ksw.c:486-489), so max, max_i/j, max_off, gscore and max_ie cannot change any more. */
+			int bound = warp_max(phi);
+			if (beg == 0) { const int fc = h0 - (o_del + e_del * (i + 1)) + maxsc * qlen; bound = bound > fc ? bound : fc; }
+			if (bound <= max && bound < gscore) break;
 		}
 		__syncwarp();
 	}
@@ -392,7 +411,7 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 						for (int it = 0; it < 2; ++it) {
 							int prev = reg.score;
 							aw0 = p.w << it;
-							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, -1, -1>(lane, s_qbeg, q_a + (s_qbeg - 1), tl, rs_a + (tl - 1), mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, -1, -1, true>(lane, s_qbeg, q_a + (s_qbeg - 1), tl, rs_a + (tl - 1), mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw0, p.pen_clip5, p.zdrop, s_len * p.a, he_a, &qle, &tle, &gtle, &gscore, &moff, &cells);
 							else reg.score = warp_ksw_extend(lane, s_qbeg, query + s_qbeg - 1, -1, tl, rseq + tl - 1, -1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw0, p.pen_clip5, p.zdrop, s_len * p.a, H, E, &qle, &tle, &gtle, &gscore, &moff, &cells);
@@ -408,7 +427,7 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 						for (int it = 0; it < 2; ++it) {
 							int prev = reg.score;
 							aw1 = p.w << it;
-							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, 1, 1>(lane, l_query - qe, q_a + qe, (int)(rmax1 - rmax0 - re), rs_a + (int)re, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
+							if (SANE) reg.score = warp_ksw_extend_fast<A, SmemAcc, 1, 1, true>(lane, l_query - qe, q_a + qe, (int)(rmax1 - rmax0 - re), rs_a + (int)re, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw1, p.pen_clip3, p.zdrop, sc0, he_a, &qle, &tle, &gtle, &gscore, &moff, &cells);
 							else reg.score = warp_ksw_extend(lane, l_query - qe, query + qe, 1, (int)(rmax1 - rmax0 - re), rseq + re, 1, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins,
 							                            aw1, p.pen_clip3, p.zdrop, sc0, H, E, &qle, &tle, &gtle, &gscore, &moff, &cells);

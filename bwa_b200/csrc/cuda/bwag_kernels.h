@@ -25,6 +25,7 @@ struct SeedArgs {
 	/* per-group scratch */
 	Intv *scratch; int cap_list, cap_mem;
 	int qstride;                                   /* bytes of a lane's shared read slot (0: read the bases from global memory) */
+	int pstride;                                   /* bytes of a lane's 2-bit packed copy of the read (0: no short-string table lookups in K1) */
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
@@ -86,6 +87,7 @@ extern "C" {
 #endif
 
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
+__global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
 __global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);

@@ -101,6 +101,75 @@ __device__ __forceinline__ void extend_step(const DevIndex &ix, u64 xs, u64 xo, 
 
 #define INIT_INTV(c, X0, X1, X2) do { int c_ = (c); X0 = SEL4(c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1; X2 = SEL4(c_, ix.L2[1], ix.L2[2], ix.L2[3], ix.L2[4]) - SEL4(c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]); X1 = SEL4(3 - c_, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1; } while (0)
 
+/* ------------------------------------------------------------------------------------------------ short-string table
+ * Two thirds of all bwt_extend calls of a read produce a string of at most 12 bases (the first steps of every forward
+ * sweep, and the many short candidates of the first steps of every backward sweep), each costing two Occ sectors because
+ * such intervals are wide.  The bi-interval of a string does not depend on how it was reached, so the index keeps the
+ * bi-intervals of ALL strings of 1..K bases in one table (K = 12: 22.4 M entries, 358 MB of the 180 GB), built once at
+ * load time with the same extend_step; a step whose result is that short becomes ONE 16-byte lookup, fetched with the
+ * same 256-bit load instruction as an Occ block so that the warp stays converged.
+ *   entry  = pack_ent(x0, x1, x2, t) with t = Occ-block touches of the forward chain that builds the string, as the
+ *            reference counts them (bwt.c:194-197): the third pass jumps over that chain and adds t to its counter;
+ *   index  = (4^len - 4)/3 + sum_t s[t] * 4^t   (all shorter strings first; first base in the low bits). */
+__device__ __forceinline__ u32 ktab_off(int len) { return ((1u << (2 * len)) - 4u) / 3u; }
+
+/* bwt_extend as extend_step, or -- for lanes with tab set -- the table entry tidx instead.  t12: the touches of this one
+ * extension as the reference counts them (valid for every lane whose xs/e2 are the real input interval); ct: the entry's
+ * chain count (table lanes only).  One converged instruction sequence for both kinds of lane. */
+__device__ __forceinline__ void extend_step2(const DevIndex &ix, u64 xs, u64 xo, u64 e2, int c, bool tab, u32 tidx, int back,
+                                             int &t12, u64 &o_s, u64 &o_o, u64 &o_x2, u32 &ct)
+{
+	const u64 k = xs - 1, l = xs - 1 + e2;
+	u64 tk[4] = {0, 0, 0, 0}, tl[4] = {0, 0, 0, 0};
+	const bool kv = k != (u64)-1, lv = l != (u64)-1;
+	const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
+	const bool same = kv && lv && (kp >> 6) == (lp >> 6);
+	uint4 b0, b1, c0, c1;
+	b0 = b1 = c0 = c1 = make_uint4(0, 0, 0, 0);
+	const uint4 *p1 = tab ? reinterpret_cast<const uint4 *>(ix.ktab + (tidx & ~1u)) : ix.bwt + ((lp >> 6) << 1);
+	if (tab || lv) bwag_ld_block(p1, b0, b1);
+	if (!tab && kv && !same) bwag_ld_block(ix.bwt + ((kp >> 6) << 1), c0, c1);
+	if (same) { c0 = b0; c1 = b1; }   /* both ranks in one block: it was fetched once */
+	if (lv) bwag_block_counts(ix, b0, b1, lp, tl);   /* table lanes: computed on the entry's bits and discarded below */
+	if (kv) bwag_block_counts(ix, c0, c1, kp, tk);
+	t12 = (kv && lv && (kp >> 7) == (lp >> 7)) ? 1 : 2;   /* as the reference counts them: its blocks hold 128 symbols (bwt.c:194-197) */
+	const u64 x2_1 = tl[1] - tk[1], x2_2 = tl[2] - tk[2], x2_3 = tl[3] - tk[3];
+	o_x2 = SEL4(c, tl[0] - tk[0], x2_1, x2_2, x2_3);
+	o_s = SEL4(c, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1 + SEL4(c, tk[0], tk[1], tk[2], tk[3]);   /* new x[!is_back] */
+	o_o = xo + ((xs <= ix.primary && xs + e2 - 1 >= ix.primary) ? 1 : 0);                                 /* new x[is_back]: bwt.c:271-274 */
+	if (c < 3) o_o += x2_3;
+	if (c < 2) o_o += x2_2;
+	if (c < 1) o_o += x2_1;
+	ct = 0;
+	if (tab) {
+		const uint4 ev = (tidx & 1u) ? b1 : b0;
+		ulonglong2 v;
+		u64 x0, x1, x2;
+		v.x = (u64)ev.y << 32 | ev.x; v.y = (u64)ev.w << 32 | ev.z;
+		unpack_ent(v, x0, x1, x2, ct);
+		o_x2 = x2; o_s = back ? x0 : x1; o_o = back ? x1 : x0;
+	}
+}
+
+/* one lane per table entry: the string's bi-interval by forward extension from its first base, exactly as a sweep would */
+__global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K)
+{
+	const u32 total = ktab_off(K + 1);
+	for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		int len = 1;
+		while (e >= ktab_off(len + 1)) ++len;
+		const u32 key = e - ktab_off(len);
+		u64 x0, x1, x2, touches = 0;
+		INIT_INTV((int)(key & 3u), x0, x1, x2);
+		for (int t = 1; t < len; ++t) {
+			u64 o_s, o_o, o_x2;
+			extend_step(ix, x1, x0, x2, 3 - (int)(key >> (2 * t) & 3u), touches, o_s, o_o, o_x2);
+			x0 = o_o; x1 = o_s; x2 = o_x2;
+		}
+		tab[e] = pack_ent(x0, x1, x2, (u32)touches);
+	}
+}
+
 /* ------------------------------------------------------------------------------------------------ K1f
  * third pass (bwamem.c:170-185, bwt_seed_strategy1 bwt.c:358-379): from every start x extend forward until the
  * interval is smaller than max_mem_intv and at least min_seed_len long; continue after the seed's end */
@@ -113,8 +182,11 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 	u64 ik0 = 0, ik1 = 0, ik2 = 0, touches = 0;
 	u32 overflow = 0;
 	Intv *out = 0;
+	/* a seed cannot end before it is min_seed_len + 1 bases long, so its first kj bases are one table lookup */
+	const int kj = ix.ktab_k < a.min_seed_len ? ix.ktab_k : a.min_seed_len;
 	for (;;) {
-		bool need = false;
+		bool need = false, jump = false;
+		u32 tidx = 0;
 		for (;;) {
 			if (!in_seed) {
 				while (x < len && q[x] > 3) ++x;
@@ -130,6 +202,12 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 				}
 				INIT_INTV(q[x], ik0, ik1, ik2);
 				i = x + 1; in_seed = true;
+				if (kj > 1 && x + kj <= len) {
+					u32 key = q[x];
+					bool ok = true;
+					for (int t = 1; t < kj; ++t) { const int b = q[x + t]; ok = ok && b < 4; key |= (u32)(b & 3) << (2 * t); }
+					if (ok) { jump = true; tidx = ktab_off(kj) + key; need = true; break; }   /* an N in range: step by step as before */
+				}
 			}
 			if (i >= len) { x = len; in_seed = false; continue; }
 			if (q[i] > 3) { x = i + 1; in_seed = false; continue; }
@@ -139,7 +217,11 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 		if (__all_sync(FULL_MASK, done)) break;
 		if (!need) continue;
 		u64 o_s, o_o, o_x2;
-		extend_step(ix, ik1, ik0, ik2, 3 - q[i], touches, o_s, o_o, o_x2);
+		u32 ct;
+		int t12;
+		extend_step2(ix, ik1, ik0, ik2, jump ? 0 : 3 - q[i], jump, tidx, 0, t12, o_s, o_o, o_x2, ct);
+		if (jump) { ik0 = o_o; ik1 = o_s; ik2 = o_x2; i = x + kj; touches += ct; continue; }
+		touches += (u64)t12;
 		if (o_x2 < a.max_mem_intv && i - x >= a.min_seed_len) {     /* bwt.c:366-375 */
 			if (o_x2 > 0) {
 				if (n_out < a.cap3) { st_intv(out + n_out, o_o, o_s, o_x2, (u64)x << 32 | (u64)(i + 1)); ++n_out; } else overflow |= 8;
@@ -168,6 +250,9 @@ k_smem(DevIndex ix, SeedArgs a)
 #endif
 	/* shared: [2 lists][K1_SLOTS][K1_THREADS] entries, then K1_THREADS read slots of qstride bytes (odd word count) */
 	const uint8_t *sq = reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)threadIdx.x * a.qstride;
+	/* then K1_THREADS packed copies of the reads (2 bits per base, pstride bytes each): the keys of the short-string table */
+	u32 *sp = reinterpret_cast<u32 *>(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)K1_THREADS * a.qstride + (size_t)threadIdx.x * a.pstride));
+	const int ktk = a.pstride ? ix.ktab_k : 0;
 	sl += threadIdx.x;
 	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
 	/* per-lane global scratch (units of 16 bytes): the tails of the two candidate lists (cap_list entries each),
@@ -249,6 +334,14 @@ k_smem(DevIndex ix, SeedArgs a)
 						const int nw = ((int)(o & 3) + len + 3) >> 2;
 						for (int w = 0; w < nw; ++w) d[w] = g[w];
 						q = sq + (o & 3);
+						if (ktk) {              /* 16 bases per word, first base in the low bits, one spare word; N packs as A (never looked up) */
+							const int nwp = ((len + 15) >> 4) + 1;
+							for (int w = 0; w < nwp; ++w) {
+								u32 pw = 0;
+								for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
+								sp[w] = pw;
+							}
+						}
 					} else q = a.codes + o;
 					continue;
 				}
@@ -295,7 +388,19 @@ k_smem(DevIndex ix, SeedArgs a)
 
 		const int cq = q[i];                               /* base to add: forward uses its complement (bwt.c:309), backward the base itself */
 		u64 o_s, o_o, o_x2;
-		extend_step(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, touches, o_s, o_o, o_x2);
+		{
+			const int rlen = back ? (int)pend - i : i + 1 - sx;   /* the string this extension produces: q[i..pend) or q[sx..i] */
+			const bool tab = rlen <= ktk;
+			u32 tidx = 0, ct;
+			int t12;
+			if (tab) {
+				const int pos = back ? i : sx;
+				const u32 win = __funnelshift_r(sp[pos >> 4], sp[(pos >> 4) + 1], (u32)(pos & 15) << 1);
+				tidx = ktab_off(rlen) + (win & ((1u << (2 * rlen)) - 1u));
+			}
+			extend_step2(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, tab, tidx, back, t12, o_s, o_o, o_x2, ct);
+			touches += (u64)t12;
+		}
 
 		/* ---- consume ---- */
 		if (st == ST_FWD) {                 /* bwt.c:307-316 */

@@ -107,6 +107,11 @@ static void densify_default(bwag_ctx_t *ctx)
 	const char *e = getenv("BWA_B200_SA_INTV");
 	int intv = e ? atoi(e) : 8;
 	if (intv > 0) bwag_ctx_densify_sa(ctx, intv);   /* a refusal (interval not below the current one, no memory) leaves the context as it was */
+	{   /* short-string table (include/bwa_b200_dev.h): BWA_B200_KTAB = depth, 0 = none; default: from the index size */
+		const char *k = getenv("BWA_B200_KTAB");
+		int depth = k ? atoi(k) : 0;
+		if (!k || depth > 0) bwag_ctx_build_ktab(ctx, depth);
+	}
 }
 
 bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)

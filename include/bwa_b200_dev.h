@@ -37,6 +37,12 @@ void bwag_ctx_destroy(bwag_ctx_t *ctx);
 /* Replace the every-32nd-row suffix-array sample by a denser one computed on the device (values are
  * exact; only the number of LF steps per bwt_sa changes).  intv must be a power of two <= 32. */
 int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
+
+/* Short-string table: the bi-intervals (bwtintv_t x[0..2]) of ALL strings of 1..depth bases, so that a bwt_extend
+ * (bwt.c:262-275) whose result is that short costs one 16-byte lookup instead of two Occ blocks (results unchanged;
+ * two thirds of a read's extensions qualify at depth 12).  depth 0 = choose from the index size (at most 12: 358 MB),
+ * depth < 0 = remove the table, depth <= 14. */
+int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
 const char *bwag_last_error(void);
 
 /* Page-locked host memory for buffers that are handed to the stage calls (reads, extension work, tasks):
