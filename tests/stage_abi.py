@@ -17,7 +17,8 @@ class Seeds(C.Structure):
                 ("rbeg", C.POINTER(C.c_int64)), ("n_intv", C.c_int64), ("n_seeds", C.c_int64)]
 
 
-def seed_stage(L, bwt, l_pac, pac, codes, off, par):
+def seed_stage(L, bwt, l_pac, pac, codes, off, par, ktab=None):
+    """ktab: depth of the short-string table to build first (None: no table, the plain rank path)"""
     L.bwag_ctx_create.restype = C.c_void_p
     L.bwag_ctx_create.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.bwag_batch_begin.restype = C.c_void_p
@@ -27,6 +28,9 @@ def seed_stage(L, bwt, l_pac, pac, codes, off, par):
     L.bwag_ctx_destroy.argtypes = [C.c_void_p]
     ctx = L.bwag_ctx_create(-1, bwt, l_pac, pac)
     assert ctx
+    if ktab is not None:
+        L.bwag_ctx_build_ktab.argtypes = [C.c_void_p, C.c_int]
+        assert L.bwag_ctx_build_ktab(ctx, ktab) == 0
     b = L.bwag_batch_begin(ctx, len(off) - 1, codes.ctypes.data, off.ctypes.data)
     out = Seeds()
     assert L.bwag_seed(b, C.byref(par), C.byref(out)) == 0
