@@ -131,6 +131,10 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #endif
 #define K4_SMEM_MAX (96 * 1024)
 
+#ifdef BWAG_CUSIM
+unsigned long long bwag_cusim_sector_loads;
+#endif
+
 /* ------------------------------------------------------------------------------------------------ index */
 
 extern "C" size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac)
@@ -331,6 +335,9 @@ extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
 	if (c->ktab) cudaFree(c->ktab);
 	c->ktab = tab;
 	c->ix.ktab = tab; c->ix.ktab_k = K;
+#ifdef BWAG_CUSIM
+	bwag_cusim_sector_loads = 0;   /* the emulator's request counter reports the alignment work only */
+#endif
 	++c->st.n_launch;
 	return 0;
 }
@@ -397,6 +404,9 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
 	}
+#ifdef BWAG_CUSIM
+	if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] emulator: %llu 32-byte block/table loads so far (K1, K1f, K2, table build)\n", bwag_cusim_sector_loads);
+#endif
 	if (getenv("BWA_B200_PROFILE"))   /* with the host's phase timer: the work counters of this batch */
 		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu\n", b->n,
 		        (unsigned long long)b->lc.st.occ_touches, (unsigned long long)b->lc.st.sa_touches, (unsigned long long)b->lc.st.ext_cells, (unsigned long long)b->lc.st.glb_cells);

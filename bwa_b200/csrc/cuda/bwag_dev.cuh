@@ -54,6 +54,9 @@ struct DevIndex {
 };
 
 #define FULL_MASK 0xffffffffu
+#ifdef BWAG_CUSIM
+extern unsigned long long bwag_cusim_sector_loads;
+#endif
 
 /* one 32-byte Occ block with ONE 256-bit load (LDG.E.256, sm_100+): the table is far larger than the TLB reach, and
  * what limits random access to it is the number of translated load-lane accesses, not bytes (tools/gather_bench.cu:
@@ -62,6 +65,7 @@ __device__ __forceinline__ void bwag_ld_block(const uint4 *p, uint4 &cn, uint4 &
 {
 #ifdef BWAG_CUSIM
 	cn = p[0]; pl = p[1];
+	__atomic_fetch_add(&bwag_cusim_sector_loads, 1ull, __ATOMIC_RELAXED);   /* emulator only: 32-byte requests of the seeding kernels */
 #else
 	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(cn.x), "=r"(cn.y), "=r"(cn.z), "=r"(cn.w), "=r"(pl.x), "=r"(pl.y), "=r"(pl.z), "=r"(pl.w) : "l"(p));

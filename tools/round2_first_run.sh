@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2: the lean K4/K5 row sweeps were written after round 1's GPU budget was spent, so (1) parity
-# on the real kernels, (2) A/B of the kernels alone (same box, same index): lean vs first sweep, (3) resident-block
+# on the real kernels, (2) A/B of the kernels alone (same box, same index): lean vs first sweep, short-string table depths, (3) resident-block
 # variants of the lean kernels (rebuilds bwag_extend.o / bwag_global.o with -DK4_MINB/-DK5_MINB), (4) ncu full capture
 # of the lean K4 for the source-line view.  Everything lands in gpurun_out/r2_first_*.
 cd /root/repo; mkdir -p gpurun_out; O=gpurun_out
@@ -18,6 +18,7 @@ PY
 B="python bench.py --worker --layout se --steps 3 --warmup 2 --cpu-sample 2000"
 $B > $O/r2_first_lean.json 2>/dev/null; line $O/r2_first_lean.json; lap lean
 BWA_B200_K4_FAST=0 BWA_B200_K5_FAST=0 $B > $O/r2_first_firstsweep.json 2>/dev/null; line $O/r2_first_firstsweep.json; lap first_sweep
+for k in 0 10 11 13; do BWA_B200_KTAB=$k $B > $O/r2_first_ktab$k.json 2>/dev/null; echo "short-string table depth $k (default 12):"; line $O/r2_first_ktab$k.json; done; lap ktab
 for mb in 4 5 8; do
   make -s NVEXTRA="-DK4_MINB=$mb -DK5_MINB=$mb" build/cuda/bwag_extend.o build/cuda/bwag_global.o -B > /dev/null 2>&1 && make -s all > /dev/null 2>&1
   $B > $O/r2_first_minb$mb.json 2>/dev/null; echo "min blocks $mb:"; line $O/r2_first_minb$mb.json; lap minb$mb
