@@ -9,6 +9,8 @@ CASES = [
     ("stress_se", "stress", dict(tag="cs", n=120, seed=33, err=(0.016, 0.002, 0.002), chimeric=0.05), []),
     ("stress_pe", "stress", dict(tag="cspe", n=60, seed=34, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05), []),
     ("two_1k", "two", dict(tag="cs1k", n=6, length=1000, seed=35), []),
+    # long reads: read bases and DP scratch in global memory (no shared slots), host chaining, seed filter (ksw_align2)
+    ("two_pacbio_4k", "two", dict(tag="cspb", n=3, length=4000, seed=36, err=(0.02, 0.05, 0.03)), ["-x", "pacbio"]),
 ]
 
 
