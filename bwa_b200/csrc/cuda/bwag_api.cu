@@ -12,6 +12,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <pthread.h>
+#include <time.h>
 #include <sched.h>
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
@@ -445,8 +446,18 @@ static cudaError_t stream_wait(bwag_ctx_t *c)
 {
 	static int mode = -1;   /* BWA_B200_SYNC=block: sleep on a blocking event (saves the cores of waiting lanes, adds wake-up latency to every
 	                         * stage); =yield: poll the stream and give the core away between polls (for boxes with fewer CPUs than threads) */
-	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = !e ? 0 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "yield") == 0 ? 2 : 0; }
+	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = !e ? 0 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "yield") == 0 ? 2 : strcmp(e, "sleep") == 0 ? 3 : 0; }
 	if (mode == 0) return cudaStreamSynchronize(c->stream);
+	if (mode == 3) {   /* =sleep: poll, sleeping 5..80 us between polls: under a CPU quota a spinning lane eats the host workers' budget */
+		long ns = 5000;
+		for (;;) {
+			cudaError_t q = cudaStreamQuery(c->stream);
+			if (q != cudaErrorNotReady) return q;
+			struct timespec ts = { 0, ns };
+			nanosleep(&ts, 0);
+			if (ns < 80000) ns <<= 1;
+		}
+	}
 	if (mode == 2) {
 		for (;;) {
 			cudaError_t q = cudaStreamQuery(c->stream);
