@@ -140,7 +140,7 @@ unsigned long long bwag_cusim_sector_loads;
 
 extern "C" size_t bwag_blob_bytes(const bwt_t *bwt, int64_t l_pac)
 {
-	return ALIGN256(sizeof(BlobHeader)) + ALIGN256((size_t)bwt->bwt_size * 4 + 64) + ALIGN256((size_t)bwt->n_sa * 8) + ALIGN256((size_t)l_pac / 4 + 1 + 64);
+	return ALIGN256(sizeof(BlobHeader)) + ALIGN256((size_t)bwt->bwt_size * 4 + 64) + ALIGN256((size_t)bwt->n_sa * 8 + 32) + ALIGN256((size_t)l_pac / 4 + 1 + 64);
 }
 
 extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac)
@@ -163,7 +163,7 @@ extern "C" int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_
 	}
 	h.off_bwt = ALIGN256(sizeof(BlobHeader));
 	h.off_sa = h.off_bwt + ALIGN256((size_t)bwt->bwt_size * 4 + 64);
-	h.off_pac = h.off_sa + ALIGN256((size_t)bwt->n_sa * 8);
+	h.off_pac = h.off_sa + ALIGN256((size_t)bwt->n_sa * 8 + 32);
 	h.total = h.off_pac + ALIGN256((size_t)l_pac / 4 + 1 + 64);
 	char *d = (char *)d_blob;
 	CK(cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice));
@@ -287,7 +287,7 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 		CK(cudaMemGetInfo(&free_b, &total_b));
 		if ((double)n_out * 8 > 0.5 * (double)free_b) return set_err("not enough free device memory for a suffix-array sample of interval %d", intv);
 	}
-	CK(cudaMalloc((void **)&out, n_out * 8));
+	CK(cudaMalloc((void **)&out, n_out * 8 + 32));   /* K2 reads the sample in aligned groups of four rows */
 	BWAG_LAUNCH(k_sa_densify, c->n_sm * 8, 256, 0, c->stream, c->ix, out, s, n_out);
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(c->stream));

@@ -46,10 +46,24 @@ k_sa(DevIndex ix, SaArgs a)
 		}
 		if (__all_sync(FULL_MASK, idx < 0)) break;
 		if (idx >= 0) {
-			if ((k & mask) == 0) {
-				a.rbeg[idx] = (i64)(steps + ix.sa[k >> ix.sa_shift]);
+			/* a lane either finishes (reads its sampled row) or takes one LF step (reads one Occ block): both are ONE
+			 * 32-byte load, issued by the same instruction so that the two kinds of lane do not serialise their latencies */
+			const bool fin = (k & mask) == 0;
+			const u64 kp = k - (k > ix.primary), row = k >> ix.sa_shift;
+			const uint4 *p = fin ? reinterpret_cast<const uint4 *>(ix.sa + (row & ~(u64)3)) : ix.bwt + ((kp >> 6) << 1);
+			uint4 cn, pl;
+			bwag_ld_block(p, cn, pl);
+			if (fin) {
+				const int e = (int)(row & 3);
+				const u32 lo = e == 0 ? cn.x : e == 1 ? cn.z : e == 2 ? pl.x : pl.z, hi = e == 0 ? cn.y : e == 1 ? cn.w : e == 2 ? pl.y : pl.w;
+				a.rbeg[idx] = (i64)(steps + ((u64)hi << 32 | lo));
 				idx = -1;
-			} else { k = lf_step(ix, k); ++steps; ++touches; }
+			} else {
+				u64 rank;
+				const int c = bwag_block_symbol_rank(ix, cn, pl, kp, &rank);
+				k = k == ix.primary ? 0 : ix.L2[c] + rank;     /* bwt.c:53-59 */
+				++steps; ++touches;
+			}
 		}
 	}
 	if (touches) atomicAdd(a.sa_touches, touches);
