@@ -142,12 +142,6 @@ __device__ __forceinline__ int warp_ksw_global_fast(int lane, int qlen, typename
 	return A::ld_he(he + 8 * qlen).x;
 }
 
-__device__ __forceinline__ void cig_push(u32 *cig, int *n, int op, int len)
-{
-	if (*n && (cig[*n - 1] & 0xf) == (u32)op) cig[*n - 1] += (u32)len << 4;
-	else cig[(*n)++] = (u32)len << 4 | (u32)op;
-}
-
 __device__ __forceinline__ int md_put_num(char *md, int l, int v)
 {
 	char buf[12];
@@ -243,16 +237,19 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 					if constexpr (FAST) score = warp_ksw_global_fast<A, SmemAcc>(lane, lq, q_a, rlen, rs_a, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins, w, he_a, want ? z : 0, n_col, &cells);
 					else score = warp_ksw_global(lane, lq, qseq, rlen, rseq, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, H, E, want ? z : 0, n_col, &cells);
 					if (want) {
-						if (lane == 0) {        /* backtrack (ksw.c:613-627) */
-							int i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1, which = 0, n = 0;
+						if (lane == 0) {        /* backtrack (ksw.c:613-627); the run being built stays in registers (push_cigar merges equal ops) */
+							int i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1, which = 0, n = 0, run_op = -1, run_len = 0;
+#define K5_PUSH(op_, len_) do { if ((op_) == run_op) run_len += (len_); else { if (run_op >= 0) cig[n++] = (u32)run_len << 4 | (u32)run_op; run_op = (op_); run_len = (len_); } } while (0)
 							while (i >= 0 && k >= 0) {
 								which = z[(i64)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
-								if (which == 0) { cig_push(cig, &n, 0, 1); --i; --k; }
-								else if (which == 1) { cig_push(cig, &n, 2, 1); --i; }
-								else { cig_push(cig, &n, 1, 1); --k; }
+								if (which == 0) { K5_PUSH(0, 1); --i; --k; }
+								else if (which == 1) { K5_PUSH(2, 1); --i; }
+								else { K5_PUSH(1, 1); --k; }
 							}
-							if (i >= 0) cig_push(cig, &n, 2, i + 1);
-							if (k >= 0) cig_push(cig, &n, 1, k + 1);
+							if (i >= 0) K5_PUSH(2, i + 1);
+							if (k >= 0) K5_PUSH(1, k + 1);
+							if (run_op >= 0) cig[n++] = (u32)run_len << 4 | (u32)run_op;
+#undef K5_PUSH
 							for (int x = 0; x < n >> 1; ++x) { u32 tmp = cig[x]; cig[x] = cig[n - 1 - x]; cig[n - 1 - x] = tmp; }
 							n_cigar = n;
 						}
