@@ -73,3 +73,33 @@ def test_emulated_kernel_variants(data, monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     assert run_sam(CUSIMBIN, args) == want
+
+
+@pytest.mark.parametrize("ktab", ["0", "3", "5", "8"])
+def test_emulated_edge_reads(data, tmp_path, monkeypatch, ktab):
+    """Ragged input through the emulated kernels at several short-string table depths: reads shorter than the table depth
+    and the seed length, all-N reads, N runs and single Ns (the third pass must fall back to single steps around them),
+    mixed lengths, lower case, homopolymers."""
+    import numpy as np
+    import gen_data
+    fa = data.ref("c1")
+    c = gen_data.read_fasta(fa)[0]
+    recs = []
+    rng = np.random.default_rng(5)
+    for i, ln in enumerate([1, 2, 3, 5, 6, 8, 9, 18, 19, 20, 33, 150, 151, 400, 149]):
+        p = int(rng.integers(0, len(c) - ln))
+        recs.append((b"e%d" % i, c[p:p + ln].copy()))
+    recs.append((b"allN", np.frombuffer(b"N" * 100, dtype=np.uint8).copy()))
+    s = c[5000:5150].copy(); s[40:60] = ord("N"); recs.append((b"nrun", s))
+    for i, pos in enumerate([0, 1, 4, 7, 18, 19, 20, 21, 75, 148, 149]):   # a single N at and around every window boundary
+        s = c[7000 + 200 * i:7150 + 200 * i].copy(); s[pos] = ord("N"); recs.append((b"n%d" % pos, s))
+    s = c[12000:12150].copy(); s[::10] = ord("N"); recs.append((b"nevery10", s))
+    recs.append((b"lower", np.frombuffer(c[9000:9150].tobytes().lower(), dtype=np.uint8).copy()))
+    recs.append((b"polyA", np.frombuffer(b"A" * 150, dtype=np.uint8).copy()))
+    recs.append((b"polyAC", np.frombuffer(b"AC" * 75, dtype=np.uint8).copy()))
+    fq = str(tmp_path / "edge.fq")
+    gen_data.write_fastq(fq, recs)
+    args = ["-K", "100000000", fa, fq]
+    want = ref_sam(args)
+    monkeypatch.setenv("BWA_B200_KTAB", ktab)
+    assert run_sam(CUSIMBIN, args) == want
