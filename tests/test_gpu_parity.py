@@ -34,8 +34,12 @@ def test_cli_sam_identical_to_reference(data, name, ref, kw, extra):
     assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
 
 
-def test_edge_reads(data, tmp_path):
-    """Empty-ish and ragged input: reads shorter than the seed length, all-N reads, N runs, mixed lengths, lower case."""
+@pytest.mark.parametrize("ktab", [None, "0", "12"])
+def test_edge_reads(data, tmp_path, monkeypatch, ktab):
+    """Empty-ish and ragged input: reads shorter than the seed length, all-N reads, N runs, mixed lengths, lower case;
+    with the short-string table at its default depth, without it, and at the depth used for 3 Gbp references."""
+    if ktab is not None:
+        monkeypatch.setenv("BWA_B200_KTAB", ktab)
     fa = data.ref("c1")
     import gen_data
     contigs = gen_data.read_fasta(fa)
@@ -49,6 +53,8 @@ def test_edge_reads(data, tmp_path):
     s = c[5000:5150].copy(); s[40:60] = ord("N"); recs.append((b"nrun", s))
     recs.append((b"lower", np.frombuffer(c[9000:9150].tobytes().lower(), dtype=np.uint8).copy()))
     recs.append((b"polyA", np.frombuffer(b"A" * 150, dtype=np.uint8).copy()))
+    for i, pos in enumerate([0, 1, 7, 11, 12, 13, 19, 20, 75, 149]):   # a single N at and around the table / seed window boundaries
+        s = c[7000 + 200 * i:7150 + 200 * i].copy(); s[pos] = ord("N"); recs.append((b"n%d" % pos, s))
     fq = str(tmp_path / "edge.fq")
     gen_data.write_fastq(fq, recs)
     args = ["-K", "100000000", fa, fq]
