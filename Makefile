@@ -4,6 +4,7 @@
 #   make testbin    -> tests/_build/bwa-b200-oracle : host glue linked against the CPU oracle stages (TEST ONLY)
 #   make tsan       -> tests/_build/bwa-b200-tsan : the same host glue + oracle stages under ThreadSanitizer (TEST ONLY)
 #   make cusim      -> tests/_build/libbwa_b200_cusim.so : the CUDA kernels compiled for the CPU SIMT emulator (TEST ONLY)
+#   make asan       -> tests/_build/bwa-b200-cusim-asan : emulated kernels + host glue under AddressSanitizer (TEST ONLY)
 NVCC  ?= /usr/local/cuda/bin/nvcc
 CC    ?= gcc
 CXX   ?= g++
@@ -71,3 +72,17 @@ tests/_build/libbwa_b200_cusim.so: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_cli.o
 	$(CXX) -shared -Wl,-Bsymbolic -o $@ $^ -lz -lm -lpthread
 tests/_build/bwa-b200-cusim: $(CUSIM_OBJ) $(HOST_OBJ) build/host/bb_main.o
 	$(CXX) -o $@ build/host/bb_main.o $(HOST_OBJ) $(CUSIM_OBJ) -lz -lm -lpthread
+
+# the emulated kernels + host glue under AddressSanitizer (TEST ONLY): make asan -> tests/_build/bwa-b200-cusim-asan.
+# Device buffers are heap blocks in the emulator, so an out-of-bounds access of a kernel is reported like any other.
+ASAN_CXX ?= $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo $(CXX))
+ASAN_CC  ?= $(shell test -x /usr/bin/gcc && echo /usr/bin/gcc || echo $(CC))
+asan: tests/_build/bwa-b200-cusim-asan
+tests/_build/bwa-b200-cusim-asan: $(CUDA_SRC) $(CUDA_HDR) $(HOST_SRC) $(HOST)/bb_cli.c $(wildcard $(HOST)/*.h) $(wildcard include/*.h) tests/cusim/cusim.cpp tests/cusim/cusim.h
+	@mkdir -p tests/_build/asan
+	for f in $(CUDA_SRC); do $(ASAN_CXX) -O1 -g -std=c++17 -fPIC -fsanitize=address -fno-omit-frame-pointer -x c++ -include tests/cusim/cusim.h -DBWAG_CUSIM -Iinclude -I$(CUDA) -Itests/cusim -Wno-unknown-pragmas -c $$f -o tests/_build/asan/k_`basename $$f .cu`.o || exit 1; done
+	$(ASAN_CXX) -O1 -g -std=c++17 -fPIC -fsanitize=address -Itests/cusim -c tests/cusim/cusim.cpp -o tests/_build/asan/rt.o
+	for f in $(HOST_SRC); do $(ASAN_CC) -O1 -g -fsanitize=address -fno-omit-frame-pointer -Iinclude -I$(HOST) -pthread -c $$f -o tests/_build/asan/h_`basename $$f .c`.o || exit 1; done
+	$(ASAN_CC) -O1 -g -fsanitize=address -fno-omit-frame-pointer -Iinclude -I$(HOST) -pthread -DBB_MAIN -c $(HOST)/bb_cli.c -o tests/_build/asan/h_main.o
+	$(ASAN_CXX) -fsanitize=address -o $@ tests/_build/asan/*.o -lz -lm -lpthread
+.PHONY: asan
