@@ -17,8 +17,9 @@ class Seeds(C.Structure):
                 ("rbeg", C.POINTER(C.c_int64)), ("n_intv", C.c_int64), ("n_seeds", C.c_int64)]
 
 
-def seed_stage(L, bwt, l_pac, pac, codes, off, par, ktab=None):
-    """ktab: depth of the short-string table to build first (None: no table, the plain rank path)"""
+def seed_stage(L, bwt, l_pac, pac, codes, off, par, ktab=None, touches=None):
+    """ktab: depth of the short-string table to build first (None: no table, the plain rank path); touches: a list that
+    receives the run's occ_touches counter"""
     L.bwag_ctx_create.restype = C.c_void_p
     L.bwag_ctx_create.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     L.bwag_batch_begin.restype = C.c_void_p
@@ -43,6 +44,11 @@ def seed_stage(L, bwt, l_pac, pac, codes, off, par, ktab=None):
             iv.append((x.x[0], x.x[1], x.x[2], x.info, tuple(out.rbeg[out.seed_beg[k] + c] for c in range(cnt))))
         res.append(iv)
     L.bwag_batch_end(b)
+    if touches is not None:      # the reference-equivalent Occ-block count of this run (bwag_stats_t.occ_touches, first field)
+        st = (C.c_uint64 * 32)()
+        L.bwag_stats_get.argtypes = [C.c_void_p, C.c_void_p]
+        L.bwag_stats_get(ctx, st)
+        touches.append(int(st[0]))
     L.bwag_ctx_destroy(ctx)
     return res
 

@@ -36,11 +36,13 @@ def test_emulated_seed_stage_buffers_equal_oracle(data):
     par = SeedPar(19, 28, 10, 500, 20)
     S = C.CDLL(os.path.join(ROOT, "tests/_build/libbwa_b200_cusim.so"), mode=C.RTLD_LOCAL)
     O = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
-    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
+    t = []
+    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t)
     assert sum(len(r) for r in want) > 500
-    assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par) == want
+    assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t) == want
     for depth in (3, 6):   # with the short-string table: same intervals (x[0], x[1], x[2], info) and positions
-        assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par, ktab=depth) == want
+        assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par, ktab=depth, touches=t) == want
+    assert len(set(t)) == 1 and t[0] > 0, t   # the Occ-block count (as the reference would touch them) is the oracle's, table or not
     par11 = SeedPar(11, 17, 10, 500, 20)   # a seed length below the table depth + 1: the third pass jumps min_seed_len bases only
     assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=6) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
 

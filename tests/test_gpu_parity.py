@@ -106,11 +106,13 @@ def test_seed_stage_buffers_equal_oracle(data):
     l_pac = C.cast(idx.bns, C.POINTER(C.c_int64))[0]
     codes, off = load_reads_as_codes(fqs[0], 1500)
     par = SeedPar(19, 28, 10, 500, 20)
-    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par)
+    t = []
+    want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t)
     assert sum(len(r) for r in want) > 5000
-    assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par) == want
+    assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t) == want
     for depth in (4, 9, 12):   # with the short-string table (12 = the depth used at 3 Gbp): same buffers
-        assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par, ktab=depth) == want
+        assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par, ktab=depth, touches=t) == want
+    assert len(set(t)) == 1 and t[0] > 0, t   # the roofline's numerator (reference-equivalent Occ-block touches) is the oracle's, table or not
     par11 = SeedPar(11, 17, 10, 500, 20)   # seed length below the table depth: the third pass may only jump min_seed_len bases
     assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=12) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
 
