@@ -99,13 +99,16 @@ static dev_slot_t g_dev[8];
 static pthread_mutex_t g_dev_mu = PTHREAD_MUTEX_INITIALIZER;
 
 /* The on-disk suffix-array sample keeps every 32nd row (bwa index); 180 GB of HBM afford a denser one, which
- * the device derives from it in well under a second and which cuts the LF walk of every seed lookup from ~15.5
- * to ~3.5 steps (interval 8) without changing any result.  BWA_B200_SA_INTV overrides (32 keeps the disk sample);
- * skipped silently when the GPU is short of memory. */
+ * the device derives from it in about a second and which cuts the LF walk of every seed lookup from ~15.5 steps
+ * to ~0.5 (every 2nd row: 24 GB for a 3 Gbp reference; every 8th row, 6 GB, was the measured default of round 1:
+ * 3.5 steps) without changing any result.  It is derived in two stages (32 -> 8 -> 2) so that each stage walks only a
+ * few steps per row.  BWA_B200_SA_INTV overrides (32 keeps the disk sample); a stage that does not fit the free
+ * device memory is skipped silently and the previous sample stays. */
 static void densify_default(bwag_ctx_t *ctx)
 {
 	const char *e = getenv("BWA_B200_SA_INTV");
-	int intv = e ? atoi(e) : 8;
+	int intv = e ? atoi(e) : 2;
+	if (intv > 0 && intv < 8) bwag_ctx_densify_sa(ctx, 8);
 	if (intv > 0) bwag_ctx_densify_sa(ctx, intv);   /* a refusal (interval not below the current one, no memory) leaves the context as it was */
 	{   /* short-string table (include/bwa_b200_dev.h): BWA_B200_KTAB = depth, 0 = none; default: from the index size */
 		const char *k = getenv("BWA_B200_KTAB");

@@ -24,6 +24,7 @@ for mb in 4 5 8; do
   $B > $O/r2_first_minb$mb.json 2>/dev/null; echo "min blocks $mb:"; line $O/r2_first_minb$mb.json; lap minb$mb
 done
 make -s build/cuda/bwag_extend.o build/cuda/bwag_global.o -B > /dev/null 2>&1 && make -s all > /dev/null 2>&1
+for sa in 8 4 1; do BWA_B200_SA_INTV=$sa $B > $O/r2_first_sa$sa.json 2>/dev/null; echo "SA sample interval $sa (default 2):"; line $O/r2_first_sa$sa.json; done; lap sa_interval
 for m in spin yield sleep; do BWA_B200_SYNC=$m python bench.py --worker --steps 4 --warmup 2 --cpu-sample 2000 > $O/r2_first_pe_$m.json 2>/dev/null; echo "stream wait = $m:"; line $O/r2_first_pe_$m.json; done; lap sync_modes
 BWA_B200_LANES=1 BWA_B200_CHUNK=1000000 timeout 600 ncu --set full --import-source on --clock-control none -k regex:^k_extend_sm_fast\$ -s 2 -c 1 -o $O/r2_first_ncu_k_extend -f python bench.py --worker --layout se --steps 1 --warmup 2 --cpu-sample 2000 > $O/r2_first_ncu_k_extend.log 2>&1; lap ncu_k4
 ls -la $O/r2_first_* | awk '{print $5, $9}'
