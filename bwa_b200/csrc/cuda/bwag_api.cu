@@ -128,7 +128,7 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #ifdef BWAG_CUSIM
 #define BWAG_KTAB_MAX_AUTO 5     /* the emulator builds the table one fiber per entry: keep it small */
 #else
-#define BWAG_KTAB_MAX_AUTO 12
+#define BWAG_KTAB_MAX_AUTO 14
 #endif
 #define K4_SMEM_MAX (96 * 1024)
 
@@ -302,7 +302,7 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
 {
 	CK(cudaSetDevice(c->device));
-	if (K == 0) {   /* deep enough that the deepest level still has a few occurrences per string, at most 12 (358 MB) */
+	if (K == 0) {   /* as deep as strings still have a few dozen occurrences (their intervals span two Occ blocks): 14 at 3 Gbp = 5.7 GB */
 		int lg = 0;
 		while (lg < 31 && ((u64)1 << (2 * (lg + 1))) <= c->ix.seq_len) ++lg;   /* floor(log4(seq_len)) */
 		K = lg - 2;

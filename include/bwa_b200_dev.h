@@ -40,8 +40,9 @@ int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
 
 /* Short-string table: the bi-intervals (bwtintv_t x[0..2]) of ALL strings of 1..depth bases, so that a bwt_extend
  * (bwt.c:262-275) whose result is that short costs one 16-byte lookup instead of two Occ blocks (results unchanged;
- * two thirds of a read's extensions qualify at depth 12).  depth 0 = choose from the index size (at most 12: 358 MB),
- * depth < 0 = remove the table, depth <= 14. */
+ * two thirds of a read's extensions qualify at depth 12).  depth 0 = choose from the index size: floor(log4(BWT length)) - 2,
+ * i.e. as deep as strings still occur a few dozen times (14 at 3 Gbp: 358 M entries, 5.7 GB); depth < 0 = remove the table;
+ * depth <= 14. */
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
 const char *bwag_last_error(void);
 

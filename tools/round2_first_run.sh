@@ -18,7 +18,7 @@ PY
 B="python bench.py --worker --layout se --steps 3 --warmup 2 --cpu-sample 2000"
 $B > $O/r2_first_lean.json 2>/dev/null; line $O/r2_first_lean.json; lap lean
 BWA_B200_K4_FAST=0 BWA_B200_K5_FAST=0 $B > $O/r2_first_firstsweep.json 2>/dev/null; line $O/r2_first_firstsweep.json; lap first_sweep
-for k in 0 10 11 13 14; do BWA_B200_KTAB=$k $B > $O/r2_first_ktab$k.json 2>/dev/null; echo "short-string table depth $k (default 12):"; line $O/r2_first_ktab$k.json; done; lap ktab
+for k in 0 10 12 13; do BWA_B200_KTAB=$k $B > $O/r2_first_ktab$k.json 2>/dev/null; echo "short-string table depth $k (default 14):"; line $O/r2_first_ktab$k.json; done; lap ktab
 for mb in 4 5 8; do
   make -s NVEXTRA="-DK4_MINB=$mb -DK5_MINB=$mb" build/cuda/bwag_extend.o build/cuda/bwag_global.o -B > /dev/null 2>&1 && make -s all > /dev/null 2>&1
   $B > $O/r2_first_minb$mb.json 2>/dev/null; echo "min blocks $mb:"; line $O/r2_first_minb$mb.json; lap minb$mb
