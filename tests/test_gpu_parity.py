@@ -34,7 +34,7 @@ def test_cli_sam_identical_to_reference(data, name, ref, kw, extra):
     assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
 
 
-@pytest.mark.parametrize("ktab", [None, "0", "12"])
+@pytest.mark.parametrize("ktab", [None, "0", "14"])
 def test_edge_reads(data, tmp_path, monkeypatch, ktab):
     """Empty-ish and ragged input: reads shorter than the seed length, all-N reads, N runs, mixed lengths, lower case;
     with the short-string table at its default depth, without it, and at the depth used for 3 Gbp references."""
@@ -110,11 +110,11 @@ def test_seed_stage_buffers_equal_oracle(data):
     want = seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t)
     assert sum(len(r) for r in want) > 5000
     assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par, touches=t) == want
-    for depth in (4, 9, 12):   # with the short-string table (12 = the depth used at 3 Gbp): same buffers
+    for depth in (4, 9, 14):   # with the short-string table (14 = the depth used at 3 Gbp, 5.7 GB): same buffers
         assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par, ktab=depth, touches=t) == want
     assert len(set(t)) == 1 and t[0] > 0, t   # the roofline's numerator (reference-equivalent Occ-block touches) is the oracle's, table or not
     par11 = SeedPar(11, 17, 10, 500, 20)   # seed length below the table depth: the third pass may only jump min_seed_len bases
-    assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=12) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
+    assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=13) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
 
 
 def test_index_builder_identical_to_bwa_index(data, tmp_path):
