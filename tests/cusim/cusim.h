@@ -187,6 +187,6 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) { (v
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute a, int v) { (void)f; (void)a; (void)v; return cudaSuccess; }
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
 static inline cudaError_t cudaDeviceSetLimit(cudaLimit l, size_t v) { (void)l; (void)v; return cudaSuccess; }
-static inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = (size_t)8 << 30; *tot = (size_t)8 << 30; return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = (size_t)32 << 30; *tot = (size_t)32 << 30; return cudaSuccess; }
 
 #endif
