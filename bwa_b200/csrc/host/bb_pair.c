@@ -220,6 +220,24 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 }
 
 /* best proper pair among the primary-assembly hits of both ends (bwamem_pair.c:208-269) */
+/* The insert-size term of a pair's score, .721 * log(2 * erfc(|dist - avg| / std / sqrt 2)) * a (bwamem_pair.c:266), depends
+ * on the distance only and distances are integers in [low, high]: each thread tabulates the term once per insert-size
+ * model (same expression, same doubles) instead of calling erfc and log for every candidate pair. */
+typedef struct { double avg, std; int low, high, a, cap, valid; double *t; } pair_memo_t;
+static __thread pair_memo_t tl_pair_memo[4];
+static inline double pair_term(const mem_opt_t *opt, const mem_pestat_t *pe, int dir, int64_t dist)
+{
+	pair_memo_t *m = &tl_pair_memo[dir];
+	if (!m->valid || m->avg != pe->avg || m->std != pe->std || m->low != pe->low || m->high != pe->high || m->a != opt->a) {
+		int64_t n = (int64_t)pe->high - pe->low + 1, k;
+		if (n <= 0 || n > 65536) { double ns = (dist - pe->avg) / pe->std; return .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
+		if (n > m->cap) { m->t = bb_realloc(m->t, (size_t)n * sizeof(double)); m->cap = (int)n; }
+		for (k = 0; k < n; ++k) { double ns = ((pe->low + k) - pe->avg) / pe->std; m->t[k] = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
+		m->avg = pe->avg; m->std = pe->std; m->low = pe->low; m->high = pe->high; m->a = opt->a; m->valid = 1;
+	}
+	return m->t[dist - pe->low];
+}
+
 static int pair_hits(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], mem_alnreg_v a[2], int id, int *sub, int *n_sub, int z[2], int n_pri[2])
 {
 	BB_VEC(bb_pair64_t) v = {0, 0, 0}, u = {0, 0, 0};
@@ -247,14 +265,12 @@ static int pair_hits(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat
 			for (k = y[which]; k >= 0; --k) {
 				int64_t dist;
 				int q;
-				double ns;
 				bb_pair64_t p;
 				if ((v.a[k].y & 3) != (uint64_t)which) continue;
 				dist = (int64_t)v.a[i].x - v.a[k].x;
 				if (dist > pes[dir].high) break;
 				if (dist < pes[dir].low) continue;
-				ns = (dist - pes[dir].avg) / pes[dir].std;
-				q = (int)((v.a[i].y >> 32) + (v.a[k].y >> 32) + .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a + .499);
+				q = (int)((v.a[i].y >> 32) + (v.a[k].y >> 32) + pair_term(opt, &pes[dir], dir, dist) + .499);
 				if (q < 0) q = 0;
 				p.y = (uint64_t)k << 32 | i;
 				p.x = (uint64_t)q << 32 | (bb_mix64(p.y ^ id << 8) & 0xffffffffU);
