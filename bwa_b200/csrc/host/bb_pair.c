@@ -379,11 +379,11 @@ int bb_sam_pe(bb_samctx_t sc[2], const mem_pestat_t pes[4], uint64_t id, bseq1_t
 		}
 		if (!dry) {
 			/* one buffer per read, sized for the usual single record up front instead of a chain of doublings and a copy */
-			bb_str_need(&str, (size_t)s[0].l_seq * 2 + strlen(s[0].name) + 192);
+			bb_str_need(&str, (size_t)s[0].l_seq * 2 + strlen(s[0].name) + 448);   /* covers what bb_aln2sam reserves for one ordinary record: no second allocation */
 			for (i = 0; i < n_aa[0]; ++i) bb_aln2sam(opt, bns, &str, &s[0], n_aa[0], aa[0], i, &h[1]);
 			s[0].sam = str.s;
 			str.s = 0; str.l = str.m = 0;
-			bb_str_need(&str, (size_t)s[1].l_seq * 2 + strlen(s[1].name) + 192);
+			bb_str_need(&str, (size_t)s[1].l_seq * 2 + strlen(s[1].name) + 448);
 			for (i = 0; i < n_aa[1]; ++i) bb_aln2sam(opt, bns, &str, &s[1], n_aa[1], aa[1], i, &h[0]);
 			s[1].sam = str.s;
 			if (strcmp(s[0].name, s[1].name) != 0) bb_fatal("mem_sam_pe", "paired reads have different names: \"%s\", \"%s\"\n", s[0].name, s[1].name);

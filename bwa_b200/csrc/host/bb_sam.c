@@ -184,61 +184,85 @@ void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_
 	p->flag |= p->is_rev ? 0x10 : 0;
 	p->flag |= m && m->is_rev ? 0x20 : 0;
 
-	bb_puts(str, s->name); bb_putc(str, '\t');
-	bb_putl(str, (p->flag & 0xffff) | (p->flag & 0x10000 ? 0x100 : 0)); bb_putc(str, '\t');
-	if (p->rid >= 0) {
-		bb_puts(str, bns->anns[p->rid].name); bb_putc(str, '\t');
-		bb_putl(str, p->pos + 1); bb_putc(str, '\t');
-		bb_putl(str, p->mapq); bb_putc(str, '\t');
-		put_cigar(opt, p, str, which);
-	} else bb_putsn(str, "*\t0\t0\t*", 7);
-	bb_putc(str, '\t');
-
-	if (m && m->rid >= 0) {
-		if (p->rid == m->rid) bb_putc(str, '=');
-		else bb_puts(str, bns->anns[m->rid].name);
-		bb_putc(str, '\t');
-		bb_putl(str, m->pos + 1); bb_putc(str, '\t');
-		if (p->rid == m->rid) {
-			int64_t p0 = p->pos + (p->is_rev ? cigar_ref_len(p->n_cigar, p->cigar) - 1 : 0);
-			int64_t p1 = m->pos + (m->is_rev ? cigar_ref_len(m->n_cigar, m->cigar) - 1 : 0);
-			if (m->n_cigar == 0 || p->n_cigar == 0) bb_putc(str, '0');
-			else bb_putl(str, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
-		} else bb_putc(str, '0');
-	} else bb_putsn(str, "*\t0\t0", 5);
-	bb_putc(str, '\t');
-
-	if (p->flag & 0x100) bb_putsn(str, "*\t*", 3);
-	else {
-		int qb = 0, qe = s->l_seq, hard = p->n_cigar && which && !(opt->flag & MEM_F_SOFTCLIP) && !p->is_alt;
-		if (hard) { /* trim what a hard clip removes; on the reverse strand the CIGAR runs the other way */
-			int c0 = p->cigar[0] & 0xf, c1 = p->cigar[p->n_cigar - 1] & 0xf;
-			if (!p->is_rev) {
-				if (c0 == 4 || c0 == 3) qb += p->cigar[0] >> 4;
-				if (c1 == 4 || c1 == 3) qe -= p->cigar[p->n_cigar - 1] >> 4;
-			} else {
-				if (c0 == 4 || c0 == 3) qe -= p->cigar[0] >> 4;
-				if (c1 == 4 || c1 == 3) qb += p->cigar[p->n_cigar - 1] >> 4;
+	{   /* the fixed columns and tags: one capacity check for all of them, then plain stores through a local pointer
+	     * (the text is the reference's, field by field: bwamem.c:881-948) */
+		const char *rname = p->rid >= 0 ? bns->anns[p->rid].name : 0, *mname = m && m->rid >= 0 && p->rid != m->rid ? bns->anns[m->rid].name : 0;
+		const char *md = p->n_cigar ? (const char *)(p->cigar + p->n_cigar) : 0;
+		const size_t l_name = strlen(s->name), l_rname = rname ? strlen(rname) : 0, l_mname = mname ? strlen(mname) : 0, l_md = md ? strlen(md) : 0;
+		const size_t l_rg = bwa_rg_id[0] ? strlen(bwa_rg_id) : 0;
+		int qb = 0, qe = s->l_seq;
+		char *w;
+		if (!(p->flag & 0x100)) {
+			const int hard = p->n_cigar && which && !(opt->flag & MEM_F_SOFTCLIP) && !p->is_alt;
+			if (hard) { /* trim what a hard clip removes; on the reverse strand the CIGAR runs the other way */
+				int c0 = p->cigar[0] & 0xf, c1 = p->cigar[p->n_cigar - 1] & 0xf;
+				if (!p->is_rev) {
+					if (c0 == 4 || c0 == 3) qb += p->cigar[0] >> 4;
+					if (c1 == 4 || c1 == 3) qe -= p->cigar[p->n_cigar - 1] >> 4;
+				} else {
+					if (c0 == 4 || c0 == 3) qe -= p->cigar[0] >> 4;
+					if (c1 == 4 || c1 == 3) qb += p->cigar[p->n_cigar - 1] >> 4;
+				}
 			}
 		}
-		bb_str_need(str, (size_t)(qe - qb) * 2 + 4);
-		bb_codes_to_text(str->s + str->l, (const uint8_t *)s->seq + qb, qe - qb, p->is_rev);
-		str->l += (size_t)(qe - qb);
-		str->s[str->l++] = '\t';
-		if (s->qual) { bb_copy_text(str->s + str->l, s->qual + qb, qe - qb, p->is_rev); str->l += (size_t)(qe - qb); }
-		else str->s[str->l++] = '*';
-		str->s[str->l] = 0;
-	}
+		bb_str_need(str, l_name + l_rname + l_mname + l_md + l_rg + 12 * ((size_t)p->n_cigar + (m ? (size_t)m->n_cigar : 0)) + 2 * (size_t)(qe > qb ? qe - qb : 0) + 320);
+		w = str->s + str->l;
+#define W_C(c) (*w++ = (char)(c))
+#define W_S(ptr, len) do { memcpy(w, (ptr), (len)); w += (len); } while (0)
+#define W_L(v) (w = bb_fmt_l(w, (int64_t)(v)))
+#define W_CIGAR(al) do { const mem_aln_t *al_ = (al); int i_; \
+			if (al_->n_cigar) { for (i_ = 0; i_ < al_->n_cigar; ++i_) { int c_ = al_->cigar[i_] & 0xf; \
+				if (!(opt->flag & MEM_F_SOFTCLIP) && !al_->is_alt && (c_ == 3 || c_ == 4)) c_ = which ? 4 : 3; \
+				W_L(al_->cigar[i_] >> 4); W_C("MIDSH"[c_]); } } else W_C('*'); } while (0)
+		W_S(s->name, l_name); W_C('\t');
+		W_L((p->flag & 0xffff) | (p->flag & 0x10000 ? 0x100 : 0)); W_C('\t');
+		if (p->rid >= 0) {
+			W_S(rname, l_rname); W_C('\t');
+			W_L(p->pos + 1); W_C('\t');
+			W_L(p->mapq); W_C('\t');
+			W_CIGAR(p);
+		} else W_S("*\t0\t0\t*", 7);
+		W_C('\t');
 
-	if (p->n_cigar) {
-		bb_putsn(str, "\tNM:i:", 6); bb_putl(str, p->NM);
-		bb_putsn(str, "\tMD:Z:", 6); bb_puts(str, (char *)(p->cigar + p->n_cigar));
+		if (m && m->rid >= 0) {
+			if (p->rid == m->rid) W_C('=');
+			else W_S(mname, l_mname);
+			W_C('\t');
+			W_L(m->pos + 1); W_C('\t');
+			if (p->rid == m->rid) {
+				int64_t p0 = p->pos + (p->is_rev ? cigar_ref_len(p->n_cigar, p->cigar) - 1 : 0);
+				int64_t p1 = m->pos + (m->is_rev ? cigar_ref_len(m->n_cigar, m->cigar) - 1 : 0);
+				if (m->n_cigar == 0 || p->n_cigar == 0) W_C('0');
+				else W_L(-(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
+			} else W_C('0');
+		} else W_S("*\t0\t0", 5);
+		W_C('\t');
+
+		if (p->flag & 0x100) W_S("*\t*", 3);
+		else {
+			bb_codes_to_text(w, (const uint8_t *)s->seq + qb, qe - qb, p->is_rev);
+			w += qe - qb;
+			W_C('\t');
+			if (s->qual) { bb_copy_text(w, s->qual + qb, qe - qb, p->is_rev); w += qe - qb; }
+			else W_C('*');
+		}
+
+		if (p->n_cigar) {
+			W_S("\tNM:i:", 6); W_L(p->NM);
+			W_S("\tMD:Z:", 6); W_S(md, l_md);
+		}
+		if (m && m->n_cigar) { W_S("\tMC:Z:", 6); W_CIGAR(m); }
+		if (m) { W_S("\tMQ:i:", 6); W_L(m->mapq); }
+		if (p->score >= 0) { W_S("\tAS:i:", 6); W_L(p->score); }
+		if (p->sub >= 0) { W_S("\tXS:i:", 6); W_L(p->sub); }
+		if (l_rg) { W_S("\tRG:Z:", 6); W_S(bwa_rg_id, l_rg); }
+#undef W_C
+#undef W_S
+#undef W_L
+#undef W_CIGAR
+		*w = 0;
+		str->l = (size_t)(w - str->s);
 	}
-	if (m && m->n_cigar) { bb_putsn(str, "\tMC:Z:", 6); put_cigar(opt, m, str, which); }
-	if (m) { bb_putsn(str, "\tMQ:i:", 6); bb_putl(str, m->mapq); }
-	if (p->score >= 0) { bb_putsn(str, "\tAS:i:", 6); bb_putl(str, p->score); }
-	if (p->sub >= 0) { bb_putsn(str, "\tXS:i:", 6); bb_putl(str, p->sub); }
-	if (bwa_rg_id[0]) { bb_putsn(str, "\tRG:Z:", 6); bb_puts(str, bwa_rg_id); }
 	if (!(p->flag & 0x100)) {
 		for (i = 0; i < n; ++i)
 			if (i != which && !(list[i].flag & 0x100)) break;
@@ -336,7 +360,7 @@ void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, co
 	int l = 0;
 	char **XA = 0;
 	if (!(opt->flag & MEM_F_ALL)) XA = bb_gen_alt(sc, a, s->l_seq, s->seq);
-	if (!sc->dry) bb_str_need(&str, (size_t)s->l_seq * 2 + strlen(s->name) + 160);   /* one allocation for the common single-record case */
+	if (!sc->dry) bb_str_need(&str, (size_t)s->l_seq * 2 + strlen(s->name) + 448);   /* one allocation for the common single-record case */
 	for (k = 0; k < a->n; ++k) {
 		mem_alnreg_t *p = &a->a[k];
 		mem_aln_t q;

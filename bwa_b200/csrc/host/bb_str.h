@@ -33,4 +33,16 @@ static inline void bb_putl(bb_str_t *s, int64_t v)
 	while (n) s->s[s->l++] = buf[--n];
 	s->s[s->l] = 0;
 }
+/* the same digits at a raw write position with room for 21 characters; returns the position after them */
+static inline char *bb_fmt_l(char *w, int64_t v)
+{
+	char buf[24];
+	int n = 0;
+	uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1u : (uint64_t)v;
+	if (v >= 0 && u < 10) { *w++ = (char)('0' + u); return w; }
+	do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (v < 0) buf[n++] = '-';
+	while (n) *w++ = buf[--n];
+	return w;
+}
 #endif
