@@ -6,6 +6,7 @@
  * sorts are the unstable introsort of bb_sort.h, so equal keys end up in the same order.
  */
 #include <math.h>
+#include <pthread.h>
 #include <limits.h>
 #include "bb_host.h"
 #include "bb_sort.h"
@@ -205,6 +206,18 @@ void bb_reorder_primary5(int T, mem_alnreg_v *a)
 }
 
 /* bwamem.c:982-1006 */
+/* log of a small non-negative integer (seed coverage, number of sub-optimal hits + 1): the same libm values, tabulated once */
+#define LOGTAB_N 4096
+static double g_logtab[LOGTAB_N];
+static pthread_once_t g_logtab_once = PTHREAD_ONCE_INIT;
+static void logtab_init(void) { int i; for (i = 0; i < LOGTAB_N; ++i) g_logtab[i] = log(i); }
+static inline double log_of_int(int n)
+{
+	if ((unsigned)n >= LOGTAB_N) return log(n);
+	pthread_once(&g_logtab_once, logtab_init);
+	return g_logtab[n];
+}
+
 int bb_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a)
 {
 	int mapq, l, sub = a->sub ? a->sub : opt->min_seed_len * opt->a;
@@ -220,10 +233,10 @@ int bb_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a)
 		tmp *= identity * identity;
 		mapq = (int)(6.02 * (a->score - sub) / opt->a * tmp * tmp + .499);
 	} else {
-		mapq = (int)(MEM_MAPQ_COEF * (1. - (double)sub / a->score) * log(a->seedcov) + .499);
+		mapq = (int)(MEM_MAPQ_COEF * (1. - (double)sub / a->score) * log_of_int(a->seedcov) + .499);
 		mapq = identity < 0.95 ? (int)(mapq * identity * identity + .499) : mapq;
 	}
-	if (a->sub_n > 0) mapq -= (int)(4.343 * log(a->sub_n + 1) + .499);
+	if (a->sub_n > 0) mapq -= (int)(4.343 * log_of_int(a->sub_n + 1) + .499);
 	if (mapq > 60) mapq = 60;
 	if (mapq < 0) mapq = 0;
 	mapq = (int)(mapq * (1. - a->frac_rep) + .499);
