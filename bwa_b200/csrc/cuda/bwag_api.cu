@@ -133,7 +133,7 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #define K4_SMEM_MAX (96 * 1024)
 
 #ifdef BWAG_CUSIM
-unsigned long long bwag_cusim_sector_loads;
+unsigned long long bwag_cusim_sector_loads, bwag_cusim_list_acc[5];
 #endif
 
 /* ------------------------------------------------------------------------------------------------ index */
@@ -406,7 +406,7 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
 	}
 #ifdef BWAG_CUSIM
-	if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] emulator: %llu 32-byte block/table loads so far (K1, K1f, K2, table build)\n", bwag_cusim_sector_loads);
+	if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] emulator: %llu 32-byte block/table loads so far (K1, K1f, K2, table build); K1 candidate-list accesses by entry index 0-3: %llu, 4-7: %llu, 8-11: %llu, 12-15: %llu, 16+: %llu (the first K1_SLOTS of a list live in shared memory)\n", bwag_cusim_sector_loads, bwag_cusim_list_acc[0], bwag_cusim_list_acc[1], bwag_cusim_list_acc[2], bwag_cusim_list_acc[3], bwag_cusim_list_acc[4]);
 #endif
 	if (getenv("BWA_B200_PROFILE"))   /* with the host's phase timer: the work counters of this batch */
 		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu\n", b->n,

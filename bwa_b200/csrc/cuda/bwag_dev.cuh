@@ -55,7 +55,7 @@ struct DevIndex {
 
 #define FULL_MASK 0xffffffffu
 #ifdef BWAG_CUSIM
-extern unsigned long long bwag_cusim_sector_loads;
+extern unsigned long long bwag_cusim_sector_loads, bwag_cusim_list_acc[5];
 #endif
 
 /* one 32-byte Occ block with ONE 256-bit load (LDG.E.256, sm_100+): the table is far larger than the TLB reach, and

@@ -271,9 +271,14 @@ k_smem(DevIndex ix, SeedArgs a)
 	u32 overflow = 0;
 
 #define ENT_PTR(l, idx) ((idx) < K1_SLOTS ? sl + ((l) * K1_SLOTS + (idx)) * K1_THREADS : gl + (l) * a.cap_list + (idx))
-#define ENT_ST(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); const ulonglong2 v_ = pack_ent(X0, X1, X2, E); \
+#ifdef BWAG_CUSIM   /* emulator only: how much of the candidate-list traffic the K1_SLOTS shared entries per list catch */
+#define ENT_COUNT(i_) __atomic_fetch_add(&bwag_cusim_list_acc[(i_) < 4 ? 0 : (i_) < 8 ? 1 : (i_) < 12 ? 2 : (i_) < 16 ? 3 : 4], 1ull, __ATOMIC_RELAXED)
+#else
+#define ENT_COUNT(i_) ((void)0)
+#endif
+#define ENT_ST(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); const ulonglong2 v_ = pack_ent(X0, X1, X2, E); ENT_COUNT(i_); \
 		if (i_ < K1_SLOTS) sl[(l_ * K1_SLOTS + i_) * K1_THREADS] = v_; else gl[l_ * a.cap_list + i_] = v_; } while (0)
-#define ENT_LD(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); ulonglong2 v_; \
+#define ENT_LD(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); ulonglong2 v_; ENT_COUNT(i_); \
 		if (i_ < K1_SLOTS) v_ = sl[(l_ * K1_SLOTS + i_) * K1_THREADS]; else v_ = gl[l_ * a.cap_list + i_]; unpack_ent(v_, X0, X1, X2, E); } while (0)
 	/* forward sweep over: candidates are visited longest match first; the call returns the end of the longest match */
 #define TURN_AROUND() do { ret = (int)ikend; pl ^= 1; n_prev = n_curr; n_curr = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; } while (0)
