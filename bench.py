@@ -187,6 +187,17 @@ def supervise(argv):
     return 3
 
 
+def selfcheck_status():
+    try:
+        import ctypes as C
+        import bwa_b200
+        L = bwa_b200.lib()
+        L.bb_selfcheck_status.restype = C.c_int
+        return int(L.bb_selfcheck_status())
+    except Exception:
+        return -1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,6 +404,7 @@ def main():
                            os.path.getsize(fa + ".bwt") / 1e9 * (1.25 + 16.0 / (a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")))) + 5.7, n_reads * a.read_len / 1e6),
                        "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
                        "pipeline": pipe_cfg + ", %d mem_process_seqs calls in flight" % inflight,
+                       "device_selfcheck": {0: "not run", 1: "passed (192 reads from the reference: default kernels == baseline kernels)", 2: "DIFFERED: the baseline kernels (first row sweeps, no short-string table) are in use"}.get(selfcheck_status(), "?"),
                        "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],

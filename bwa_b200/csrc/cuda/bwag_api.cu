@@ -79,6 +79,7 @@ struct bwag_ctx {
 	DevIndex ix;
 	u64 *dense_sa;
 	ulonglong2 *ktab;            /* short-string table (bwag_ctx_build_ktab) */
+	int baseline;                /* bwag_ctx_baseline(): first row sweeps in K4/K5 and no table lookups */
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1, ev_wait;
 	Counters *d_cnt, *h_cnt;
@@ -343,6 +344,18 @@ extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
 	return 0;
 }
 
+/* on = 1: batches begun from now on use the first formulation of the K4/K5 row sweeps and no short-string table (the
+ * configuration measured in round 1); on = 0: back to the defaults.  Used by the host's start-up self-check. */
+extern "C" void bwag_ctx_baseline(bwag_ctx_t *c, int on) { pthread_mutex_lock(&c->mu); c->baseline = on != 0; pthread_mutex_unlock(&c->mu); }
+extern "C" int bwag_is_emulator(void)
+{
+#ifdef BWAG_CUSIM
+	return 1;
+#else
+	return 0;
+#endif
+}
+
 extern "C" void bwag_stats_get(bwag_ctx_t *c, bwag_stats_t *s) { pthread_mutex_lock(&c->mu); *s = c->st; pthread_mutex_unlock(&c->mu); }
 extern "C" void bwag_stats_reset(bwag_ctx_t *c) { pthread_mutex_lock(&c->mu); memset(&c->st, 0, sizeof(c->st)); pthread_mutex_unlock(&c->mu); }
 
@@ -374,6 +387,8 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 		b->lc_ready = 1;
 	}
 	b->lc.device = c->device; b->lc.n_sm = c->n_sm; b->lc.ix = c->ix; b->lc.parent = c;
+	b->lc.baseline = c->baseline;
+	if (c->baseline) { b->lc.ix.ktab = 0; b->lc.ix.ktab_k = 0; }
 	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k1f = c->grid_k1f; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
 	memset(&b->lc.st, 0, sizeof(b->lc.st));
 	b->max_len = 0; b->seeded = 0;
@@ -599,7 +614,7 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K4_SM") && atoi(getenv("BWA_B200_K4_SM")) == 0);
 	/* the leaner row sweep (and its row cut-off) needs non-negative gap penalties (every real scoring scheme); BWA_B200_K4_FAST=0 forces the general one */
 	const int fast = a.par.e_ins >= 0 && a.par.o_ins + a.par.e_ins >= 0 && a.par.e_del >= 0 && a.par.o_del + a.par.e_del >= 0 &&
-	                 !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
+	                 !c->baseline && !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
 #ifndef BWAG_CUSIM
 	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast ? k_extend_sm_fast : k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
 #endif
@@ -808,7 +823,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	const int k5_per_warp = (8 * (cap_q + 2) + cap_r + cap_q + 2 + 15) & ~15;
 	const size_t k5_smem = (size_t)k5_per_warp * (K5_THREADS / 32);
 	int k5_sm = k5_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K5_SM") && atoi(getenv("BWA_B200_K5_SM")) == 0);
-	const int k5_fast = !(getenv("BWA_B200_K5_FAST") && atoi(getenv("BWA_B200_K5_FAST")) == 0);   /* 0: the first formulation of the row sweep */
+	const int k5_fast = !c->baseline && !(getenv("BWA_B200_K5_FAST") && atoi(getenv("BWA_B200_K5_FAST")) == 0);   /* 0: the first formulation of the row sweep */
 #ifndef BWAG_CUSIM
 	if (k5_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k5_fast ? k_global_sm_fast : k_global_sm, K5_THREADS, k5_smem)); if (nb < 2) k5_sm = 0; else grid = c->n_sm * nb; }
 #endif

@@ -121,6 +121,8 @@ void bb_aln2sam(const mem_opt_t *opt, const bntseq_t *bns, bb_str_t *str, bseq1_
 void bb_reg2sam(bb_samctx_t *sc, bseq1_t *s, mem_alnreg_v *a, int extra_flag, const mem_aln_t *m);
 char **bb_gen_alt(bb_samctx_t *sc, const mem_alnreg_v *a, int l_query, const char *query);
 
+int bb_selfcheck_status(void);   /* start-up self-check of the device kernels: 0 not run, 1 passed, 2 differed (running on the baseline kernels) */
+
 /* ---- paired-end (bb_pair.c) ---- */
 uint64_t bb_pestat_pair(const mem_opt_t *opt, int64_t l_pac, const mem_alnreg_v *r0, const mem_alnreg_v *r1);
 void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v, mem_pestat_t pes[4]);

@@ -117,10 +117,80 @@ static void densify_default(bwag_ctx_t *ctx)
 	}
 }
 
+/* Start-up self-check.  The lean row sweeps of K4/K5 and the short-string table of K1 compute exactly what the first
+ * formulations compute; to make a platform-specific fault in them visible (and harmless) the moment an index goes to the
+ * device, a few hundred reads drawn from the reference itself (with substitutions, small insertions and deletions, both
+ * strands) are aligned twice -- defaults, then baseline (bwag_ctx_baseline) -- and the SAM records compared.  Any
+ * difference: a warning on stderr and the context stays on the baseline, whose parity was measured on the B200.
+ * BWA_B200_SELFCHECK = number of reads (default 192 on a CUDA device, 0 = off; off by default in the test emulator). */
+static __thread bwag_ctx_t *tl_attach_override;   /* the self-check aligns through mem_process_seqs while the registry lock is held */
+static int g_selfcheck_status;                    /* 0 not run, 1 passed, 2 differed: running on the baseline */
+int bb_selfcheck_status(void) { return __atomic_load_n(&g_selfcheck_status, __ATOMIC_RELAXED); }
+
+static bseq1_t *selfcheck_reads(const bntseq_t *bns, const uint8_t *pac, int n, int len)
+{
+	bseq1_t *seqs = bb_calloc((size_t)n, sizeof(bseq1_t));
+	uint64_t rng = 0x9e3779b97f4a7c15ULL;
+	int i, k;
+	for (i = 0; i < n; ++i) {
+		char *s = bb_malloc((size_t)len + 8), name[32];
+		int l = 0;
+		int64_t pos;
+		rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+		pos = (int64_t)((rng >> 11) % (uint64_t)(bns->l_pac - len - 8));
+		for (k = 0; k < len + 4 && l < len; ++k) {
+			int c = pac[(pos + k) >> 2] >> ((~(pos + k) & 3) << 1) & 3;
+			if (k == 17 + i % 23 || k == len - 9 - i % 11) c = (c + 1 + i % 3) & 3;      /* two substitutions */
+			if (i % 3 == 1 && (k == len / 2 || k == len / 2 + 1)) continue;            /* a 2-base deletion */
+			if (i % 5 == 2 && k == len / 3) { s[l++] = "ACGT"[(c + 2) & 3]; if (l < len) s[l++] = "ACGT"[(c + 1) & 3]; if (l < len) s[l++] = "ACGT"[c]; }   /* a 3-base insertion */
+			if (l < len) s[l++] = "ACGT"[c];
+		}
+		if (i & 1) {   /* reverse complement */
+			for (k = 0; k < l / 2; ++k) { char t = s[k]; s[k] = s[l - 1 - k]; s[l - 1 - k] = t; }
+			for (k = 0; k < l; ++k) s[k] = s[k] == 'A' ? 'T' : s[k] == 'C' ? 'G' : s[k] == 'G' ? 'C' : 'A';
+		}
+		s[l] = 0;
+		snprintf(name, sizeof(name), "selfcheck%d", i);
+		seqs[i].l_seq = l; seqs[i].seq = s; seqs[i].name = bb_malloc(strlen(name) + 1); strcpy(seqs[i].name, name);
+	}
+	return seqs;
+}
+static void selfcheck_free(bseq1_t *seqs, int n) { int i; for (i = 0; i < n; ++i) { free(seqs[i].seq); free(seqs[i].name); free(seqs[i].sam); } free(seqs); }
+
+static void device_selfcheck(bwag_ctx_t *ctx, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
+{
+	const char *e = getenv("BWA_B200_SELFCHECK");
+	int n = e ? atoi(e) : (bwag_is_emulator() ? 0 : 192), i, differ = 0;
+	const int len = 120;
+	bseq1_t *a, *b;
+	mem_opt_t *opt;
+	if (n <= 0 || bwag_is_emulator() == 2 || bns->l_pac < 4 * len) return;
+	opt = mem_opt_init();
+	opt->n_threads = 2;
+	a = selfcheck_reads(bns, pac, n, len); b = selfcheck_reads(bns, pac, n, len);
+	tl_attach_override = ctx;
+	mem_process_seqs(opt, bwt, bns, pac, 0, n, a, 0);
+	bwag_ctx_baseline(ctx, 1);
+	mem_process_seqs(opt, bwt, bns, pac, 0, n, b, 0);
+	tl_attach_override = 0;
+	if (getenv("BWA_B200_SELFCHECK_INJECT") && a[0].sam && a[0].sam[0]) a[0].sam[strlen(a[0].sam) / 2] ^= 1;   /* test hook: pretend a difference */
+	for (i = 0; i < n; ++i) if (!a[i].sam || !b[i].sam || strcmp(a[i].sam, b[i].sam) != 0) { ++differ; if (differ == 1 && bwa_verbose >= 1) fprintf(stderr, "[W::bwa_b200] self-check: first differing record\n  default : %s  baseline: %s", a[i].sam ? a[i].sam : "(none)\n", b[i].sam ? b[i].sam : "(none)\n"); }
+	if (differ) {
+		fprintf(stderr, "[W::bwa_b200] start-up self-check: %d of %d records differ between the default kernels and the baseline; staying on the baseline kernels\n", differ, n);
+		__atomic_store_n(&g_selfcheck_status, 2, __ATOMIC_RELAXED);
+	} else {
+		bwag_ctx_baseline(ctx, 0);
+		__atomic_store_n(&g_selfcheck_status, 1, __ATOMIC_RELAXED);
+	}
+	selfcheck_free(a, n); selfcheck_free(b, n);
+	free(opt);
+}
+
 bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 {
 	int i;
 	bwag_ctx_t *ctx = 0;
+	if (tl_attach_override) return tl_attach_override;
 	pthread_mutex_lock(&g_dev_mu);
 	for (i = 0; i < 8; ++i) if (g_dev[i].bwt == bwt && g_dev[i].ctx) { ctx = g_dev[i].ctx; break; }
 	if (!ctx) {
@@ -130,6 +200,7 @@ bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_
 		if (!ctx) bb_fatal("bb_device_attach", "cannot place the index on the GPU: %s", bwag_last_error());
 		densify_default(ctx);
 		g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
+		device_selfcheck(ctx, bwt, bns, pac);   /* other callers wait for the verdict */
 	}
 	pthread_mutex_unlock(&g_dev_mu);
 	return ctx;

@@ -44,6 +44,13 @@ int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
  * i.e. as deep as strings still occur a few dozen times (14 at 3 Gbp: 358 M entries, 5.7 GB); depth < 0 = remove the table;
  * depth <= 14. */
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
+
+/* on != 0: batches begun from now on run the first formulation of the extension / global-alignment row sweeps and do no
+ * short-string table lookups (same results, the configuration measured in round 1); 0: the defaults again.  The host's
+ * start-up self-check compares the two on a few hundred reads drawn from the reference and stays on the baseline if
+ * they ever disagree. */
+void bwag_ctx_baseline(bwag_ctx_t *ctx, int on);
+int bwag_is_emulator(void);   /* 0: CUDA device; 1: the CPU SIMT emulator of the tests; 2: the CPU oracle stages (tests) */
 const char *bwag_last_error(void);
 
 /* Page-locked host memory for buffers that are handed to the stage calls (reads, extension work, tasks):

@@ -76,6 +76,8 @@ int bwag_blob_fill(int device, void *d_blob, const bwt_t *bwt, int64_t l_pac, co
 bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own) { (void)device; (void)d_blob; (void)own; return 0; }
 int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv) { (void)ctx; (void)intv; return 0; }
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth) { (void)ctx; (void)depth; return 0; }
+void bwag_ctx_baseline(bwag_ctx_t *ctx, int on) { (void)ctx; (void)on; }
+int bwag_is_emulator(void) { return 2; }
 
 bwag_ctx_t *bwag_ctx_create(int device, const bwt_t *bwt, int64_t l_pac, const uint8_t *pac)
 {

@@ -152,3 +152,15 @@ def test_kernel_variants(data, monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     assert run_sam(bwa_b200.CLI_PATH, args) == want
+
+
+def test_startup_selfcheck_passed(data):
+    """Attaching an index runs the start-up self-check (192 reads drawn from the reference: default kernels vs the baseline
+    kernels).  It must have passed; had it not, the library would be running on the baseline kernels and every other test
+    here would still be green, so this is the test that says so."""
+    idx = bwa_b200.Index(data.ref("stress"))
+    idx.attach()
+    L = bwa_b200.lib()
+    L.bb_selfcheck_status.restype = C.c_int
+    assert L.bb_selfcheck_status() == 1
+    idx.close()
