@@ -6,7 +6,11 @@
 #define K1_THREADS 128
 #define K1F_THREADS 128
 #ifndef K1_SLOTS
+#ifdef K1_PACKED8
+#define K1_SLOTS 8
+#else
 #define K1_SLOTS 4
+#endif
 #endif
 //       /* candidate-list entries per list kept in shared memory */
 #define K1B_THREADS 128
@@ -26,6 +30,7 @@ struct SeedArgs {
 	Intv *scratch; int cap_list, cap_mem;
 	int qstride;                                   /* bytes of a lane's shared read slot (0: read the bases from global memory) */
 	int pstride;                                   /* bytes of a lane's 2-bit packed copy of the read (0: no short-string table lookups in K1) */
+	int nstride;                                   /* variant K1_PACKED8 only: bytes of a lane's N bitmap (the byte copy of the read is dropped: qstride = 0) */
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;

@@ -253,6 +253,17 @@ k_smem(DevIndex ix, SeedArgs a)
 	/* then K1_THREADS packed copies of the reads (2 bits per base, pstride bytes each): the keys of the short-string table */
 	u32 *sp = reinterpret_cast<u32 *>(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)K1_THREADS * a.qstride + (size_t)threadIdx.x * a.pstride));
 	const int ktk = a.pstride ? ix.ktab_k : 0;
+#ifdef K1_PACKED8
+	/* variant (not the default; tools/k1_variants.sh -DK1_PACKED8): the read lives in shared memory ONLY as the 2-bit packed
+	 * copy plus one N bit per base (64 instead of 200 bytes per lane at 150 bp), which pays for K1_SLOTS = 8 list entries per
+	 * list at the same footprint: 79 % instead of 47 % of the candidate-list accesses stay in shared memory */
+	u32 *sn = reinterpret_cast<u32 *>(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)K1_THREADS * (a.qstride + a.pstride) + (size_t)threadIdx.x * a.nstride));
+#define QISN(i_) (a.pstride ? (int)(sn[(i_) >> 5] >> ((i_) & 31) & 1u) : (int)(q[i_] > 3))
+#define QBASE(i_) (a.pstride ? (int)(sp[(i_) >> 4] >> (((i_) & 15) << 1) & 3u) : (int)q[i_])
+#else
+#define QISN(i_) (q[i_] > 3)
+#define QBASE(i_) ((int)q[i_])
+#endif
 	sl += threadIdx.x;
 	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
 	/* per-lane global scratch (units of 16 bytes): the tails of the two candidate lists (cap_list entries each),
@@ -301,7 +312,7 @@ k_smem(DevIndex ix, SeedArgs a)
 		for (;;) {
 			if (st == ST_IDLE) {
 				if (pass == 0) {            /* first pass: all SMEMs (bwamem.c:147-157) */
-					while (x < len && q[x] > 3) ++x;
+					while (x < len && QISN(x)) ++x;
 					if (x >= len) { pass = 1; k2 = 0; old_n = mem_n; continue; }
 					sx = x; min_intv = 1;
 				} else if (pass == 1) {     /* second pass: re-seed inside long, rare SMEMs (bwamem.c:159-168) */
@@ -333,6 +344,22 @@ k_smem(DevIndex ix, SeedArgs a)
 					len = (int)(a.off[rid + 1] - o);
 					pass = 0; x = 0; mem_n = 0;
 					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
+#ifdef K1_PACKED8
+					if (a.pstride) {            /* pack straight from global memory: 2 bits per base + an N bit per base */
+						q = a.codes + o;
+						const int nwp = ((len + 15) >> 4) + 1, nwn = (len + 31) >> 5;
+						for (int w = 0; w < nwp; ++w) {
+							u32 pw = 0;
+							for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
+							sp[w] = pw;
+						}
+						for (int w = 0; w < nwn; ++w) {
+							u32 nb = 0;
+							for (int t = 0; t < 32; ++t) { const int idx = (w << 5) + t; if (idx < len && q[idx] > 3) nb |= 1u << t; }
+							sn[w] = nb;
+						}
+					} else
+#endif
 					if (a.qstride) {            /* the read moves to this lane's shared slot (whole aligned words) */
 						const u32 *g = reinterpret_cast<const u32 *>(a.codes + (o & ~(i64)3));
 						u32 *d = reinterpret_cast<u32 *>(const_cast<uint8_t *>(sq));
@@ -351,20 +378,20 @@ k_smem(DevIndex ix, SeedArgs a)
 					continue;
 				}
 				/* start bwt_smem1(sx, min_intv) (bwt.c:289-303) */
-				INIT_INTV(q[sx], ik0, ik1, ik2);
+				INIT_INTV(QBASE(sx), ik0, ik1, ik2);
 				ikend = (u32)sx + 1;
 				i = sx + 1; n_curr = 0; m1_n = 0; st = ST_FWD;
 				continue;
 			}
 			if (st == ST_FWD) {
-				if (i < len && q[i] < 4) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; break; }
+				if (i < len && !QISN(i)) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; break; }
 				/* end of read or ambiguous base: keep the current interval, then turn around (bwt.c:317-326) */
 				ENT_ST(pl ^ 1, n_curr, ik0, ik1, ik2, ikend); ++n_curr;
 				TURN_AROUND();
 				continue;
 			}
 			if (st == ST_BWD) {
-				const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
+				const int c = i < 0 ? -1 : (QISN(i) ? -1 : QBASE(i));
 				if (c < 0) {
 					/* nothing extends: only the longest candidate (first in visiting order) can be an SMEM (bwt.c:332-338) */
 					if (m1_n == 0 || i + 1 < last_start) {
@@ -391,7 +418,7 @@ k_smem(DevIndex ix, SeedArgs a)
 		if (__all_sync(FULL_MASK, st == ST_NONE)) break;
 		if (!need) continue;
 
-		const int cq = q[i];                               /* base to add: forward uses its complement (bwt.c:309), backward the base itself */
+		const int cq = QBASE(i);                           /* base to add: forward uses its complement (bwt.c:309), backward the base itself */
 		u64 o_s, o_o, o_x2;
 		{
 			const int rlen = back ? (int)pend - i : i + 1 - sx;   /* the string this extension produces: q[i..pend) or q[sx..i] */
