@@ -10,7 +10,7 @@ line() { python - "$1" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print(sys.argv[1], "e2e %.0f reads/s, %.1f ms/step" % (d["e2e"]["value"], d["ms_per_step"]), {k: round(v, 1) for k, v in d["kernels_ms_per_step"].items()}, d.get("cpu_baseline", {}).get("sam_identical_on_sample"))
+    print(sys.argv[1], "e2e %.0f reads/s, %.1f ms/step" % (d["e2e"]["value"], d["ms_per_step"]), {k: round(v, 1) for k, v in d["kernels_ms_per_step"].items()}, d.get("cpu_baseline", {}).get("sam_identical_on_sample"), "| self-check:", d["config"].get("device_selfcheck", "?")[:40])
 except Exception as e:
     print(sys.argv[1], "unreadable:", e)
 PY
