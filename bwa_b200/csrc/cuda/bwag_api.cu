@@ -394,7 +394,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 	b->max_len = 0; b->seeded = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
 	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
-	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { free(b); return 0; }
+	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { batch_free(b); return 0; }
 	c = &b->lc;
 	CKP(cudaEventRecord(c->ev0, c->stream));
 	CKP(cudaMemcpyAsync(b->d_codes.p, codes, (size_t)b->total_bases, cudaMemcpyHostToDevice, c->stream));

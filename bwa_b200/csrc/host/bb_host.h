@@ -34,6 +34,7 @@ void bb_clamp_to_contig(const bntseq_t *bns, int64_t *beg, int64_t mid, int64_t 
 bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac);
 void bb_device_release(const bwt_t *bwt);
 void bb_device_adopt(const bwt_t *bwt, bwag_ctx_t *ctx);
+void bb_device_adopt2(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, bwag_ctx_t *ctx);
 
 /* ---- chaining (bb_chain.c) ---- */
 typedef struct { int64_t rbeg; int32_t qbeg, len; int score; } bb_seed_t;

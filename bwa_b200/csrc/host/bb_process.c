@@ -176,6 +176,10 @@ static void device_selfcheck(bwag_ctx_t *ctx, const bwt_t *bwt, const bntseq_t *
 	if (getenv("BWA_B200_SELFCHECK_INJECT") && a[0].sam && a[0].sam[0]) a[0].sam[strlen(a[0].sam) / 2] ^= 1;   /* test hook: pretend a difference */
 	for (i = 0; i < n; ++i) if (!a[i].sam || !b[i].sam || strcmp(a[i].sam, b[i].sam) != 0) { ++differ; if (differ == 1 && bwa_verbose >= 1) fprintf(stderr, "[W::bwa_b200] self-check: first differing record\n  default : %s  baseline: %s", a[i].sam ? a[i].sam : "(none)\n", b[i].sam ? b[i].sam : "(none)\n"); }
 	if (differ) {
+		/* a difference is a fault of this platform or build: stop (every failure of this library is fatal, as in the reference),
+		 * unless the caller asked to continue on the baseline kernels (BWA_B200_SELFCHECK_FALLBACK=1) */
+		if (!(getenv("BWA_B200_SELFCHECK_FALLBACK") && atoi(getenv("BWA_B200_SELFCHECK_FALLBACK"))))
+			bb_fatal("bwa_b200 self-check", "%d of %d records differ between the default kernels and the baseline kernels; set BWA_B200_SELFCHECK_FALLBACK=1 to run on the baseline kernels", differ, n);
 		fprintf(stderr, "[W::bwa_b200] start-up self-check: %d of %d records differ between the default kernels and the baseline; staying on the baseline kernels\n", differ, n);
 		__atomic_store_n(&g_selfcheck_status, 2, __ATOMIC_RELAXED);
 	} else {
@@ -206,17 +210,20 @@ bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_
 	return ctx;
 }
 
-/* register a context created elsewhere (e.g. from an NCCL-broadcast blob) for this host index */
-void bb_device_adopt(const bwt_t *bwt, bwag_ctx_t *ctx)
+/* register a context created elsewhere (e.g. from an NCCL-broadcast blob) for this host index; with bns/pac given the
+ * start-up self-check runs here as it does in bb_device_attach.  The slot becomes visible only when the context is ready. */
+void bb_device_adopt2(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, bwag_ctx_t *ctx)
 {
 	int i;
 	pthread_mutex_lock(&g_dev_mu);
 	for (i = 0; i < 8 && g_dev[i].ctx; ++i) {}
 	if (i == 8) bb_fatal("bb_device_adopt", "too many resident indexes");
-	g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
-	pthread_mutex_unlock(&g_dev_mu);
 	densify_default(ctx);
+	g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
+	if (bns && pac) device_selfcheck(ctx, bwt, bns, pac);
+	pthread_mutex_unlock(&g_dev_mu);
 }
+void bb_device_adopt(const bwt_t *bwt, bwag_ctx_t *ctx) { bb_device_adopt2(bwt, 0, 0, ctx); }
 
 void bb_device_release(const bwt_t *bwt)
 {
@@ -992,7 +999,12 @@ mem_alnreg_v mem_align1(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *
 	sw_par_from_opt(opt, &swp);
 	batch = run_to_regs(&j, bb_device_attach(bwt, bns, pac), &swp);
 	bwag_batch_end(batch);
-	out = j.rs[0].regs; j.rs[0].regs.a = 0;
+	{   /* the caller owns (and frees) the array: never hand out a slice of the batch-wide region block */
+		const mem_alnreg_v *r = &j.rs[0].regs;
+		out.n = r->n; out.m = r->n + 4;
+		out.a = bb_malloc(out.m * sizeof(mem_alnreg_t));
+		if (r->n) memcpy(out.a, r->a, r->n * sizeof(mem_alnreg_t));
+	}
 	bb_mark_primary_se(opt, (int)out.n, out.a, lrand48());
 	job_free(&j);
 	free(s.seq);

@@ -286,9 +286,11 @@ def _refine_ties(W, T, key, pos, n, torch, verbose):
         q = p + off
         ended = q >= n                           # ran off the text: sorts before everything else in its group
         k2 = _suffix_keys(W, torch.where(ended, torch.zeros_like(q), q), n, torch)
-        # order by (group, ended first, key): three stable sorts, least significant first
+        # order by (group, ended first -- the shorter suffix first: '$' sorts below every base, and two suffixes that ran off
+        # the text in the same group are A-padded copies of each other --, then key): three stable sorts, least significant first
         o = torch.sort(k2, stable=True).indices
-        o = o[torch.sort((~ended[o]).to(torch.int8), stable=True).indices]
+        ekey = torch.where(ended, -p, torch.full_like(p, 0x7fffffffffffffff))
+        o = o[torch.sort(ekey[o], stable=True).indices]
         o = o[torch.sort(g[o], stable=True).indices]
         g, p, k2, ended = g[o], p[o], k2[o], ended[o]
         pos[sel] = p                             # slots of a group are contiguous and sel is sorted, so this writes each group in its new order

@@ -34,7 +34,7 @@ def _bind(L):
     L.bwag_blob_fill.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.bwag_ctx_from_blob.restype = C.c_void_p
     L.bwag_ctx_from_blob.argtypes = [C.c_int, C.c_void_p, C.c_int]
-    L.bb_device_adopt.argtypes = [C.c_void_p, C.c_void_p]
+    L.bb_device_adopt2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bb_cli_set_index.argtypes = [C.c_void_p]
     L.bwa_idx_load.restype = C.POINTER(bwa_b200.BwaIdx)
     L.bwa_idx_load.argtypes = [C.c_char_p, C.c_int]
@@ -74,7 +74,7 @@ def replicate_index(L, prefix, rank, device, dist=None, on_gpu=True):
         key = C.create_string_buffer(256)
         i.bwt = C.cast(key, C.c_void_p)
         keep.append(key)
-    L.bb_device_adopt(i.bwt, ctx)
+    L.bb_device_adopt2(i.bwt, i.bns, i.pac, ctx)   # densifies the SA sample, builds the short-string table, runs the start-up self-check
     keep.append(blob)
     return idx, keep
 

@@ -169,6 +169,17 @@ typedef struct {                 /* bwamem.h:114-124, sizeof == 56 */
 	int score, sub, alt_sc;
 } mem_aln_t;
 
+/* the layouts above are the reference's ([measured sizeof] in SURVEY.md 8b); a caller compiled against bwamem.h/bwa.h/bwt.h
+ * passes these structs by pointer and by value */
+#if defined(__cplusplus)
+#define BB_SIZE_CHECK(t, n) static_assert(sizeof(t) == (n), "layout of " #t " differs from the reference")
+#else
+#define BB_SIZE_CHECK(t, n) _Static_assert(sizeof(t) == (n), "layout of " #t " differs from the reference")
+#endif
+BB_SIZE_CHECK(bwt_t, 1120); BB_SIZE_CHECK(bwtintv_t, 32); BB_SIZE_CHECK(bntann1_t, 40); BB_SIZE_CHECK(bntseq_t, 48);
+BB_SIZE_CHECK(bwaidx_t, 48); BB_SIZE_CHECK(bseq1_t, 48); BB_SIZE_CHECK(mem_opt_t, 168); BB_SIZE_CHECK(mem_alnreg_t, 88);
+BB_SIZE_CHECK(mem_alnreg_v, 24); BB_SIZE_CHECK(mem_pestat_t, 32); BB_SIZE_CHECK(mem_aln_t, 56);
+
 mem_opt_t *mem_opt_init(void);                                       /* bwamem.h:136, bwamem.c:74 */
 
 /* The drop-in boundary (bwamem.h:161, bwamem.c:1235).  Same contract as the reference:

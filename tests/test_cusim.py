@@ -110,7 +110,8 @@ def test_emulated_edge_reads(data, tmp_path, monkeypatch, ktab):
 def test_startup_selfcheck_passes_and_falls_back(data, monkeypatch):
     """BWA_B200_SELFCHECK=n: when an index goes to the device, n reads drawn from the reference are aligned with the default
     kernels and with the baseline (first row sweeps, no short-string table) and compared.  Agreement is silent; a difference
-    (here injected by the test hook) is reported and the run continues on the baseline, with the same SAM."""
+    (here injected by the test hook) is fatal; with BWA_B200_SELFCHECK_FALLBACK=1 it is reported and the run continues on
+    the baseline, with the same SAM."""
     import subprocess
     fa, fqs = data.reads("stress", tag="cs", n=120, seed=33, err=(0.016, 0.002, 0.002), chimeric=0.05)
     args = ["-K", "100000000", "-t", "2", fa] + fqs
@@ -121,6 +122,9 @@ def test_startup_selfcheck_passes_and_falls_back(data, monkeypatch):
     from conftest import strip_pg
     assert strip_pg(p.stdout) == want
     monkeypatch.setenv("BWA_B200_SELFCHECK_INJECT", "1")
+    p = subprocess.run([CUSIMBIN, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode != 0 and b"records differ" in p.stderr          # a difference is fatal by default
+    monkeypatch.setenv("BWA_B200_SELFCHECK_FALLBACK", "1")
     p = subprocess.run([CUSIMBIN, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert p.returncode == 0 and b"staying on the baseline kernels" in p.stderr
     assert strip_pg(p.stdout) == want
