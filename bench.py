@@ -74,8 +74,12 @@ def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0, paired=Fals
         else:
             # `bwa index` needs hours at this size (bwa.1:767): same files from the GPU builder (bwa_b200/index_build.py,
             # byte-identical to `bwa index` where both can run, see tests/test_gpu_parity.py::test_index_builder)
-            import bwa_b200.index_build as ib
-            ib.build_from_contigs(contigs, fa, verbose=True)
+            # ... in a child process: the builder's torch allocations (tens of GB of cached blocks) must be gone before
+            # the aligner places its 34 GB index on the same GPU (a build inside this process ended in cudaMalloc: out of memory)
+            del contigs
+            code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import gen_data, bwa_b200.index_build as ib; "
+                    "ib.build_from_contigs(gen_data.random_contigs(%d, %d, 7), %r, verbose=True)" % (ROOT, os.path.join(ROOT, "tools"), n_contigs, contig_len, fa))
+            subprocess.run([sys.executable, "-c", code], check=True, stdout=sys.stderr)
         log("[bench] reference %d Mbp generated and indexed in %.1fs" % (ref_mbp, time.time() - t0))
         open(done, "w").write("ok")
     while not os.path.exists(done):
@@ -390,9 +394,9 @@ def main():
         smem_gbs = ks["occ_touches"] * 64 / (ks["ms_smem"] * 1e-3) / 1e9 if ks["ms_smem"] > 0 else 0.0
         traffic = None
         try:   # DRAM bytes of the seeding kernels per launch, from the committed ncu --set full captures
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            # the capture predates the short-string table (fewer sectors per read now): only valid with BWA_B200_KTAB=0
-            if a.read_len == 150 and a.ref_mbp == 3000 and os.environ.get("BWA_B200_KTAB") == "0":
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            # captured on the default configuration (short-string table depth 14) of the 3 Gbp / 150-bp workload: valid there only
+            if a.read_len == 150 and a.ref_mbp == 3000 and os.environ.get("BWA_B200_KTAB") is None:
                 traffic = (tr["k_smem"]["dram_bytes_per_read"] + tr["k_smem_fwd"]["dram_bytes_per_read"]) * n_reads
         except Exception:
             pass
@@ -411,7 +415,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "k_smem_fwd + k_smem + k_seed_post (SMEM seeding over the FM-index)", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": smem_gbs / hbm_peak if hbm_peak else None, "traffic": traffic,
-                         "traffic_note": "null: the committed ncu capture (profiles/r1_traffic.json, 83 GB per 1 M reads) is of the seeding kernels before the short-string table, which removes about a third of their sector requests; to be re-captured (BWA_B200_KTAB=0 reproduces the captured kernels and reports that figure)",
+                         "traffic_note": "DRAM bytes of k_smem + k_smem_fwd per launch from the committed ncu --set full capture (profiles/r2_traffic.json), scaled to the reads of one launch; null when the workload is not the captured one",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
             "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
