@@ -27,6 +27,10 @@ build/host/%.o: $(HOST)/%.c $(wildcard $(HOST)/*.h) $(wildcard include/*.h)
 build/cuda/%.o: $(CUDA)/%.cu $(CUDA_HDR)
 	@mkdir -p build/cuda
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+# stage 4 decides integers (MAPQ, pair scores) from double expressions that must round as the host's do: no a*b+c contraction
+build/cuda/bwag_tail.o: $(CUDA)/bwag_tail.cu $(CUDA_HDR)
+	@mkdir -p build/cuda
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 
 bwa_b200/libbwa_b200.so: $(HOST_OBJ) build/host/bb_cli.o $(CUDA_OBJ)
 	$(NVCC) -shared -o $@ $^ -lz -lm -lpthread -cudart shared

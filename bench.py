@@ -191,6 +191,26 @@ def supervise(argv):
     return 3
 
 
+# SASS instructions per DP cell of the kernels' inner loops (cuobjdump -sass, counted by tools/sass_loops.py / by hand from the
+# unrolled 8-cell chunk of k_extend_lane: 220 instructions; k_global_sm_fast: 71 per 32-column chunk + per-row work, see profiles/)
+SASS_OPS_PER_CELL = {"extend": 27.5, "global": 71.0 / 32}
+
+
+def roofline_sw(ks, clocks, ksteps):
+    """Integer-issue roofline of the two Smith-Waterman kernels: achieved cell updates/s against
+    (lanes x SMs x measured SM clock) / (SASS instructions per cell of the kernel's cell loop)."""
+    mhz = (clocks or {}).get("sm_mhz") or 1965
+    lane_ops = 148 * 128 * mhz * 1e6
+    out = {"int_lane_ops_per_s": lane_ops, "int_peak_source": "148 SMs x 128 INT32 lanes x SM clock sampled under load (nvidia-smi)"}
+    for name, cells, ms in (("extend", ks["ext_cells"], ks["ms_extend"]), ("global", ks["glb_cells"], ks["ms_global"])):
+        if ms > 0:
+            ach = cells / (ms * 1e-3)
+            peak = lane_ops / SASS_OPS_PER_CELL[name]
+            out[name] = {"kernel": "k_extend_lane (ksw_extend2)" if name == "extend" else "k_global_sm_fast (ksw_global2 + backtrack, NM, MD)", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "GCUPS",
+                         "frac": ach / peak, "ops_per_cell": SASS_OPS_PER_CELL[name]}
+    return out
+
+
 def selfcheck_status():
     try:
         import ctypes as C
@@ -377,7 +397,7 @@ def main():
             os.environ.pop(k, None)
         else:
             os.environ[k] = v
-    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_chain"] + ks["ms_extend"] + ks["ms_global"]) / KSTEPS * a.steps
+    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_chain"] + ks["ms_extend"] + ks["ms_global"] + ks.get("ms_tail", 0.0)) / KSTEPS * a.steps
     vals = torch.tensor([dt, k_ms / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -406,7 +426,8 @@ def main():
             "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
                        "l2": "inputs larger than L2 (resident index %.1f GB = Occ blocks + SA sample + pac + short-string table, reads %.0f MB per step)" % (
                            os.path.getsize(fa + ".bwt") / 1e9 * (1.25 + 16.0 / (a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")))) + 5.7, n_reads * a.read_len / 1e6),
-                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension and global-alignment kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
+                       "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension, global-alignment and post-processing (stage 4) kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",
+                       "timed_region_note": "every step re-submits the same host batch (bases already 0..4 codes after the first call: the in-place encode then re-writes them); releasing the SAM strings (what the reference's caller does after printing, fastmap.c:114-119) is outside the timed region",
                        "pipeline": pipe_cfg + ", %d mem_process_seqs calls in flight" % inflight,
                        "device_selfcheck": {0: "not run", 1: "passed (192 reads from the reference: default kernels == baseline kernels)", 2: "DIFFERED: the baseline kernels (first row sweeps, no short-string table) are in use"}.get(selfcheck_status(), "?"),
                        "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
@@ -418,9 +439,12 @@ def main():
                          "traffic_note": "DRAM bytes of k_smem + k_smem_fwd per launch from the committed ncu --set full capture (profiles/r2_traffic.json), scaled to the reads of one launch; null when the workload is not the captured one",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
-            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_h2d", "ms_d2h")},
+            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_tail", "ms_h2d", "ms_d2h")},
+            "device_tail": {"reads": st["tail_reads"] // a.steps, "handed_back_to_host_postprocessing": st["tail_complex"] // a.steps,
+                            "note": "stage 4 (bwag_tail.cu): de-duplication, CIGAR requests, pairing, MAPQ and SAM records on the device; reads it hands back are re-aligned with host-side post-processing"},
             "work_per_read": {"occ_touches": st["occ_touches"] / (n_reads * a.steps), "sa_touches": st["sa_touches"] / (n_reads * a.steps),
                               "ext_cells": st["ext_cells"] / (n_reads * a.steps), "glb_cells": st["glb_cells"] / (n_reads * a.steps)},
+            "roofline_sw": roofline_sw(ks, clocks, KSTEPS),
             "sw_gcups": {"extend": ks["ext_cells"] / (ks["ms_extend"] * 1e-3) / 1e9 if ks["ms_extend"] > 0 else None,
                          "global": ks["glb_cells"] / (ks["ms_global"] * 1e-3) / 1e9 if ks["ms_global"] > 0 else None,
                          "note": "cells the kernels computed; the extension kernel stops a sweep at the first row after which no output of ksw_extend2 can change "

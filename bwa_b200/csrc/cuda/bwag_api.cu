@@ -13,6 +13,7 @@
 #include <stdarg.h>
 #include <pthread.h>
 #include <time.h>
+#include <math.h>
 #include <sched.h>
 #include "bwag_dev.cuh"
 #include "bwag_kernels.h"
@@ -48,6 +49,9 @@ struct Counters {
 	u64 occ_touches, sa_touches, ext_cells, glb_cells;
 	u64 n_cig, n_md;
 	u32 flags, pad2;
+	/* stage 4 */
+	u64 t_dregs, t_tasks, t_max_z, t_text, t_complex;
+	int t_max_lq, t_max_rl;
 };
 
 struct DevBuf { void *p; size_t cap; };
@@ -92,6 +96,8 @@ struct bwag_ctx {
 	struct bwag_batch *spare[N_SPARE]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
 	pthread_mutex_t mu;
 	struct bwag_ctx *parent;     /* set in the per-batch view of the context */
+	/* stage 4: contig table (offsets, lengths, ALT flags, names) and log(i) table, resident once per context */
+	void *d_tail; TailCtg tctg; const double *d_logtab; int have_ctg;
 };
 
 struct bwag_batch {
@@ -116,6 +122,11 @@ struct bwag_batch {
 	/* stage 3 */
 	DevBuf d_tasks, d_res, d_cig, d_md;
 	HostBuf h_res, h_cig, h_md;
+	/* stage 4 */
+	DevBuf d_dregs, d_dreg_beg, d_dreg_n, d_task_beg, d_cflag, d_pe_is, d_rec, d_text, d_ptab;
+	HostBuf h_pe_is, h_cflag, h_rec, h_text, h_ptab;
+	int tail_ready;              /* bwag_tail_regs ran on this batch */
+	int regs_on_device;          /* bwag_chain_extend left the regions in HBM */
 };
 
 static void batch_free(bwag_batch_t *b);
@@ -132,6 +143,7 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #define BWAG_KTAB_MAX_AUTO 14
 #endif
 #define K4_SMEM_MAX (96 * 1024)
+#define K4L_SMEM_MAX (200 * 1024)
 
 #ifdef BWAG_CUSIM
 unsigned long long bwag_cusim_sector_loads, bwag_cusim_list_acc[5];
@@ -202,6 +214,7 @@ static int pick_grid(bwag_ctx_t *c)
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend, K4_THREADS, 0)); c->grid_k4 = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaFuncSetAttribute(k_extend_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaFuncSetAttribute(k_extend_sm_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
+	CK(cudaFuncSetAttribute(k_extend_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, K4L_SMEM_MAX));
 	CK(cudaFuncSetAttribute(k_global_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaFuncSetAttribute(k_global_sm_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global, K5_THREADS, 0)); c->grid_k5 = c->n_sm * (nb > 0 ? nb : 1);
@@ -268,6 +281,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->ktab) cudaFree(c->ktab);
+	if (c->d_tail) cudaFree(c->d_tail);
 	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_wait);
@@ -391,7 +405,7 @@ extern "C" bwag_batch_t *bwag_batch_begin(bwag_ctx_t *c, int n, const uint8_t *c
 	if (c->baseline) { b->lc.ix.ktab = 0; b->lc.ix.ktab_k = 0; }
 	b->lc.grid_k1 = c->grid_k1; b->lc.grid_k1f = c->grid_k1f; b->lc.grid_k2 = c->grid_k2; b->lc.grid_k4 = c->grid_k4; b->lc.grid_k5 = c->grid_k5;
 	memset(&b->lc.st, 0, sizeof(b->lc.st));
-	b->max_len = 0; b->seeded = 0;
+	b->max_len = 0; b->seeded = 0; b->tail_ready = 0; b->regs_on_device = 0;
 	b->ctx = c; b->n = n; b->h_off = (const i64 *)off; b->total_bases = off[n];
 	for (int i = 0; i < n; ++i) { int l = (int)(off[i + 1] - off[i]); if (l > b->max_len) b->max_len = l; }
 	if (buf_reserve(&b->d_codes, (size_t)b->total_bases + 16) || buf_reserve(&b->d_off, sizeof(i64) * ((size_t)n + 1))) { batch_free(b); return 0; }
@@ -419,13 +433,15 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ext_cells += x->ext_cells; d->glb_cells += x->glb_cells;
 		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
+		d->ms_tail += x->ms_tail; d->tail_reads += x->tail_reads; d->tail_complex += x->tail_complex;
 	}
 #ifdef BWAG_CUSIM
 	if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] emulator: %llu 32-byte block/table loads so far (K1, K1f, K2, table build); K1 candidate-list accesses by entry index 0-3: %llu, 4-7: %llu, 8-11: %llu, 12-15: %llu, 16+: %llu (the first K1_SLOTS of a list live in shared memory)\n", bwag_cusim_sector_loads, bwag_cusim_list_acc[0], bwag_cusim_list_acc[1], bwag_cusim_list_acc[2], bwag_cusim_list_acc[3], bwag_cusim_list_acc[4]);
 #endif
 	if (getenv("BWA_B200_PROFILE"))   /* with the host's phase timer: the work counters of this batch */
-		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu\n", b->n,
-		        (unsigned long long)b->lc.st.occ_touches, (unsigned long long)b->lc.st.sa_touches, (unsigned long long)b->lc.st.ext_cells, (unsigned long long)b->lc.st.glb_cells);
+		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu; stage 4: %llu reads, %llu handed back to the host-side post-processing\n", b->n,
+		        (unsigned long long)b->lc.st.occ_touches, (unsigned long long)b->lc.st.sa_touches, (unsigned long long)b->lc.st.ext_cells, (unsigned long long)b->lc.st.glb_cells,
+		        (unsigned long long)b->lc.st.tail_reads, (unsigned long long)b->lc.st.tail_complex);
 	for (int i = 0; i < N_SPARE; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
 	pthread_mutex_unlock(&c->mu);
 	if (b) batch_free(b);
@@ -447,6 +463,8 @@ static void batch_free(bwag_batch_t *b)
 	free_host(&b->h_regs); free_host(&b->h_nregs); free_host(&b->h_cregs); free_host(&b->h_creg_beg); free_host(&b->h_tmp);
 	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
+	free_dev(&b->d_dregs); free_dev(&b->d_dreg_beg); free_dev(&b->d_dreg_n); free_dev(&b->d_task_beg); free_dev(&b->d_cflag); free_dev(&b->d_pe_is); free_dev(&b->d_rec); free_dev(&b->d_text); free_dev(&b->d_ptab);
+	free_host(&b->h_pe_is); free_host(&b->h_cflag); free_host(&b->h_rec); free_host(&b->h_text); free_host(&b->h_ptab);
 	free(b);
 }
 
@@ -621,6 +639,27 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	/* the leaner row sweep (and its row cut-off) needs non-negative gap penalties (every real scoring scheme); BWA_B200_K4_FAST=0 forces the general one */
 	const int fast = a.par.e_ins >= 0 && a.par.o_ins + a.par.e_ins >= 0 && a.par.e_del >= 0 && a.par.o_del + a.par.e_del >= 0 &&
 	                 !c->baseline && !(getenv("BWA_B200_K4_FAST") && atoi(getenv("BWA_B200_K4_FAST")) == 0);
+	{   /* short reads: one lane per read (bwag_extend_lane.cu) when every score fits its 13-bit cells and a block's columns fit shared memory */
+		int maxsc = 0;
+		for (int k = 0; k < 25; ++k) maxsc = maxsc > a.par.mat[k] ? maxsc : a.par.mat[k];
+		const size_t lsm = (size_t)(a.cap_q + 2 + 8) * K4L_THREADS * 4;   /* + the chunk's spare columns (K4L_CH) */
+		const int lane_ok = fast && (i64)a.cap_q * maxsc < 8192 && a.par.a <= maxsc && lsm <= K4L_SMEM_MAX && !(getenv("BWA_B200_K4_LANE") && atoi(getenv("BWA_B200_K4_LANE")) == 0);
+		if (lane_ok) {
+			int lgrid = c->n_sm;
+#ifndef BWAG_CUSIM
+			{ int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend_lane, K4L_THREADS, lsm)); lgrid = c->n_sm * (nb > 0 ? nb : 1); }
+#else
+			lgrid = 2;
+#endif
+			const i64 lneed = ((i64)n_units + K4L_THREADS - 1) / K4L_THREADS;
+			if (lgrid > lneed) lgrid = (int)(lneed > 0 ? lneed : 1);
+			a.eh = 0; a.rseq = 0; a.smem_per_warp = 0;
+			if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] extension: lane-per-read kernel, grid %d x %d, %zu bytes of shared memory per block\n", lgrid, K4L_THREADS, lsm);
+			BWAG_LAUNCH(k_extend_lane, lgrid, K4L_THREADS, lsm, c->stream, c->ix, a);
+			CK(cudaGetLastError());
+			return 0;
+		}
+	}
 #ifndef BWAG_CUSIM
 	if (use_sm) { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fast ? k_extend_sm_fast : k_extend_sm, K4_THREADS, smem)); if (nb < 2) use_sm = 0; else grid = c->n_sm * nb; }
 #endif
@@ -773,6 +812,14 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	CK(cudaEventRecord(c->ev0, c->stream));
 	if (launch_extend(c, a, n)) return 1;
 	CK(cudaEventRecord(c->ev1, c->stream));
+	if (!out) {   /* the regions stay in HBM for bwag_tail_regs */
+		if (fetch_counters(c)) return 1;
+		c->st.ms_extend += elapsed(c); ++c->st.n_launch;
+		if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
+		c->st.ext_cells += c->h_cnt->ext_cells;
+		b->regs_on_device = 1;
+		return 0;
+	}
 	/* dense copy of the regions (with contig id and repeat fraction of their chain) for the download */
 	RegCompactArgs rc;
 	rc.n_reads = n; rc.n_regs = (const int *)b->d_nregs.p; rc.regs = (const bwag_xreg_t *)b->d_regs.p; rc.reg_base = (const i64 *)b->d_reg_base.p;
@@ -802,26 +849,14 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 
 /* ------------------------------------------------------------------------------------------------ stage 3 */
 
-extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out)
+/* K5 over n_tasks requests that already sit in b->d_tasks; results stay in b->d_res / d_cig / d_md, their pool sizes in *nc, *nm */
+static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, int cap_q, int cap_r, i64 cap_z, i64 n_aln, i64 *nc_out, i64 *nm_out)
 {
 	bwag_ctx_t *c = &b->lc;
-	CK(cudaSetDevice(c->device));
-	if (n_tasks <= 0) { out->res = 0; out->cigar = 0; out->md = 0; return 0; }
-	i64 cap_z = 64, n_aln = 0;
-	int cap_q = 4, cap_r = 16;
-	for (int t = 0; t < n_tasks; ++t) {
-		i64 lq = tasks[t].qe - tasks[t].qb, rl = tasks[t].re - tasks[t].rb;
-		if (lq > cap_q) cap_q = (int)lq;
-		if (rl > cap_r) cap_r = (int)rl;
-		if (tasks[t].mode == BWAG_G_REG2ALN) { /* backtrack bytes of the widest band this task can reach */
-			i64 d = rl > lq ? rl - lq : lq - rl, wmax = (i64)par->w << 2;
-			if (d + 3 > wmax) wmax = d + 3;
-			i64 ncol = lq < 2 * wmax + 1 ? lq : 2 * wmax + 1;
-			if (ncol * rl > cap_z) cap_z = ncol * rl;
-			++n_aln;
-		}
-	}
 	cap_q = (cap_q + 3) & ~3; cap_r = (cap_r + 15) & ~15; cap_z = (cap_z + 15) & ~(i64)15;
+	if (cap_q < 4) cap_q = 4;
+	if (cap_r < 16) cap_r = 16;
+	if (cap_z < 64) cap_z = 64;
 	/* one task's CIGAR has at most lq+rlen ops, its MD at most 3 characters per reference base */
 	const int cap_wcig = cap_q + cap_r + 4, cap_wmd = 3 * cap_r + cap_q + 16;
 	int grid = c->grid_k5;
@@ -844,12 +879,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	if (buf_reserve(&c->s_eh, n_warps * 2 * (size_t)(cap_q + 2) * 4) || buf_reserve(&c->s_rseq, n_warps * (size_t)cap_r) ||
 	    buf_reserve(&c->s_qseq, n_warps * (size_t)(cap_q + 2)) || buf_reserve(&c->s_z, n_warps * (size_t)cap_z) ||
 	    buf_reserve(&c->s_wcig, n_warps * (size_t)cap_wcig * 4) || buf_reserve(&c->s_wmd, n_warps * (size_t)cap_wmd)) return 1;
-	if (buf_reserve(&b->d_tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
-	CK(cudaEventRecord(c->ev0, c->stream));
-	H2D(c, b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks);
-	CK(cudaEventRecord(c->ev1, c->stream));
-	CK(stream_wait(c));
-	c->st.ms_h2d += elapsed(c);
+	if (buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
 	i64 cap_cig = n_aln * 6 + 1024, cap_md = n_aln * 24 + 4096;   /* typical short-read sizes; grown on demand */
 	for (int attempt = 0;; ++attempt) {
 		if (buf_reserve(&b->d_cig, 4 * (size_t)cap_cig) || buf_reserve(&b->d_md, (size_t)cap_md)) return 1;
@@ -880,7 +910,37 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 		cap_cig = (i64)c->h_cnt->n_cig + 1024; cap_md = (i64)c->h_cnt->n_md + 4096;
 	}
 	c->st.glb_cells += c->h_cnt->glb_cells;
-	const i64 nc = (i64)c->h_cnt->n_cig, nm = (i64)c->h_cnt->n_md;
+	*nc_out = (i64)c->h_cnt->n_cig; *nm_out = (i64)c->h_cnt->n_md;
+	return 0;
+}
+
+extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out)
+{
+	bwag_ctx_t *c = &b->lc;
+	CK(cudaSetDevice(c->device));
+	if (n_tasks <= 0) { out->res = 0; out->cigar = 0; out->md = 0; return 0; }
+	i64 cap_z = 64, n_aln = 0, nc = 0, nm = 0;
+	int cap_q = 4, cap_r = 16;
+	for (int t = 0; t < n_tasks; ++t) {
+		i64 lq = tasks[t].qe - tasks[t].qb, rl = tasks[t].re - tasks[t].rb;
+		if (lq > cap_q) cap_q = (int)lq;
+		if (rl > cap_r) cap_r = (int)rl;
+		if (tasks[t].mode == BWAG_G_REG2ALN) { /* backtrack bytes of the widest band this task can reach */
+			i64 d = rl > lq ? rl - lq : lq - rl, wmax = (i64)par->w << 2;
+			if (d + 3 > wmax) wmax = d + 3;
+			i64 ncol = lq < 2 * wmax + 1 ? lq : 2 * wmax + 1;
+			if (ncol * rl > cap_z) cap_z = ncol * rl;
+			++n_aln;
+		}
+	}
+	if (buf_reserve(&b->d_tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks)) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	H2D(c, b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks);
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(stream_wait(c));
+	c->st.ms_h2d += elapsed(c);
+	b->tail_ready = 0;   /* the request pool of a preceding bwag_tail_regs is gone */
+	if (run_global(b, par, n_tasks, cap_q, cap_r, cap_z, n_aln, &nc, &nm)) return 1;
 	if (hbuf_reserve(&b->h_res, sizeof(bwag_gres_t) * (size_t)n_tasks) || hbuf_reserve(&b->h_cig, 4 * (size_t)(nc + 1)) || hbuf_reserve(&b->h_md, (size_t)nm + 16)) return 1;
 	CK(cudaEventRecord(c->ev0, c->stream));
 	D2H(c, b->h_res.p, b->d_res.p, sizeof(bwag_gres_t) * (size_t)n_tasks);
@@ -890,5 +950,164 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);
 	out->res = (const bwag_gres_t *)b->h_res.p; out->cigar = (const uint32_t *)b->h_cig.p; out->md = (const char *)b->h_md.p;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ stage 4 */
+
+#define TAIL_LOGN 4096
+extern "C" int bwag_ctx_set_contigs(bwag_ctx_t *c, int n_seqs, const int64_t *offset, const int32_t *len, const uint8_t *is_alt, const char *const *names)
+{
+	CK(cudaSetDevice(c->device));
+	size_t l_names = 0;
+	for (int i = 0; i < n_seqs; ++i) l_names += strlen(names[i]);
+	/* one block: offsets | lengths | name offsets | ALT flags | names | log table (8-byte aligned first) */
+	const size_t o_off = 0, o_log = o_off + 8 * (size_t)n_seqs, o_len = o_log + 8 * TAIL_LOGN, o_noff = o_len + 4 * (size_t)n_seqs, o_alt = o_noff + 4 * ((size_t)n_seqs + 1), o_names = o_alt + (size_t)n_seqs, total = o_names + l_names + 16;
+	char *h = (char *)malloc(total);
+	if (!h) return set_err("out of memory");
+	memset(h, 0, total);
+	memcpy(h + o_off, offset, 8 * (size_t)n_seqs);
+	memcpy(h + o_len, len, 4 * (size_t)n_seqs);
+	memcpy(h + o_alt, is_alt, (size_t)n_seqs);
+	{
+		int *no = (int *)(h + o_noff), at = 0;
+		for (int i = 0; i < n_seqs; ++i) { const size_t l = strlen(names[i]); no[i] = at; memcpy(h + o_names + at, names[i], l); at += (int)l; }
+		no[n_seqs] = at;
+		double *lt = (double *)(h + o_log);
+		for (int i = 0; i < TAIL_LOGN; ++i) lt[i] = log((double)i);   /* the host's libm: log(0) = -inf included */
+	}
+	pthread_mutex_lock(&c->mu);
+	if (c->d_tail) { cudaStreamSynchronize(c->stream); cudaFree(c->d_tail); c->d_tail = 0; c->have_ctg = 0; }
+	cudaError_t e = cudaMalloc(&c->d_tail, total);
+	if (e == cudaSuccess) e = cudaMemcpy(c->d_tail, h, total, cudaMemcpyHostToDevice);
+	free(h);
+	if (e != cudaSuccess) { pthread_mutex_unlock(&c->mu); return set_err("contig table upload failed: %s", cudaGetErrorString(e)); }
+	char *d = (char *)c->d_tail;
+	c->tctg.l_pac = c->ix.l_pac; c->tctg.n_seqs = n_seqs;
+	c->tctg.off = (const i64 *)(d + o_off); c->tctg.len = (const int *)(d + o_len); c->tctg.alt = (const uint8_t *)(d + o_alt);
+	c->tctg.names = d + o_names; c->tctg.name_off = (const int *)(d + o_noff);
+	c->d_logtab = (const double *)(d + o_log);
+	c->have_ctg = 1;
+	pthread_mutex_unlock(&c->mu);
+	return 0;
+}
+
+extern "C" int bwag_tail_regs(bwag_batch_t *b, const mem_opt_t *opt, const bwag_sw_par_t *sp, const uint64_t **pe_is, const uint8_t **cflag)
+{
+	bwag_ctx_t *c = &b->lc, *pc = b->ctx;
+	CK(cudaSetDevice(c->device));
+	if (!pc->have_ctg) return BWAG_UNSUPPORTED;
+	if (c->baseline) return BWAG_DECLINED;   /* the baseline of the start-up self-check is the host-side post-processing */
+	if (!b->regs_on_device) return set_err("bwag_tail_regs needs a preceding bwag_chain_extend(..., NULL) on the same batch");
+	const int n = b->n, pe = !!(opt->flag & MEM_F_PE);
+	if (pe && (n & 1)) return set_err("paired-end batch with an odd number of reads");
+	const i64 cap = b->n_seeds + 1;   /* regions <= seeds */
+	if (buf_reserve(&b->d_dregs, sizeof(mem_alnreg_t) * (size_t)cap) || buf_reserve(&b->d_tasks, sizeof(bwag_gtask_t) * (size_t)cap) ||
+	    buf_reserve(&b->d_dreg_beg, 8 * (size_t)(n + 1)) || buf_reserve(&b->d_dreg_n, 4 * (size_t)(n + 1)) || buf_reserve(&b->d_task_beg, 8 * (size_t)(n + 1)) ||
+	    buf_reserve(&b->d_cflag, (size_t)n + 16) || buf_reserve(&b->d_pe_is, 8 * (size_t)(n / 2 + 1))) return 1;
+	TailRegsArgs a;
+	memset(&a, 0, sizeof(a));
+	a.n_reads = n; a.pe = pe; a.opt = *opt; a.ctg = pc->tctg;
+	a.n_raw = (const int *)b->d_nregs.p; a.xregs = (const bwag_xreg_t *)b->d_regs.p; a.reg_base = (const i64 *)b->d_reg_base.p; a.chain_beg = (const i64 *)b->d_chain_beg.p;
+	a.chain_rid = (const int *)b->d_chain_rid.p; a.chain_frac = (const float *)b->d_chain_frac.p;
+	a.dregs = (mem_alnreg_t *)b->d_dregs.p; a.dreg_beg = (i64 *)b->d_dreg_beg.p; a.dreg_n = (int *)b->d_dreg_n.p; a.task_beg = (i64 *)b->d_task_beg.p; a.cflag = (uint8_t *)b->d_cflag.p;
+	a.cap_dregs = cap; a.tasks = (bwag_gtask_t *)b->d_tasks.p; a.cap_tasks = cap; a.pe_is = (u64 *)b->d_pe_is.p;
+	a.n_dregs = &c->d_cnt->t_dregs; a.n_tasks = &c->d_cnt->t_tasks; a.max_z = &c->d_cnt->t_max_z; a.max_lq = &c->d_cnt->t_max_lq; a.max_rl = &c->d_cnt->t_max_rl;
+	if (reset_counters(c)) return 1;
+	const int n_units = pe ? n >> 1 : n;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	BWAG_LAUNCH(k_tail_regs, (n_units + 127) / 128, 128, 0, c->stream, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	if (fetch_counters(c)) return 1;
+	c->st.ms_tail += elapsed(c); ++c->st.n_launch;
+	const i64 n_tasks = (i64)c->h_cnt->t_tasks;
+	if (n_tasks > cap || (i64)c->h_cnt->t_dregs > cap) return set_err("stage 4: more regions than seeds?");
+	if (n_tasks >= ((i64)1 << 31)) return set_err("stage 4: too many alignment requests in one batch; use smaller chunks");
+	const int cap_q = c->h_cnt->t_max_lq, cap_r = c->h_cnt->t_max_rl;
+	const i64 cap_z = (i64)c->h_cnt->t_max_z;
+	if (n_tasks > 0) {
+		i64 nc = 0, nm = 0;
+		if (run_global(b, sp, (int)n_tasks, cap_q, cap_r, cap_z, n_tasks, &nc, &nm)) return 1;
+	}
+	if (hbuf_reserve(&b->h_cflag, (size_t)n + 16) || hbuf_reserve(&b->h_pe_is, 8 * (size_t)(n / 2 + 1))) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	D2H(c, b->h_cflag.p, b->d_cflag.p, (size_t)n);
+	if (pe) D2H(c, b->h_pe_is.p, b->d_pe_is.p, 8 * (size_t)(n / 2));
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(stream_wait(c));
+	c->st.ms_d2h += elapsed(c);
+	b->tail_ready = 1;
+	if (pe_is) *pe_is = pe ? (const uint64_t *)b->h_pe_is.p : 0;
+	if (cflag) *cflag = (const uint8_t *)b->h_cflag.p;
+	return 0;
+}
+
+extern "C" int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pestat_t pes[4], const double *const pair_tab[4], const double *log_tab,
+                             int64_t n_processed, const char *rg_id, bwag_sam_t *out)
+{
+	bwag_ctx_t *c = &b->lc, *pc = b->ctx;
+	(void)log_tab;   /* the context keeps its own copy (bwag_ctx_set_contigs computes it with the same libm) */
+	CK(cudaSetDevice(c->device));
+	if (!pc->have_ctg) return BWAG_UNSUPPORTED;
+	if (!b->tail_ready) return set_err("bwag_tail_sam needs a preceding bwag_tail_regs on the same batch");
+	const int n = b->n, pe = !!(opt->flag & MEM_F_PE);
+	TailSamArgs g;
+	memset(&g, 0, sizeof(g));
+	g.n_reads = n; g.pe = pe; g.opt = *opt; g.ctg = pc->tctg; g.logtab = pc->d_logtab; g.n_processed = n_processed;
+	size_t tab_bytes = 256;   /* read-group id first */
+	if (pe) {
+		memcpy(g.pes, pes, 4 * sizeof(mem_pestat_t));
+		for (int d = 0; d < 4; ++d) if (pair_tab && pair_tab[d] && !pes[d].failed && pes[d].high >= pes[d].low) tab_bytes += 8 * ((size_t)pes[d].high - pes[d].low + 1);
+	}
+	if (buf_reserve(&b->d_ptab, tab_bytes) || hbuf_reserve(&b->h_ptab, tab_bytes)) return 1;
+	{
+		char *h = (char *)b->h_ptab.p;
+		size_t at = 256;
+		const size_t l_rg = rg_id ? strlen(rg_id) : 0;
+		memset(h, 0, 256);
+		if (l_rg > 255) return set_err("read-group id too long");
+		if (l_rg) memcpy(h, rg_id, l_rg);
+		g.rg = (const char *)b->d_ptab.p; g.l_rg = (int)l_rg;
+		if (pe) for (int d = 0; d < 4; ++d) if (pair_tab && pair_tab[d] && !pes[d].failed && pes[d].high >= pes[d].low) {
+			const size_t bytes = 8 * ((size_t)pes[d].high - pes[d].low + 1);
+			memcpy(h + at, pair_tab[d], bytes);
+			g.ptab[d] = (const double *)((char *)b->d_ptab.p + at);
+			at += bytes;
+		}
+		H2D(c, b->d_ptab.p, h, tab_bytes);
+	}
+	g.codes = (const uint8_t *)b->d_codes.p; g.off = (const i64 *)b->d_off.p;
+	g.dregs = (const mem_alnreg_t *)b->d_dregs.p; g.dreg_beg = (const i64 *)b->d_dreg_beg.p; g.dreg_n = (const int *)b->d_dreg_n.p; g.task_beg = (const i64 *)b->d_task_beg.p; g.cflag = (const uint8_t *)b->d_cflag.p;
+	g.res = (const bwag_gres_t *)b->d_res.p; g.cigar = (const u32 *)b->d_cig.p; g.md = (const char *)b->d_md.p;
+	if (buf_reserve(&b->d_rec, sizeof(bwag_samrec_t) * (size_t)(n + 1))) return 1;
+	g.rec = (bwag_samrec_t *)b->d_rec.p;
+	g.n_text = &c->d_cnt->t_text; g.n_complex = &c->d_cnt->t_complex;
+	i64 cap_text = b->total_bases + 176 * (i64)n + 4096;
+	const int n_units = pe ? n >> 1 : n;
+	for (int attempt = 0;; ++attempt) {
+		if (buf_reserve(&b->d_text, (size_t)cap_text)) return 1;
+		g.text = (char *)b->d_text.p; g.cap_text = cap_text;
+		if (reset_counters(c)) return 1;
+		CK(cudaEventRecord(c->ev0, c->stream));
+		BWAG_LAUNCH(k_tail_sam, (n_units + 127) / 128, 128, 0, c->stream, g);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev1, c->stream));
+		if (fetch_counters(c)) return 1;
+		c->st.ms_tail += elapsed(c); ++c->st.n_launch;
+		if ((i64)c->h_cnt->t_text <= cap_text) break;
+		if (attempt >= 2) return set_err("stage 4: the text pool keeps overflowing");
+		cap_text = (i64)c->h_cnt->t_text + 4096;
+	}
+	const i64 n_text = (i64)c->h_cnt->t_text;
+	if (hbuf_reserve(&b->h_rec, sizeof(bwag_samrec_t) * (size_t)(n + 1)) || hbuf_reserve(&b->h_text, (size_t)n_text + 16)) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	D2H(c, b->h_rec.p, b->d_rec.p, sizeof(bwag_samrec_t) * (size_t)n);
+	if (n_text) D2H(c, b->h_text.p, b->d_text.p, (size_t)n_text);
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(stream_wait(c));
+	c->st.ms_d2h += elapsed(c);
+	c->st.tail_reads += (u64)n; c->st.tail_complex += c->h_cnt->t_complex;
+	out->rec = (const bwag_samrec_t *)b->h_rec.p; out->text = (const char *)b->h_text.p; out->n_text = n_text; out->n_complex = (int64_t)c->h_cnt->t_complex;
 	return 0;
 }

@@ -18,6 +18,10 @@
 #define K3_THREADS 128
 #define K4_THREADS 128
 #define K5_THREADS 128
+#define K4L_THREADS 128   /* lane-per-read extension kernel (bwag_extend_lane.cu) */
+#ifndef K4L_MINB
+#define K4L_MINB 2
+#endif
 
 struct Intv;
 
@@ -84,12 +88,36 @@ struct GlbArgs {
 	int *next_task; u64 *cells; u32 *flags;
 };
 
-#ifdef __cplusplus
-extern "C" {
-#endif
-#ifdef __cplusplus
-}
-#endif
+/* ---- stage 4 (device tail, bwag_tail.cu) ---- */
+struct TailCtg { i64 l_pac; int n_seqs; const i64 *off; const int *len; const uint8_t *alt; const char *names; const int *name_off; };   /* bntann1_t columns; names back to back, name_off[n_seqs+1] */
+
+struct TailRegsArgs {
+	int n_reads, pe;
+	mem_opt_t opt;
+	TailCtg ctg;
+	/* K4's output */
+	const int *n_raw; const bwag_xreg_t *xregs; const i64 *reg_base, *chain_beg; const int *chain_rid; const float *chain_frac;
+	/* per read: its de-duplicated regions in dregs[], its CIGAR requests in tasks[] (request k belongs to region k), why it left the simple path (0: it did not) */
+	mem_alnreg_t *dregs; i64 *dreg_beg; int *dreg_n; i64 *task_beg; uint8_t *cflag; i64 cap_dregs;
+	bwag_gtask_t *tasks; i64 cap_tasks;
+	u64 *pe_is;                       /* per pair: mem_pestat's candidate ((orientation+1) << 48 | insert size, 0: none) */
+	u64 *n_dregs, *n_tasks, *max_z; int *max_lq, *max_rl;
+};
+
+struct TailSamArgs {
+	int n_reads, pe;
+	mem_opt_t opt;
+	TailCtg ctg;
+	mem_pestat_t pes[4];
+	const double *ptab[4];            /* per orientation: .721*log(2*erfc(|d-avg|/std/sqrt2))*a for d = low..high (host libm), or 0 */
+	const double *logtab;             /* log(i), i < 4096 (host libm) */
+	i64 n_processed;
+	const uint8_t *codes; const i64 *off;
+	const mem_alnreg_t *dregs; const i64 *dreg_beg; const int *dreg_n; const i64 *task_beg; const uint8_t *cflag;
+	const bwag_gres_t *res; const u32 *cigar; const char *md;
+	const char *rg; int l_rg;
+	bwag_samrec_t *rec; char *text; i64 cap_text; u64 *n_text, *n_complex;
+};
 
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
@@ -104,9 +132,12 @@ __global__ void k_extend(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm(DevIndex ix, ExtArgs a);
 __global__ void k_extend_fast(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm_fast(DevIndex ix, ExtArgs a);
+__global__ void k_extend_lane(DevIndex ix, ExtArgs a);
 __global__ void k_global(DevIndex ix, GlbArgs a);
 __global__ void k_global_sm(DevIndex ix, GlbArgs a);
 __global__ void k_global_fast(DevIndex ix, GlbArgs a);
 __global__ void k_global_sm_fast(DevIndex ix, GlbArgs a);
+__global__ void k_tail_regs(TailRegsArgs a);
+__global__ void k_tail_sam(TailSamArgs g);
 
 #endif

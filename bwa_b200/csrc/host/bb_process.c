@@ -190,6 +190,20 @@ static void device_selfcheck(bwag_ctx_t *ctx, const bwt_t *bwt, const bntseq_t *
 	free(opt);
 }
 
+/* stage 4 needs the contig table (offsets, lengths, ALT flags, names) next to the index */
+static void set_contigs(bwag_ctx_t *ctx, const bntseq_t *bns)
+{
+	int c, n = bns->n_seqs, rc;
+	int64_t *off = bb_malloc(sizeof(int64_t) * ((size_t)n + 1));
+	int32_t *len = bb_malloc(sizeof(int32_t) * ((size_t)n + 1));
+	uint8_t *alt = bb_malloc((size_t)n + 1);
+	const char **names = bb_malloc(sizeof(char *) * ((size_t)n + 1));
+	for (c = 0; c < n; ++c) { off[c] = bns->anns[c].offset; len[c] = bns->anns[c].len; alt[c] = !!bns->anns[c].is_alt; names[c] = bns->anns[c].name; }
+	rc = bwag_ctx_set_contigs(ctx, n, off, len, alt, names);
+	if (rc != 0 && rc != BWAG_UNSUPPORTED) bb_fatal("bb_device_attach", "cannot place the contig table on the GPU: %s", bwag_last_error());
+	free(off); free(len); free(alt); free(names);
+}
+
 bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 {
 	int i;
@@ -203,6 +217,7 @@ bwag_ctx_t *bb_device_attach(const bwt_t *bwt, const bntseq_t *bns, const uint8_
 		ctx = bwag_ctx_create(-1, bwt, bns->l_pac, pac);
 		if (!ctx) bb_fatal("bb_device_attach", "cannot place the index on the GPU: %s", bwag_last_error());
 		densify_default(ctx);
+		set_contigs(ctx, bns);
 		g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
 		device_selfcheck(ctx, bwt, bns, pac);   /* other callers wait for the verdict */
 	}
@@ -219,6 +234,7 @@ void bb_device_adopt2(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (i = 0; i < 8 && g_dev[i].ctx; ++i) {}
 	if (i == 8) bb_fatal("bb_device_adopt", "too many resident indexes");
 	densify_default(ctx);
+	if (bns) set_contigs(ctx, bns);
 	g_dev[i].bwt = bwt; g_dev[i].ctx = ctx;
 	if (bns && pac) device_selfcheck(ctx, bwt, bns, pac);
 	pthread_mutex_unlock(&g_dev_mu);
@@ -321,7 +337,7 @@ typedef struct { /* per-thread output of the chaining step */
 
 typedef struct { int tid; int64_t c0, s0; int nc, ns; } rslice_t; /* where read i's chains sit in its thread's buffers */
 
-typedef struct {
+typedef struct job_s {
 	const mem_opt_t *opt;
 	const bwt_t *bwt;
 	const bntseq_t *bns;
@@ -357,6 +373,15 @@ typedef struct {
 	int lane, chunk_id;      /* which lane (device batch object) runs this chunk */
 	bwag_batch_t *batch;
 	bwag_sw_par_t swp;
+	/* device tail (stage 4): the chunk's reads are post-processed on the device; reads it hands back go through `sub` jobs,
+	 * which are ordinary jobs over copies of their bseq1_t records */
+	int tail;                      /* 1: bwag_tail_regs ran for this chunk */
+	int no_tail;                   /* the caller wants the regions on the host (mem_align1) */
+	const uint8_t *cflag;          /* [n] from bwag_tail_regs: non-zero = the read left the simple path before pairing */
+	struct job_s *sub0, *sub1;     /* reads handed back by bwag_tail_regs (aligned up to regions before the insert-size model) / by bwag_tail_sam */
+	int *sub_map;                  /* sub job only: index of each of its reads in the parent chunk */
+	const int64_t *ids;            /* sub job only: global index (n_processed + position) of each read: the hash tie-breaks depend on it */
+	const struct tail_shared_s *ts;
 } job_t;
 
 /* Bases to codes, in place (the caller's buffer, bwamem.c:1087: seq[i] < 4 ? seq[i] : nst_nt4_table[seq[i]]) and into the
@@ -657,7 +682,7 @@ static void run_sam(job_t *j, long i, int dry)
 		uint32_t cg[128];
 		bb_samctx_t sc = { opt, j->bns, j->pac, &r->gc, dry, cg, 128, 0 };
 		copy_regs(&w, &r->regs, st0);
-		bb_mark_primary_se(opt, (int)w.n, w.a, j->n_processed + i);
+		bb_mark_primary_se(opt, (int)w.n, w.a, j->ids ? j->ids[i] : j->n_processed + i);
 		if (opt->flag & MEM_F_PRIMARY5) bb_reorder_primary5(opt->T, &w);
 		bb_reg2sam(&sc, &j->seqs[i], &w, 0, 0);
 		drop_regs(&w, st0);
@@ -667,7 +692,7 @@ static void run_sam(job_t *j, long i, int dry)
 		uint32_t cg[2][128];
 		bb_samctx_t sc[2] = { { opt, j->bns, j->pac, &j->rs[i << 1].gc, dry, cg[0], 128, 0 }, { opt, j->bns, j->pac, &j->rs[i << 1 | 1].gc, dry, cg[1], 128, 0 } };
 		copy_regs(&w[0], &j->rs[i << 1].regs, st0); copy_regs(&w[1], &j->rs[i << 1 | 1].regs, st1);
-		bb_sam_pe(sc, j->pes, (uint64_t)((j->n_processed >> 1) + i), &j->seqs[i << 1], w, 1);
+		bb_sam_pe(sc, j->pes, (uint64_t)(j->ids ? j->ids[i << 1] >> 1 : (j->n_processed >> 1) + i), &j->seqs[i << 1], w, 1);
 		drop_regs(&w[0], st0); drop_regs(&w[1], st1);
 	}
 }
@@ -745,6 +770,154 @@ static void host_chain_extend(job_t *j, bwag_batch_t *batch, const bwag_sw_par_t
 
 }
 
+/* ---------------------------------------------------------------- device tail (stage 4)
+ * Chunks of short reads are post-processed on the device (include/bwa_b200_dev.h, stage 4): the host only splices each
+ * record's text with what it alone has (read name, quality string, comment).  Reads the device hands back -- and whole
+ * batches whose options reach into what it does not do (-a, -V, -5) -- take the host-side post-processing below.
+ * BWA_B200_TAIL=0 switches the stage off. */
+static int g_no_tail;   /* the stage library has no stage 4 (the CPU oracle of the tests) */
+typedef struct tail_shared_s { double *ptab[4]; } tail_shared_t;   /* per call: the insert-size term of a pair's score by distance (bwamem_pair.c:266) */
+
+static int tail_wanted(const job_t *j)
+{
+	static int env_ = -1;
+	int env = __atomic_load_n(&env_, __ATOMIC_RELAXED);
+	if (env < 0) { const char *e = getenv("BWA_B200_TAIL"); env = e ? atoi(e) != 0 : 1; __atomic_store_n(&env_, env, __ATOMIC_RELAXED); }
+	if (!env || j->sub_map || j->no_tail || __atomic_load_n(&g_no_tail, __ATOMIC_RELAXED)) return 0;
+	if (j->opt->flag & (MEM_F_ALL | MEM_F_REF_HDR | MEM_F_PRIMARY5)) return 0;
+	if ((j->opt->flag & MEM_F_PE) && (j->n & 1)) return 0;
+	return 1;
+}
+
+static void tail_tables(const mem_opt_t *opt, const mem_pestat_t pes[4], tail_shared_t *ts)
+{
+	int d;
+	memset(ts, 0, sizeof(*ts));
+	for (d = 0; d < 4; ++d) {
+		const mem_pestat_t *pe = &pes[d];
+		int64_t n = (int64_t)pe->high - pe->low + 1, k;
+		if (pe->failed || n <= 0 || n > 65536) continue;
+		ts->ptab[d] = bb_malloc((size_t)n * sizeof(double));
+		for (k = 0; k < n; ++k) { double ns = ((pe->low + k) - pe->avg) / pe->std; ts->ptab[d][k] = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
+	}
+}
+static void tail_tables_free(tail_shared_t *ts) { int d; for (d = 0; d < 4; ++d) { free(ts->ptab[d]); ts->ptab[d] = 0; } }
+
+/* a job over the reads idx[0..n_sub) of chunk j (pairs stay together): copies of their records, their global indices */
+static job_t *sub_job(job_t *j, int n_sub, const int *idx)
+{
+	job_t *s = bb_calloc(1, sizeof(job_t));
+	int64_t *ids = bb_malloc(sizeof(int64_t) * ((size_t)n_sub + 1));
+	int k;
+	s->opt = j->opt; s->bwt = j->bwt; s->bns = j->bns; s->pac = j->pac; s->pes = j->pes; s->swp = j->swp; s->lane = j->lane; s->chunk_id = j->chunk_id;
+	s->n = n_sub; s->seqs = bb_malloc(sizeof(bseq1_t) * ((size_t)n_sub + 1));
+	s->sub_map = bb_malloc(sizeof(int) * ((size_t)n_sub + 1));
+	for (k = 0; k < n_sub; ++k) { s->seqs[k] = j->seqs[idx[k]]; s->sub_map[k] = idx[k]; ids[k] = j->ids ? j->ids[idx[k]] : j->n_processed + idx[k]; }
+	s->ids = ids;
+	if (j->pe_is) s->pe_is = bb_calloc((size_t)(n_sub >> 1) + 1, sizeof(uint64_t));
+	return s;
+}
+static void sub_job_done(job_t *j, job_t *s)   /* hand the records to the parent's reads */
+{
+	int k;
+	for (k = 0; k < s->n; ++k) j->seqs[s->sub_map[k]].sam = s->seqs[k].sam;
+	free(s->seqs); free(s->sub_map); free((void *)s->ids); free(s->pe_is); free(s);
+}
+
+typedef struct { job_t *j; const bwag_sam_t *out; } splice_t;
+static void w_splice(void *d, long u, int tid)   /* one read (pair): name + part A + QUAL + part B [+ comment] + newline */
+{
+	const splice_t *sp = d;
+	job_t *j = sp->j;
+	const int pe = !!(j->opt->flag & MEM_F_PE), n_ends = pe ? 2 : 1;
+	int e;
+	(void)tid;
+	for (e = 0; e < n_ends; ++e) {
+		const long i = pe ? (u << 1 | e) : u;
+		const bwag_samrec_t *r = &sp->out->rec[i];
+		bseq1_t *s = &j->seqs[i];
+		size_t l_name, l_com, l_qual;
+		char *w;
+		if (!(r->flags & BWAG_REC_TEXT)) continue;
+		l_name = strlen(s->name); l_com = s->comment ? strlen(s->comment) + 1 : 0; l_qual = s->qual ? (size_t)s->l_seq : 1;
+		w = s->sam = bb_malloc(l_name + (size_t)r->len_a + l_qual + (size_t)r->len_b + l_com + 2);
+		memcpy(w, s->name, l_name); w += l_name;
+		memcpy(w, sp->out->text + r->off, (size_t)r->len_a); w += r->len_a;
+		if (s->qual) { bb_copy_text(w, s->qual, s->l_seq, !!(r->flags & BWAG_REC_QREV)); w += s->l_seq; } else *w++ = '*';
+		memcpy(w, sp->out->text + r->off + r->len_a, (size_t)r->len_b); w += r->len_b;
+		if (s->comment) { *w++ = '\t'; memcpy(w, s->comment, l_com - 1); w += l_com - 1; }
+		*w++ = '\n'; *w = 0;
+	}
+	if (pe && (sp->out->rec[u << 1].flags & BWAG_REC_TEXT) && strcmp(j->seqs[u << 1].name, j->seqs[u << 1 | 1].name) != 0)
+		bb_fatal("mem_sam_pe", "paired reads have different names: \"%s\", \"%s\"\n", j->seqs[u << 1].name, j->seqs[u << 1 | 1].name);
+}
+
+static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t *swp);
+static void job_finish(job_t *j, bwag_ctx_t *ctx);
+static void job_free(job_t *j);
+static void w_pe_pairs(void *d, long c, int tid);
+
+/* first half of a tail chunk, after bwag_tail_regs: the reads it handed back are aligned up to regions the host-side way now,
+ * because the insert-size model of the batch needs their pairs too */
+static void tail_phase0(job_t *j, bwag_ctx_t *ctx)
+{
+	const int pe = !!(j->opt->flag & MEM_F_PE);
+	int i, n_sub = 0, *idx;
+	if (!pe) return;                       /* single-end: everything handed back is collected after bwag_tail_sam */
+	for (i = 0; i < j->n; i += 2) if (j->cflag[i] || j->cflag[i + 1]) n_sub += 2;
+	if (n_sub == 0) return;
+	idx = bb_malloc(sizeof(int) * (size_t)n_sub);
+	for (i = 0, n_sub = 0; i < j->n; i += 2) if (j->cflag[i] || j->cflag[i + 1]) { idx[n_sub++] = i; idx[n_sub++] = i + 1; }
+	j->sub0 = sub_job(j, n_sub, idx);
+	free(idx);
+	j->sub0->batch = run_to_regs(j->sub0, ctx, &j->sub0->swp);
+	bwag_batch_end(j->sub0->batch); j->sub0->batch = 0;
+	if (j->pe_is) {
+		int k;
+		bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_pe_pairs, j->sub0, ((j->sub0->n >> 1) + 1023) / 1024);
+		for (k = 0; k < j->sub0->n; k += 2) j->pe_is[j->sub0->sub_map[k] >> 1] = j->sub0->pe_is[k >> 1];
+	}
+	PH(j, "tail_sub0");
+}
+
+/* second half of a tail chunk: pairing + records on the device, text splice, then the reads that were handed back */
+static void tail_finish(job_t *j, bwag_ctx_t *ctx)
+{
+	const mem_opt_t *opt = j->opt;
+	const int nt = opt->n_threads > 0 ? opt->n_threads : 1, pe = !!(opt->flag & MEM_F_PE);
+	const long n_units = pe ? j->n >> 1 : j->n;
+	bwag_sam_t out;
+	splice_t sp;
+	int i, n_sub = 0, *idx;
+	if (bwag_tail_sam(j->batch, opt, j->pes, j->ts ? (const double *const *)j->ts->ptab : 0, 0, j->n_processed, bwa_rg_id[0] ? bwa_rg_id : 0, &out) != 0)
+		bb_fatal("mem_process_seqs", "stage 4 (records) failed: %s", bwag_last_error());
+	PH(j, "tail_sam");
+	sp.j = j; sp.out = &out;
+	bb_parallel_for_lane(j->lane, nt, w_splice, &sp, n_units);
+	PH(j, "splice");
+	/* reads handed back here (mate rescue would align, XA, several records, ...): host-side post-processing from scratch */
+#define HANDED_BACK(i_) ((out.rec[i_].flags & BWAG_REC_COMPLEX) && !(pe && j->sub0 && (j->cflag[(i_) & ~1] || j->cflag[(i_) | 1])))
+	for (i = 0; i < j->n; ++i) if (HANDED_BACK(i)) ++n_sub;
+	if (n_sub) {
+		idx = bb_malloc(sizeof(int) * (size_t)n_sub);
+		for (i = 0, n_sub = 0; i < j->n; ++i) if (HANDED_BACK(i)) idx[n_sub++] = i;
+		j->sub1 = sub_job(j, n_sub, idx);
+		free(idx);
+	}
+#undef HANDED_BACK
+	bwag_batch_end(j->batch); j->batch = 0;   /* out.* is gone from here on */
+	if (j->sub1) {
+		free(j->sub1->pe_is); j->sub1->pe_is = 0;
+		j->sub1->batch = run_to_regs(j->sub1, ctx, &j->sub1->swp);
+		job_finish(j->sub1, ctx);
+		sub_job_done(j, j->sub1); j->sub1 = 0;
+	}
+	if (j->sub0) { job_finish(j->sub0, ctx); sub_job_done(j, j->sub0); j->sub0 = 0; }
+	PH(j, "tail_subs");
+	job_free(j);
+	PH(j, "cleanup");
+}
+
 /* stages up to de-duplicated regions for all reads of the job (worker1 of the reference) */
 static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t *swp)
 {
@@ -789,9 +962,26 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 			ctg.n_seqs = n_seqs; ctg.offset = c_off; ctg.len = c_len; ctg.is_alt = c_alt;
 			cp.w = opt->w; cp.max_chain_gap = opt->max_chain_gap; cp.max_occ = opt->max_occ; cp.min_seed_len = opt->min_seed_len;
 			cp.min_chain_weight = opt->min_chain_weight; cp.max_chain_extend = opt->max_chain_extend; cp.mask_level = opt->mask_level; cp.drop_ratio = opt->drop_ratio;
+			const int want_tail = tail_wanted(j);
 			if (bwag_seed(batch, &sp, 0) != 0) bb_fatal("mem_process_seqs", "seeding stage failed: %s", bwag_last_error());
 			PH(j, "seed_stage");
-			rc = bwag_chain_extend(batch, &cp, swp, &ctg, &j->cregs);
+			rc = bwag_chain_extend(batch, &cp, swp, &ctg, want_tail ? 0 : &j->cregs);
+			if (rc == 0 && want_tail) {   /* stage 4: de-duplication, CIGAR requests and K5 on the device; the regions never come to the host */
+				const uint64_t *pis = 0;
+				int rc2;
+				PH(j, "chain_extend");
+				rc2 = bwag_tail_regs(batch, opt, swp, &pis, &j->cflag);
+				if (rc2 == 0) {
+					free(c_off); free(c_len); free(c_alt);
+					j->tail = 1;
+					if (j->pe_is && pis) memcpy(j->pe_is, pis, sizeof(uint64_t) * (size_t)(n >> 1));
+					PH(j, "tail_regs");
+					return batch;
+				}
+				if (rc2 == BWAG_UNSUPPORTED) __atomic_store_n(&g_no_tail, 1, __ATOMIC_RELAXED);
+				else if (rc2 != BWAG_DECLINED) bb_fatal("mem_process_seqs", "stage 4 (regions) failed: %s", bwag_last_error());
+				rc = bwag_chain_extend(batch, &cp, swp, &ctg, &j->cregs);   /* host-side post-processing after all: bring the regions over */
+			}
 			free(c_off); free(c_len); free(c_alt);
 			if (rc == BWAG_UNSUPPORTED) { __atomic_store_n(&no_dev_chain, 1, __ATOMIC_RELAXED); dev_chain = 0; }
 			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
@@ -899,12 +1089,16 @@ static void *lane_main(void *a_)
 		if (g_trace > 0) j->t_last = trace_now();
 		if (a->phase == 0) {
 			j->batch = run_to_regs(j, a->ctx, &j->swp);
-			if (a->pe) {   /* the insert-size model needs every chunk first; with few chunks each keeps its device batch (reads resident) for the second phase */
+			if (j->tail) {   /* stage 4 runs this chunk's post-processing on the device; its batch object stays alive (regions, CIGARs in HBM) */
+				tail_phase0(j, a->ctx);
+				if (!a->pe) tail_finish(j, a->ctx);
+			} else if (a->pe) {   /* the insert-size model needs every chunk first; with few chunks each keeps its device batch (reads resident) for the second phase */
 				if (a->n_jobs > 6) { bwag_batch_end(j->batch); j->batch = 0; }
 				if (j->pe_is) { bb_parallel_for_lane(j->lane, j->opt->n_threads > 0 ? j->opt->n_threads : 1, w_pe_pairs, j, ((j->n >> 1) + 1023) / 1024); PH(j, "pe_pairs"); }
 			}
 			else job_finish(j, a->ctx);
-		} else job_finish(j, a->ctx);
+		} else if (j->tail) tail_finish(j, a->ctx);
+		else job_finish(j, a->ctx);
 	}
 	return 0;
 }
@@ -972,9 +1166,17 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 			bb_pestat_from_pairs(opt, n >> 1, pe_is, pes);
 		}
 		big_free(pe_is);
-		ph("pestat");
-		if (g_trace > 0) fprintf(stderr, "[trace] pestat done %8.1f\n", trace_now());
-		run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
+		{
+			tail_shared_t ts;
+			int any = 0;
+			for (k = 0; k < n_jobs; ++k) any |= jobs[k].tail;
+			memset(&ts, 0, sizeof(ts));
+			if (any) { tail_tables(opt, pes, &ts); for (k = 0; k < n_jobs; ++k) jobs[k].ts = &ts; }
+			ph("pestat");
+			if (g_trace > 0) fprintf(stderr, "[trace] pestat done %8.1f\n", trace_now());
+			run_lanes(jobs, n_jobs, n_lanes, ctx, 1, pe);
+			tail_tables_free(&ts);
+		}
 	}
 	free(jobs);
 	__sync_sub_and_fetch(&n_calls, 1);
@@ -995,7 +1197,7 @@ mem_alnreg_v mem_align1(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *
 	mem_alnreg_v out;
 	memset(&j, 0, sizeof(j)); memset(&s, 0, sizeof(s));
 	s.l_seq = l_seq; s.seq = bb_malloc((size_t)l_seq + 1); memcpy(s.seq, seq_, l_seq);
-	j.opt = opt; j.bwt = bwt; j.bns = bns; j.pac = pac; j.n = 1; j.seqs = &s;
+	j.opt = opt; j.bwt = bwt; j.bns = bns; j.pac = pac; j.n = 1; j.seqs = &s; j.no_tail = 1;
 	sw_par_from_opt(opt, &swp);
 	batch = run_to_regs(&j, bb_device_attach(bwt, bns, pac), &swp);
 	bwag_batch_end(batch);

@@ -90,6 +90,7 @@ typedef struct {
 } bwag_sw_par_t;
 
 #define BWAG_UNSUPPORTED 77           /* returned by a stage an implementation does not provide */
+#define BWAG_DECLINED    78           /* returned by a stage that does not run in the context's current mode (stage 4 while bwag_ctx_baseline is on) */
 #define BWAG_XSEED_ZEROKEY 0x80000000u   /* the seed's sort key (score<<32|index) is 0, see bwamem.c:720 */
 typedef struct { int64_t rbeg; int32_t qbeg; uint32_t len; } bwag_xseed_t;  /* seeds of a chain in ks_introsort_64 order (bwamem.c:688-691) */
 typedef struct { int64_t rmax0, rmax1; int32_t seed_off, n_seeds; } bwag_xchain_t; /* rmax after bns_fetch_seq clamping (bwamem.c:668-685) */
@@ -119,7 +120,7 @@ typedef struct {
 	const int64_t *reg_beg;    /* [n_reads] first region of each read in regs[] */
 	const bwag_creg_t *regs;
 } bwag_cregs_t;
-int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *sp, const bwag_contigs_t *ctg, bwag_cregs_t *out);
+int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *sp, const bwag_contigs_t *ctg, bwag_cregs_t *out);   /* out == NULL: the regions stay in HBM (for bwag_tail_regs) */
 
 /* ---- stage 3: banded global alignment -> CIGAR/NM/MD (replaces bwa_gen_cigar2 + ksw_global2) -- */
 #define BWAG_G_REG2ALN 0   /* the do-while of mem_reg2aln (bwamem.c:1144-1152): up to 3 band doublings, CIGAR+NM+MD */
@@ -135,6 +136,28 @@ typedef struct {
 
 int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out);
 
+/* ---- stage 4: the reference's per-read work AFTER the extension, on the device, for the reads whose post-processing is
+ * "simple" (bwag_tail.cu): mem_sort_dedup_patch, one CIGAR request per region, mem_pestat's per-pair candidate
+ * (bwag_tail_regs); mem_mark_primary_se, mem_approx_mapq_se, the mate-rescue trigger test, mem_pair, mem_sam_pe's pair
+ * logic, mem_reg2aln and the SAM record (bwag_tail_sam).  Reads that leave the simple case come back flagged and are
+ * aligned by the caller's host-side post-processing instead.  Both need bwag_ctx_set_contigs once per context and a
+ * preceding bwag_chain_extend(b, ..., NULL) (regions stay in HBM).  BWAG_UNSUPPORTED from the CPU oracle of the tests. ---- */
+int bwag_ctx_set_contigs(bwag_ctx_t *ctx, int n_seqs, const int64_t *offset, const int32_t *len, const uint8_t *is_alt, const char *const *names);
+/* pe_is (PE only, else NULL is stored): [n_reads/2] per-pair insert-size candidates, pinned; cflag: [n_reads], non-zero =
+ * the read left the simple path already here (too many regions, ALT contig, a region merge that needs an alignment) */
+int bwag_tail_regs(bwag_batch_t *b, const mem_opt_t *opt, const bwag_sw_par_t *sp, const uint64_t **pe_is, const uint8_t **cflag);
+#define BWAG_REC_TEXT    1u    /* the record's text is in the pool */
+#define BWAG_REC_QREV    2u    /* the quality string goes in reversed */
+#define BWAG_REC_COMPLEX 4u    /* no text: the read needs the host-side post-processing (reason in bits 8-15) */
+enum { BWAG_CX_MANY = 1, BWAG_CX_ALT, BWAG_CX_PATCH, BWAG_CX_CAP, BWAG_CX_RESCUE, BWAG_CX_PAIR, BWAG_CX_XA, BWAG_CX_MULTI, BWAG_CX_CIGAR, BWAG_CX_LONG };
+/* one read's record: name + text[off, off+len_a) + QUAL + text[off+len_a, off+len_a+len_b) + [\t comment] + \n */
+typedef struct { int64_t off; int32_t len_a, len_b; uint32_t flags; int32_t pad; } bwag_samrec_t;
+typedef struct { const bwag_samrec_t *rec; const char *text; int64_t n_text, n_complex; } bwag_sam_t;
+/* pair_tab[d]: the insert-size term of a pair's score for distances pes[d].low..pes[d].high (bwamem_pair.c:266), NULL = orientation
+ * unusable; log_tab: log(i) for i < 4096; both from the host's libm so that the integer decisions are the host's */
+int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pestat_t pes[4], const double *const pair_tab[4], const double *log_tab,
+                  int64_t n_processed, const char *rg_id, bwag_sam_t *out);
+
 /* ---- work / time counters for the roofline ---------------------------------------------------- */
 typedef struct {
 	uint64_t occ_touches;      /* 64-byte Occ blocks touched by bwt_extend (1 or 2 per call, bwt.c:194-197) */
@@ -147,6 +170,8 @@ typedef struct {
 	uint64_t n_launch;         /* kernels launched */
 	uint64_t h2d_bytes, d2h_bytes;   /* bytes copied host->device / device->host by the stage calls */
 	double ms_chain;           /* CUDA-event time of the chaining kernel */
+	double ms_tail;            /* CUDA-event time of the stage-4 kernels (de-duplication/requests, pairing/SAM records) */
+	uint64_t tail_reads, tail_complex;   /* reads that went through stage 4 / that it handed back to the host-side post-processing */
 } bwag_stats_t;
 void bwag_stats_get(bwag_ctx_t *ctx, bwag_stats_t *s);
 void bwag_stats_reset(bwag_ctx_t *ctx);

@@ -142,6 +142,7 @@ static inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __sync_fetch_and_add(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __sync_fetch_and_add(p, v); }
 static inline int atomicMax(int *p, int v) { int o = *p; while (o < v && !__sync_bool_compare_and_swap(p, o, v)) o = *p; return o; }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; while (o < v && !__sync_bool_compare_and_swap(p, o, v)) o = *p; return o; }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __sync_fetch_and_or(p, v); }
 static inline int atomicExch(int *p, int v) { return __sync_lock_test_and_set(p, v); }
 static inline int atomicCAS(int *p, int c, int v) { return __sync_val_compare_and_swap(p, c, v); }

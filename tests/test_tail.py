@@ -1,0 +1,78 @@
+"""Stage 4 (bwag_tail.cu: de-duplication, CIGAR requests, pairing, MAPQ and SAM records on the device) and the
+lane-per-read extension kernel (bwag_extend_lane.cu) against the reference binary, with the stage really taken (its
+counters say so), with reads it must hand back to the host-side post-processing (repeat-rich reference: XA lists,
+supplementary records, mate rescue, region merges), with read groups / comments / FASTA input (no qualities), and with
+each of the two switched off (the remaining paths must give the same bytes).  CPU: the SIMT emulator; -m gpu: the B200."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import bwa_b200
+from conftest import CUSIMBIN, ref_sam, run_sam, strip_pg
+
+
+def _counts(binary, args, env=None):
+    e = dict(os.environ, BWA_B200_PROFILE="1", **(env or {}))
+    p = subprocess.run([binary, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=e)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    took = handed = 0
+    for m in re.finditer(rb"stage 4: (\d+) reads, (\d+) handed back", p.stderr):
+        took += int(m.group(1)); handed += int(m.group(2))
+    return strip_pg(p.stdout), took, handed, b"lane-per-read kernel" in p.stderr
+
+
+def _check(binary, data, n_c1, n_stress):
+    # unique reference, proper pairs: everything stays on the device
+    fa, fqs = data.reads("c1", tag="tl_pe", n=n_c1, seed=31, paired=True)
+    args = ["-K", "100000000", "-t", "4", "-R", "@RG\\tID:grp1\\tSM:x", fa] + fqs
+    sam, took, handed, lane = _counts(binary, args)
+    assert sam == ref_sam(args)
+    assert took == 2 * n_c1 and handed * 50 <= took and lane
+    # repeat-rich reference, chimeric reads: many reads are handed back, the merged output is still the reference's
+    for paired in (True, False):
+        fa, fqs = data.reads("stress", tag="tl_pe" if paired else "tl_se", n=n_stress, seed=32, paired=paired, err=(0.016, 0.002, 0.002), chimeric=0.05)
+        args = ["-K", "100000000", "-t", "4", "-C", fa] + fqs
+        sam, took, handed, lane = _counts(binary, args)
+        assert sam == ref_sam(args)
+        assert took >= n_stress and 0 < handed < took
+        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}):
+            s2, t2, _, l2 = _counts(binary, args, env)
+            assert s2 == sam
+            assert (t2 == 0) == ("BWA_B200_TAIL" in env) and l2 == ("BWA_B200_K4_LANE" not in env)
+    # options that keep stage 4 out (-a lists secondary hits, -5 reorders) and options it handles (-M, -Y, -P, -S)
+    fa, fqs = data.reads("stress", tag="tl_pe", n=n_stress, seed=32, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    for extra, on in ((["-a"], False), (["-5"], False), (["-M", "-Y"], True), (["-P"], True), (["-S"], True), (["-T", "60", "-U", "9"], True)):
+        args = extra + ["-K", "100000000", "-t", "4", fa] + fqs
+        sam, took, handed, lane = _counts(binary, args)
+        assert sam == ref_sam(args), extra
+        assert (took > 0) == on, extra
+
+
+def test_device_tail_emulated(data):
+    _check(CUSIMBIN, data, 160, 120)
+
+
+def test_device_tail_fasta_input_and_several_chunks(data, tmp_path, monkeypatch):
+    """No quality strings (FASTA): QUAL is '*'; chunks smaller than the batch: the insert-size model still sees every pair."""
+    fa, fqs = data.reads("c1", tag="tl_pe", n=300, seed=31, paired=True)
+    fas = []
+    for f in fqs:
+        out = str(tmp_path / (os.path.basename(f) + ".fa"))
+        with open(f) as i, open(out, "w") as o:
+            for k, line in enumerate(i):
+                if k % 4 == 0:
+                    o.write(">" + line[1:])
+                elif k % 4 == 1:
+                    o.write(line)
+        fas.append(out)
+    args = ["-K", "100000000", "-t", "3", fa] + fas
+    monkeypatch.setenv("BWA_B200_CHUNK", "64")
+    monkeypatch.setenv("BWA_B200_LANES", "2")
+    assert run_sam(CUSIMBIN, args) == ref_sam(args)
+
+
+@pytest.mark.gpu
+def test_device_tail_gpu(data):
+    _check(bwa_b200.CLI_PATH, data, 4000, 3000)
