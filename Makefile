@@ -90,3 +90,19 @@ tests/_build/bwa-b200-cusim-asan: $(CUDA_SRC) $(CUDA_HDR) $(HOST_SRC) $(HOST)/bb
 	$(ASAN_CC) -O1 -g -fsanitize=address -fno-omit-frame-pointer -Iinclude -I$(HOST) -pthread -DBB_MAIN -c $(HOST)/bb_cli.c -o tests/_build/asan/h_main.o
 	$(ASAN_CXX) -fsanitize=address -o $@ tests/_build/asan/*.o -lz -lm -lpthread
 .PHONY: asan
+
+# Variant with 2^16-symbol Occ superblocks (TEST ONLY): the u32-relative counts, the per-superblock absolute counts and every
+# carry across a superblock boundary are exercised by a 1 Mbp reference the way a 3 Gbp reference exercises them in production
+# (whose only superblock boundaries are at 2^31 and 2^32).  sb16: emulator build; sb16-cuda: the same for the GPU (prebuilt here, runs on the box).
+SB16 := -DBWAG_SB_SHIFT=16 -DBWAG_MAX_SB=64
+sb16: tests/_build/bwa-b200-cusim-sb16
+tests/_build/bwa-b200-cusim-sb16: $(CUDA_SRC) $(CUDA_HDR) $(HOST_OBJ) build/host/bb_main.o tests/_build/cusim_rt.o
+	@mkdir -p tests/_build/sb16
+	for f in $(CUDA_SRC); do $(CXX) $(CUSIM_FLAGS) $(SB16) -c $$f -o tests/_build/sb16/c_`basename $$f .cu`.o || exit 1; done
+	$(CXX) -o $@ build/host/bb_main.o $(HOST_OBJ) tests/_build/sb16/c_*.o tests/_build/cusim_rt.o -lz -lm -lpthread
+sb16-cuda: tests/_build/bwa-b200-sb16
+tests/_build/bwa-b200-sb16: $(CUDA_SRC) $(CUDA_HDR) $(HOST_OBJ) build/host/bb_main.o
+	@mkdir -p tests/_build/sb16
+	for f in $(CUDA_SRC); do $(NVCC) $(NVFLAGS) $(SB16) `test $$f = $(CUDA)/bwag_tail.cu && echo -fmad=false` -c $$f -o tests/_build/sb16/g_`basename $$f .cu`.o || exit 1; done
+	$(CC) -o $@ build/host/bb_main.o $(HOST_OBJ) tests/_build/sb16/g_*.o -L/usr/local/cuda/lib64 -lcudart -lstdc++ -lz -lm -lpthread -Wl,-rpath,/usr/local/cuda/lib64
+.PHONY: sb16 sb16-cuda

@@ -90,7 +90,7 @@ struct bwag_ctx {
 	bwag_stats_t st;
 	int sa_intv_disk;
 	/* scratch reused across batches */
-	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd;
+	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd, s_pack;
 	int grid_k1, grid_k1f, grid_k2, grid_k4, grid_k5;
 #define N_SPARE 12
 	struct bwag_batch *spare[N_SPARE]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
@@ -246,7 +246,7 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	c->ix.primary = h.primary; c->ix.seq_len = h.seq_len; c->ix.n_sa = h.n_sa; c->ix.l_pac = (i64)h.l_pac; c->ix.sa_shift = (int)h.sa_shift;
 	for (int i = 0; i < 5; ++i) c->ix.L2[i] = h.L2[i];
 	for (int s = 0; s < BWAG_MAX_SB; ++s)
-		for (int k = 0; k < 4; ++k) c->ix.sb[s][k] = h.sb[s][k];
+		for (int k = 0; k < 4; ++k) { c->ix.sb[s][k] = h.sb[s][k]; c->ix.sbgt[s][k] = 0; for (int t = k + 1; t < 4; ++t) c->ix.sbgt[s][k] += h.sb[s][t]; }
 	c->sa_intv_disk = 1 << h.sa_shift;
 	CKP(cudaStreamCreate(&c->stream));
 	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
@@ -277,7 +277,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
+	free_dev(&c->s_pack); free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
 	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->ktab) cudaFree(c->ktab);
@@ -450,7 +450,7 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 static void batch_free(bwag_batch_t *b)
 {
 	if (b->lc_ready) {
-		free_dev(&b->lc.s_k1); free_dev(&b->lc.s_k1f); free_dev(&b->lc.s_n3); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
+		free_dev(&b->lc.s_pack); free_dev(&b->lc.s_k1); free_dev(&b->lc.s_k1f); free_dev(&b->lc.s_n3); free_dev(&b->lc.s_eh); free_dev(&b->lc.s_rseq); free_dev(&b->lc.s_qseq); free_dev(&b->lc.s_z); free_dev(&b->lc.s_wcig); free_dev(&b->lc.s_wmd);
 		cudaFree(b->lc.d_cnt); cudaFreeHost(b->lc.h_cnt);
 		cudaEventDestroy(b->lc.ev0); cudaEventDestroy(b->lc.ev1); cudaEventDestroy(b->lc.ev_wait); cudaStreamDestroy(b->lc.stream);
 	}
@@ -473,13 +473,13 @@ static int reset_counters(bwag_ctx_t *c)
 	CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
 	return 0;
 }
-/* wait for the context's stream.  Default: cudaStreamSynchronize (the runtime spins: lowest latency, one core per
- * waiting lane); optionally without spinning */
+/* wait for the context's stream.  Default: poll with short sleeps (a waiting lane costs no core; with the post-processing on the
+ * device the host threads are few); BWA_B200_SYNC=spin: cudaStreamSynchronize, =yield / =block: see below */
 static cudaError_t stream_wait(bwag_ctx_t *c)
 {
 	static int mode = -1;   /* BWA_B200_SYNC=block: sleep on a blocking event (saves the cores of waiting lanes, adds wake-up latency to every
 	                         * stage); =yield: poll the stream and give the core away between polls (for boxes with fewer CPUs than threads) */
-	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = !e ? 0 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "yield") == 0 ? 2 : strcmp(e, "sleep") == 0 ? 3 : 0; }
+	if (mode < 0) { const char *e = getenv("BWA_B200_SYNC"); mode = !e ? 3 : strcmp(e, "spin") == 0 ? 0 : strcmp(e, "block") == 0 ? 1 : strcmp(e, "yield") == 0 ? 2 : 3; }   /* default: sleep-poll (measured: profiles/r2_call2_*) */
 	if (mode == 0) return cudaStreamSynchronize(c->stream);
 	if (mode == 3) {   /* =sleep: poll, sleeping 5..80 us between polls: under a CPU quota a spinning lane eats the host workers' budget */
 		long ns = 5000;
@@ -559,6 +559,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		}
 		if (buf_reserve(&c->s_k1, per_group * (size_t)grid * groups_per_block)) return 1;
 		if (buf_reserve(&c->s_k1f, 32 * (size_t)cap3 * (size_t)n + 64) || buf_reserve(&c->s_n3, sizeof(int) * (size_t)(n + 1))) return 1;
+		if (pstride && buf_reserve(&c->s_pack, 4 * ((size_t)(b->total_bases >> 4) + 2 * (size_t)n + 8))) return 1;
 		if (buf_reserve(&b->d_intv_beg, sizeof(i64) * (size_t)(n + 1)) || buf_reserve(&b->d_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
 		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
@@ -570,6 +571,12 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		a.next_read = &c->d_cnt->next_read; a.n_intv = &c->d_cnt->n_intv; a.n_seeds = &c->d_cnt->n_seeds; a.occ_touches = &c->d_cnt->occ_touches; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
+		if (pstride) {   /* the packed copies K1's table lookups key on */
+			a.packed = (const u32 *)c->s_pack.p;
+			BWAG_LAUNCH(k_pack_reads, (n + 127) / 128, 128, 0, c->stream, a.codes, a.off, n, (u32 *)c->s_pack.p);
+			CK(cudaGetLastError());
+			++c->st.n_launch;
+		}
 		if (a.n3) {   /* third pass first: K1 appends its seeds to the read's list */
 			int g3 = c->grid_k1f;
 			if (g3 > (n + K1F_THREADS - 1) / K1F_THREADS) g3 = (n + K1F_THREADS - 1) / K1F_THREADS;

@@ -35,12 +35,17 @@ typedef unsigned long long u64;
 typedef long long i64;
 typedef unsigned int u32;
 
+#ifndef BWAG_SB_SHIFT
 #define BWAG_SB_SHIFT 31     /* symbols per superblock = 2^31: block counts fit u32 */
-#define BWAG_MAX_SB 8
+#endif
+#ifndef BWAG_MAX_SB
+#define BWAG_MAX_SB 8        /* tests build a variant with 2^16-symbol superblocks so that a 1 Mbp reference crosses dozens of them */
+#endif
 
 struct DevIndex {
 	const uint4 *bwt;   /* 2 x uint4 per 64-symbol block: {counts}, {plane hi (2 words), plane lo (2 words)} */
 	u64 sb[BWAG_MAX_SB][4];   /* counts of A,C,G,T before each superblock */
+	u64 sbgt[BWAG_MAX_SB][4]; /* [s][c]: symbols greater than c before superblock s (sums of sb[s][c+1..3]) */
 	const u64 *sa;
 	const uint8_t *pac;
 	u64 primary, seq_len;

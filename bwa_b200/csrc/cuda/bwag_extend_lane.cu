@@ -28,7 +28,7 @@
 #define XSEED_LEN(x) ((int)((x) & 0x3fffffffu))
 #define K4L_CH 8
 
-enum { L_FETCH = 0, L_CHAIN, L_SEED, L_EXT_BEGIN, L_ROWS, L_EXT_END, L_DONE };
+enum { L_FETCH = 0, L_CHAIN, L_SEED, L_EXT_BEGIN, L_INIT, L_ROWS, L_EXT_END, L_DONE };
 
 #ifdef BWAG_CUSIM
 #define K4L_LD(addr) (*reinterpret_cast<const u32 *>(addr))
@@ -91,17 +91,18 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 	int qlen = 0, tlen = 0, h0 = 0, w = 0, i = 0, beg = 0, end = 0, mx = 0, max_i = 0, max_j = 0, max_ie = 0, gscore = 0, max_off = 0, pot0 = 0;
 	i64 tbase = 0; int tdir = 1, t_cur = 0, t_next = 0;
 	/* row */
-	int jcur = 0, f = 0, hp = 0, key = -1;
+	int jcur = 0, f = 0, hp = 0, key = -1, jmin = 0x7fffffff, jmax = -1, phi = 0, H1 = 0;
+	const uint8_t *qp = 0; int qs = 1;
 	u32 rlo = 0, rhi = 0;
 	u64 cells = 0;
 	int overflow = 0, waited = 0;
 
 	for (;;) {
 		/* ---- divergent part: lanes that are not inside a DP advance their read's control flow ---- */
-		const u32 want = __ballot_sync(FULL_MASK, st != L_ROWS && st != L_DONE);
-		const bool go = want && (__popc(want) >= 4 || waited >= 6 || !__any_sync(FULL_MASK, st == L_ROWS));
+		const u32 want = __ballot_sync(FULL_MASK, st != L_ROWS && st != L_INIT && st != L_DONE);
+		const bool go = want && (__popc(want) >= 4 || waited >= 6 || !__any_sync(FULL_MASK, st == L_ROWS || st == L_INIT));
 		waited = go ? 0 : waited + 1;
-		if (go && st != L_ROWS && st != L_DONE) {
+		if (go && st != L_ROWS && st != L_INIT && st != L_DONE) {
 			for (;;) {
 				if (st == L_FETCH) {
 					rid = atomicAdd(a.next_read, 1);
@@ -210,16 +211,9 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 					}
 					{
 						const int oe_ins = o_ins + e_ins;
-						const int H1 = h0 > oe_ins ? h0 - oe_ins : 0;
-						const uint8_t *qp = phase == 0 ? query + s_qbeg - 1 : query + s_qbeg + s_len;
-						const int qs = phase == 0 ? -1 : 1;
-						k4l_addr ad = he0;
-						for (int j = 0; j <= qlen; ++j, ad += K4L_COL) {
-							int v = j == 0 ? h0 : H1 - (j - 1) * e_ins;
-							v = v > 0 ? v : 0;
-							const u32 qc = j < qlen ? qp[j * qs] : 4;
-							K4L_ST(ad, (u32)v | (qc > 4 ? 4u : qc) << 29);      /* 8 x code in the top six bits */
-						}
+						H1 = h0 > oe_ins ? h0 - oe_ins : 0;
+						qp = phase == 0 ? query + s_qbeg - 1 : query + s_qbeg + s_len;
+						qs = phase == 0 ? -1 : 1;
 						int max_ins = (int)((double)(qlen * maxsc + end_bonus - o_ins) / e_ins + 1.); max_ins = max_ins > 1 ? max_ins : 1;
 						w = w < max_ins ? w : max_ins;
 						int max_del = (int)((double)(qlen * maxsc + end_bonus - o_del) / e_del + 1.); max_del = max_del > 1 ? max_del : 1;
@@ -231,29 +225,49 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 					if (tlen <= 0) { st = L_EXT_END; continue; }
 					t_cur = bwag_ref_base(ix, tbase);
 					t_next = tlen > 1 ? bwag_ref_base(ix, tbase + tdir) : 0;
-					{   /* first row (i = 0): band, first-column carry (ksw.c:448-459) */
-						if (end > w + 1) end = w + 1;
-						if (end > qlen) end = qlen;
-						hp = h0 - (o_del + e_del); if (hp < 0) hp = 0;
-						f = 0; key = -1; jcur = 0;
-						const unsigned long long rw = s_row[t_cur];
-						rlo = (u32)rw; rhi = (u32)(rw >> 32);
-						if (end > 0) cells += (u64)end;
-					}
-					st = L_ROWS;
+					jcur = 0;
+					st = L_INIT;   /* the first row's columns are written by the converged part below, K4L_CH per iteration */
 				}
-				if (st == L_ROWS || st == L_DONE) break;
+				if (st == L_ROWS || st == L_INIT || st == L_DONE) break;
 			}
 		}
 		if (__all_sync(FULL_MASK, st == L_DONE)) break;
 
-		/* ---- converged part: up to K4L_CH cells of the current row (ksw.c:460-484) ---- */
-		if (st == L_ROWS) {
+		/* ---- converged part 1: K4L_CH columns of a new extension's first row (ksw.c:431-433), then its band and first-column carry ---- */
+		if (st == L_INIT) {
+			k4l_addr ad = he0 + jcur * K4L_COL;
+#pragma unroll
+			for (int cc = 0; cc < K4L_CH; ++cc) {
+				const int j = jcur + cc;
+				if (j <= qlen) {
+					int v = j == 0 ? h0 : H1 - (j - 1) * e_ins;
+					v = v > 0 ? v : 0;
+					const u32 qc = j < qlen ? qp[j * qs] : 4;
+					K4L_ST(ad + cc * K4L_COL, (u32)v | (qc > 4 ? 4u : qc) << 29);      /* 8 x code in the top six bits */
+				}
+			}
+			jcur += K4L_CH;
+			if (jcur > qlen) {   /* row 0: band, first-column carry (ksw.c:448-459) */
+				if (end > w + 1) end = w + 1;
+				if (end > qlen) end = qlen;
+				hp = h0 - (o_del + e_del); if (hp < 0) hp = 0;
+				f = 0; key = -1; jcur = 0; jmin = 0x7fffffff; jmax = -1; phi = 0;
+				const unsigned long long rw = s_row[t_cur];
+				rlo = (u32)rw; rhi = (u32)(rw >> 32);
+				if (end > 0) cells += (u64)end;
+				st = L_ROWS;
+			}
+		}
+		/* ---- converged part 2: up to K4L_CH cells of the current row (ksw.c:460-484) ---- */
+		else if (st == L_ROWS) {
 			int nact = end - jcur;
 			nact = nact < K4L_CH ? nact : K4L_CH;
 			k4l_addr ad = he0 + jcur * K4L_COL;
+			u32 nzm = 0;
+			int pot = pot0 - maxsc * jcur;
 			/* straight-line code: cells past the row's end (only ever the tail of the chunk that ends the row) are computed on
-			 * whatever their columns hold and masked -- no store, h1 and the row maximum keep their values; F is dead by then */
+			 * whatever their columns hold and masked -- no store, h1, the row maximum, the non-zero marks and the cut-off bound
+			 * keep their values; F is dead by then */
 #pragma unroll
 			for (int cc = 0; cc < K4L_CH; ++cc) {
 				const bool act = cc < nact;
@@ -266,14 +280,21 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 				f = __viaddmax_s32(f, ne_ins, __viaddmax_s32(M, noe_ins, 0));
 				const int kk = act ? (h << 16) + (jcur + cc) : -1;
 				key = key > kk ? key : kk;
-				if (act) K4L_ST(ad + cc * K4L_COL, (wd & K4L_Q_MASK) | (u32)hp | (u32)e << 13);
+				const u32 he = (u32)hp | (u32)e << 13;                   /* the stored cell: H(i, j-1), E(i+1, j) */
+				if (act) K4L_ST(ad + cc * K4L_COL, (wd & K4L_Q_MASK) | he);
+				nzm |= (act && he != 0) ? 1u << cc : 0u;
+				phi = act ? __viaddmax_s32(h, pot - maxsc * cc, phi) : phi;    /* potential of the cell: score + maxsc per remaining column */
 				hp = act ? h : hp;
+			}
+			if (nzm) {   /* first / last column of the row whose stored cell is non-zero: the next band (ksw.c:501-505) */
+				const int lo = jcur + __ffs((int)nzm) - 1;
+				jmax = jcur + 31 - __clz((int)nzm);
+				jmin = jmin < lo ? jmin : lo;
 			}
 			if (nact > 0) jcur += nact;
 		}
 		/* ---- end of a row (ksw.c:485-506), then the next row's set-up ---- */
 		if (st == L_ROWS && jcur >= end) {
-			const int row_beg = beg, row_end = end;
 			const int h1 = hp;
 			{
 				const k4l_addr ae = he0 + end * K4L_COL;
@@ -298,18 +319,17 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 					else { if (mx - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) stop = true; }
 				}
 			}
-			if (!stop) {   /* next band: skip leading and trailing all-zero cells (ksw.c:501-505) */
-				int j;
-				for (j = beg; j < end && (K4L_LD(he0 + j * K4L_COL) & K4L_HE_MASK) == 0; ++j) {}
-				beg = j;
-				for (j = end; j >= beg && (K4L_LD(he0 + j * K4L_COL) & K4L_HE_MASK) == 0; --j) {}
-				end = j + 2 < qlen ? j + 2 : qlen;
-				if (falling && to_end && gscore > 0) {
-					/* exact row cut-off (bwag_extend.cu): no later row can beat `mx` or reach `gscore` once every stored cell's
-					 * potential (score + maxsc per remaining column) is below them; the bound needs the row just finished, whose
-					 * H(i, j) sits in column j + 1 */
-					int bound = 0;
-					for (j = row_beg; j < row_end; ++j) bound = __viaddmax_s32((int)(K4L_LD(he0 + (j + 1) * K4L_COL) & 0x1fffu), pot0 - maxsc * j, bound);
+			if (!stop) {   /* next band: first non-zero stored cell .. last non-zero stored cell + 2, column `end` included (ksw.c:501-505) */
+				const int nb = jmin == 0x7fffffff ? end : jmin;
+				int jl = jmax;
+				if (h1 != 0) jl = end;
+				if (jl < 0) jl = nb - 1;
+				beg = nb;
+				end = jl + 2 < qlen ? jl + 2 : qlen;
+				if (falling && to_end) {
+					/* exact row cut-off (bwag_extend.cu): no later row can beat `mx` or reach `gscore` once every cell's potential
+					 * (score + maxsc per remaining column) of the row just finished, and the first-column entry, are below them */
+					int bound = phi;
 					if (beg == 0) { const int fc = h0 - (o_del + e_del * (i + 1)) + maxsc * qlen; bound = bound > fc ? bound : fc; }
 					if (bound <= mx && bound < gscore) stop = true;
 				}
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 				if (end > qlen) end = qlen;
 				hp = 0;
 				if (beg == 0) { hp = h0 - (o_del + e_del * (i + 1)); if (hp < 0) hp = 0; }
-				f = 0; key = -1; jcur = beg;
+				f = 0; key = -1; jcur = beg; jmin = 0x7fffffff; jmax = -1; phi = 0;
 				t_cur = t_next;
 				if (i + 1 < tlen) t_next = bwag_ref_base(ix, tbase + (i64)tdir * (i + 1));
 				const unsigned long long rw = s_row[t_cur];

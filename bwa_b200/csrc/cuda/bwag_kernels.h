@@ -36,6 +36,7 @@ struct SeedArgs {
 	int pstride;                                   /* bytes of a lane's 2-bit packed copy of the read (0: no short-string table lookups in K1) */
 	int nstride;                                   /* variant K1_PACKED8 only: bytes of a lane's N bitmap (the byte copy of the read is dropped: qstride = 0) */
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
+	const u32 *packed;                             /* k_pack_reads: 2-bit copy of every read, read r at word (off[r] >> 4) + 2 r */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
 	i64 cap_intv, cap_seeds;
@@ -121,6 +122,7 @@ struct TailSamArgs {
 
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
+__global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
 __global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);

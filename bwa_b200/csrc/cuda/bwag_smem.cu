@@ -151,6 +151,56 @@ __device__ __forceinline__ void extend_step2(const DevIndex &ix, u64 xs, u64 xo,
 	}
 }
 
+/* within positions [0,p] of its 64-symbol block: occurrences of symbol c and of symbols greater than c, plus the block's counts of
+ * both before it (relative to the superblock): all a bwt_extend by ONE known symbol needs -- 32-bit selects instead of four
+ * 64-bit ranks per position */
+__device__ __forceinline__ void block_eq_gt(const uint4 &cn, const uint4 &pl, u64 p, int c, u32 &eq, u32 &gt)
+{
+	const int n = (int)(p & 63) + 1;
+	const u32 m0 = bwag_plane_mask(n), m1 = bwag_plane_mask(n - 32);
+	const u32 h0 = pl.x & m0, h1 = pl.y & m1, l0 = pl.z & m0, l1 = pl.w & m1;
+	const u32 nH = __popc(h0) + __popc(h1), nL = __popc(l0) + __popc(l1), nT = __popc(h0 & l0) + __popc(h1 & l1);
+	const u32 s2 = cn.z + cn.w, s1 = cn.y + s2;
+	eq = SEL4(c, cn.x + (u32)n + nT - nH - nL, cn.y + nL - nT, cn.z + nH - nT, cn.w + nT);
+	gt = SEL4(c, s1 + nH + nL - nT, s2 + nH, cn.w + nT, 0u);
+}
+
+/* extend_step2 with the ranks of the one symbol that is asked for (same results): x[2] = occ_c(l) - occ_c(k), the extended
+ * side = L2[c] + 1 + occ_c(k), the other side moves by the symbols greater than c inside the interval (bwt.c:262-275) */
+__device__ __forceinline__ void extend_step3(const DevIndex &ix, u64 xs, u64 xo, u64 e2, int c, bool tab, u32 tidx, int back,
+                                             int &t12, u64 &o_s, u64 &o_o, u64 &o_x2, u32 &ct)
+{
+	const u64 k = xs - 1, l = xs - 1 + e2;
+	const bool kv = k != (u64)-1, lv = l != (u64)-1;
+	const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
+	const bool same = kv && lv && (kp >> 6) == (lp >> 6);
+	uint4 b0, b1, c0, c1;
+	b0 = b1 = c0 = c1 = make_uint4(0, 0, 0, 0);
+	const uint4 *p1 = tab ? reinterpret_cast<const uint4 *>(ix.ktab + (tidx & ~1u)) : ix.bwt + ((lp >> 6) << 1);
+	if (tab || lv) bwag_ld_block(p1, b0, b1);
+	if (!tab && kv && !same) bwag_ld_block(ix.bwt + ((kp >> 6) << 1), c0, c1);
+	if (same) { c0 = b0; c1 = b1; }   /* both ranks in one block: it was fetched once */
+	u32 eq_l = 0, gt_l = 0, eq_k = 0, gt_k = 0;
+	block_eq_gt(b0, b1, lp, c, eq_l, gt_l);            /* table lanes: computed on the entry's bits and discarded below */
+	block_eq_gt(c0, c1, kp, c, eq_k, gt_k);
+	t12 = (kv && lv && (kp >> 7) == (lp >> 7)) ? 1 : 2;   /* as the reference counts them: its blocks hold 128 symbols (bwt.c:194-197) */
+	const int sl = lv ? (int)(lp >> BWAG_SB_SHIFT) : 0, sk = kv ? (int)(kp >> BWAG_SB_SHIFT) : 0;
+	const u64 occ_l = lv ? ix.sb[sl][c] + eq_l : 0, occ_k = kv ? ix.sb[sk][c] + eq_k : 0;
+	const u64 big_l = lv ? ix.sbgt[sl][c] + gt_l : 0, big_k = kv ? ix.sbgt[sk][c] + gt_k : 0;
+	o_x2 = occ_l - occ_k;
+	o_s = SEL4(c, ix.L2[0], ix.L2[1], ix.L2[2], ix.L2[3]) + 1 + occ_k;                                     /* new x[!is_back] */
+	o_o = xo + ((xs <= ix.primary && xs + e2 - 1 >= ix.primary) ? 1 : 0) + (big_l - big_k);             /* new x[is_back]: bwt.c:271-274 */
+	ct = 0;
+	if (tab) {
+		const uint4 ev = (tidx & 1u) ? b1 : b0;
+		ulonglong2 v;
+		u64 x0, x1, x2;
+		v.x = (u64)ev.y << 32 | ev.x; v.y = (u64)ev.w << 32 | ev.z;
+		unpack_ent(v, x0, x1, x2, ct);
+		o_x2 = x2; o_s = back ? x0 : x1; o_o = back ? x1 : x0;
+	}
+}
+
 /* one lane per table entry: the string's bi-interval by forward extension from its first base, exactly as a sweep would */
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K)
 {
@@ -219,7 +269,7 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 		u64 o_s, o_o, o_x2;
 		u32 ct;
 		int t12;
-		extend_step2(ix, ik1, ik0, ik2, jump ? 0 : 3 - q[i], jump, tidx, 0, t12, o_s, o_o, o_x2, ct);
+		extend_step3(ix, ik1, ik0, ik2, jump ? 0 : 3 - q[i], jump, tidx, 0, t12, o_s, o_o, o_x2, ct);
 		if (jump) { ik0 = o_o; ik1 = o_s; ik2 = o_x2; i = x + kj; touches += ct; continue; }
 		touches += (u64)t12;
 		if (o_x2 < a.max_mem_intv && i - x >= a.min_seed_len) {     /* bwt.c:366-375 */
@@ -233,6 +283,27 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(a.occ_touches, touches);
 	overflow = __reduce_or_sync(FULL_MASK, overflow);
 	if ((threadIdx.x & 31) == 0 && overflow) atomicOr(a.flags, overflow);
+}
+
+/* ------------------------------------------------------------------------------------------------ K0
+ * 2-bit packed copy of every read (16 bases per word, first base in the low bits, one spare word; N packs as A and is never
+ * looked up): the keys of the short-string table.  One lane per read, once per batch; K1 used to build this itself, one lane
+ * at a time (5 % of its instructions at 1.1 active lanes, profiles/r2_k_smem_by_source_line.txt).  Read r's words start at
+ * (off[r] >> 4) + 2 r. */
+__global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const i64 o = off[r];
+	const int len = (int)(off[r + 1] - o);
+	const uint8_t *q = codes + o;
+	u32 *dst = packed + (o >> 4) + 2 * (i64)r;
+	const int nwp = ((len + 15) >> 4) + 1;
+	for (int w = 0; w < nwp; ++w) {
+		u32 pw = 0;
+		for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
+		dst[w] = pw;
+	}
 }
 
 /* ------------------------------------------------------------------------------------------------ K1 */
@@ -366,13 +437,10 @@ k_smem(DevIndex ix, SeedArgs a)
 						const int nw = ((int)(o & 3) + len + 3) >> 2;
 						for (int w = 0; w < nw; ++w) d[w] = g[w];
 						q = sq + (o & 3);
-						if (ktk) {              /* 16 bases per word, first base in the low bits, one spare word; N packs as A (never looked up) */
+						if (ktk) {              /* the 2-bit packed copy k_pack_reads made */
 							const int nwp = ((len + 15) >> 4) + 1;
-							for (int w = 0; w < nwp; ++w) {
-								u32 pw = 0;
-								for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
-								sp[w] = pw;
-							}
+							const u32 *gp = a.packed + (o >> 4) + 2 * (i64)rid;
+							for (int w = 0; w < nwp; ++w) sp[w] = gp[w];
 						}
 					} else q = a.codes + o;
 					continue;
@@ -430,7 +498,7 @@ k_smem(DevIndex ix, SeedArgs a)
 				const u32 win = __funnelshift_r(sp[pos >> 4], sp[(pos >> 4) + 1], (u32)(pos & 15) << 1);
 				tidx = ktab_off(rlen) + (win & ((1u << (2 * rlen)) - 1u));
 			}
-			extend_step2(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, tab, tidx, back, t12, o_s, o_o, o_x2, ct);
+			extend_step3(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, tab, tidx, back, t12, o_s, o_o, o_x2, ct);
 			touches += (u64)t12;
 		}
 

@@ -14,7 +14,7 @@ from conftest import CUSIMBIN, ref_sam, run_sam, strip_pg
 
 
 def _counts(binary, args, env=None):
-    e = dict(os.environ, BWA_B200_PROFILE="1", **(env or {}))
+    e = dict(os.environ, BWA_B200_PROFILE="1", BWA_B200_SELFCHECK="0", **(env or {}))   # the start-up self-check would add its own 192 reads to the counters
     p = subprocess.run([binary, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, env=e)
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     took = handed = 0
@@ -25,14 +25,14 @@ def _counts(binary, args, env=None):
 
 def _check(binary, data, n_c1, n_stress):
     # unique reference, proper pairs: everything stays on the device
-    fa, fqs = data.reads("c1", tag="tl_pe", n=n_c1, seed=31, paired=True)
+    fa, fqs = data.reads("c1", tag="tl_pe%d" % n_c1, n=n_c1, seed=31, paired=True)
     args = ["-K", "100000000", "-t", "4", "-R", "@RG\\tID:grp1\\tSM:x", fa] + fqs
     sam, took, handed, lane = _counts(binary, args)
     assert sam == ref_sam(args)
     assert took == 2 * n_c1 and handed * 50 <= took and lane
     # repeat-rich reference, chimeric reads: many reads are handed back, the merged output is still the reference's
     for paired in (True, False):
-        fa, fqs = data.reads("stress", tag="tl_pe" if paired else "tl_se", n=n_stress, seed=32, paired=paired, err=(0.016, 0.002, 0.002), chimeric=0.05)
+        fa, fqs = data.reads("stress", tag=("tl_pe%d" if paired else "tl_se%d") % n_stress, n=n_stress, seed=32, paired=paired, err=(0.016, 0.002, 0.002), chimeric=0.05)
         args = ["-K", "100000000", "-t", "4", "-C", fa] + fqs
         sam, took, handed, lane = _counts(binary, args)
         assert sam == ref_sam(args)
@@ -42,7 +42,7 @@ def _check(binary, data, n_c1, n_stress):
             assert s2 == sam
             assert (t2 == 0) == ("BWA_B200_TAIL" in env) and l2 == ("BWA_B200_K4_LANE" not in env)
     # options that keep stage 4 out (-a lists secondary hits, -5 reorders) and options it handles (-M, -Y, -P, -S)
-    fa, fqs = data.reads("stress", tag="tl_pe", n=n_stress, seed=32, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    fa, fqs = data.reads("stress", tag="tl_pe%d" % n_stress, n=n_stress, seed=32, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
     for extra, on in ((["-a"], False), (["-5"], False), (["-M", "-Y"], True), (["-P"], True), (["-S"], True), (["-T", "60", "-U", "9"], True)):
         args = extra + ["-K", "100000000", "-t", "4", fa] + fqs
         sam, took, handed, lane = _counts(binary, args)
@@ -56,7 +56,7 @@ def test_device_tail_emulated(data):
 
 def test_device_tail_fasta_input_and_several_chunks(data, tmp_path, monkeypatch):
     """No quality strings (FASTA): QUAL is '*'; chunks smaller than the batch: the insert-size model still sees every pair."""
-    fa, fqs = data.reads("c1", tag="tl_pe", n=300, seed=31, paired=True)
+    fa, fqs = data.reads("c1", tag="tl_fa", n=300, seed=31, paired=True)
     fas = []
     for f in fqs:
         out = str(tmp_path / (os.path.basename(f) + ".fa"))
@@ -76,3 +76,26 @@ def test_device_tail_fasta_input_and_several_chunks(data, tmp_path, monkeypatch)
 @pytest.mark.gpu
 def test_device_tail_gpu(data):
     _check(bwa_b200.CLI_PATH, data, 4000, 3000)
+
+
+def _sb16(binary, data):
+    """Occ superblocks of 2^16 symbols (make sb16 / sb16-cuda): a 1 Mbp reference then spans 31 of them, so relative counts,
+    per-superblock bases and boundary-crossing rank pairs behave as they do at 2^31 / 2^32 in a 3 Gbp index."""
+    if not os.path.exists(binary):
+        from conftest import ROOT
+        subprocess.run(["make", "-C", ROOT, "sb16" if "cusim" in binary else "sb16-cuda"], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    for kw in (dict(tag="sb_se", n=400, seed=41), dict(tag="sb_pe", n=200, seed=42, paired=True)):
+        fa, fqs = data.reads("c1", **kw)
+        args = ["-K", "100000000", "-t", "4", fa] + fqs
+        assert run_sam(binary, args) == ref_sam(args)
+
+
+def test_small_superblocks_emulated(data):
+    from conftest import ROOT
+    _sb16(os.path.join(ROOT, "tests", "_build", "bwa-b200-cusim-sb16"), data)
+
+
+@pytest.mark.gpu
+def test_small_superblocks_gpu(data):
+    from conftest import ROOT
+    _sb16(os.path.join(ROOT, "tests", "_build", "bwa-b200-sb16"), data)
