@@ -55,11 +55,27 @@ def effective_cpus():
     return n
 
 
-def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0, paired=False):
+# Other workloads of BASELINE.json (configs 4 and 5) and a repeat-rich reference, selected with --workload; the default (the
+# headline) stays 2x150-bp pairs against the 3 Gbp uniform-random reference.  reads = per GPU per step.
+WORKLOADS = {
+    "pe":      dict(layout="pe", read_len=150, reads=1_000_000),
+    "se":      dict(layout="se", read_len=150, reads=1_000_000),
+    "len36":   dict(layout="se", read_len=36, reads=2_000_000),
+    "len75":   dict(layout="se", read_len=75, reads=2_000_000),
+    "len300":  dict(layout="se", read_len=300, reads=500_000),
+    "len1000": dict(layout="se", read_len=1000, reads=100_000),
+    "pacbio":  dict(layout="se", read_len=10000, reads=10_000, err=(0.02, 0.05, 0.03), mem_args=["-x", "pacbio"]),   # 10 % error: 20 % sub / 50 % ins / 30 % del
+    "stress":  dict(layout="pe", read_len=150, reads=200_000, ref="stress", ref_mbp=1000, err=(0.016, 0.002, 0.002), chimeric=0.05),
+}
+
+
+def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0, paired=False, ref="random", err=(0.008, 0.001, 0.001), chimeric=0.0):
     """Reference FASTA + index (once per box) and this rank's reads."""
     import gen_data
     import numpy as np
     os.makedirs(workdir, exist_ok=True)
+    if ref == "stress":
+        return make_stress_workload(workdir, ref_mbp, n_reads, read_len, seed, rank, paired, err, chimeric)
     fa = os.path.join(workdir, "ref_%d.fa" % ref_mbp)
     contig_len = min(125_000_000, ref_mbp * 1_000_000)
     n_contigs = max(1, (ref_mbp * 1_000_000) // contig_len)
@@ -84,17 +100,43 @@ def make_workload(workdir, ref_mbp, n_reads, read_len, seed, rank=0, paired=Fals
         open(done, "w").write("ok")
     while not os.path.exists(done):
         time.sleep(0.5)
-    tag = os.path.join(workdir, "reads_%s%d_%d_r%d" % ("pe" if paired else "se", n_reads, read_len, rank))
+    tag = os.path.join(workdir, "reads_%s%d_%d_e%d_r%d" % ("pe" if paired else "se", n_reads, read_len, int(round(1000 * sum(err))), rank))
     fqs = [tag + "_1.fq", tag + "_2.fq"] if paired else [tag + ".fq"]
     if not all(os.path.exists(f) for f in fqs):
         t0 = time.time()
         # reads are drawn without materialising the FASTA again: regenerate the contigs from the seed
         contigs = gen_data.random_contigs(n_contigs, contig_len, 7)
-        r1, r2 = gen_data.gen_reads(contigs, n_reads // 2 if paired else n_reads, read_len, seed + rank, paired=paired)
+        r1, r2 = gen_data.gen_reads(contigs, n_reads // 2 if paired else n_reads, read_len, seed + rank, err=err, paired=paired, chimeric=chimeric)
         gen_data.write_fastq(fqs[0], r1)
         if paired:
             gen_data.write_fastq(fqs[1], r2)
         log("[bench] %d reads written in %.1fs" % (n_reads, time.time() - t0))
+    return fa, fqs
+
+
+def make_stress_workload(workdir, ref_mbp, n_reads, read_len, seed, rank, paired, err, chimeric):
+    """Repeat-rich reference (tools/gen_data.py stress_contigs: a 1 kb family at 3 % divergence over ~15 % of the sequence, tandem
+    repeats, N runs, two contigs), indexed by the GPU builder; reads with 2 % error and 5 % chimeras as in the parity tests."""
+    import gen_data
+    fa = os.path.join(workdir, "stress_%d.fa" % ref_mbp)
+    done = fa + ".done"
+    if rank == 0 and not os.path.exists(done):
+        t0 = time.time()
+        gen_data.write_fasta(fa, gen_data.stress_contigs(ref_mbp * 1_000_000, 5))
+        code = ("import sys; sys.path.insert(0, %r); import bwa_b200.index_build as ib; ib.build(%r, verbose=True)" % (ROOT, fa))
+        subprocess.run([sys.executable, "-c", code], check=True, stdout=sys.stderr)
+        log("[bench] repeat-rich reference %d Mbp generated and indexed in %.1fs" % (ref_mbp, time.time() - t0))
+        open(done, "w").write("ok")
+    while not os.path.exists(done):
+        time.sleep(0.5)
+    tag = os.path.join(workdir, "stress_reads_%s%d_%d_r%d" % ("pe" if paired else "se", n_reads, read_len, rank))
+    fqs = [tag + "_1.fq", tag + "_2.fq"] if paired else [tag + ".fq"]
+    if not all(os.path.exists(f) for f in fqs):
+        contigs = gen_data.stress_contigs(ref_mbp * 1_000_000, 5)
+        r1, r2 = gen_data.gen_reads(contigs, n_reads // 2 if paired else n_reads, read_len, seed + rank, err=err, paired=paired, chimeric=chimeric)
+        gen_data.write_fastq(fqs[0], r1)
+        if paired:
+            gen_data.write_fastq(fqs[1], r2)
     return fa, fqs
 
 
@@ -129,7 +171,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference(fa, fqs, n_sample, threads, keep_sam=False):
+def time_reference(fa, fqs, n_sample, threads, keep_sam=False, mem_args=()):
     """`bwa mem -t threads` of the unmodified reference on the first n_sample reads; reads/s from its own
     '[M::mem_process_seqs] Processed N reads in X CPU sec, Y real sec' lines (excludes index load and I/O)."""
     samples = []
@@ -145,7 +187,7 @@ def time_reference(fa, fqs, n_sample, threads, keep_sam=False):
         samples.append(sample)
     ref_out = samples[0] + ".ref.sam" if keep_sam else os.devnull
     with open(ref_out, "wb") as so:
-        r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000", fa] + samples, stdout=so, stderr=subprocess.PIPE, text=True)
+        r = subprocess.run([REF_BWA, "mem", "-t", str(threads), "-K", "100000000"] + list(mem_args) + [fa] + samples, stdout=so, stderr=subprocess.PIPE, text=True)
     time_reference.last = (samples, ref_out)
     n, real = 0, 0.0
     for m in re.finditer(r"Processed (\d+) reads in ([\d.]+) CPU sec, ([\d.]+) real sec", r.stderr):
@@ -232,6 +274,7 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BWA_B200_BENCH_READS", "1000000")))
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--layout", default=os.environ.get("BWA_B200_BENCH_LAYOUT", "pe"), choices=["pe", "se"], help="pe: 2x150 bp pairs (FR, insert N(400,50)); se: single-end")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="a named workload (overrides --layout/--reads/--read-len): BASELINE.json configs 4-5 and a repeat-rich reference")
     ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
     ap.add_argument("--cpu-sample", type=int, default=100000)
@@ -239,6 +282,13 @@ def main():
     ap.add_argument("--worker", action="store_true", help="(internal) run the measurement in this process; without it a parent process supervises the run")
     ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
     a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload]) if a.workload else {}
+    if wl:
+        a.layout, a.read_len, a.reads = wl["layout"], wl["read_len"], wl["reads"]
+        a.ref_mbp = wl.get("ref_mbp", a.ref_mbp)
+        a.cpu_sample = min(a.cpu_sample, max(200, 3_000_000 // a.read_len))
+    wl_kw = dict(ref=wl.get("ref", "random"), err=wl.get("err", (0.008, 0.001, 0.001)), chimeric=wl.get("chimeric", 0.0))
+    mem_args = wl.get("mem_args", [])
 
     if a.impl == "b200" and not a.worker and "RANK" not in os.environ:
         return supervise(sys.argv[1:])
@@ -251,16 +301,19 @@ def main():
     paired = a.layout == "pe"
     workload = "%d synthetic %s reads per GPU per step (%s), 1%% error, vs %d Mbp uniform-random reference" % (
         a.reads, "2x%d-bp PE" % a.read_len if paired else "%d-bp SE" % a.read_len, "%d pairs, FR, insert N(400,50)" % (a.reads // 2) if paired else "single-end", a.ref_mbp)
+    if wl:
+        workload += " [--workload %s: error profile sub/ins/del %s%s%s%s]" % (a.workload, wl_kw["err"], ", %.0f %% chimeric reads" % (100 * wl_kw["chimeric"]) if wl_kw["chimeric"] else "",
+                                                                          ", repeat-rich reference (gen_data.stress_contigs)" if wl_kw["ref"] == "stress" else "", ", bwa mem " + " ".join(mem_args) if mem_args else "")
 
     if a.impl == "reference":
         if rank != 0:
             return
-        fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, 0, paired)
+        fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, 0, paired, **wl_kw)
         n_sample = min(a.reads, a.cpu_sample)
         vals = []
         for s in range(a.warmup + a.steps):
             t0 = time.time()
-            v, n = time_reference(fa, fq, n_sample, ncores)
+            v, n = time_reference(fa, fq, n_sample, ncores, mem_args=mem_args)
             if s >= a.warmup:
                 vals.append((v, n, time.time() - t0))
             if s == 0 and (time.time() - t0) * (a.warmup + a.steps) > 240:   # keep the whole run within minutes
@@ -290,7 +343,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank, paired)
+    fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank, paired, **wl_kw)
     if world > 1:
         dist.barrier()
 
@@ -313,6 +366,18 @@ def main():
 
     opt = L.mem_opt_init()
     opt.contents.n_threads = threads
+    if mem_args == ["-x", "pacbio"]:   # the preset of the command line (fastmap.c:330-358), applied to the library call
+        o = opt.contents
+        o.o_del = o.e_del = o.o_ins = o.e_ins = 1
+        o.b = 1
+        o.split_factor = 10.0
+        o.min_chain_weight = 40
+        o.min_seed_len = 17
+        o.pen_clip5 = o.pen_clip3 = 0
+        L.bwa_fill_scmat.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.bwa_fill_scmat(o.a, o.b, C.addressof(o.mat))
+    elif mem_args:
+        raise SystemExit("bench.py: no library mapping for bwa mem options %r" % (mem_args,))
     inflight = max(1, min(4, a.inflight))
     batches = [bwa_b200.ReadBatch(*fq) for _ in range(inflight)]     # one host copy of the step's reads per call in flight
     batch = batches[0]
@@ -453,13 +518,13 @@ def main():
         if world == 1:
             try:
                 n_sample = min(a.reads, a.cpu_sample)
-                v, n = time_reference(fa, fq, n_sample, ncores, keep_sam=True)
+                v, n = time_reference(fa, fq, n_sample, ncores, keep_sam=True, mem_args=mem_args)
                 line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
                                         "sample": "first %d reads of the workload, oracle/_ref/bwa mem -t %d, rate from its own Processed-lines" % (n, ncores)}
                 # the same sample through `bwa-b200 mem` on the full-size index: its SAM must equal the reference's byte for byte
                 samples, ref_out = time_reference.last
                 mine = samples[0] + ".b200.sam"
-                rc = bwa_b200.run_cli(["mem", "-t", str(threads), "-K", "100000000", fa] + samples, mine)
+                rc = bwa_b200.run_cli(["mem", "-t", str(threads), "-K", "100000000"] + list(mem_args) + [fa] + samples, mine)
                 strip = lambda path: b"\n".join(l for l in open(path, "rb").read().split(b"\n") if not l.startswith(b"@PG"))
                 line["cpu_baseline"]["sam_identical_on_sample"] = bool(rc == 0 and strip(mine) == strip(ref_out))
                 for f in (mine, ref_out):

@@ -45,7 +45,8 @@ class Stats(C.Structure):
     _fields_ = [("occ_touches", C.c_uint64), ("sa_touches", C.c_uint64), ("sa_touches_algo", C.c_uint64), ("ext_cells", C.c_uint64),
                 ("glb_cells", C.c_uint64), ("ms_smem", C.c_double), ("ms_sa", C.c_double), ("ms_extend", C.c_double), ("ms_global", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("n_launch", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ms_chain", C.c_double),
-                ("ms_tail", C.c_double), ("tail_reads", C.c_uint64), ("tail_complex", C.c_uint64)]
+                ("ms_tail", C.c_double), ("tail_reads", C.c_uint64), ("tail_complex", C.c_uint64),
+                ("ms_localsw", C.c_double), ("sw_tasks", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -124,6 +124,7 @@ struct bwag_batch {
 	HostBuf h_res, h_cig, h_md;
 	/* stage 4 */
 	DevBuf d_dregs, d_dreg_beg, d_dreg_n, d_task_beg, d_cflag, d_pe_is, d_rec, d_text, d_ptab;
+	DevBuf d_swtasks, d_swres, d_swpool, d_swscratch; HostBuf h_swres;   /* K6 */
 	HostBuf h_pe_is, h_cflag, h_rec, h_text, h_ptab;
 	int tail_ready;              /* bwag_tail_regs ran on this batch */
 	int regs_on_device;          /* bwag_chain_extend left the regions in HBM */
@@ -433,15 +434,15 @@ extern "C" void bwag_batch_end(bwag_batch_t *b)
 		d->ext_cells += x->ext_cells; d->glb_cells += x->glb_cells;
 		d->ms_smem += x->ms_smem; d->ms_sa += x->ms_sa; d->ms_chain += x->ms_chain; d->ms_extend += x->ms_extend; d->ms_global += x->ms_global;
 		d->ms_h2d += x->ms_h2d; d->ms_d2h += x->ms_d2h; d->n_launch += x->n_launch; d->h2d_bytes += x->h2d_bytes; d->d2h_bytes += x->d2h_bytes;
-		d->ms_tail += x->ms_tail; d->tail_reads += x->tail_reads; d->tail_complex += x->tail_complex;
+		d->ms_tail += x->ms_tail; d->tail_reads += x->tail_reads; d->tail_complex += x->tail_complex; d->ms_localsw += x->ms_localsw; d->sw_tasks += x->sw_tasks;
 	}
 #ifdef BWAG_CUSIM
 	if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] emulator: %llu 32-byte block/table loads so far (K1, K1f, K2, table build); K1 candidate-list accesses by entry index 0-3: %llu, 4-7: %llu, 8-11: %llu, 12-15: %llu, 16+: %llu (the first K1_SLOTS of a list live in shared memory)\n", bwag_cusim_sector_loads, bwag_cusim_list_acc[0], bwag_cusim_list_acc[1], bwag_cusim_list_acc[2], bwag_cusim_list_acc[3], bwag_cusim_list_acc[4]);
 #endif
 	if (getenv("BWA_B200_PROFILE"))   /* with the host's phase timer: the work counters of this batch */
-		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu; stage 4: %llu reads, %llu handed back to the host-side post-processing\n", b->n,
+		fprintf(stderr, "[prof] batch counters: %d reads, occ_touches %llu, sa_touches %llu, ext_cells %llu, glb_cells %llu; stage 4: %llu reads, %llu handed back to the host-side post-processing; K6: %llu local alignments\n", b->n,
 		        (unsigned long long)b->lc.st.occ_touches, (unsigned long long)b->lc.st.sa_touches, (unsigned long long)b->lc.st.ext_cells, (unsigned long long)b->lc.st.glb_cells,
-		        (unsigned long long)b->lc.st.tail_reads, (unsigned long long)b->lc.st.tail_complex);
+		        (unsigned long long)b->lc.st.tail_reads, (unsigned long long)b->lc.st.tail_complex, (unsigned long long)b->lc.st.sw_tasks);
 	for (int i = 0; i < N_SPARE; ++i) if (!c->spare[i]) { c->spare[i] = b; b = 0; break; }
 	pthread_mutex_unlock(&c->mu);
 	if (b) batch_free(b);
@@ -463,6 +464,7 @@ static void batch_free(bwag_batch_t *b)
 	free_host(&b->h_regs); free_host(&b->h_nregs); free_host(&b->h_cregs); free_host(&b->h_creg_beg); free_host(&b->h_tmp);
 	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
+	free_dev(&b->d_swtasks); free_dev(&b->d_swres); free_dev(&b->d_swpool); free_dev(&b->d_swscratch); free_host(&b->h_swres);
 	free_dev(&b->d_dregs); free_dev(&b->d_dreg_beg); free_dev(&b->d_dreg_n); free_dev(&b->d_task_beg); free_dev(&b->d_cflag); free_dev(&b->d_pe_is); free_dev(&b->d_rec); free_dev(&b->d_text); free_dev(&b->d_ptab);
 	free_host(&b->h_pe_is); free_host(&b->h_cflag); free_host(&b->h_rec); free_host(&b->h_text); free_host(&b->h_ptab);
 	free(b);
@@ -1116,5 +1118,49 @@ extern "C" int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pe
 	c->st.ms_d2h += elapsed(c);
 	c->st.tail_reads += (u64)n; c->st.tail_complex += c->h_cnt->t_complex;
 	out->rec = (const bwag_samrec_t *)b->h_rec.p; out->text = (const char *)b->h_text.p; out->n_text = n_text; out->n_complex = (int64_t)c->h_cnt->t_complex;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ K6 */
+
+extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out)
+{
+	bwag_ctx_t *c = &b->lc;
+	CK(cudaSetDevice(c->device));
+	*out = 0;
+	if (n_tasks <= 0) return 0;
+	int cap_q = 16, cap_t = 16;
+	for (int t = 0; t < n_tasks; ++t) { if (tasks[t].qlen > cap_q) cap_q = tasks[t].qlen; if (tasks[t].tlen > cap_t) cap_t = tasks[t].tlen; }
+	cap_q = (cap_q + 15) & ~15; cap_t = (cap_t + 15) & ~15;
+	const int cap_n = cap_q + 16;                                       /* query length rounded up to a whole number of vectors */
+	const i64 per_thread = ((i64)cap_n * 8 + (i64)cap_t * 8 + cap_q + cap_t + 63) & ~(i64)63;
+	int grid = c->n_sm * 16;
+	{
+		const i64 need = ((i64)n_tasks + 63) / 64;
+		if (grid > need) grid = (int)need;
+		const i64 max_threads = ((i64)4 << 30) / per_thread;            /* bound the scratch to ~4 GB */
+		if ((i64)grid * 64 > max_threads) grid = (int)(max_threads / 64 > 0 ? max_threads / 64 : 1);
+	}
+	if (buf_reserve(&b->d_swtasks, sizeof(bwag_swtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_swres, sizeof(bwag_swres_t) * (size_t)n_tasks) ||
+	    buf_reserve(&b->d_swscratch, (size_t)per_thread * (size_t)grid * 64) || buf_reserve(&b->d_swpool, pool_bytes + 16) ||
+	    hbuf_reserve(&b->h_swres, sizeof(bwag_swres_t) * (size_t)n_tasks)) return 1;
+	if (reset_counters(c)) return 1;
+	H2D(c, b->d_swtasks.p, tasks, sizeof(bwag_swtask_t) * (size_t)n_tasks);
+	if (pool && pool_bytes) H2D(c, b->d_swpool.p, pool, pool_bytes);
+	SwArgs a;
+	memset(&a, 0, sizeof(a));
+	a.tasks = (const bwag_swtask_t *)b->d_swtasks.p; a.n_tasks = n_tasks; a.par = *par;
+	a.codes = (const uint8_t *)b->d_codes.p; a.pool = (const uint8_t *)b->d_swpool.p; a.res = (bwag_swres_t *)b->d_swres.p;
+	a.scratch = (unsigned char *)b->d_swscratch.p; a.per_thread = per_thread; a.cap_n = cap_n; a.cap_q = cap_q; a.cap_t = cap_t;
+	a.next_task = &c->d_cnt->next_task; a.flags = &c->d_cnt->flags;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	BWAG_LAUNCH(k_localsw, grid, 64, 0, c->stream, c->ix, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	D2H(c, b->h_swres.p, b->d_swres.p, sizeof(bwag_swres_t) * (size_t)n_tasks);
+	if (fetch_counters(c)) return 1;
+	c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_tasks;
+	if (c->h_cnt->flags & 32u) return set_err("local alignment: a task exceeded the scratch capacity");
+	*out = (const bwag_swres_t *)b->h_swres.p;
 	return 0;
 }

@@ -120,6 +120,18 @@ struct TailSamArgs {
 	bwag_samrec_t *rec; char *text; i64 cap_text; u64 *n_text, *n_complex;
 };
 
+/* ---- K6 (bwag_localsw.cu) ---- */
+struct SwArgs {
+	const bwag_swtask_t *tasks; int n_tasks;
+	bwag_sw_par_t par;
+	const uint8_t *codes;            /* the batch's reads (BWAG_SWF_QREAD) */
+	const uint8_t *pool;             /* caller bytes (queries / targets given explicitly) */
+	bwag_swres_t *res;
+	unsigned char *scratch; i64 per_thread; int cap_n, cap_q, cap_t;   /* per lane: 4 x short[cap_n], u64[cap_t], query[cap_q], target[cap_t] */
+	int *next_task; u32 *flags;
+};
+
+__global__ void k_localsw(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
 __global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed);

@@ -131,7 +131,26 @@ void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v,
 
 /* mate rescue for one anchor region (bwamem_pair.c:137-206): local SW of the mate inside the window the
  * insert-size model predicts; hits are inserted into ma (kept sorted by score) and de-duplicated */
-int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a, int l_ms, const uint8_t *ms, mem_alnreg_v *ma)
+static const bb_swr_t *swcache_get(bb_swcache_t *c, int which, int is_rev, int64_t rb, int64_t re)
+{
+	size_t k;
+	bb_swent_t e;
+	for (k = 0; k < c->v.n; ++k) {
+		const bb_swent_t *x = &c->v.a[k];
+		if (x->which == which && x->is_rev == is_rev && x->rb == rb && x->re == re) {
+			if (x->done) return &x->res;
+			++c->pending;
+			return 0;
+		}
+	}
+	memset(&e, 0, sizeof(e));
+	e.which = which; e.is_rev = is_rev; e.rb = rb; e.re = re;
+	bb_vec_push(c->v, e);
+	++c->pending;
+	return 0;
+}
+
+int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a, int l_ms, const uint8_t *ms, mem_alnreg_v *ma, bb_swcache_t *swc, int which)
 {
 	int64_t l_pac = bns->l_pac;
 	int i, r, skip[4], n = 0, rid = -1;
@@ -149,7 +168,7 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 		if (skip[r]) continue;
 		is_rev = (r >> 1 != (r & 1));
 		is_larger = !(r >> 1);
-		if (is_rev) {
+		if (is_rev && !swc) {
 			rev = bb_malloc(l_ms);
 			for (i = 0; i < l_ms; ++i) rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
 			seq = rev;
@@ -163,12 +182,16 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 		}
 		if (rb < 0) rb = 0;
 		if (re > l_pac << 1) re = l_pac << 1;
-		if (rb < re) ref = bb_fetch_seq(bns, pac, &rb, (rb + re) >> 1, &re, &rid);
+		if (rb < re) { if (swc) bb_clamp_to_contig(bns, &rb, (rb + re) >> 1, &re, &rid); else ref = bb_fetch_seq(bns, pac, &rb, (rb + re) >> 1, &re, &rid); }
 		if (a->rid == rid && re - rb >= opt->min_seed_len) {
 			bb_swr_t aln;
 			mem_alnreg_t b;
 			int tmp, xtra = BB_SW_XSUBO | BB_SW_XSTART | (l_ms * opt->a < 250 ? BB_SW_XBYTE : 0) | (opt->min_seed_len * opt->a);
-			aln = bb_local_sw(l_ms, seq, (int)(re - rb), ref, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra);
+			if (swc) {   /* the alignment comes from the device: (query read, strand, window) identifies it */
+				const bb_swr_t *got = swcache_get(swc, which, is_rev, rb, re);
+				if (!got) return -1;
+				aln = *got;
+			} else aln = bb_local_sw(l_ms, seq, (int)(re - rb), ref, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra);
 			memset(&b, 0, sizeof(b));
 			if (aln.score >= opt->min_seed_len && aln.qb >= 0) {
 				b.rid = a->rid;
@@ -198,7 +221,7 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 }
 
 /* the rescue block at the top of mem_sam_pe (bwamem_pair.c:289-301); modifies a[0], a[1] */
-int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], bseq1_t s[2], mem_alnreg_v a[2])
+int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], bseq1_t s[2], mem_alnreg_v a[2], bb_swcache_t *swc)
 {
 	int i, n = 0;
 	size_t j;
@@ -211,9 +234,12 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 		for (j = 0; j < a[i].n; ++j)
 			if (a[i].a[j].score >= a[i].a[0].score - opt->pen_unpaired) bb_vec_push(b[i], a[i].a[j]);
 	}
-	for (i = 0; i < 2; ++i)
-		for (j = 0; j < b[i].n && (int)j < opt->max_matesw; ++j)
-			n += bb_matesw(opt, bns, pac, pes, &b[i].a[j], s[!i].l_seq, (uint8_t *)s[!i].seq, &a[!i]);
+	for (i = 0; i < 2 && n >= 0; ++i)
+		for (j = 0; j < b[i].n && (int)j < opt->max_matesw; ++j) {
+			int k = bb_matesw(opt, bns, pac, pes, &b[i].a[j], s[!i].l_seq, (uint8_t *)s[!i].seq, &a[!i], swc, !i);
+			if (k < 0) { n = -1; break; }   /* an alignment was requested from the device: this pass is void */
+			n += k;
+		}
 	if (b[0].a != st[0]) free(b[0].a);
 	if (b[1].a != st[1]) free(b[1].a);
 	return n;

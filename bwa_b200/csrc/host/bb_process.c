@@ -377,6 +377,7 @@ typedef struct job_s {
 	 * which are ordinary jobs over copies of their bseq1_t records */
 	int tail;                      /* 1: bwag_tail_regs ran for this chunk */
 	int no_tail;                   /* the caller wants the regions on the host (mem_align1) */
+	bb_swcache_t *swc;             /* PE: per pair, the mate-rescue alignments asked from / served by K6 */
 	const uint8_t *cflag;          /* [n] from bwag_tail_regs: non-zero = the read left the simple path before pairing */
 	struct job_s *sub0, *sub1;     /* reads handed back by bwag_tail_regs (aligned up to regions before the insert-size model) / by bwag_tail_sam */
 	int *sub_map;                  /* sub job only: index of each of its reads in the parent chunk */
@@ -653,10 +654,78 @@ static void w_rescue(void *d, long i, int tid)
 	job_t *j = d;
 	mem_alnreg_v a[2];
 	tl_memo = j->arenas ? &j->arenas[tid] : 0;
+	if (j->swc) {   /* alignments from the device (K6): work on copies; a pass that had to request one is void and is replayed later */
+		bb_swcache_t *c = &j->swc[i];
+		int e;
+		if (c->pending < 0) { tl_memo = 0; return; }          /* this pair is done */
+		for (e = 0; e < 2; ++e) {
+			const mem_alnreg_v *src = &j->rs[i << 1 | e].regs;
+			a[e].n = src->n; a[e].m = src->n + 4;
+			a[e].a = bb_malloc(a[e].m * sizeof(mem_alnreg_t));
+			if (src->n) memcpy(a[e].a, src->a, src->n * sizeof(mem_alnreg_t));
+		}
+		c->pending = 0;
+		if (bb_rescue_pe(j->opt, j->bns, j->pac, j->pes, &j->seqs[i << 1], a, c) < 0) { free(a[0].a); free(a[1].a); }
+		else {
+			for (e = 0; e < 2; ++e) {
+				mem_alnreg_v *dst = &j->rs[i << 1 | e].regs;
+				if (!(dst->m & BB_BORROWED)) free(dst->a);
+				*dst = a[e];
+			}
+			c->pending = -1;
+			free(c->v.a); c->v.a = 0; c->v.n = c->v.m = 0;
+		}
+		tl_memo = 0;
+		return;
+	}
 	a[0] = j->rs[i << 1].regs; a[1] = j->rs[i << 1 | 1].regs;
-	bb_rescue_pe(j->opt, j->bns, j->pac, j->pes, &j->seqs[i << 1], a);
+	bb_rescue_pe(j->opt, j->bns, j->pac, j->pes, &j->seqs[i << 1], a, 0);
 	j->rs[i << 1].regs = a[0]; j->rs[i << 1 | 1].regs = a[1];
 	tl_memo = 0;
+}
+
+/* serve the mate-rescue alignments the pairs of this chunk asked for with one launch of K6; returns the number served, -1 if the
+ * stage library has no K6 */
+static int g_no_dev_sw;
+static long sw_round(job_t *j)
+{
+	const mem_opt_t *opt = j->opt;
+	const long n_pairs = j->n >> 1;
+	long i, t = 0, k;
+	bwag_swtask_t *tasks;
+	const bwag_swres_t *res = 0;
+	int rc;
+	for (i = 0; i < n_pairs; ++i) if (j->swc[i].pending > 0) { size_t x; for (x = 0; x < j->swc[i].v.n; ++x) t += !j->swc[i].v.a[x].done; }
+	if (t == 0) return 0;
+	tasks = big_alloc_x(sizeof(bwag_swtask_t) * (size_t)t, 1);
+	for (i = 0, k = 0; i < n_pairs; ++i) if (j->swc[i].pending > 0) {
+		size_t x;
+		for (x = 0; x < j->swc[i].v.n; ++x) {
+			const bb_swent_t *e = &j->swc[i].v.a[x];
+			const long r = i << 1 | e->which;
+			bwag_swtask_t *q = &tasks[k];
+			if (e->done) continue;
+			q->t_beg = e->rb; q->tlen = (int32_t)(e->re - e->rb); q->q_beg = j->off[r]; q->qlen = j->seqs[r].l_seq;
+			q->xtra = BWAG_SW_XSUBO | BWAG_SW_XSTART | (j->seqs[r].l_seq * opt->a < 250 ? BWAG_SW_XBYTE : 0) | (uint32_t)(opt->min_seed_len * opt->a);
+			q->flags = BWAG_SWF_QREAD | BWAG_SWF_TREF | (e->is_rev ? BWAG_SWF_QREV : 0);
+			++k;
+		}
+	}
+	rc = bwag_localsw(j->batch, &j->swp, (int)t, tasks, 0, 0, &res);
+	if (rc == BWAG_UNSUPPORTED) { big_free(tasks); return -1; }
+	if (rc != 0) bb_fatal("mem_process_seqs", "local-alignment stage (mate rescue) failed: %s", bwag_last_error());
+	for (i = 0, k = 0; i < n_pairs; ++i) if (j->swc[i].pending > 0) {
+		size_t x;
+		for (x = 0; x < j->swc[i].v.n; ++x) {
+			bb_swent_t *e = &j->swc[i].v.a[x];
+			if (e->done) continue;
+			e->res.score = res[k].score; e->res.te = res[k].te; e->res.qe = res[k].qe; e->res.score2 = res[k].score2; e->res.te2 = res[k].te2; e->res.tb = res[k].tb; e->res.qb = res[k].qb;
+			e->done = 1;
+			++k;
+		}
+	}
+	big_free(tasks);
+	return t;
 }
 
 #define STACK_REGS 8
@@ -1046,7 +1115,28 @@ static void job_finish(job_t *j, bwag_ctx_t *ctx)
 		j->batch = bwag_batch_begin(ctx, j->n, j->codes, j->off);
 		if (!j->batch) bb_fatal("mem_process_seqs", "cannot start a device batch: %s", bwag_last_error());
 	}
-	if (pe) { bb_parallel_for_lane(j->lane, nt, w_rescue, j, n_units); PH(j, "rescue"); }
+	if (pe && !(opt->flag & MEM_F_NO_RESCUE)) {   /* mate rescue; its local alignments are K6's, asked for pair by pair and served in rounds */
+		static int env_ = -1;
+		int env = __atomic_load_n(&env_, __ATOMIC_RELAXED);
+		if (env < 0) { const char *e = getenv("BWA_B200_DEVICE_SW"); env = e ? atoi(e) != 0 : 1; __atomic_store_n(&env_, env, __ATOMIC_RELAXED); }
+		if (env && !__atomic_load_n(&g_no_dev_sw, __ATOMIC_RELAXED)) j->swc = bb_calloc((size_t)n_units + 1, sizeof(bb_swcache_t));
+		for (;;) {
+			long left = 0, u, served;
+			bb_parallel_for_lane(j->lane, nt, w_rescue, j, n_units);
+			PH(j, "rescue");
+			if (!j->swc) break;
+			for (u = 0; u < n_units; ++u) left += j->swc[u].pending >= 0;
+			if (left == 0) break;
+			served = sw_round(j);
+			PH(j, "sw_round");
+			if (served < 0) {   /* no K6 behind this stage library (the CPU oracle of the tests): align on the host */
+				__atomic_store_n(&g_no_dev_sw, 1, __ATOMIC_RELAXED);
+				for (u = 0; u < n_units; ++u) free(j->swc[u].v.a);
+				free(j->swc); j->swc = 0;
+			} else if (served == 0) bb_fatal("mem_process_seqs", "internal error: unfinished mate rescue without requests");
+		}
+		if (j->swc) { free(j->swc); j->swc = 0; }
+	}
 	for (j->pass_dry = 0;; j->pass_dry = 0) { /* SAM; a read that misses an alignment is retried after a device round */
 		long i, left = 0;
 		bb_parallel_for_lane(j->lane, nt, w_sam, j, n_units);

@@ -136,6 +136,23 @@ typedef struct {
 
 int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_gtask_t *tasks, bwag_galn_t *out);
 
+/* ---- K6: batched local Smith-Waterman with start recovery (replaces ksw_align2, ksw.c:379-401, in mem_matesw
+ * bwamem_pair.c:137-206 and mem_seed_sw bwamem.c:597-622).  Same numbers as the reference's striped SSE2 kernels (score, te, qe,
+ * score2, te2, tb, qb); xtra as ksw.h:29-33.  The query of a task is a stretch of the batch's reads (optionally
+ * reverse-complemented) or bytes of `pool`; the target a window of the reference (doubled coordinates) or bytes of `pool`. ---- */
+#define BWAG_SW_XBYTE  0x10000u
+#define BWAG_SW_XSTOP  0x20000u
+#define BWAG_SW_XSUBO  0x40000u
+#define BWAG_SW_XSTART 0x80000u
+#define BWAG_SWF_QREV  1    /* query = reverse complement of the given stretch */
+#define BWAG_SWF_TREF  2    /* target = reference positions [t_beg, t_beg + tlen) */
+#define BWAG_SWF_QREAD 4    /* query = batch codes [q_beg, q_beg + qlen) (offset into the batch's concatenated reads) */
+typedef struct { int64_t t_beg, q_beg; int32_t tlen, qlen; uint32_t xtra; int32_t flags; } bwag_swtask_t;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb; } bwag_swres_t;
+/* pool (host pointer, pool_bytes) may be NULL when every task reads the batch and the reference; results: pinned, valid until the
+ * next call on this batch */
+int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out);
+
 /* ---- stage 4: the reference's per-read work AFTER the extension, on the device, for the reads whose post-processing is
  * "simple" (bwag_tail.cu): mem_sort_dedup_patch, one CIGAR request per region, mem_pestat's per-pair candidate
  * (bwag_tail_regs); mem_mark_primary_se, mem_approx_mapq_se, the mate-rescue trigger test, mem_pair, mem_sam_pe's pair
@@ -172,6 +189,8 @@ typedef struct {
 	double ms_chain;           /* CUDA-event time of the chaining kernel */
 	double ms_tail;            /* CUDA-event time of the stage-4 kernels (de-duplication/requests, pairing/SAM records) */
 	uint64_t tail_reads, tail_complex;   /* reads that went through stage 4 / that it handed back to the host-side post-processing */
+	double ms_localsw;         /* CUDA-event time of K6 (local Smith-Waterman: mate rescue) */
+	uint64_t sw_tasks;         /* local alignments K6 computed */
 } bwag_stats_t;
 void bwag_stats_get(bwag_ctx_t *ctx, bwag_stats_t *s);
 void bwag_stats_reset(bwag_ctx_t *ctx);

@@ -20,6 +20,7 @@ def _counts(binary, args, env=None):
     took = handed = 0
     for m in re.finditer(rb"stage 4: (\d+) reads, (\d+) handed back", p.stderr):
         took += int(m.group(1)); handed += int(m.group(2))
+    _counts.sw = sum(int(m.group(1)) for m in re.finditer(rb"K6: (\d+) local alignments", p.stderr))
     return strip_pg(p.stdout), took, handed, b"lane-per-read kernel" in p.stderr
 
 
@@ -37,10 +38,13 @@ def _check(binary, data, n_c1, n_stress):
         sam, took, handed, lane = _counts(binary, args)
         assert sam == ref_sam(args)
         assert took >= n_stress and 0 < handed < took
-        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}):
+        if paired:
+            assert _counts.sw > 0          # mate rescue ran its local alignments on the device (K6)
+        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}, {"BWA_B200_DEVICE_SW": "0"}):
             s2, t2, _, l2 = _counts(binary, args, env)
             assert s2 == sam
             assert (t2 == 0) == ("BWA_B200_TAIL" in env) and l2 == ("BWA_B200_K4_LANE" not in env)
+            assert (_counts.sw == 0) == ("BWA_B200_DEVICE_SW" in env or not paired)
     # options that keep stage 4 out (-a lists secondary hits, -5 reorders) and options it handles (-M, -Y, -P, -S)
     fa, fqs = data.reads("stress", tag="tl_pe%d" % n_stress, n=n_stress, seed=32, paired=True, err=(0.016, 0.002, 0.002), chimeric=0.05)
     for extra, on in ((["-a"], False), (["-5"], False), (["-M", "-Y"], True), (["-P"], True), (["-S"], True), (["-T", "60", "-U", "9"], True)):
