@@ -64,8 +64,8 @@ WORKLOADS = {
     "len75":   dict(layout="se", read_len=75, reads=2_000_000),
     "len300":  dict(layout="se", read_len=300, reads=500_000),
     "len1000": dict(layout="se", read_len=1000, reads=100_000),
-    "pacbio":  dict(layout="se", read_len=10000, reads=10_000, err=(0.02, 0.05, 0.03), mem_args=["-x", "pacbio"]),   # 10 % error: 20 % sub / 50 % ins / 30 % del
-    "stress":  dict(layout="pe", read_len=150, reads=200_000, ref="stress", ref_mbp=1000, err=(0.016, 0.002, 0.002), chimeric=0.05),
+    "pacbio":  dict(layout="se", read_len=10000, reads=2_000, err=(0.02, 0.05, 0.03), mem_args=["-x", "pacbio"]),   # 10 % error: 20 % sub / 50 % ins / 30 % del
+    "stress":  dict(layout="pe", read_len=150, reads=100_000, ref="stress", ref_mbp=1000, err=(0.016, 0.002, 0.002), chimeric=0.05),
 }
 
 
@@ -299,8 +299,9 @@ def main():
     ncores = effective_cpus()
     threads = a.threads or max(1, ncores // max(1, world))
     paired = a.layout == "pe"
-    workload = "%d synthetic %s reads per GPU per step (%s), 1%% error, vs %d Mbp uniform-random reference" % (
+    workload = "%d synthetic %s reads per GPU per step (%s), ERRPCT error, vs %d Mbp uniform-random reference" % (
         a.reads, "2x%d-bp PE" % a.read_len if paired else "%d-bp SE" % a.read_len, "%d pairs, FR, insert N(400,50)" % (a.reads // 2) if paired else "single-end", a.ref_mbp)
+    workload = workload.replace("ERRPCT", "%g%%" % round(100 * sum(wl_kw["err"]), 2))
     if wl:
         workload += " [--workload %s: error profile sub/ins/del %s%s%s%s]" % (a.workload, wl_kw["err"], ", %.0f %% chimeric reads" % (100 * wl_kw["chimeric"]) if wl_kw["chimeric"] else "",
                                                                           ", repeat-rich reference (gen_data.stress_contigs)" if wl_kw["ref"] == "stress" else "", ", bwa mem " + " ".join(mem_args) if mem_args else "")

@@ -651,7 +651,8 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 	{   /* short reads: one lane per read (bwag_extend_lane.cu) when every score fits its 13-bit cells and a block's columns fit shared memory */
 		int maxsc = 0;
 		for (int k = 0; k < 25; ++k) maxsc = maxsc > a.par.mat[k] ? maxsc : a.par.mat[k];
-		const size_t lsm = (size_t)(a.cap_q + 2 + 8) * K4L_THREADS * 4;   /* + the chunk's spare columns (K4L_CH) */
+		const int lcols = a.cap_q - (a.min_seed > 0 && a.min_seed < a.cap_q ? a.min_seed - 3 : 0) + 2 + 8;   /* longest extension (read minus its shortest possible seed; cap_q rounds the read length up by <= 3) + column `end` + the chunk's spare columns (K4L_CH) */
+		const size_t lsm = (size_t)lcols * K4L_THREADS * 4;
 		const int lane_ok = fast && (i64)a.cap_q * maxsc < 8192 && a.par.a <= maxsc && lsm <= K4L_SMEM_MAX && !(getenv("BWA_B200_K4_LANE") && atoi(getenv("BWA_B200_K4_LANE")) == 0);
 		if (lane_ok) {
 			int lgrid = c->n_sm;
@@ -662,7 +663,7 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 #endif
 			const i64 lneed = ((i64)n_units + K4L_THREADS - 1) / K4L_THREADS;
 			if (lgrid > lneed) lgrid = (int)(lneed > 0 ? lneed : 1);
-			a.eh = 0; a.rseq = 0; a.smem_per_warp = 0;
+			a.eh = 0; a.rseq = 0; a.smem_per_warp = lcols;   /* here: the number of columns of a lane's row */
 			if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] extension: lane-per-read kernel, grid %d x %d, %zu bytes of shared memory per block\n", lgrid, K4L_THREADS, lsm);
 			BWAG_LAUNCH(k_extend_lane, lgrid, K4L_THREADS, lsm, c->stream, c->ix, a);
 			CK(cudaGetLastError());
@@ -816,7 +817,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	a.chain_beg = (const i64 *)b->d_chain_beg.p; a.chain_cnt = (const int *)b->d_chain_cnt.p; a.reg_base = (const i64 *)b->d_reg_base.p;
 	a.chains = (const bwag_xchain_t *)b->d_chains.p; a.seeds = (const bwag_xseed_t *)b->d_seeds.p;
 	a.regs = (bwag_xreg_t *)b->d_regs.p; a.n_regs = (int32_t *)b->d_nregs.p;
-	a.cap_q = cap_q; a.cap_r = cap_r;
+	a.cap_q = cap_q; a.cap_r = cap_r; a.min_seed = cp->min_seed_len;
 	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
 	CK(cudaEventRecord(c->ev0, c->stream));
 	if (launch_extend(c, a, n)) return 1;
@@ -870,7 +871,8 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 	const int cap_wcig = cap_q + cap_r + 4, cap_wmd = 3 * cap_r + cap_q + 16;
 	int grid = c->grid_k5;
 	/* H/E rows and the sequences in shared memory when a block's share fits (BWA_B200_K5_SM=0 keeps them in global memory) */
-	const int k5_per_warp = (8 * (cap_q + 2) + cap_r + cap_q + 2 + 15) & ~15;
+	const int k5_zsm = getenv("BWA_B200_K5_ZSM") ? atoi(getenv("BWA_B200_K5_ZSM")) & ~15 : 6144;   /* backtrack bytes per warp in shared memory */
+	const int k5_per_warp = ((8 * (cap_q + 2) + cap_r + cap_q + 2 + 15) & ~15) + k5_zsm;
 	const size_t k5_smem = (size_t)k5_per_warp * (K5_THREADS / 32);
 	int k5_sm = k5_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K5_SM") && atoi(getenv("BWA_B200_K5_SM")) == 0);
 	const int k5_fast = !c->baseline && !(getenv("BWA_B200_K5_FAST") && atoi(getenv("BWA_B200_K5_FAST")) == 0);   /* 0: the first formulation of the row sweep */
@@ -904,7 +906,7 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 		a.next_task = &c->d_cnt->next_task; a.cells = &c->d_cnt->glb_cells; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
-		a.smem_per_warp = k5_sm ? k5_per_warp : 0;
+		a.smem_per_warp = k5_sm ? k5_per_warp : 0; a.z_sm_bytes = k5_sm ? k5_zsm : 0;
 		if (k5_sm && k5_fast) BWAG_LAUNCH(k_global_sm_fast, grid, K5_THREADS, k5_smem, c->stream, c->ix, a);
 		else if (k5_sm) BWAG_LAUNCH(k_global_sm, grid, K5_THREADS, k5_smem, c->stream, c->ix, a);
 		else if (k5_fast) BWAG_LAUNCH(k_global_fast, grid, K5_THREADS, 0, c->stream, c->ix, a);

@@ -222,32 +222,36 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 					mx = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
 					beg = 0; end = qlen; i = 0;
 					pot0 = maxsc * (qlen - 1);
+					if (qlen + 1 + K4L_CH > a.smem_per_warp) { overflow = 1; st = L_EXT_END; continue; }   /* more columns than the launch provided (a seed shorter than min_seed): reported, the batch fails */
 					if (tlen <= 0) { st = L_EXT_END; continue; }
 					t_cur = bwag_ref_base(ix, tbase);
 					t_next = tlen > 1 ? bwag_ref_base(ix, tbase + tdir) : 0;
 					jcur = 0;
-					st = L_INIT;   /* the first row's columns are written by the converged part below, K4L_CH per iteration */
+					st = L_INIT;   /* the first row's columns are written by the whole warp in the converged part below */
 				}
 				if (st == L_ROWS || st == L_INIT || st == L_DONE) break;
 			}
 		}
 		if (__all_sync(FULL_MASK, st == L_DONE)) break;
 
-		/* ---- converged part 1: K4L_CH columns of a new extension's first row (ksw.c:431-433), then its band and first-column carry ---- */
-		if (st == L_INIT) {
-			k4l_addr ad = he0 + jcur * K4L_COL;
-#pragma unroll
-			for (int cc = 0; cc < K4L_CH; ++cc) {
-				const int j = jcur + cc;
-				if (j <= qlen) {
-					int v = j == 0 ? h0 : H1 - (j - 1) * e_ins;
-					v = v > 0 ? v : 0;
-					const u32 qc = j < qlen ? qp[j * qs] : 4;
-					K4L_ST(ad + cc * K4L_COL, (u32)v | (qc > 4 ? 4u : qc) << 29);      /* 8 x code in the top six bits */
-				}
+		/* ---- converged part 1: the first row of a new extension (ksw.c:431-433).  Written by the WHOLE WARP for one lane at a time
+		 * (lane l writes columns l, l + 32, ... of that lane's row): the ~40 columns of a 150-bp read's extension are two
+		 * iterations of 32 lanes instead of 40 iterations of one ---- */
+		for (u32 todo = __ballot_sync(FULL_MASK, st == L_INIT); todo; todo &= todo - 1) {
+			const int src = __ffs((int)todo) - 1;
+			const int lane = threadIdx.x & 31;
+			const int s_qlen = __shfl_sync(FULL_MASK, qlen, src), s_h0 = __shfl_sync(FULL_MASK, h0, src), s_H1 = __shfl_sync(FULL_MASK, H1, src), s_qs = __shfl_sync(FULL_MASK, qs, src);
+			const unsigned long long s_qp = __shfl_sync(FULL_MASK, (unsigned long long)(size_t)qp, src);
+			const uint8_t *sq = reinterpret_cast<const uint8_t *>((size_t)s_qp);
+			const k4l_addr row = he0 + (src - lane) * 4;            /* the row of lane `src` (same warp, same block) */
+			for (int j = lane; j <= s_qlen; j += 32) {
+				int v = j == 0 ? s_h0 : s_H1 - (j - 1) * e_ins;
+				v = v > 0 ? v : 0;
+				const u32 qc = j < s_qlen ? sq[j * s_qs] : 4;
+				K4L_ST(row + j * K4L_COL, (u32)v | (qc > 4 ? 4u : qc) << 29);      /* 8 x code in the top six bits */
 			}
-			jcur += K4L_CH;
-			if (jcur > qlen) {   /* row 0: band, first-column carry (ksw.c:448-459) */
+			__syncwarp();
+			if (lane == src) {   /* row 0: band, first-column carry (ksw.c:448-459) */
 				if (end > w + 1) end = w + 1;
 				if (end > qlen) end = qlen;
 				hp = h0 - (o_del + e_del); if (hp < 0) hp = 0;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 			}
 		}
 		/* ---- converged part 2: up to K4L_CH cells of the current row (ksw.c:460-484) ---- */
-		else if (st == L_ROWS) {
+		if (st == L_ROWS) {
 			int nact = end - jcur;
 			nact = nact < K4L_CH ? nact : K4L_CH;
 			k4l_addr ad = he0 + jcur * K4L_COL;

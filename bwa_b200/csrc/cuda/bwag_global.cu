@@ -162,7 +162,7 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 	const int lane = threadIdx.x & 31;
 	const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int *H, *E;
-	uint8_t *rseq, *qseq, *z = a.z + wid * a.cap_z;
+	uint8_t *rseq, *qseq, *z_glob = a.z + wid * a.cap_z, *z_sm = 0;
 	if (SM) {
 #ifdef BWAG_CUSIM
 		unsigned char *dyn = cusim_dyn_smem;
@@ -174,6 +174,7 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 		H = reinterpret_cast<int *>(mine); E = H + a.cap_q + 2;
 		rseq = reinterpret_cast<uint8_t *>(E + a.cap_q + 2);
 		qseq = rseq + a.cap_r;
+		if (a.z_sm_bytes) z_sm = mine + a.smem_per_warp - a.z_sm_bytes;   /* the warp's slice ends with its backtrack bytes */
 	} else {
 		H = a.eh + wid * (i64)(2 * (a.cap_q + 2)); E = H + a.cap_q + 2;
 		rseq = a.rseq + wid * (i64)a.cap_r; qseq = a.qseq + wid * (i64)(a.cap_q + 2);
@@ -234,6 +235,9 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 					w = w > min_w ? w : min_w;
 					const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
 					if (want && (i64)n_col * rlen > a.cap_z) { overflow |= 4; score = 0; break; }
+					/* the direction bytes of a typical task (band ~11, 150 rows: 3.5 KB) stay in shared memory: the sweep's byte stores and,
+					 * above all, the serial backtrack walk (one dependent load per step) then never leave the SM */
+					uint8_t *z = z_sm && (i64)n_col * rlen <= a.z_sm_bytes ? z_sm : z_glob;
 					if constexpr (FAST) score = warp_ksw_global_fast<A, SmemAcc>(lane, lq, q_a, rlen, rs_a, mat_a, p.o_del, p.e_del, p.o_ins, p.e_ins, w, he_a, want ? z : 0, n_col, &cells);
 					else score = warp_ksw_global(lane, lq, qseq, rlen, rseq, s_mat, p.o_del, p.e_del, p.o_ins, p.e_ins, w, H, E, want ? z : 0, n_col, &cells);
 					if (want) {

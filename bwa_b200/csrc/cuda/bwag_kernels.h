@@ -20,7 +20,7 @@
 #define K5_THREADS 128
 #define K4L_THREADS 128   /* lane-per-read extension kernel (bwag_extend_lane.cu) */
 #ifndef K4L_MINB
-#define K4L_MINB 2
+#define K4L_MINB 3
 #endif
 
 struct Intv;
@@ -73,6 +73,7 @@ struct ExtArgs {
 	/* per-warp scratch: H, E (int32 each, cap_q+2), reference window (cap_r bytes) */
 	int *eh; uint8_t *rseq; int cap_q, cap_r;
 	int smem_per_warp;   /* k_extend_sm: bytes of shared scratch per warp = 8*(cap_q+2) + cap_r + cap_q, rounded up to 16 */
+	int min_seed;        /* no seed is shorter than this (0 if unknown): an extension has at most cap_q - min_seed query columns */
 	int *next_read; u64 *cells; u32 *flags;
 };
 
@@ -85,7 +86,8 @@ struct GlbArgs {
 	u32 *w_cig; char *w_md; int cap_wcig, cap_wmd;   /* per-warp staging of one task's CIGAR / MD */
 	int *eh; uint8_t *rseq; uint8_t *qseq; uint8_t *z;   /* per-warp scratch: H/E rows, reference, query, backtrack matrix */
 	int cap_q, cap_r; i64 cap_z;
-	int smem_per_warp;   /* k_global_sm: 8*(cap_q+2) + cap_r + cap_q + 2, rounded up to 16 */
+	int smem_per_warp;   /* k_global_sm: 8*(cap_q+2) + cap_r + cap_q + 2, rounded up to 16, + z_sm_bytes */
+	int z_sm_bytes;      /* backtrack bytes per warp kept in shared memory (tasks whose n_col x rows fit); 0: all in global memory */
 	int *next_task; u64 *cells; u32 *flags;
 };
 

@@ -121,6 +121,14 @@ static int next_line(FILE *fp, bb_str_t *ln)
 	return any;
 }
 
+static const bntann1_t *g_sort_anns;   /* set under the caller's single-threaded index load */
+static int cmp_ann_name(const void *a, const void *b)
+{
+	const int x = *(const int *)a, y = *(const int *)b;
+	const int c = strcmp(g_sort_anns[x].name, g_sort_anns[y].name);
+	return c ? c : (x > y) - (x < y);   /* equal names: by index, so that the last one is found last */
+}
+
 static bntseq_t *load_bns(const char *prefix)
 {
 	bntseq_t *bns = bb_calloc(1, sizeof(bntseq_t));
@@ -171,15 +179,28 @@ static bntseq_t *load_bns(const char *prefix)
 	fclose(fp);
 
 	sprintf(fn, "%s.alt", prefix);
-	if ((fp = fopen(fn, "r")) != 0) { /* first column of every non-@ line names an ALT contig (bntseq.c:178-209) */
-		while (next_line(fp, &ln)) {
-			char *e = ln.s;
-			if (ln.s[0] == '@') continue;
-			while (*e && *e != '\t' && *e != '\r') ++e;
-			*e = 0;
-			for (i = 0; i < bns->n_seqs; ++i)
-				if (strcmp(bns->anns[i].name, ln.s) == 0) { bns->anns[i].is_alt = 1; break; }
+	if ((fp = fopen(fn, "r")) != 0) {
+		/* The first field of every line that does not start with '@' names an ALT contig (bntseq.c:178-209).  As there: a name
+		 * counts only once a tab / newline / carriage return ends it (a last line without one is ignored), it is cut at 1022
+		 * characters, and of several contigs with the same name the LAST one is marked.  Names are looked up in a sorted copy. */
+		int *order = bb_malloc(sizeof(int) * ((size_t)bns->n_seqs + 1)), c, l = 0;
+		char str[1024];
+		for (i = 0; i < bns->n_seqs; ++i) order[i] = i;
+		g_sort_anns = bns->anns;
+		qsort(order, (size_t)bns->n_seqs, sizeof(int), cmp_ann_name);
+		while ((c = fgetc(fp)) != EOF) {
+			if (c == '\t' || c == '\n' || c == '\r') {
+				str[l] = 0;
+				if (str[0] != '@') {
+					int lo = 0, hi = bns->n_seqs;   /* first entry whose name is greater: the one before it is the last with this name */
+					while (lo < hi) { int mid = (lo + hi) >> 1; if (strcmp(bns->anns[order[mid]].name, str) <= 0) lo = mid + 1; else hi = mid; }
+					if (lo > 0 && strcmp(bns->anns[order[lo - 1]].name, str) == 0) bns->anns[order[lo - 1]].is_alt = 1;
+				}
+				while (c != '\n' && c != EOF) c = fgetc(fp);
+				l = 0;
+			} else if (l < 1022) str[l++] = (char)c;
 		}
+		free(order);
 		fclose(fp);
 	}
 	free(ln.s); free(fn);
