@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /* bb_index.c -- load the index files written by the reference's own `bwa index`, unchanged.
  *
  * On-disk formats:
@@ -121,11 +122,11 @@ static int next_line(FILE *fp, bb_str_t *ln)
 	return any;
 }
 
-static const bntann1_t *g_sort_anns;   /* set under the caller's single-threaded index load */
-static int cmp_ann_name(const void *a, const void *b)
+static int cmp_ann_name(const void *a, const void *b, void *anns_)
 {
+	const bntann1_t *anns = anns_;
 	const int x = *(const int *)a, y = *(const int *)b;
-	const int c = strcmp(g_sort_anns[x].name, g_sort_anns[y].name);
+	const int c = strcmp(anns[x].name, anns[y].name);
 	return c ? c : (x > y) - (x < y);   /* equal names: by index, so that the last one is found last */
 }
 
@@ -186,8 +187,7 @@ static bntseq_t *load_bns(const char *prefix)
 		int *order = bb_malloc(sizeof(int) * ((size_t)bns->n_seqs + 1)), c, l = 0;
 		char str[1024];
 		for (i = 0; i < bns->n_seqs; ++i) order[i] = i;
-		g_sort_anns = bns->anns;
-		qsort(order, (size_t)bns->n_seqs, sizeof(int), cmp_ann_name);
+		qsort_r(order, (size_t)bns->n_seqs, sizeof(int), cmp_ann_name, bns->anns);
 		while ((c = fgetc(fp)) != EOF) {
 			if (c == '\t' || c == '\n' || c == '\r') {
 				str[l] = 0;
@@ -198,7 +198,10 @@ static bntseq_t *load_bns(const char *prefix)
 				}
 				while (c != '\n' && c != EOF) c = fgetc(fp);
 				l = 0;
-			} else if (l < 1022) str[l++] = (char)c;
+			} else {
+				if (l >= 1022) bb_fatal("bns_restore_core", "sequence name longer than 1023 characters. Abort!");
+				str[l++] = (char)c;
+			}
 		}
 		free(order);
 		fclose(fp);
