@@ -364,6 +364,16 @@ def main():
     idx.attach()
     if a.dense_sa:
         idx.densify_sa(a.dense_sa)
+    index_verified = None
+    if a.ref_mbp > 60 and rank == 0 and os.environ.get("BWA_B200_BENCH_VERIFY", "1") != "0":
+        # the index files of this workload come from this repository's GPU builder, not from `bwa index`: check EVERY row of the
+        # resident BWT / suffix array against the resident text before trusting any alignment made with it (k_index_verify)
+        t0 = time.time()
+        index_verified = idx.verify(0, 1)
+        index_verified["seconds"] = round(time.time() - t0, 2)
+        log("[bench] index verified against the text: %r" % (index_verified,))
+        if index_verified["bwt_text_sa_mismatches"] or index_verified["order_violations"]:
+            raise SystemExit("bench.py: the index does not describe the reference text")
 
     opt = L.mem_opt_init()
     opt.contents.n_threads = threads
@@ -496,6 +506,7 @@ def main():
                        "timed_region_note": "every step re-submits the same host batch (bases already 0..4 codes after the first call: the in-place encode then re-writes them); releasing the SAM strings (what the reference's caller does after printing, fastmap.c:114-119) is outside the timed region",
                        "pipeline": pipe_cfg + ", %d mem_process_seqs calls in flight" % inflight,
                        "device_selfcheck": {0: "not run", 1: "passed (192 reads from the reference: default kernels == baseline kernels)", 2: "DIFFERED: the baseline kernels (first row sweeps, no short-string table) are in use"}.get(selfcheck_status(), "?"),
+                       "index_verified": index_verified,
                        "sa_interval": a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")), "sa_interval_note": "index files sample every 32nd row; the device re-samples it at load time"},
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],
@@ -530,6 +541,22 @@ def main():
                 line["cpu_baseline"]["sam_identical_on_sample"] = bool(rc == 0 and strip(mine) == strip(ref_out))
                 for f in (mine, ref_out):
                     os.remove(f)
+                if not mem_args and a.ref_mbp >= 1000:
+                    # the full-size index is the only place where >1 Occ superblock, 33-bit rows and the depth-14 short-string table are live:
+                    # one more sample there, single-end with non-default scoring / seeding / output options (host post-processing path: -a)
+                    opts = ["-k", "17", "-A", "2", "-B", "5", "-O", "5,7", "-E", "2,1", "-T", "40", "-Y", "-a"]
+                    n2 = min(20000, n_sample)
+                    one = samples[0] + ".se%d" % n2
+                    with open(samples[0], "rb") as f, open(one, "wb") as o:
+                        for i, l in enumerate(f):
+                            if i >= 4 * n2:
+                                break
+                            o.write(l)
+                    want = subprocess.run([REF_BWA, "mem", "-v", "1", "-t", str(ncores), "-K", "100000000"] + opts + [fa, one], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+                    rc2 = bwa_b200.run_cli(["mem", "-v", "1", "-t", str(threads), "-K", "100000000"] + opts + [fa, one], one + ".sam")
+                    spg = lambda b: b"\n".join(l for l in b.split(b"\n") if not l.startswith(b"@PG"))
+                    line["cpu_baseline"]["sam_identical_on_se_sample_with_options"] = {"options": " ".join(opts), "reads": n2, "identical": bool(rc2 == 0 and spg(open(one + ".sam", "rb").read()) == spg(want))}
+                    os.remove(one + ".sam")
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
         print(json.dumps(line))

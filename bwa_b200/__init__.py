@@ -130,6 +130,14 @@ class Index:
         if self.L.bwag_ctx_densify_sa(self.attach(), intv) != 0:
             raise RuntimeError(self.L.bwag_last_error().decode())
 
+    def verify(self, first=0, stride=1):
+        """Check the resident FM-index against the resident text (bwag_ctx_verify); stride 1 = every row."""
+        out = (C.c_uint64 * 4)()
+        self.L.bwag_ctx_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        if self.L.bwag_ctx_verify(self.attach(), first, stride, out) != 0:
+            raise RuntimeError(self.L.bwag_last_error().decode())
+        return {"rows": int(out[0]), "bwt_text_sa_mismatches": int(out[1]), "order_violations": int(out[2]), "undecided": int(out[3])}
+
     def close(self):
         if self.p:
             self.L.bwa_idx_destroy(self.p)

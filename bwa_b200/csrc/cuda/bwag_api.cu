@@ -359,6 +359,28 @@ extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
 	return 0;
 }
 
+/* Check the resident index against the resident text on rows first, first + stride, ... (stride 1 = every row, a complete check;
+ * see k_index_verify).  out: rows checked, BWT/text/SA mismatches, order violations, pairs of suffixes equal over 8192 bases. */
+extern "C" int bwag_ctx_verify(bwag_ctx_t *c, uint64_t first, uint64_t stride, uint64_t out[4])
+{
+	CK(cudaSetDevice(c->device));
+	if (stride == 0) stride = 1;
+	const u64 n_check = first > c->ix.seq_len ? 0 : (c->ix.seq_len - first) / stride + 1;
+	u64 *d = 0;
+	CK(cudaMalloc((void **)&d, 4 * sizeof(u64)));
+	CK(cudaMemsetAsync(d, 0, 4 * sizeof(u64), c->stream));
+	if (n_check) {
+		const u64 nb = (n_check + 255) / 256;
+		BWAG_LAUNCH(k_index_verify, (int)(nb < (u64)c->n_sm * 64 ? nb : (u64)c->n_sm * 64), 256, 0, c->stream, c->ix, (u64)first, (u64)stride, n_check, d);
+		CK(cudaGetLastError());
+	}
+	CK(cudaMemcpyAsync(out, d, 4 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d);
+	++c->st.n_launch;
+	return 0;
+}
+
 /* on = 1: batches begun from now on use the first formulation of the K4/K5 row sweeps and no short-string table (the
  * configuration measured in round 1); on = 0: back to the defaults.  Used by the host's start-up self-check. */
 extern "C" void bwag_ctx_baseline(bwag_ctx_t *c, int on) { pthread_mutex_lock(&c->mu); c->baseline = on != 0; pthread_mutex_unlock(&c->mu); }
@@ -561,7 +583,8 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		}
 		if (buf_reserve(&c->s_k1, per_group * (size_t)grid * groups_per_block)) return 1;
 		if (buf_reserve(&c->s_k1f, 32 * (size_t)cap3 * (size_t)n + 64) || buf_reserve(&c->s_n3, sizeof(int) * (size_t)(n + 1))) return 1;
-		if (pstride && buf_reserve(&c->s_pack, 4 * ((size_t)(b->total_bases >> 4) + 2 * (size_t)n + 8))) return 1;
+		const size_t pack_words = (size_t)(b->total_bases >> 4) + 2 * (size_t)n + 8, nmask_words = nstride ? (size_t)(b->total_bases >> 5) + 2 * (size_t)n + 8 : 0;
+		if (pstride && buf_reserve(&c->s_pack, 4 * (pack_words + nmask_words))) return 1;
 		if (buf_reserve(&b->d_intv_beg, sizeof(i64) * (size_t)(n + 1)) || buf_reserve(&b->d_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
 		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
@@ -574,8 +597,8 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
 		if (pstride) {   /* the packed copies K1's table lookups key on */
-			a.packed = (const u32 *)c->s_pack.p;
-			BWAG_LAUNCH(k_pack_reads, (n + 127) / 128, 128, 0, c->stream, a.codes, a.off, n, (u32 *)c->s_pack.p);
+			a.packed = (const u32 *)c->s_pack.p; a.nmask = nstride ? (const u32 *)c->s_pack.p + pack_words : 0;
+			BWAG_LAUNCH(k_pack_reads, (n + 127) / 128, 128, 0, c->stream, a.codes, a.off, n, (u32 *)c->s_pack.p, nstride ? (u32 *)c->s_pack.p + pack_words : (u32 *)0);
 			CK(cudaGetLastError());
 			++c->st.n_launch;
 		}

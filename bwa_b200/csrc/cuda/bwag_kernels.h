@@ -37,6 +37,7 @@ struct SeedArgs {
 	int nstride;                                   /* variant K1_PACKED8 only: bytes of a lane's N bitmap (the byte copy of the read is dropped: qstride = 0) */
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
 	const u32 *packed;                             /* k_pack_reads: 2-bit copy of every read, read r at word (off[r] >> 4) + 2 r */
+	const u32 *nmask;                              /* k_pack_reads: one bit per base (ambiguous), read r at word (off[r] >> 5) + 2 r; variant K1_PACKED8 only */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
 	i64 cap_intv, cap_seeds;
@@ -136,12 +137,13 @@ struct SwArgs {
 __global__ void k_localsw(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
-__global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed);
+__global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
 __global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);
 __global__ void k_sa(DevIndex ix, SaArgs a);
 __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
+__global__ void k_index_verify(DevIndex ix, u64 first, u64 stride, u64 n_check, u64 *out);
 __global__ void k_chain(ChainArgs a);
 __global__ void k_regs_compact(RegCompactArgs a);
 __global__ void k_extend(DevIndex ix, ExtArgs a);

@@ -117,3 +117,56 @@ __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks)
 		bwt[b * 4] = out[0]; bwt[b * 4 + 1] = out[1]; bwt[b * 4 + 2] = out[2]; bwt[b * 4 + 3] = out[3];
 	}
 }
+
+/* ------------------------------------------------------------------------------------------------ index verification
+ * Is the resident FM-index (Occ/BWT blocks + suffix-array sample) the index of the resident text (pac, forward + reverse
+ * complement)?  For every checked row r with suffix-array value v = SA[r] (LF walk to the sample):
+ *   (a) the BWT symbol of row r is the text base before position v            (BWT <-> text <-> SA, and through the LF walk the Occ counts), and
+ *   (b) suffix v sorts strictly before the suffix of row r + 1                  (SA order; strictness also rules out a repeated position),
+ * Over all rows this is a complete check of .bwt/.sa against .pac; it exists because indexes of benchmark size come from this
+ * repository's own builder (bwa_b200/index_build.py) -- `bwa index` needs hours there -- and must not be trusted on faith. */
+__device__ u64 verify_sa(const DevIndex &ix, u64 k)
+{
+	const u64 mask = ((u64)1 << ix.sa_shift) - 1;
+	u64 steps = 0;
+	while (k & mask) { k = lf_step(ix, k); ++steps; }
+	return steps + ix.sa[k >> ix.sa_shift];      /* sa[0] = -1: the row of the empty suffix */
+}
+__global__ void k_index_verify(DevIndex ix, u64 first, u64 stride, u64 n_check, u64 *out)
+{
+	const u64 n = ix.seq_len;
+	u64 bad_bwt = 0, bad_order = 0, unresolved = 0, done = 0;
+	for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n_check; t += (u64)gridDim.x * blockDim.x) {
+		const u64 r = first + t * stride;
+		if (r > n) break;
+		const u64 v = r == 0 ? n : verify_sa(ix, r);
+		++done;
+		if (v > n) { ++bad_bwt; continue; }
+		if (r == ix.primary) { if (v != 0) ++bad_bwt; }
+		else {   /* (a) */
+			const u64 kp = r - (r > ix.primary);
+			uint4 cn, pl;
+			u64 rank;
+			bwag_ld_block(ix.bwt + ((kp >> 6) << 1), cn, pl);
+			const int c = bwag_block_symbol_rank(ix, cn, pl, kp, &rank);
+			if (v == 0 || c != bwag_ref_base(ix, (i64)(v - 1))) ++bad_bwt;
+		}
+		if (r < n) {   /* (b) */
+			const u64 v2 = verify_sa(ix, r + 1);
+			if (v2 >= n) { ++bad_order; continue; }     /* only row 0 holds the empty suffix */
+			int cmp = 0;
+			u64 x;
+			for (x = 0; x < 8192 && cmp == 0; ++x) {
+				if (v + x >= n) { cmp = -1; break; }      /* the shorter suffix is the smaller one */
+				if (v2 + x >= n) { cmp = 1; break; }
+				const int a = bwag_ref_base(ix, (i64)(v + x)), b = bwag_ref_base(ix, (i64)(v2 + x));
+				cmp = a < b ? -1 : a > b ? 1 : 0;
+			}
+			if (cmp == 0) ++unresolved; else if (cmp > 0) ++bad_order;
+		}
+	}
+	if (done) atomicAdd(&out[0], done);
+	if (bad_bwt) atomicAdd(&out[1], bad_bwt);
+	if (bad_order) atomicAdd(&out[2], bad_order);
+	if (unresolved) atomicAdd(&out[3], unresolved);
+}

@@ -290,7 +290,7 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
  * looked up): the keys of the short-string table.  One lane per read, once per batch; K1 used to build this itself, one lane
  * at a time (5 % of its instructions at 1.1 active lanes, profiles/r2_k_smem_by_source_line.txt).  Read r's words start at
  * (off[r] >> 4) + 2 r. */
-__global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed)
+__global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
@@ -303,6 +303,15 @@ __global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const 
 		u32 pw = 0;
 		for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
 		dst[w] = pw;
+	}
+	if (nmask) {   /* one bit per base: ambiguous (variant K1_PACKED8, which keeps no byte copy of the read); read r's words start at (off[r] >> 5) + 2 r */
+		u32 *dn = nmask + (o >> 5) + 2 * (i64)r;
+		const int nwn = (len + 31) >> 5;
+		for (int w = 0; w < nwn; ++w) {
+			u32 nb = 0;
+			for (int t = 0; t < 32; ++t) { const int idx = (w << 5) + t; if (idx < len && q[idx] > 3) nb |= 1u << t; }
+			dn[w] = nb;
+		}
 	}
 }
 
@@ -416,19 +425,12 @@ k_smem(DevIndex ix, SeedArgs a)
 					pass = 0; x = 0; mem_n = 0;
 					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
 #ifdef K1_PACKED8
-					if (a.pstride) {            /* pack straight from global memory: 2 bits per base + an N bit per base */
+					if (a.pstride) {            /* the packed copy and the N bitmap k_pack_reads made */
 						q = a.codes + o;
 						const int nwp = ((len + 15) >> 4) + 1, nwn = (len + 31) >> 5;
-						for (int w = 0; w < nwp; ++w) {
-							u32 pw = 0;
-							for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
-							sp[w] = pw;
-						}
-						for (int w = 0; w < nwn; ++w) {
-							u32 nb = 0;
-							for (int t = 0; t < 32; ++t) { const int idx = (w << 5) + t; if (idx < len && q[idx] > 3) nb |= 1u << t; }
-							sn[w] = nb;
-						}
+						const u32 *gp = a.packed + (o >> 4) + 2 * (i64)rid, *gn = a.nmask + (o >> 5) + 2 * (i64)rid;
+						for (int w = 0; w < nwp; ++w) sp[w] = gp[w];
+						for (int w = 0; w < nwn; ++w) sn[w] = gn[w];
 					} else
 #endif
 					if (a.qstride) {            /* the read moves to this lane's shared slot (whole aligned words) */

@@ -45,6 +45,12 @@ int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
  * depth <= 14. */
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
 
+/* Verify the resident FM-index against the resident text: for rows first, first + stride, ... the BWT symbol must be the text base
+ * before the row's suffix-array value, and the row's suffix must sort strictly before the next row's (stride 1: every row = a
+ * complete check of .bwt/.sa against .pac; seconds for 3 Gbp).  out[4]: rows checked, BWT/text/SA mismatches, order violations,
+ * suffix pairs equal over 8192 bases (undecided).  For indexes that did not come from `bwa index` (bwa_b200/index_build.py). */
+int bwag_ctx_verify(bwag_ctx_t *ctx, uint64_t first, uint64_t stride, uint64_t out[4]);
+
 /* on != 0: batches begun from now on run the first formulation of the extension / global-alignment row sweeps and do no
  * short-string table lookups (same results, the configuration measured in round 1); 0: the defaults again.  The host's
  * start-up self-check compares the two on a few hundred reads drawn from the reference and stays on the baseline if

@@ -78,6 +78,7 @@ int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv) { (void)ctx; (void)intv; retu
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth) { (void)ctx; (void)depth; return 0; }
 void bwag_ctx_baseline(bwag_ctx_t *ctx, int on) { (void)ctx; (void)on; }
 int bwag_is_emulator(void) { return 2; }
+int bwag_ctx_verify(bwag_ctx_t *ctx, uint64_t first, uint64_t stride, uint64_t out[4]) { (void)ctx; (void)first; (void)stride; (void)out; return BWAG_UNSUPPORTED; }
 /* stage 4 (the post-processing on the device) has no oracle restatement: the host-side post-processing IS the checker for it */
 int bwag_ctx_set_contigs(bwag_ctx_t *ctx, int n_seqs, const int64_t *offset, const int32_t *len, const uint8_t *is_alt, const char *const *names) { (void)ctx; (void)n_seqs; (void)offset; (void)len; (void)is_alt; (void)names; return BWAG_UNSUPPORTED; }
 int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out) { (void)b; (void)par; (void)n_tasks; (void)tasks; (void)pool; (void)pool_bytes; (void)out; return BWAG_UNSUPPORTED; }
