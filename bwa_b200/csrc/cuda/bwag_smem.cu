@@ -372,7 +372,14 @@ k_smem(DevIndex ix, SeedArgs a)
 #define ENT_LD(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); ulonglong2 v_; ENT_COUNT(i_); \
 		if (i_ < K1_SLOTS) v_ = sl[(l_ * K1_SLOTS + i_) * K1_THREADS]; else v_ = gl[l_ * a.cap_list + i_]; unpack_ent(v_, X0, X1, X2, E); } while (0)
 	/* forward sweep over: candidates are visited longest match first; the call returns the end of the longest match */
-#define TURN_AROUND() do { ret = (int)ikend; pl ^= 1; n_prev = n_curr; n_curr = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; } while (0)
+#ifdef K1_PREFETCH
+	ulonglong2 nxt; nxt.x = nxt.y = 0;
+	bool have_nxt = false;
+#define K1_PF_RESET() (have_nxt = false)
+#else
+#define K1_PF_RESET() ((void)0)
+#endif
+#define TURN_AROUND() do { ret = (int)ikend; pl ^= 1; n_prev = n_curr; n_curr = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; K1_PF_RESET(); } while (0)
 	/* bwt_smem1 returns (bwt.c:346-350 + bwamem.c:150-155): keep matches of at least min_seed_len, ascending start */
 #define CALL_DONE() do { \
 		for (int e_ = m1_n - 1; e_ >= 0; --e_) { \
@@ -473,13 +480,27 @@ k_smem(DevIndex ix, SeedArgs a)
 					continue;
 				}
 				if (j < n_prev) {
+#ifdef K1_PREFETCH   /* variant: the next candidate's entry is requested one step ahead, so that a list tail in global memory is not a serial round trip before the Occ load */
+					{
+						ulonglong2 v_;
+						if (have_nxt) v_ = nxt;
+						else { const int i_ = rev_first ? n_prev - 1 - j : j; v_ = i_ < K1_SLOTS ? sl[(pl * K1_SLOTS + i_) * K1_THREADS] : gl[pl * a.cap_list + i_]; }
+						unpack_ent(v_, e0, e1, e2, pend);
+						have_nxt = j + 1 < n_prev;
+						if (have_nxt) { const int i_ = rev_first ? n_prev - 2 - j : j + 1; nxt = i_ < K1_SLOTS ? sl[(pl * K1_SLOTS + i_) * K1_THREADS] : gl[pl * a.cap_list + i_]; }
+					}
+#else
 					ENT_LD(pl, rev_first ? n_prev - 1 - j : j, e0, e1, e2, pend);
+#endif
 					need = true; back = 1;
 					break;
 				}
 				if (n_curr == 0) { CALL_DONE(); continue; }
 				pl ^= 1;
 				n_prev = n_curr; n_curr = 0; rev_first = 0; --i; j = 0;
+#ifdef K1_PREFETCH
+				have_nxt = false;
+#endif
 				continue;
 			}
 			break; /* ST_NONE */
