@@ -539,6 +539,16 @@ def main():
                 rc = bwa_b200.run_cli(["mem", "-t", str(threads), "-K", "100000000"] + list(mem_args) + [fa] + samples, mine)
                 strip = lambda path: b"\n".join(l for l in open(path, "rb").read().split(b"\n") if not l.startswith(b"@PG"))
                 line["cpu_baseline"]["sam_identical_on_sample"] = bool(rc == 0 and strip(mine) == strip(ref_out))
+                if not line["cpu_baseline"]["sam_identical_on_sample"]:   # say where: first differing record pair, and keep both files for inspection
+                    la, lb = strip(ref_out).split(b"\n"), strip(mine).split(b"\n")
+                    k = next((i for i, (x, y) in enumerate(zip(la, lb)) if x != y), min(len(la), len(lb)))
+                    cut = lambda l: b"\t".join(l.split(b"\t")[:9] + l.split(b"\t")[11:]).decode("latin1")[:600]
+                    line["cpu_baseline"]["sam_diff"] = {"rc": rc, "lines_reference": len(la), "lines_b200": len(lb), "differing_lines": sum(1 for x, y in zip(la, lb) if x != y), "first_at": k,
+                                                        "reference": cut(la[k]) if k < len(la) else None, "b200": cut(lb[k]) if k < len(lb) else None}
+                    keep = os.path.join(ROOT, "gpurun_out")
+                    if os.path.isdir(keep):
+                        import shutil
+                        shutil.copy(ref_out, os.path.join(keep, "sam_diff_reference.sam")); shutil.copy(mine, os.path.join(keep, "sam_diff_b200.sam"))
                 for f in (mine, ref_out):
                     os.remove(f)
                 if not mem_args and a.ref_mbp >= 1000:

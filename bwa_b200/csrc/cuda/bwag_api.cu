@@ -665,6 +665,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 {
 	const int wpb = K4_THREADS / 32;
+	a.chain_lo = 0; a.chain_hi = 0x7fffffff;
 	int per_warp = (8 * (a.cap_q + 2) + a.cap_r + a.cap_q + 15) & ~15;
 	size_t smem = (size_t)per_warp * wpb;
 	int grid = c->grid_k4, use_sm = smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K4_SM") && atoi(getenv("BWA_B200_K4_SM")) == 0);
@@ -686,11 +687,18 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 #endif
 			const i64 lneed = ((i64)n_units + K4L_THREADS - 1) / K4L_THREADS;
 			if (lgrid > lneed) lgrid = (int)(lneed > 0 ? lneed : 1);
-			a.eh = 0; a.rseq = 0; a.smem_per_warp = lcols;   /* here: the number of columns of a lane's row */
+			/* a lane works through its read's chains one after the other, which is right for the usual one or two chains and hopeless for a
+			 * read from a repeat family with hundreds (measured on the repeat-rich workload): those go to the warp-per-read kernel below */
+			const int many = getenv("BWA_B200_K4_LANE_MAXCHAINS") ? atoi(getenv("BWA_B200_K4_LANE_MAXCHAINS")) : 8;
+			ExtArgs la = a;
+			la.eh = 0; la.rseq = 0; la.smem_per_warp = lcols;   /* here: the number of columns of a lane's row */
+			la.chain_lo = 0; la.chain_hi = many;
 			if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] extension: lane-per-read kernel, grid %d x %d, %zu bytes of shared memory per block\n", lgrid, K4L_THREADS, lsm);
-			BWAG_LAUNCH(k_extend_lane, lgrid, K4L_THREADS, lsm, c->stream, c->ix, a);
+			BWAG_LAUNCH(k_extend_lane, lgrid, K4L_THREADS, lsm, c->stream, c->ix, la);
 			CK(cudaGetLastError());
-			return 0;
+			CK(cudaMemsetAsync(a.next_read, 0, sizeof(int), c->stream));
+			a.chain_lo = many + 1; a.chain_hi = 0x7fffffff;
+			++c->st.n_launch;
 		}
 	}
 #ifndef BWAG_CUSIM

@@ -338,6 +338,7 @@ __device__ __forceinline__ void extend_body(const DevIndex &ix, const ExtArgs &a
 		if (lane == 0) rid = atomicAdd(a.next_read, 1);
 		rid = __shfl_sync(FULL_MASK, rid, 0);
 		if (rid >= a.n_reads) break;
+		{ const int cc = a.chain_cnt[rid]; if (cc < a.chain_lo || cc > a.chain_hi) continue; }   /* another launch's read */
 		const i64 c0 = a.chain_beg[rid], c1 = c0 + a.chain_cnt[rid];
 		int n_regs = 0;
 		if (c1 > c0) {

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 				if (st == L_FETCH) {
 					rid = atomicAdd(a.next_read, 1);
 					if (rid >= a.n_reads) { rid = -1; st = L_DONE; break; }
+					{ const int cc = a.chain_cnt[rid]; if (cc < a.chain_lo || cc > a.chain_hi) continue; }   /* another launch's read */
 					c = a.chain_beg[rid]; c1 = c + a.chain_cnt[rid]; c_idx = 0; n_regs = 0;
 					l_query = (int)(a.off[rid + 1] - a.off[rid]);
 					query = a.codes + a.off[rid];

@@ -75,6 +75,7 @@ struct ExtArgs {
 	int *eh; uint8_t *rseq; int cap_q, cap_r;
 	int smem_per_warp;   /* k_extend_sm: bytes of shared scratch per warp = 8*(cap_q+2) + cap_r + cap_q, rounded up to 16 */
 	int min_seed;        /* no seed is shorter than this (0 if unknown): an extension has at most cap_q - min_seed query columns */
+	int chain_lo, chain_hi;   /* this launch takes the reads whose number of chains lies in [chain_lo, chain_hi]: reads with many chains go to the warp-per-read kernel */
 	int *next_read; u64 *cells; u32 *flags;
 };
 

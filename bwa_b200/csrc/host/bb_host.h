@@ -130,7 +130,7 @@ void bb_pestat_from_pairs(const mem_opt_t *opt, long n_pairs, const uint64_t *v,
 /* Mate-rescue alignments come from the device (K6, bwag_localsw) the way global alignments do: a per-pair cache; a miss records
  * a request and the pair's rescue pass is abandoned (return -1) and replayed after the device has served the batch's requests. */
 typedef struct { int64_t rb, re; int32_t which, is_rev, done; bb_swr_t res; } bb_swent_t;   /* which: the read of the pair that is the query */
-typedef struct { BB_VEC(bb_swent_t) v; int pending; } bb_swcache_t;
+typedef struct { BB_VEC(bb_swent_t) v; int pending, probe; } bb_swcache_t;   /* probe: the pass only collects the requests of every anchor (nothing is applied) */
 int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], const mem_alnreg_t *a, int l_ms, const uint8_t *ms, mem_alnreg_v *ma, bb_swcache_t *swc, int which);
 int bb_sam_pe(bb_samctx_t sc[2], const mem_pestat_t pes[4], uint64_t id, bseq1_t s[2], mem_alnreg_v a[2], int rescue_done);
 int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], bseq1_t s[2], mem_alnreg_v a[2], bb_swcache_t *swc);   /* swc == NULL: align on the host (SSE2) */

@@ -189,7 +189,7 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 			int tmp, xtra = BB_SW_XSUBO | BB_SW_XSTART | (l_ms * opt->a < 250 ? BB_SW_XBYTE : 0) | (opt->min_seed_len * opt->a);
 			if (swc) {   /* the alignment comes from the device: (query read, strand, window) identifies it */
 				const bb_swr_t *got = swcache_get(swc, which, is_rev, rb, re);
-				if (!got) return -1;
+				if (!got) { if (swc->probe) continue; return -1; }
 				aln = *got;
 			} else aln = bb_local_sw(l_ms, seq, (int)(re - rb), ref, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, xtra);
 			memset(&b, 0, sizeof(b));
@@ -234,6 +234,10 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 		for (j = 0; j < a[i].n; ++j)
 			if (a[i].a[j].score >= a[i].a[0].score - opt->pen_unpaired) bb_vec_push(b[i], a[i].a[j]);
 	}
+	/* First attempt with device alignments: ask for the alignment of EVERY anchor and orientation that the hits present now do not
+	 * rule out.  Rescued hits can only rule out more (bwamem_pair.c:143-147), so this is a superset of what the pass will use, and
+	 * one device round serves the pair instead of one round per alignment. */
+	if (swc) swc->probe = swc->v.n == 0;
 	for (i = 0; i < 2 && n >= 0; ++i)
 		for (j = 0; j < b[i].n && (int)j < opt->max_matesw; ++j) {
 			int k = bb_matesw(opt, bns, pac, pes, &b[i].a[j], s[!i].l_seq, (uint8_t *)s[!i].seq, &a[!i], swc, !i);
@@ -242,6 +246,7 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 		}
 	if (b[0].a != st[0]) free(b[0].a);
 	if (b[1].a != st[1]) free(b[1].a);
+	if (swc && swc->probe) { swc->probe = 0; if (swc->pending > 0) return -1; }   /* requests collected: the pass is void */
 	return n;
 }
 

@@ -20,9 +20,6 @@ for v in "6" "7" "8"; do
   make -j16 NVEXTRA="-DK1_PACKED8 -DK1_SLOTS=4 -DK1_MIN_BLOCKS=$v" all >> $O/r2e_build.log 2>&1
   $K > $O/r2e_k1_packed_mb$v.json 2>$O/r2e_k1_packed_mb$v.err; echo "K1 packed read, $v blocks/SM:"; line $O/r2e_k1_packed_mb$v.json; lap k1_mb$v
 done
-rm -f build/cuda/bwag_smem.o build/cuda/bwag_api.o
-make -j16 NVEXTRA="-DK1_SLOTS=2 -DK1_MIN_BLOCKS=6" all >> $O/r2e_build.log 2>&1
-$K > $O/r2e_k1_slots2_mb6.json 2>/dev/null; echo "K1 byte read, 2 shared slots, 6 blocks/SM:"; line $O/r2e_k1_slots2_mb6.json; lap k1_slots2
 for v in "-DK1_PREFETCH" "-DK1_PREFETCH -DK1_PACKED8 -DK1_SLOTS=4 -DK1_MIN_BLOCKS=6"; do
   rm -f build/cuda/bwag_smem.o build/cuda/bwag_api.o
   make -j16 NVEXTRA="$v" all >> $O/r2e_build.log 2>&1
@@ -33,4 +30,8 @@ B="python bench.py --worker --steps 8 --warmup 3 --cpu-sample 20000"
 for i in 2 3 4; do BWA_B200_INFLIGHT=$i $B --inflight $i > $O/r2e_pe_if$i.json 2>/dev/null; echo "inflight=$i:"; line $O/r2e_pe_if$i.json; done; lap inflight
 BWA_B200_INFLIGHT=3 BWA_B200_LANES=3 $B --inflight 3 > $O/r2e_pe_if3_l3.json 2>/dev/null; echo "inflight=3 lanes=3:"; line $O/r2e_pe_if3_l3.json
 BWA_B200_CHUNK=131072 $B > $O/r2e_pe_chunk128k.json 2>/dev/null; echo "chunk=131072:"; line $O/r2e_pe_chunk128k.json; lap chunk
-ls -la $O/r2e_* | awk '{print $5, $9}'
+unset BWA_B200_BENCH_VERIFY
+timeout 900 python bench.py --worker --workload pacbio --steps 2 --warmup 1 > $O/r2e_wl_pacbio.json 2>$O/r2e_wl_pacbio.err; echo "workload pacbio:"; line $O/r2e_wl_pacbio.json; python -c "import json; d=json.loads(open('$O/r2e_wl_pacbio.json').read().strip().splitlines()[-1]); print(json.dumps(d['cpu_baseline'].get('sam_diff'), indent=1)[:3000])"; lap pacbio
+BWA_B200_PROFILE=1 BWA_B200_LANES=1 timeout 1500 python bench.py --worker --inflight 1 --workload stress --steps 2 --warmup 1 > $O/r2e_wl_stress_prof.json 2>$O/r2e_wl_stress_prof.err; echo "workload stress (1 lane, profile):"; line $O/r2e_wl_stress_prof.json; grep "\[prof\]" $O/r2e_wl_stress_prof.err | grep -v "loop\|extension:\|batch counters" | awk '{a[$2]+=$3; n[$2]++} END {for (k in a) printf "%-16s %10.1f ms  x%d\n", k, a[k], n[k]}' | sort -k2 -n -r | head -24; grep "loop" $O/r2e_wl_stress_prof.err | awk '{a[$3]+=$4} END {for (k in a) printf "loop %-12s %8.2f CPU-s\n", k, a[k]}' | sort -k3 -n -r | head; lap stress_prof
+timeout 900 python bench.py --worker --workload stress --steps 3 --warmup 1 > $O/r2e_wl_stress.json 2>$O/r2e_wl_stress.err; echo "workload stress:"; line $O/r2e_wl_stress.json; lap stress
+ls -la $O/r2e_* $O/sam_diff* 2>/dev/null | awk '{print $5, $9}'
