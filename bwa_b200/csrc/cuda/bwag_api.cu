@@ -125,6 +125,7 @@ struct bwag_batch {
 	/* stage 4 */
 	DevBuf d_dregs, d_dreg_beg, d_dreg_n, d_task_beg, d_cflag, d_pe_is, d_rec, d_text, d_ptab;
 	DevBuf d_swtasks, d_swres, d_swpool, d_swscratch; HostBuf h_swres;   /* K6 */
+	DevBuf d_sel;
 	HostBuf h_pe_is, h_cflag, h_rec, h_text, h_ptab;
 	int tail_ready;              /* bwag_tail_regs ran on this batch */
 	int regs_on_device;          /* bwag_chain_extend left the regions in HBM */
@@ -486,7 +487,7 @@ static void batch_free(bwag_batch_t *b)
 	free_host(&b->h_regs); free_host(&b->h_nregs); free_host(&b->h_cregs); free_host(&b->h_creg_beg); free_host(&b->h_tmp);
 	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
-	free_dev(&b->d_swtasks); free_dev(&b->d_swres); free_dev(&b->d_swpool); free_dev(&b->d_swscratch); free_host(&b->h_swres);
+	free_dev(&b->d_sel); free_dev(&b->d_swtasks); free_dev(&b->d_swres); free_dev(&b->d_swpool); free_dev(&b->d_swscratch); free_host(&b->h_swres);
 	free_dev(&b->d_dregs); free_dev(&b->d_dreg_beg); free_dev(&b->d_dreg_n); free_dev(&b->d_task_beg); free_dev(&b->d_cflag); free_dev(&b->d_pe_is); free_dev(&b->d_rec); free_dev(&b->d_text); free_dev(&b->d_ptab);
 	free_host(&b->h_pe_is); free_host(&b->h_cflag); free_host(&b->h_rec); free_host(&b->h_text); free_host(&b->h_ptab);
 	free(b);
@@ -881,6 +882,39 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	if (n_regs) D2H(c, b->h_cregs.p, b->d_cregs.p, sizeof(bwag_creg_t) * (size_t)n_regs);
 	D2H(c, b->h_creg_beg.p, b->d_creg_beg.p, 8 * (size_t)n);
 	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
+	CK(cudaEventRecord(c->ev1, c->stream));
+	CK(stream_wait(c));
+	c->st.ms_d2h += elapsed(c);
+	out->n_regs = (const int32_t *)b->h_nregs.p; out->reg_beg = (const int64_t *)b->h_creg_beg.p; out->regs = (const bwag_creg_t *)b->h_cregs.p;
+	return 0;
+}
+
+extern "C" int bwag_fetch_cregs(bwag_batch_t *b, int n_sel, const int32_t *sel, bwag_cregs_t *out)
+{
+	bwag_ctx_t *c = &b->lc;
+	CK(cudaSetDevice(c->device));
+	if (!b->regs_on_device) return set_err("bwag_fetch_cregs needs a preceding bwag_chain_extend(..., NULL) on the same batch");
+	out->n_regs = 0; out->reg_beg = 0; out->regs = 0;
+	if (n_sel <= 0) return 0;
+	const i64 ns = b->n_seeds;
+	if (buf_reserve(&b->d_cregs, sizeof(bwag_creg_t) * (size_t)(ns + 1)) || buf_reserve(&b->d_creg_beg, 8 * (size_t)(b->n + 1)) || buf_reserve(&b->d_sel, 8 * (size_t)(n_sel + 1))) return 1;
+	if (reset_counters(c)) return 1;
+	H2D(c, b->d_sel.p, sel, 4 * (size_t)n_sel);
+	RegCompactArgs rc;
+	rc.n_reads = b->n; rc.n_regs = (const int *)b->d_nregs.p; rc.regs = (const bwag_xreg_t *)b->d_regs.p; rc.reg_base = (const i64 *)b->d_reg_base.p;
+	rc.chain_beg = (const i64 *)b->d_chain_beg.p; rc.chain_rid = (const int *)b->d_chain_rid.p; rc.chain_frac = (const float *)b->d_chain_frac.p;
+	rc.out_beg = (i64 *)b->d_creg_beg.p; rc.total = &c->d_cnt->n_cig; rc.out = (bwag_creg_t *)b->d_cregs.p;
+	int *d_out_n = (int *)b->d_sel.p + n_sel;
+	BWAG_LAUNCH(k_regs_compact_sel, (n_sel + 127) / 128, 128, 0, c->stream, rc, (const int *)b->d_sel.p, n_sel, d_out_n);
+	CK(cudaGetLastError());
+	if (fetch_counters(c)) return 1;
+	++c->st.n_launch;
+	const i64 n_regs = (i64)c->h_cnt->n_cig;
+	if (hbuf_reserve(&b->h_cregs, sizeof(bwag_creg_t) * (size_t)(n_regs + 1)) || hbuf_reserve(&b->h_creg_beg, 8 * (size_t)(n_sel + 1)) || hbuf_reserve(&b->h_nregs, 4 * (size_t)(n_sel + 1))) return 1;
+	CK(cudaEventRecord(c->ev0, c->stream));
+	if (n_regs) D2H(c, b->h_cregs.p, b->d_cregs.p, sizeof(bwag_creg_t) * (size_t)n_regs);
+	D2H(c, b->h_creg_beg.p, b->d_creg_beg.p, 8 * (size_t)n_sel);
+	D2H(c, b->h_nregs.p, d_out_n, 4 * (size_t)n_sel);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
 	c->st.ms_d2h += elapsed(c);

@@ -340,31 +340,45 @@ k_chain(ChainArgs a)
 		int *kept = w.idx, n_kept = 0;
 #define QBEG(c) (w.sn[(c).first].qbeg)
 #define QEND(c) (w.sn[(c).last].qbeg + w.sn[(c).last].len)
-		w.ch[ord[0]].kept = 3;
-		kept[n_kept++] = 0;
+		/* The kept chains are compared with every later chain (quadratic for a read from a repeat family: thousands of chains), so
+		 * what the comparison reads -- query span, weight, ALT flag, first shadowed chain -- sits in one dense array in kept order (the
+		 * B-tree nodes are dead by now): one sequential 24-byte load per comparison instead of five dependent ones through the
+		 * chain and seed records. */
+		struct KeptE { int qb, qe, w, fs, alt, pad; };
+		KeptE *kk = reinterpret_cast<KeptE *>(w.bt);
+		{
+			ChainRec &c0 = w.ch[ord[0]];
+			c0.kept = 3;
+			KeptE e; e.qb = QBEG(c0); e.qe = QEND(c0); e.w = c0.w; e.fs = -1; e.alt = c0.is_alt; e.pad = 0;
+			kk[0] = e;
+			kept[n_kept++] = 0;
+		}
 		for (int i = 1; i < n_chn; ++i) {
 			ChainRec &ci = w.ch[ord[i]];
+			const int qb_i = QBEG(ci), qe_i = QEND(ci), w_i = ci.w, alt_i = ci.is_alt;
 			int large_ovlp = 0, k;
 			for (k = 0; k < n_kept; ++k) {
-				ChainRec &cj = w.ch[ord[kept[k]]];
-				const int b_max = QBEG(cj) > QBEG(ci) ? QBEG(cj) : QBEG(ci);
-				const int e_min = QEND(cj) < QEND(ci) ? QEND(cj) : QEND(ci);
-				if (e_min > b_max && (!cj.is_alt || ci.is_alt)) {
-					const int li = QEND(ci) - QBEG(ci), lj = QEND(cj) - QBEG(cj);
+				const KeptE e = kk[k];
+				const int b_max = e.qb > qb_i ? e.qb : qb_i;
+				const int e_min = e.qe < qe_i ? e.qe : qe_i;
+				if (e_min > b_max && (!e.alt || alt_i)) {
+					const int li = qe_i - qb_i, lj = e.qe - e.qb;
 					const int min_l = li < lj ? li : lj;
 					if (e_min - b_max >= min_l * a.mask_level && min_l < a.max_chain_gap) {
 						large_ovlp = 1;
-						if (cj.first_shadow < 0) cj.first_shadow = i;
-						if (ci.w < cj.w * a.drop_ratio && cj.w - ci.w >= a.min_seed_len << 1) break;
+						if (e.fs < 0) kk[k].fs = i;
+						if (w_i < e.w * a.drop_ratio && e.w - w_i >= a.min_seed_len << 1) break;
 					}
 				}
 			}
-			if (k == n_kept) { kept[n_kept++] = i; ci.kept = large_ovlp ? 2 : 3; }
+			if (k == n_kept) {
+				KeptE e; e.qb = qb_i; e.qe = qe_i; e.w = w_i; e.fs = -1; e.alt = alt_i; e.pad = 0;
+				kk[n_kept] = e;
+				kept[n_kept++] = i; ci.kept = large_ovlp ? 2 : 3;
+			}
 		}
-		for (int i = 0; i < n_kept; ++i) {
-			ChainRec &c = w.ch[ord[kept[i]]];
-			if (c.first_shadow >= 0) w.ch[ord[c.first_shadow]].kept = 1;
-		}
+		for (int i = 0; i < n_kept; ++i)
+			if (kk[i].fs >= 0) w.ch[ord[kk[i].fs]].kept = 1;
 		{
 			int i, k;
 			for (i = k = 0; i < n_chn; ++i) {
@@ -446,5 +460,26 @@ __global__ void k_regs_compact(RegCompactArgs a)
 		o.rid = a.chain_rid[cb + src[k].chain];
 		o.frac_rep = a.chain_frac[cb + src[k].chain];
 		a.out[base + k] = o;
+	}
+}
+
+/* the same for a selection of reads (the reads stage 4 hands back): out_beg / out_n are indexed by position in sel[] */
+__global__ void k_regs_compact_sel(RegCompactArgs a, const int *sel, int n_sel, int *out_n)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_sel) return;
+	const int rid = sel[k];
+	const int n = a.n_regs[rid];
+	i64 base = 0;
+	if (n > 0) base = (i64)atomicAdd(a.total, (u64)n);
+	a.out_beg[k] = base; out_n[k] = n;
+	const bwag_xreg_t *src = a.regs + a.reg_base[rid];
+	const i64 cb = a.chain_beg[rid];
+	for (int x = 0; x < n; ++x) {
+		bwag_creg_t o;
+		o.r = src[x];
+		o.rid = a.chain_rid[cb + src[x].chain];
+		o.frac_rep = a.chain_frac[cb + src[x].chain];
+		a.out[base + x] = o;
 	}
 }

@@ -56,6 +56,31 @@ __device__ __forceinline__ int k4l_max_gap(const bwag_sw_par_t &p, int qlen) /* 
 	return l < p.w << 1 ? l : p.w << 1;
 }
 
+/* reference bases of up to 16 consecutive rows of an extension, 2 bits each, first row in the low bits: rows step by tdir from
+ * doubled position p0, all on one strand (a chain's window never crosses l_pac), so they are 16 consecutive forward bases =
+ * at most five bytes of pac, fetched together -- one memory round trip per 16 rows instead of one per row */
+__device__ __forceinline__ u32 k4l_window(const DevIndex &ix, i64 p0, int tdir, int n)
+{
+	const bool rev = p0 >= ix.l_pac;
+	const i64 f0 = rev ? (ix.l_pac << 1) - 1 - p0 : p0;       /* forward position of the first row */
+	const int fdir = rev ? -tdir : tdir;
+	const i64 lo = fdir > 0 ? f0 : f0 - (n - 1);               /* lowest forward position */
+	const uint8_t *b = ix.pac + (lo >> 2);
+	const int nb = (int)(((lo + n - 1) >> 2) - (lo >> 2)) + 1;  /* 1..5 bytes */
+	unsigned long long v = 0;
+#pragma unroll
+	for (int k = 0; k < 5; ++k) v = v << 8 | (k < nb ? (unsigned long long)b[k] : 0ull);   /* first base of byte 0 in bits 39..38 */
+	const int s0 = 38 - 2 * (int)(lo & 3);
+	u32 w = 0;
+	for (int k = 0; k < n; ++k) {
+		const int m = fdir > 0 ? k : n - 1 - k;
+		u32 c = (u32)(v >> (s0 - 2 * m)) & 3u;
+		if (rev) c = 3u - c;
+		w |= c << (2 * k);
+	}
+	return w;
+}
+
 __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex ix, ExtArgs a)
 {
 #ifdef BWAG_CUSIM
@@ -89,7 +114,7 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 	reg.rb = reg.re = 0; reg.qb = reg.qe = reg.score = reg.truesc = reg.w = reg.seedcov = reg.seedlen0 = reg.chain = 0;
 	/* extension */
 	int qlen = 0, tlen = 0, h0 = 0, w = 0, i = 0, beg = 0, end = 0, mx = 0, max_i = 0, max_j = 0, max_ie = 0, gscore = 0, max_off = 0, pot0 = 0;
-	i64 tbase = 0; int tdir = 1, t_cur = 0, t_next = 0;
+	i64 tbase = 0; int tdir = 1, t_cur = 0; u32 tw = 0;
 	/* row */
 	int jcur = 0, f = 0, hp = 0, key = -1, jmin = 0x7fffffff, jmax = -1, phi = 0, H1 = 0;
 	const uint8_t *qp = 0; int qs = 1;
@@ -225,8 +250,8 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 					pot0 = maxsc * (qlen - 1);
 					if (qlen + 1 + K4L_CH > a.smem_per_warp) { overflow = 1; st = L_EXT_END; continue; }   /* more columns than the launch provided (a seed shorter than min_seed): reported, the batch fails */
 					if (tlen <= 0) { st = L_EXT_END; continue; }
-					t_cur = bwag_ref_base(ix, tbase);
-					t_next = tlen > 1 ? bwag_ref_base(ix, tbase + tdir) : 0;
+					tw = k4l_window(ix, tbase, tdir, tlen < 16 ? tlen : 16);
+					t_cur = (int)(tw & 3u); tw >>= 2;
 					jcur = 0;
 					st = L_INIT;   /* the first row's columns are written by the whole warp in the converged part below */
 				}
@@ -348,8 +373,8 @@ __global__ void __launch_bounds__(K4L_THREADS, K4L_MINB) k_extend_lane(DevIndex 
 				hp = 0;
 				if (beg == 0) { hp = h0 - (o_del + e_del * (i + 1)); if (hp < 0) hp = 0; }
 				f = 0; key = -1; jcur = beg; jmin = 0x7fffffff; jmax = -1; phi = 0;
-				t_cur = t_next;
-				if (i + 1 < tlen) t_next = bwag_ref_base(ix, tbase + (i64)tdir * (i + 1));
+				if ((i & 15) == 0) tw = k4l_window(ix, tbase + (i64)tdir * i, tdir, tlen - i < 16 ? tlen - i : 16);
+				t_cur = (int)(tw & 3u); tw >>= 2;
 				const unsigned long long rw = s_row[t_cur];
 				rlo = (u32)rw; rhi = (u32)(rw >> 32);
 				if (end > beg) cells += (u64)(end - beg);

@@ -147,6 +147,7 @@ __global__ void k_sa_densify(DevIndex ix, u64 *out, int out_shift, u64 n_out);
 __global__ void k_index_verify(DevIndex ix, u64 first, u64 stride, u64 n_check, u64 *out);
 __global__ void k_chain(ChainArgs a);
 __global__ void k_regs_compact(RegCompactArgs a);
+__global__ void k_regs_compact_sel(RegCompactArgs a, const int *sel, int n_sel, int *out_n);
 __global__ void k_extend(DevIndex ix, ExtArgs a);
 __global__ void k_extend_sm(DevIndex ix, ExtArgs a);
 __global__ void k_extend_fast(DevIndex ix, ExtArgs a);

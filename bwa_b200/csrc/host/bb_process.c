@@ -382,6 +382,7 @@ typedef struct job_s {
 	struct job_s *sub0, *sub1;     /* reads handed back by bwag_tail_regs (aligned up to regions before the insert-size model) / by bwag_tail_sam */
 	int *sub_map;                  /* sub job only: index of each of its reads in the parent chunk */
 	const int64_t *ids;            /* sub job only: global index (n_processed + position) of each read: the hash tie-breaks depend on it */
+	int32_t *pre_n; int64_t *pre_beg; bwag_creg_t *pre_regs;   /* sub job only: the raw regions of its reads, taken over from the parent chunk's device stages */
 	const struct tail_shared_s *ts;
 } job_t;
 
@@ -890,7 +891,20 @@ static void sub_job_done(job_t *j, job_t *s)   /* hand the records to the parent
 {
 	int k;
 	for (k = 0; k < s->n; ++k) j->seqs[s->sub_map[k]].sam = s->seqs[k].sam;
-	free(s->seqs); free(s->sub_map); free((void *)s->ids); free(s->pe_is); free(s);
+	free(s->seqs); free(s->sub_map); free((void *)s->ids); free(s->pe_is); free(s->pre_n); free(s->pre_beg); free(s->pre_regs); free(s);
+}
+/* the sub job's reads were seeded, chained and extended as part of the parent chunk: take their raw regions over instead of doing it again */
+static void sub_job_take_regs(job_t *j, job_t *s)
+{
+	bwag_cregs_t cr;
+	int64_t tot = 0;
+	int k, rc = bwag_fetch_cregs(j->batch, s->n, s->sub_map, &cr);
+	if (rc == BWAG_UNSUPPORTED) return;
+	if (rc != 0) bb_fatal("mem_process_seqs", "fetching regions failed: %s", bwag_last_error());
+	for (k = 0; k < s->n; ++k) tot += cr.n_regs[k];
+	s->pre_n = bb_malloc(sizeof(int32_t) * ((size_t)s->n + 1)); s->pre_beg = bb_malloc(sizeof(int64_t) * ((size_t)s->n + 1)); s->pre_regs = bb_malloc(sizeof(bwag_creg_t) * ((size_t)tot + 1));
+	memcpy(s->pre_n, cr.n_regs, sizeof(int32_t) * (size_t)s->n); memcpy(s->pre_beg, cr.reg_beg, sizeof(int64_t) * (size_t)s->n);
+	if (tot) { int64_t mx = 0; for (k = 0; k < s->n; ++k) if (cr.reg_beg[k] + cr.n_regs[k] > mx) mx = cr.reg_beg[k] + cr.n_regs[k]; memcpy(s->pre_regs, cr.regs, sizeof(bwag_creg_t) * (size_t)mx); }
 }
 
 typedef struct { job_t *j; const bwag_sam_t *out; } splice_t;
@@ -939,6 +953,7 @@ static void tail_phase0(job_t *j, bwag_ctx_t *ctx)
 	for (i = 0, n_sub = 0; i < j->n; i += 2) if (j->cflag[i] || j->cflag[i + 1]) { idx[n_sub++] = i; idx[n_sub++] = i + 1; }
 	j->sub0 = sub_job(j, n_sub, idx);
 	free(idx);
+	sub_job_take_regs(j, j->sub0);
 	j->sub0->batch = run_to_regs(j->sub0, ctx, &j->sub0->swp);
 	bwag_batch_end(j->sub0->batch); j->sub0->batch = 0;
 	if (j->pe_is) {
@@ -972,6 +987,7 @@ static void tail_finish(job_t *j, bwag_ctx_t *ctx)
 		for (i = 0, n_sub = 0; i < j->n; ++i) if (HANDED_BACK(i)) idx[n_sub++] = i;
 		j->sub1 = sub_job(j, n_sub, idx);
 		free(idx);
+		sub_job_take_regs(j, j->sub1);
 	}
 #undef HANDED_BACK
 	bwag_batch_end(j->batch); j->batch = 0;   /* out.* is gone from here on */
@@ -1015,6 +1031,10 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	     * (mem_flt_chained_seeds, bwamem.c:626-628) is inactive; otherwise (or if the stage is not provided) on the host */
 		static int no_dev_chain = 0;   /* set once if the stage library has no device chaining (the CPU oracle of the tests) */
 		int dev_chain = !__atomic_load_n(&no_dev_chain, __ATOMIC_RELAXED) && !(getenv("BWA_B200_DEVICE_CHAIN") && atoi(getenv("BWA_B200_DEVICE_CHAIN")) == 0);
+		if (j->pre_n) {   /* regions inherited from the parent chunk */
+			j->cregs.n_regs = j->pre_n; j->cregs.reg_beg = j->pre_beg; j->cregs.regs = j->pre_regs; j->have_cregs = 1;
+			dev_chain = 0;
+		}
 		for (i = 0; i < n && dev_chain; ++i) {
 			int l = j->seqs[i].l_seq;
 			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l > 0 ? l : 1);
@@ -1056,7 +1076,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
 			else { j->have_cregs = 1; PH(j, "chain_extend"); }
 		}
-		if (!dev_chain) host_chain_extend(j, batch, swp, &sp, nt);
+		if (!dev_chain && !j->pre_n) host_chain_extend(j, batch, swp, &sp, nt);
 	}
 
 	{ /* region arrays of all reads in one block; the rare array that must grow (mate rescue) moves to the heap */

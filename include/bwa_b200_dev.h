@@ -128,6 +128,10 @@ typedef struct {
 } bwag_cregs_t;
 int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *sp, const bwag_contigs_t *ctg, bwag_cregs_t *out);   /* out == NULL: the regions stay in HBM (for bwag_tail_regs) */
 
+/* The raw regions of a selection of reads after bwag_chain_extend(b, ..., NULL) left them in HBM: what a caller needs to run its own
+ * post-processing for the reads stage 4 hands back without aligning them again.  out->n_regs / reg_beg are indexed by position in sel[]. */
+int bwag_fetch_cregs(bwag_batch_t *b, int n_sel, const int32_t *sel, bwag_cregs_t *out);
+
 /* ---- stage 3: banded global alignment -> CIGAR/NM/MD (replaces bwa_gen_cigar2 + ksw_global2) -- */
 #define BWAG_G_REG2ALN 0   /* the do-while of mem_reg2aln (bwamem.c:1144-1152): up to 3 band doublings, CIGAR+NM+MD */
 #define BWAG_G_SCORE   1   /* one bwa_gen_cigar2 call, score only (mem_patch_reg, bwamem.c:454) */

@@ -82,6 +82,7 @@ int bwag_ctx_verify(bwag_ctx_t *ctx, uint64_t first, uint64_t stride, uint64_t o
 /* stage 4 (the post-processing on the device) has no oracle restatement: the host-side post-processing IS the checker for it */
 int bwag_ctx_set_contigs(bwag_ctx_t *ctx, int n_seqs, const int64_t *offset, const int32_t *len, const uint8_t *is_alt, const char *const *names) { (void)ctx; (void)n_seqs; (void)offset; (void)len; (void)is_alt; (void)names; return BWAG_UNSUPPORTED; }
 int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out) { (void)b; (void)par; (void)n_tasks; (void)tasks; (void)pool; (void)pool_bytes; (void)out; return BWAG_UNSUPPORTED; }
+int bwag_fetch_cregs(bwag_batch_t *b, int n_sel, const int32_t *sel, bwag_cregs_t *out) { (void)b; (void)n_sel; (void)sel; (void)out; return BWAG_UNSUPPORTED; }
 int bwag_tail_regs(bwag_batch_t *b, const mem_opt_t *opt, const bwag_sw_par_t *sp, const uint64_t **pe_is, const uint8_t **cflag) { (void)b; (void)opt; (void)sp; (void)pe_is; (void)cflag; return BWAG_UNSUPPORTED; }
 int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pestat_t pes[4], const double *const pair_tab[4], const double *log_tab, int64_t n_processed, const char *rg_id, bwag_sam_t *out) { (void)b; (void)opt; (void)pes; (void)pair_tab; (void)log_tab; (void)n_processed; (void)rg_id; (void)out; return BWAG_UNSUPPORTED; }
 
