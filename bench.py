@@ -278,7 +278,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
     ap.add_argument("--cpu-sample", type=int, default=100000)
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BWA_B200_INFLIGHT", "2")), help="mem_process_seqs calls issued at a time (host threads), as bwa-b200 mem does")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BWA_B200_INFLIGHT", "3")), help="mem_process_seqs calls issued at a time (host threads), as bwa-b200 mem does")
     ap.add_argument("--worker", action="store_true", help="(internal) run the measurement in this process; without it a parent process supervises the run")
     ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
     a = ap.parse_args()

@@ -52,6 +52,8 @@ struct Counters {
 	/* stage 4 */
 	u64 t_dregs, t_tasks, t_max_z, t_text, t_complex;
 	int t_max_lq, t_max_rl;
+	int n_many;      /* reads with more chains than the lane kernel takes (K3) */
+	int pad3;
 };
 
 struct DevBuf { void *p; size_t cap; };
@@ -545,7 +547,10 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	bwag_ctx_t *c = &b->lc;
 	CK(cudaSetDevice(c->device));
 	const int n = b->n;
-	i64 cap_intv = (i64)n * 16 + b->total_bases / 8 + 1024, cap_seeds = (i64)n * 32 + b->total_bases / 4 + 4096;
+	/* pools: typical short reads need ~8 intervals / ~10 seeds each; long noisy reads against a large index pick up chance matches of
+	 * their minimum seed length all along (measured: 10-kbp reads at 10 % error against 3 Gbp), hence the per-base terms */
+	i64 cap_intv = (i64)n * 16 + b->total_bases / 4 + 1024, cap_seeds = (i64)n * 32 + b->total_bases / 2 + 4096;
+	if (getenv("BWA_B200_TEST_SMALL_POOLS")) { cap_intv = n / 2 + 8; cap_seeds = n / 2 + 8; }   /* test hook: start with pools that overflow, so that the repeat-with-reported-sizes path runs */
 	int cap_list = b->max_len + 1, cap_mem = 2 * b->max_len + 64;
 	SeedArgs a;
 	memset(&a, 0, sizeof(a));
@@ -663,7 +668,10 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 /* ------------------------------------------------------------------------------------------------ stage 2 */
 
 /* K4 with its per-warp scratch in shared memory when that fits, else in global memory; n_units = reads to process */
-static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
+static int k4_lane_maxchains(void) { const char *e = getenv("BWA_B200_K4_LANE_MAXCHAINS"); return e ? atoi(e) : 8; }
+
+/* n_many: reads with more chains than the lane kernel takes, if the caller knows (K3 counts them), else -1 */
+static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units, int n_many = -1)
 {
 	const int wpb = K4_THREADS / 32;
 	a.chain_lo = 0; a.chain_hi = 0x7fffffff;
@@ -690,16 +698,17 @@ static int launch_extend(bwag_ctx_t *c, ExtArgs &a, int n_units)
 			if (lgrid > lneed) lgrid = (int)(lneed > 0 ? lneed : 1);
 			/* a lane works through its read's chains one after the other, which is right for the usual one or two chains and hopeless for a
 			 * read from a repeat family with hundreds (measured on the repeat-rich workload): those go to the warp-per-read kernel below */
-			const int many = getenv("BWA_B200_K4_LANE_MAXCHAINS") ? atoi(getenv("BWA_B200_K4_LANE_MAXCHAINS")) : 8;
+			const int many = k4_lane_maxchains();
 			ExtArgs la = a;
 			la.eh = 0; la.rseq = 0; la.smem_per_warp = lcols;   /* here: the number of columns of a lane's row */
 			la.chain_lo = 0; la.chain_hi = many;
 			if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] extension: lane-per-read kernel, grid %d x %d, %zu bytes of shared memory per block\n", lgrid, K4L_THREADS, lsm);
 			BWAG_LAUNCH(k_extend_lane, lgrid, K4L_THREADS, lsm, c->stream, c->ix, la);
 			CK(cudaGetLastError());
+			++c->st.n_launch;
+			if (n_many == 0) return 0;                 /* no read is left for the warp-per-read kernel */
 			CK(cudaMemsetAsync(a.next_read, 0, sizeof(int), c->stream));
 			a.chain_lo = many + 1; a.chain_hi = 0x7fffffff;
-			++c->st.n_launch;
 		}
 	}
 #ifndef BWAG_CUSIM
@@ -826,7 +835,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	k.s_bt = b->s_bt.p; k.s_sn = b->s_sn.p; k.s_ch = b->s_ch.p; k.s_order = (int *)b->s_order.p; k.s_idx = (int *)b->s_idx.p; k.s_keys = (u64 *)b->s_keys.p;
 	k.xchains = (bwag_xchain_t *)b->d_chains.p; k.xseeds = (bwag_xseed_t *)b->d_seeds.p; k.chain_rid = (int *)b->d_chain_rid.p; k.chain_frac = (float *)b->d_chain_frac.p;
 	k.chain_beg = (i64 *)b->d_chain_beg.p; k.reg_base = (i64 *)b->d_reg_base.p; k.n_chains = (int *)b->d_chain_cnt.p;
-	k.max_rlen = &c->d_cnt->max_rlen;
+	k.max_rlen = &c->d_cnt->max_rlen; k.n_many = &c->d_cnt->n_many; k.many = k4_lane_maxchains();
 	CK(cudaEventRecord(c->ev0, c->stream));
 	BWAG_LAUNCH(k_chain, (n + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, c->stream, k);
 	CK(cudaGetLastError());
@@ -852,7 +861,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	a.cap_q = cap_q; a.cap_r = cap_r; a.min_seed = cp->min_seed_len;
 	a.next_read = &c->d_cnt->next_read; a.cells = &c->d_cnt->ext_cells; a.flags = &c->d_cnt->flags;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	if (launch_extend(c, a, n)) return 1;
+	if (launch_extend(c, a, n, c->h_cnt->n_many)) return 1;
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (!out) {   /* the regions stay in HBM for bwag_tail_regs */
 		if (fetch_counters(c)) return 1;

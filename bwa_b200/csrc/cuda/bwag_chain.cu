@@ -441,6 +441,7 @@ k_chain(ChainArgs a)
 		}
 	}
 	a.n_chains[rid] = n_out;
+	if (n_out > a.many) atomicAdd(a.n_many, 1);
 }
 
 /* compact the regions of all reads into one dense array for the download */

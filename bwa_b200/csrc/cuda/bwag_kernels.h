@@ -58,6 +58,7 @@ struct ChainArgs {
 	bwag_xchain_t *xchains; bwag_xseed_t *xseeds; int *chain_rid; float *chain_frac;   /* outputs, indexed by seed slot */
 	i64 *chain_beg, *reg_base; int *n_chains;                          /* per read */
 	int *max_rlen;                                                     /* longest reference window of any chain (sizes K4's scratch) */
+	int *n_many; int many;                                             /* counts the reads with more than `many` chains (they go to the warp-per-read extension kernel) */
 };
 
 struct RegCompactArgs {

@@ -570,6 +570,7 @@ k_seed_post(SeedArgs a)
 	if (rid >= a.n_reads) return;
 	const int n = a.intv_n[rid];
 	if (n == 0) return;
+	if (a.intv_beg[rid] + n > a.cap_intv) return;   /* K1 ran out of pool space for this read (flag set, the stage is repeated with larger pools): its slice does not exist */
 	Intv *v = reinterpret_cast<Intv *>(a.intv) + a.intv_beg[rid];
 	for (int e = 1; e < n; ++e) {           /* insertion sort; lists are short (about 8 entries for 150-bp reads) */
 		Intv p = ld_intv(v + e);

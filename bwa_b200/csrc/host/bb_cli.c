@@ -394,11 +394,11 @@ int main_mem(int argc, char *argv[])
 	} else {
 		pthread_create(&th_r, 0, reader_main, &run);
 		pthread_create(&th_w, 0, writer_main, &run);
-		/* BWA_B200_INFLIGHT batches are aligned at a time (default 2): while one is in its host-only phases
-		 * (pairing, SAM text) the GPU works on the next; the writer restores the input order */
+		/* BWA_B200_INFLIGHT batches are aligned at a time (default 3, measured: profiles/r2_call5_bench_pe_if{2,3,4}.json): while one
+		 * waits for a device stage or splices its text, the GPU works on another; the writer restores the input order */
 		{
 			const char *e = getenv("BWA_B200_INFLIGHT");
-			int n_al = e ? atoi(e) : 2, t;
+			int n_al = e ? atoi(e) : 3, t;
 			pthread_t th_a[4];
 			if (n_al < 1) n_al = 1;
 			if (n_al > 4) n_al = 4;

@@ -128,3 +128,14 @@ def test_startup_selfcheck_passes_and_falls_back(data, monkeypatch):
     p = subprocess.run([CUSIMBIN, "mem", "-v", "1"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert p.returncode == 0 and b"staying on the baseline kernels" in p.stderr
     assert strip_pg(p.stdout) == want
+
+
+def test_pool_overflow_is_repeated_not_corrupting(data, monkeypatch):
+    """The seeding stage sizes its interval / seed pools from typical reads and repeats itself with the sizes the device counters report
+    when they overflow (long noisy reads against a large index do that).  The epilogue kernel once sorted slices that did not exist in
+    that case (out-of-bounds writes: a crash and a SAM mismatch on the 3 Gbp pacbio workload).  Here the pools start far too small."""
+    fa, fqs = data.reads("stress", tag="cs", n=120, seed=33, err=(0.016, 0.002, 0.002), chimeric=0.05)
+    args = ["-K", "100000000", "-t", "2", fa] + fqs
+    want = ref_sam(args)
+    monkeypatch.setenv("BWA_B200_TEST_SMALL_POOLS", "1")
+    assert run_sam(CUSIMBIN, args) == want

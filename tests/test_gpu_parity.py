@@ -164,3 +164,14 @@ def test_startup_selfcheck_passed(data):
     L.bb_selfcheck_status.restype = C.c_int
     assert L.bb_selfcheck_status() == 1
     idx.close()
+
+
+def test_pool_overflow_is_repeated_not_corrupting(data, monkeypatch):
+    """Seeding pools that start too small (test hook): the stage is repeated with the sizes the device counters report; no slice of a
+    read that did not fit may be touched (once an out-of-bounds sort in the epilogue kernel: crash on the 3 Gbp pacbio workload)."""
+    monkeypatch.setenv("BWA_B200_TEST_SMALL_POOLS", "1")
+    for ref, kw, extra in (("stress", dict(tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05), []),
+                           ("two", dict(tag="gpb", n=12, length=8000, seed=9, err=(0.02, 0.05, 0.03)), ["-x", "pacbio"])):
+        fa, fqs = data.reads(ref, **kw)
+        args = extra + ["-K", "100000000", "-t", "8", fa] + fqs
+        assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
