@@ -1209,16 +1209,30 @@ extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tas
 	for (int t = 0; t < n_tasks; ++t) { if (tasks[t].qlen > cap_q) cap_q = tasks[t].qlen; if (tasks[t].tlen > cap_t) cap_t = tasks[t].tlen; }
 	cap_q = (cap_q + 15) & ~15; cap_t = (cap_t + 15) & ~15;
 	const int cap_n = cap_q + 16;                                       /* query length rounded up to a whole number of vectors */
-	const i64 per_thread = ((i64)cap_n * 8 + (i64)cap_t * 8 + cap_q + cap_t + 63) & ~(i64)63;
+	/* warp per task (vectors in shared memory) when a block's share fits, else lane per task (everything in a global scratch slice) */
+	const size_t w_smem = (size_t)(8 * cap_n + cap_q) * 4;
+	const int warp_ok = w_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K6_WARP") && atoi(getenv("BWA_B200_K6_WARP")) == 0);
+	const i64 per_thread = warp_ok ? (((i64)cap_t * 8 + cap_t + 63) & ~(i64)63) : (((i64)cap_n * 8 + (i64)cap_t * 8 + cap_q + cap_t + 63) & ~(i64)63);   /* per warp / per lane */
 	int grid = c->n_sm * 16;
-	{
+	if (warp_ok) {
+#ifndef BWAG_CUSIM
+		int nb = 0;
+		CK(cudaFuncSetAttribute(k_localsw_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_localsw_warp, 128, w_smem));
+		grid = c->n_sm * (nb > 0 ? nb : 1);
+#else
+		grid = 2;
+#endif
+		const i64 need = ((i64)n_tasks + 3) / 4;
+		if (grid > need) grid = (int)need;
+	} else {
 		const i64 need = ((i64)n_tasks + 63) / 64;
 		if (grid > need) grid = (int)need;
 		const i64 max_threads = ((i64)4 << 30) / per_thread;            /* bound the scratch to ~4 GB */
 		if ((i64)grid * 64 > max_threads) grid = (int)(max_threads / 64 > 0 ? max_threads / 64 : 1);
 	}
 	if (buf_reserve(&b->d_swtasks, sizeof(bwag_swtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_swres, sizeof(bwag_swres_t) * (size_t)n_tasks) ||
-	    buf_reserve(&b->d_swscratch, (size_t)per_thread * (size_t)grid * 64) || buf_reserve(&b->d_swpool, pool_bytes + 16) ||
+	    buf_reserve(&b->d_swscratch, (size_t)per_thread * (size_t)grid * (warp_ok ? 4 : 64)) || buf_reserve(&b->d_swpool, pool_bytes + 16) ||
 	    hbuf_reserve(&b->h_swres, sizeof(bwag_swres_t) * (size_t)n_tasks)) return 1;
 	if (reset_counters(c)) return 1;
 	H2D(c, b->d_swtasks.p, tasks, sizeof(bwag_swtask_t) * (size_t)n_tasks);
@@ -1230,7 +1244,8 @@ extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tas
 	a.scratch = (unsigned char *)b->d_swscratch.p; a.per_thread = per_thread; a.cap_n = cap_n; a.cap_q = cap_q; a.cap_t = cap_t;
 	a.next_task = &c->d_cnt->next_task; a.flags = &c->d_cnt->flags;
 	CK(cudaEventRecord(c->ev0, c->stream));
-	BWAG_LAUNCH(k_localsw, grid, 64, 0, c->stream, c->ix, a);
+	if (warp_ok) BWAG_LAUNCH(k_localsw_warp, grid, 128, w_smem, c->stream, c->ix, a);
+	else BWAG_LAUNCH(k_localsw, grid, 64, 0, c->stream, c->ix, a);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(c->ev1, c->stream));
 	D2H(c, b->h_swres.p, b->d_swres.p, sizeof(bwag_swres_t) * (size_t)n_tasks);

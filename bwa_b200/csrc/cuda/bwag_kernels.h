@@ -137,6 +137,7 @@ struct SwArgs {
 };
 
 __global__ void k_localsw(DevIndex ix, SwArgs a);
+__global__ void k_localsw_warp(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
 __global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask);

@@ -74,11 +74,16 @@ def _run(S, data):
     S.bwag_ctx_destroy(ctx)
 
 
-def test_localsw_kernel_emulated_equals_ksw_align2(built, data):
+@pytest.mark.parametrize("warp", ["1", "0"])
+def test_localsw_kernel_emulated_equals_ksw_align2(built, data, warp, monkeypatch):
+    """warp=1: a warp per alignment (vectors in shared memory); warp=0: a lane per alignment (the fallback for long queries)."""
+    monkeypatch.setenv("BWA_B200_K6_WARP", warp)
     _run(C.CDLL(os.path.join(ROOT, "tests/_build/libbwa_b200_cusim.so"), mode=C.RTLD_LOCAL), data)
 
 
 @pytest.mark.gpu
-def test_localsw_kernel_equals_ksw_align2(data):
+@pytest.mark.parametrize("warp", ["1", "0"])
+def test_localsw_kernel_equals_ksw_align2(data, warp, monkeypatch):
     import bwa_b200
+    monkeypatch.setenv("BWA_B200_K6_WARP", warp)
     _run(bwa_b200.lib(), data)
