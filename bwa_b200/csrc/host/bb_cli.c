@@ -14,7 +14,7 @@
 
 #define BB_VERSION "0.7.19-r1273-b200"
 
-typedef struct { int n; bseq1_t *seqs; int last; int skip; long no; int64_t n_before; } batch_t;   /* skip: another rank's batch (multi-GPU runs) */
+typedef struct { int n; bseq1_t *seqs; int last; int skip; long no, seq_no; int64_t n_before; } batch_t;   /* skip: another rank's batch (multi-GPU runs); no: number in the whole run; seq_no: number in this process (the writer's order) */
 
 typedef struct { /* single-slot mailbox */
 	pthread_mutex_t mu;
@@ -56,8 +56,8 @@ static void ro_init(reorder_t *o) { pthread_mutex_init(&o->mu, 0); pthread_cond_
 static void ro_post(reorder_t *o, batch_t *b)
 {
 	pthread_mutex_lock(&o->mu);
-	while (b->no - o->next_write >= RO_SLOTS) pthread_cond_wait(&o->cv, &o->mu);
-	o->slot[b->no % RO_SLOTS] = b;
+	while (b->seq_no - o->next_write >= RO_SLOTS) pthread_cond_wait(&o->cv, &o->mu);
+	o->slot[b->seq_no % RO_SLOTS] = b;
 	pthread_cond_broadcast(&o->cv);
 	pthread_mutex_unlock(&o->mu);
 }
@@ -89,10 +89,27 @@ typedef struct {
 	int rank, world;
 	long n_batches;
 	FILE *shard_idx;
+	const char *fn1, *fn2;    /* input paths (planned batches reopen them by byte range) */
 } run_t;
 
 static bwaidx_t *g_cli_idx;   /* an index the caller already holds (and has made resident): used instead of loading */
 void bb_cli_set_index(bwaidx_t *idx) { g_cli_idx = idx; }
+
+/* striped ingest (include/bwa_b200.h): the batches of this process as byte ranges of the input files, set by the launcher */
+static const bb_planned_batch_t *g_plan;
+static int64_t g_plan_n = -1, g_plan_total;
+void bb_cli_set_plan(const bb_planned_batch_t *mine, int64_t n_mine, int64_t n_batches_total) { g_plan = mine; g_plan_n = mine ? n_mine : -1; g_plan_total = n_batches_total; }
+
+/* a planned batch: everything in its byte range(s), read the way bseq_read reads (pairs interleaved, warnings included) */
+static bseq1_t *read_planned(const run_t *r, const bb_planned_batch_t *p, int *n)
+{
+	bb_fq_t *f1 = bb_fq_open_range(r->fn1, p->beg1, p->end1), *f2 = r->fn2 ? bb_fq_open_range(r->fn2, p->beg2, p->end2) : 0;
+	bseq1_t *seqs;
+	if (!f1 || (r->fn2 && !f2)) bb_fatal("main_mem", "fail to reopen the input for batch %ld", (long)p->no);
+	seqs = bseq_read(0x7fffffff, n, f1, f2);
+	bb_fq_close(f1); bb_fq_close(f2);
+	return seqs;
+}
 
 static void w_free_reads(void *d, long c, int tid)   /* 1024 reads per item */
 {
@@ -123,15 +140,23 @@ static void write_batch(run_t *r, batch_t *b)
 static void *reader_main(void *a)
 {
 	run_t *r = a;
+	int64_t k = 0;
 	for (;;) {
 		batch_t *b = bb_calloc(1, sizeof(*b));
 		int i;
 		int64_t size = 0;
-		b->seqs = bseq_read(r->chunk, &b->n, r->f1, r->f2);
-		if (!b->seqs) { free(b); ro_finish(&r->done, r->n_batches); mbox_put(&r->to_align, 0); return 0; }
-		b->no = r->n_batches++;
-		b->n_before = r->n_processed; r->n_processed += b->n;
-		if (b->no % r->world != r->rank) { b->skip = 1; free_reads(b); mbox_put(&r->to_align, b); continue; }
+		if (g_plan_n >= 0) {   /* only this process's batches, each from its byte range; the writer sees just those */
+			if (k >= g_plan_n) { free(b); ro_finish(&r->done, k); mbox_put(&r->to_align, 0); return 0; }
+			b->seqs = read_planned(r, &g_plan[k], &b->n);
+			b->no = g_plan[k].no; b->n_before = g_plan[k].n_before; b->seq_no = k++;
+			if (!b->seqs) bb_fatal("main_mem", "planned batch %ld is empty", b->no);
+		} else {
+			b->seqs = bseq_read(r->chunk, &b->n, r->f1, r->f2);
+			if (!b->seqs) { free(b); ro_finish(&r->done, r->n_batches); mbox_put(&r->to_align, 0); return 0; }
+			b->no = b->seq_no = r->n_batches++;
+			b->n_before = r->n_processed; r->n_processed += b->n;
+		}
+		if (g_plan_n < 0 && b->no % r->world != r->rank) { b->skip = 1; free_reads(b); mbox_put(&r->to_align, b); continue; }
 		if (!r->copy_comment)
 			for (i = 0; i < b->n; ++i) { free(b->seqs[i].comment); b->seqs[i].comment = 0; }
 		for (i = 0; i < b->n; ++i) size += b->seqs[i].l_seq;
@@ -353,6 +378,7 @@ int main_mem(int argc, char *argv[])
 	if (g_cli_idx) run.idx = g_cli_idx;
 	else if ((run.idx = bwa_idx_load(argv[optind], BWA_IDX_ALL)) == 0) return 1;
 	if (ignore_alt) for (i = 0; i < run.idx->bns->n_seqs; ++i) run.idx->bns->anns[i].is_alt = 0;
+	run.fn1 = argv[optind + 1];
 	if ((run.f1 = bb_fq_open(argv[optind + 1])) == 0) {
 		if (bwa_verbose >= 1) fprintf(stderr, "[E::%s] fail to open file `%s'.\n", __func__, argv[optind + 1]);
 		return 1;
@@ -365,6 +391,7 @@ int main_mem(int argc, char *argv[])
 				if (bwa_verbose >= 1) fprintf(stderr, "[E::%s] fail to open file `%s'.\n", __func__, argv[optind + 2]);
 				return 1;
 			}
+			run.fn2 = argv[optind + 2];
 			opt->flag |= MEM_F_PE;
 		}
 	}
@@ -378,14 +405,22 @@ int main_mem(int argc, char *argv[])
 
 	mbox_init(&run.to_align); ro_init(&run.done);
 	if (no_mt_io) {
+		int64_t k = 0;
 		for (;;) {
 			batch_t bb;
 			memset(&bb, 0, sizeof(bb));
-			bb.seqs = bseq_read(run.chunk, &bb.n, run.f1, run.f2);
-			if (!bb.seqs) break;
-			bb.no = run.n_batches++;
-			bb.n_before = run.n_processed; run.n_processed += bb.n;
-			bb.skip = bb.no % run.world != run.rank;
+			if (g_plan_n >= 0) {
+				if (k >= g_plan_n) break;
+				bb.seqs = read_planned(&run, &g_plan[k], &bb.n);
+				bb.no = g_plan[k].no; bb.n_before = g_plan[k].n_before; ++k;
+				if (!bb.seqs) bb_fatal("main_mem", "planned batch %ld is empty", bb.no);
+			} else {
+				bb.seqs = bseq_read(run.chunk, &bb.n, run.f1, run.f2);
+				if (!bb.seqs) break;
+				bb.no = run.n_batches++;
+				bb.n_before = run.n_processed; run.n_processed += bb.n;
+				bb.skip = bb.no % run.world != run.rank;
+			}
 			if (!bb.skip && !run.copy_comment) for (i = 0; i < bb.n; ++i) { free(bb.seqs[i].comment); bb.seqs[i].comment = 0; }
 			align_batch(&run, &bb);
 			if (!bb.skip) write_batch(&run, &bb);

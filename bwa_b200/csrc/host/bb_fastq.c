@@ -5,6 +5,9 @@
 #include <zlib.h>
 #include <ctype.h>
 #include <pthread.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include "bb_host.h"
 
 /* Parsing runs ahead of the consumer in one background thread per file (started by the first bseq_read on the
@@ -19,6 +22,7 @@ struct bb_fq {
 	gzFile fp;
 	unsigned char *buf;
 	int beg, end, eof;
+	int64_t left;             /* bytes the reader may still take from the file (a byte range of it), or -1: up to its end */
 	int pending_hdr;          /* header character already consumed ('>' or '@'), or 0 */
 	bb_str_t name, comment, seq, qual;
 	/* producer/consumer state */
@@ -40,6 +44,23 @@ bb_fq_t *bb_fq_open(const char *fn)
 	if (!f->fp) { free(f); return 0; }
 	gzbuffer(f->fp, 1 << 18);
 	f->buf = bb_malloc(FQ_BUFSZ);
+	f->left = -1;
+	return f;
+}
+
+/* reader over the bytes [beg, end) of an uncompressed file; beg is the first byte of a record (bb_fq_scan_stripe finds such offsets) */
+bb_fq_t *bb_fq_open_range(const char *fn, int64_t beg, int64_t end)
+{
+	bb_fq_t *f;
+	int fd = open(fn, O_RDONLY);
+	if (fd < 0) return 0;
+	if (lseek(fd, (off_t)beg, SEEK_SET) < 0) { close(fd); return 0; }
+	f = bb_calloc(1, sizeof(*f));
+	f->fp = gzdopen(fd, "r");
+	if (!f->fp) { close(fd); free(f); return 0; }
+	gzbuffer(f->fp, 1 << 18);
+	f->buf = bb_malloc(FQ_BUFSZ);
+	f->left = end > beg ? end - beg : 0;
 	return f;
 }
 
@@ -72,8 +93,10 @@ static inline int fq_fill(bb_fq_t *f)
 {
 	if (f->eof) return 0;
 	f->beg = 0;
-	f->end = gzread(f->fp, f->buf, FQ_BUFSZ);
+	if (f->left == 0) { f->end = 0; f->eof = 1; return 0; }
+	f->end = gzread(f->fp, f->buf, f->left >= 0 && f->left < FQ_BUFSZ ? (unsigned)f->left : FQ_BUFSZ);
 	if (f->end <= 0) { f->end = 0; f->eof = 1; return 0; }
+	if (f->left > 0) f->left -= f->end;
 	return 1;
 }
 
@@ -237,4 +260,133 @@ bseq1_t *bseq_read(int chunk_size, int *n_, void *ks1_, void *ks2_)
 	}
 	*n_ = n;
 	return seqs;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- striped ingest
+ * A multi-GPU run (bwa_b200/multi.py) must form the batches a single process would (fastmap.c:64-123: records until >= chunk bases
+ * and an even count), yet no rank should parse more than its share.  Each rank scans ONE byte stripe of the file with the line
+ * scanner below (record lengths and offsets only, no strings), the ranks exchange the lengths, compute the same batch boundaries,
+ * and then parse just the byte ranges of their own batches (bb_fq_open_range).  Only strictly laid out uncompressed files qualify:
+ * four-line FASTQ ('@' line, one sequence line, '+' line, one quality line of the same length) or two-line FASTA; anything else
+ * (gzip, wrapped lines, stdin) makes the scan return BB_SCAN_UNFIT and the launcher falls back to every rank parsing everything. */
+typedef struct { int fd; unsigned char *buf; int64_t base, size; int64_t n, i; int eof; } lines_t;   /* buf holds bytes [base, base + n) of the file; i = cursor */
+#define LN_BUFSZ (8 << 20)
+
+static int ln_fill(lines_t *l)   /* keep the unread tail, append fresh bytes; 0 when nothing was added */
+{
+	int64_t keep = l->n - l->i;
+	ssize_t got;
+	if (l->eof) return 0;
+	if (keep > 0 && l->i > 0) memmove(l->buf, l->buf + l->i, (size_t)keep);
+	l->base += l->i; l->i = 0; l->n = keep;
+	if (l->n >= LN_BUFSZ) return 0;   /* a line longer than the buffer: not the kind of file this path is for */
+	got = pread(l->fd, l->buf + l->n, (size_t)(LN_BUFSZ - l->n), (off_t)(l->base + l->n));
+	if (got <= 0) { l->eof = 1; return 0; }
+	l->n += got;
+	return 1;
+}
+/* next line: its offset in the file, its length without the line terminator(s), its first byte (0 if empty); 0 at the end of the file */
+static int ln_next(lines_t *l, int64_t *off, int *len, int *c0)
+{
+	unsigned char *nl;
+	for (;;) {
+		nl = l->i < l->n ? memchr(l->buf + l->i, '\n', (size_t)(l->n - l->i)) : 0;
+		if (nl) break;
+		if (!ln_fill(l)) {
+			if (l->n >= LN_BUFSZ) return -1;
+			if (l->i >= l->n) return 0;
+			nl = l->buf + l->n;          /* last line without a terminator */
+			break;
+		}
+	}
+	{
+		int64_t e = nl - l->buf, n = e - l->i;
+		*off = l->base + l->i;
+		*c0 = n > 0 ? l->buf[l->i] : 0;
+		if (n > 1 && l->buf[e - 1] == '\r') --n;   /* as the record reader does (a lone CR stays) */
+		if (n > 0x7fffffff) return -1;
+		*len = (int)n;
+		l->i = e < l->n ? e + 1 : e;
+	}
+	return 1;
+}
+static void ln_seek(lines_t *l, int64_t off) { l->base = off; l->n = l->i = 0; l->eof = 0; }
+
+void bb_fq_stripe_free(bb_fqstripe_t *s) { if (s) { free(s->len); free(s->off); memset(s, 0, sizeof(*s)); } }
+
+int64_t bb_fq_plain_size(const char *fn)   /* size of a regular uncompressed FASTA/FASTQ file, else -1 */
+{
+	struct stat st;
+	unsigned char m[2];
+	int fd = open(fn, O_RDONLY);
+	int64_t size = -1;
+	if (fd < 0) return -1;
+	if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= 2 && pread(fd, m, 2, 0) == 2 && (m[0] == '@' || m[0] == '>')) size = (int64_t)st.st_size;
+	close(fd);
+	return size;
+}
+
+int bb_fq_scan_stripe(const char *fn, int64_t beg, int64_t end, bb_fqstripe_t *out)
+{
+	lines_t l;
+	int64_t off[4], m = 0, size = bb_fq_plain_size(fn);
+	int len[4], c[4], rc = BB_SCAN_UNFIT, st, kind;
+	unsigned char first;
+	memset(out, 0, sizeof(*out));
+	if (size < 0) return BB_SCAN_UNFIT;
+	memset(&l, 0, sizeof(l));
+	if ((l.fd = open(fn, O_RDONLY)) < 0) return BB_SCAN_UNFIT;
+	if (pread(l.fd, &first, 1, 0) != 1) { close(l.fd); return BB_SCAN_UNFIT; }
+	kind = first;   /* '@': FASTQ, '>': FASTA */
+	l.buf = bb_malloc(LN_BUFSZ);
+	l.size = size;
+	if (end > size) end = size;
+	/* the first record whose header starts at or after beg: for FASTQ a line starting with '@' whose second successor starts with
+	 * '+' (a quality line may start with '@', but then the line two below it is a sequence); for FASTA any line starting with '>' */
+	if (beg <= 0) ln_seek(&l, 0);
+	else {
+		ln_seek(&l, beg - 1);
+		if ((st = ln_next(&l, &off[0], &len[0], &c[0])) <= 0) { rc = st < 0 ? BB_SCAN_UNFIT : 0; goto done; }   /* the (rest of the) line that holds byte beg-1 */
+	}
+	if (kind == '@' && beg > 0) {
+		int have = 0;
+		int64_t start = -1;
+		while (start < 0) {
+			while (have < 3) { if ((st = ln_next(&l, &off[have], &len[have], &c[have])) <= 0) break; ++have; }
+			if (have < 3) { rc = st < 0 ? BB_SCAN_UNFIT : 0; goto done; }   /* fewer than three lines left: no record starts here */
+			if (off[0] >= end) { rc = 0; goto done; }
+			if (c[0] == '@' && c[2] == '+') start = off[0];
+			else { off[0] = off[1]; off[1] = off[2]; len[0] = len[1]; len[1] = len[2]; c[0] = c[1]; c[1] = c[2]; have = 2; }
+		}
+		ln_seek(&l, start);
+	} else if (kind == '>' && beg > 0) {
+		int64_t start = -1;
+		while (start < 0) {
+			if ((st = ln_next(&l, &off[0], &len[0], &c[0])) <= 0) { rc = st < 0 ? BB_SCAN_UNFIT : 0; goto done; }
+			if (off[0] >= end) { rc = 0; goto done; }
+			if (c[0] == '>') start = off[0];
+		}
+		ln_seek(&l, start);
+	}
+	for (;;) {
+		const int want = kind == '@' ? 4 : 2;
+		int k;
+		if ((st = ln_next(&l, &off[0], &len[0], &c[0])) < 0) goto done;
+		if (st == 0 || off[0] >= end) break;
+		if (len[0] == 0) {   /* blank lines are legal after the last record only (the record grammar skips them there) */
+			while ((st = ln_next(&l, &off[0], &len[0], &c[0])) > 0) if (len[0] != 0) goto done;
+			if (st < 0) goto done;
+			break;
+		}
+		for (k = 1; k < want; ++k) if (ln_next(&l, &off[k], &len[k], &c[k]) <= 0) goto done;   /* truncated record */
+		if (c[0] != kind || c[1] == '@' || c[1] == '>' || c[1] == '+') goto done;
+		if (kind == '@' && (c[2] != '+' || len[3] != len[1])) goto done;
+		if (out->n == m) { m = m ? m << 1 : 1 << 16; out->len = bb_realloc(out->len, (size_t)m * sizeof(int32_t)); out->off = bb_realloc(out->off, (size_t)m * sizeof(int64_t)); }
+		out->len[out->n] = len[1]; out->off[out->n] = off[0]; ++out->n;
+	}
+	rc = 0;
+done:
+	if (rc != 0) bb_fq_stripe_free(out);
+	free(l.buf); close(l.fd);
+	return rc;
 }

@@ -138,6 +138,7 @@ int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, 
 /* ---- FASTA/FASTQ input (bb_fastq.c) ---- */
 typedef struct bb_fq bb_fq_t;
 bb_fq_t *bb_fq_open(const char *fn);
+bb_fq_t *bb_fq_open_range(const char *fn, int64_t beg, int64_t end);
 void bb_fq_close(bb_fq_t *f);
 
 #ifdef __cplusplus

@@ -6,9 +6,12 @@
 What is distributed:
   - the index: rank 0 loads the files of `bwa index` and fills the device blob; ONE broadcast (NCCL over
     NVLink) gives every GPU its copy; the other ranks only read .ann/.amb/.pac for the SAM text;
-  - the reads: every rank parses the input into the batches a single-GPU run would form (-K bases each) and
-    aligns batch b iff b % world == rank, so batch boundaries -- and the per-batch insert-size model of
-    paired-end data -- do not depend on the number of GPUs: the merged SAM is the single-GPU SAM;
+  - the reads: batch b (the batches a single-GPU run would form, -K bases each) is aligned by rank b % world, so
+    batch boundaries -- and the per-batch insert-size model of paired-end data -- do not depend on the number
+    of GPUs: the merged SAM is the single-GPU SAM.  Striped ingest (plan_batches): each rank scans one byte
+    stripe of the input for record lengths, the ranks exchange those, compute the same boundaries and then
+    parse only the byte ranges of their own batches -- nobody parses more than 1/world of the input.  Inputs
+    that cannot be cut by byte offset (gzip, stdin, wrapped lines) fall back to every rank parsing everything;
   - the output: each rank writes its batches to a part file, rank 0 merges the parts in batch order.
 The alignment itself is the C library's `main_mem` (bb_cli.c), unchanged; this module is only plumbing.
 With BWA_B200_LIB pointing at the CPU-emulated build (tests/_build/libbwa_b200_cusim.so) the same code runs
@@ -79,6 +82,141 @@ def replicate_index(L, prefix, rank, device, dist=None, on_gpu=True):
     return idx, keep
 
 
+class Stripe(C.Structure):
+    _fields_ = [("n", C.c_int64), ("len", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int64))]
+
+
+class PlannedBatch(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("no", "n_before", "beg1", "end1", "beg2", "end2")]
+
+
+def _getopt(argv):
+    """(options {flag: last value or True}, positionals) the way getopt sees argv for bb_cli.c's option string."""
+    flags_with_arg = set("kcvsrtRABOEUwLdTQDmINofWxGhyKXHFz")   # the ':' options of bb_cli.c's getopt string
+    opts, pos, k = {}, [], 0
+    while k < len(argv):
+        a = argv[k]
+        if a == "--":
+            pos += argv[k + 1:]
+            break
+        if a.startswith("-") and len(a) > 1:
+            j = 1
+            while j < len(a):
+                c = a[j]
+                if c in flags_with_arg:
+                    if j + 1 < len(a):
+                        opts[c] = a[j + 1:]
+                    elif k + 1 < len(argv):
+                        k += 1
+                        opts[c] = argv[k]
+                    break
+                opts[c] = True
+                j += 1
+        else:
+            pos.append(a)
+        k += 1
+    return opts, pos
+
+
+def batch_bounds(pair_bases, chunk):
+    """Batch boundaries from the bases of each record PAIR (two files: mate 1 + mate 2; one file: records 2k and 2k+1),
+    the rule of bseq_read (bwa.c:79-112): a batch ends after the first pair that brings its bases to >= chunk.
+    Returns the pair index each batch starts at, plus the total as the last element."""
+    import numpy as np
+    cum = np.cumsum(np.asarray(pair_bases, dtype=np.int64))
+    starts, s = [0], 0
+    n = len(cum)
+    while s < n:
+        before = int(cum[s - 1]) if s else 0
+        e = int(np.searchsorted(cum, before + chunk, side="left"))   # first pair p with cum[p] - before >= chunk
+        s = min(e, n - 1) + 1
+        starts.append(s)
+    return starts
+
+
+def plan_batches(L, files, chunk, rank, world, dist=None, device="cpu"):
+    """Striped ingest: the (batch no, reads before, byte ranges) of the batches of `rank`, and the number of batches in all.
+    None when the input does not qualify (every rank must then parse everything).  Collective: every rank calls it."""
+    import numpy as np
+    import torch
+    L.bb_fq_plain_size.restype = C.c_int64
+    L.bb_fq_plain_size.argtypes = [C.c_char_p]
+    L.bb_fq_scan_stripe.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.POINTER(Stripe)]
+    L.bb_fq_stripe_free.argtypes = [C.POINTER(Stripe)]
+
+    def gather(t):   # variable-length all-gather of a 1-d int64 tensor
+        if world == 1:
+            return [t]
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=device)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        m = max(int(x) for x in ns)
+        pad = torch.zeros(m, dtype=torch.int64, device=device)
+        pad[:t.numel()] = t
+        outs = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(outs, pad)
+        return [o[:int(k)] for o, k in zip(outs, ns)]
+
+    sizes = [L.bb_fq_plain_size(f.encode()) for f in files]
+    lens, offs, fit = [], [], all(s >= 0 for s in sizes)
+    for f, size in zip(files, sizes):
+        st = Stripe()
+        if fit and L.bb_fq_scan_stripe(f.encode(), size * rank // world, size * (rank + 1) // world, C.byref(st)) != 0:
+            fit = False
+        if fit and st.n:
+            lens.append(np.ctypeslib.as_array(st.len, shape=(st.n,)).astype(np.int64))
+            offs.append(np.ctypeslib.as_array(st.off, shape=(st.n,)).copy())
+        else:
+            lens.append(np.zeros(0, dtype=np.int64))
+            offs.append(np.zeros(0, dtype=np.int64))
+        L.bb_fq_stripe_free(C.byref(st))
+    ok = torch.tensor([1 if fit else 0], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok[0]) == 0:
+        return None
+    all_lens, first_rec = [], []     # per file: every record's length in file order; index of this rank's first record
+    for k in range(len(files)):
+        parts = [p.cpu().numpy() for p in gather(torch.from_numpy(lens[k]).to(device))]
+        first_rec.append(sum(len(p) for p in parts[:rank]))
+        all_lens.append(np.concatenate(parts))
+    if len(files) == 2:
+        if len(all_lens[0]) != len(all_lens[1]):
+            return None                  # the reference stops at the shorter file with a warning: leave that to the classic reader
+        pair_bases, per_pair = all_lens[0] + all_lens[1], [1, 1]
+    else:
+        a = all_lens[0]
+        pair_bases = a[0::2].copy()
+        pair_bases[:len(a) // 2] += a[1::2]
+        per_pair = [2]
+    if len(pair_bases) == 0:
+        return None
+    starts = batch_bounds(pair_bases, chunk)
+    n_batches = len(starts) - 1
+    # byte offset of every batch's first record, per file: the stripe owner knows it; max-reduce over the ranks
+    begs = []
+    for k in range(len(files)):
+        rec = np.asarray(starts[:-1], dtype=np.int64) * per_pair[k]
+        t = torch.full((n_batches,), -1, dtype=torch.int64)
+        mine = (rec >= first_rec[k]) & (rec < first_rec[k] + len(offs[k]))
+        t[torch.from_numpy(mine)] = torch.from_numpy(offs[k][rec[mine] - first_rec[k]])
+        t = t.to(device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        b = t.cpu().numpy()
+        if (b < 0).any():
+            raise RuntimeError("striped ingest: a batch start was found by no rank")
+        begs.append(np.concatenate([b, [sizes[k]]]))
+    recs_per_pair = sum(per_pair)
+    n_records = sum(len(x) for x in all_lens)
+    mine = []
+    for b in range(rank, n_batches, world):
+        pb = PlannedBatch(no=b, n_before=min(starts[b] * recs_per_pair, n_records), beg1=int(begs[0][b]), end1=int(begs[0][b + 1]),
+                          beg2=int(begs[1][b]) if len(files) == 2 else 0, end2=int(begs[1][b + 1]) if len(files) == 2 else 0)
+        mine.append(pb)
+    return (PlannedBatch * max(len(mine), 1))(*mine), len(mine), n_batches
+
+
 def merge_parts(out_path, parts):
     """parts: [(sam part file, its index file)] by rank; writes the header, then the batches in batch order."""
     where = {}
@@ -143,6 +281,19 @@ def main(argv=None):
     part, part_idx = "%s.part%d" % (out, rank), "%s.part%d.idx" % (out, rank)
     os.environ["BWA_B200_RANK"], os.environ["BWA_B200_WORLD"], os.environ["BWA_B200_SHARD_IDX"] = str(rank), str(world), part_idx
     L.bb_cli_set_index(idx)
+    # striped ingest when the input allows it (BWA_B200_STRIPED=0: every rank parses everything, the round-1 behaviour)
+    plan = None
+    opts, _ = _getopt(argv)
+    if world > 1 and os.environ.get("BWA_B200_STRIPED", "1") != "0":
+        chunk = int(opts["K"]) if "K" in opts and int(opts["K"]) > 0 else 10000000 * max(1, int(opts.get("t", 1)))
+        files = positional[1:2] if ("p" in opts or len(positional) < 3) else positional[1:3]
+        plan = plan_batches(L, files, chunk, rank, world, dist, torch.device("cuda", local_rank) if on_gpu else torch.device("cpu"))
+        if plan is not None:
+            L.bb_cli_set_plan.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+            L.bb_cli_set_plan(C.cast(plan[0], C.c_void_p), plan[1], plan[2])
+            keep.append(plan)
+    if world > 1 and rank == 0:
+        print("[bwa_b200.multi] striped ingest: %s" % ("%d batches over %d ranks" % (plan[2], world) if plan else "off (switched off, or the input cannot be cut by byte offset): every rank parses everything"), file=sys.stderr)
     args = ["mem"] + [part if (k > 0 and argv[k - 1] in ("-o", "-f")) else a for k, a in enumerate(argv)]
     arr = (C.c_char_p * (len(args) + 1))(*[a.encode() for a in args], None)
     rc = L.main_mem(len(args), arr)
@@ -167,21 +318,7 @@ def main(argv=None):
 
 def _positionals(argv):
     """Non-option arguments the way getopt sees them for bb_cli.c's option string."""
-    flags_with_arg = set("kcvsrtRABOEUwLdTQDmINofWxGhyKXHFz")   # the ':' options of bb_cli.c's getopt string
-    pos, k = [], 0
-    while k < len(argv):
-        a = argv[k]
-        if a == "--":
-            pos += argv[k + 1:]
-            break
-        if a.startswith("-") and len(a) > 1:
-            c = a[1]
-            if c in flags_with_arg and len(a) == 2:
-                k += 1
-        else:
-            pos.append(a)
-        k += 1
-    return pos
+    return _getopt(argv)[1]
 
 
 if __name__ == "__main__":

@@ -205,6 +205,20 @@ int main_mem(int argc, char *argv[]);
  * aligns only the batches b with b % world == rank */
 void bb_cli_set_index(bwaidx_t *idx);
 
+/* Striped ingest for multi-GPU runs (no counterpart in the reference, whose step 0 is one reader thread, fastmap.c:64-123).
+ * bb_fq_scan_stripe lists the records whose header starts in the bytes [beg, end) of a strictly laid out uncompressed
+ * FASTQ/FASTA file: sequence length and byte offset of each.  BB_SCAN_UNFIT: the file is not of that kind (gzip, wrapped
+ * lines, truncated): the launcher then lets every rank parse the whole input as before.
+ * bb_cli_set_plan hands main_mem the batches THIS process aligns: batch number, reads before it, and the byte range of the
+ * batch in each input file; main_mem then reads only those ranges.  n_batches_total: batches of the whole run. */
+#define BB_SCAN_UNFIT 1
+typedef struct { int64_t n; int32_t *len; int64_t *off; } bb_fqstripe_t;
+int64_t bb_fq_plain_size(const char *fn);
+int bb_fq_scan_stripe(const char *fn, int64_t beg, int64_t end, bb_fqstripe_t *out);
+void bb_fq_stripe_free(bb_fqstripe_t *s);
+typedef struct { int64_t no, n_before, beg1, end1, beg2, end2; } bb_planned_batch_t;
+void bb_cli_set_plan(const bb_planned_batch_t *mine, int64_t n_mine, int64_t n_batches_total);
+
 #ifdef __cplusplus
 }
 #endif
