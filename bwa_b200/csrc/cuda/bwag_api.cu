@@ -575,7 +575,16 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 #ifdef BWAG_CUSIM
 		grid = 2;
 #else
-		{ int nb; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, smem)); grid = c->n_sm * (nb > 0 ? nb : 1); }
+		{
+			/* BWA_B200_K1_BLOCKS: resident blocks per SM K1 may take.  K1 waits on DRAM, K4/K5 on shared memory and the integer
+			 * pipes: leaving room lets another lane's K4/K5 run beside it (chunks travel on independent streams) */
+			static int cap = -1;
+			int nb;
+			if (cap < 0) { const char *e = getenv("BWA_B200_K1_BLOCKS"); cap = e ? atoi(e) : 0; }
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, smem));
+			if (cap > 0 && nb > cap) nb = cap;
+			grid = c->n_sm * (nb > 0 ? nb : 1);
+		}
 #endif
 		const int cap3 = b->max_len / (par->min_seed_len + 1) + 2;
 		size_t per_group = (size_t)(4 * cap_list + 2 * cap_mem) * 16;
