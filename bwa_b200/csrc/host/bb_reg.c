@@ -1,9 +1,11 @@
-/* bb_reg.c -- alignment regions of one read after extension: redundancy removal / merging of colinear
- * neighbours, primary-vs-secondary marking, approximate single-end MAPQ.
+/* bb_reg.c -- host side of region post-processing, for the reads the device tail (bwag_tail.cu) hands back:
+ * removal of contained regions and joining of colinear neighbours, parent/child (primary/secondary) marking,
+ * single-end MAPQ.  Behaviour to match: bwamem.c:417-584 and 982-1030.
  *
- * Integer and floating-point expressions keep the reference's operand types and order
- * (bwamem.c:417-584, 982-1030): thresholds are float products compared against ints, and the
- * sorts are the unstable introsort of bb_sort.h, so equal keys end up in the same order.
+ * What bit-exactness pins down here, and nothing more: the float/double operand types of every threshold test, the
+ * evaluation order of the floating-point expressions (marked "order matters"), and the unstable introsort of bb_sort.h
+ * (equal keys must land where the reference's sort puts them).  Passes, helpers and names are this file's own; the
+ * device formulation of the same rules for the common small case is t_dedup / t_mark_primary / t_mapq_se.
  */
 #include <math.h>
 #include <pthread.h>
@@ -23,82 +25,119 @@ BB_SORT_DEFINE(static, sort_regs_score_hash, mem_alnreg_t, by_score_hash)
 #define by_alt_score_hash(a, b) ((a).is_alt < (b).is_alt || ((a).is_alt == (b).is_alt && ((a).score > (b).score || ((a).score == (b).score && (a).hash < (b).hash))))
 BB_SORT_DEFINE(static, sort_regs_alt_score_hash, mem_alnreg_t, by_alt_score_hash)
 
-/* Can regions a (left) and b (right) be joined by one banded global alignment?  Returns the joint
- * score (>0) and the band in *w_out, 0 if not, -1 if the alignment had to be requested from the
- * device first (bwamem.c:432-461). */
-static int try_patch(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, const mem_alnreg_t *a, const mem_alnreg_t *b, int *w_out)
+static inline int imin(int x, int y) { return x < y ? x : y; }
+static inline int imax(int x, int y) { return x > y ? x : y; }
+static inline int64_t lmin(int64_t x, int64_t y) { return x < y ? x : y; }
+static inline int qspan(const mem_alnreg_t *r) { return r->qe - r->qb; }
+static inline int64_t rspan(const mem_alnreg_t *r) { return r->re - r->rb; }
+static inline int is_dropped(const mem_alnreg_t *r) { return r->qe <= r->qb; }   /* an emptied query interval marks a region for removal */
+static inline void drop(mem_alnreg_t *r) { r->qe = r->qb; }
+
+/* largest single-event penalty of the scoring scheme: two hits whose scores differ by no more count as "equally good" */
+static inline int tie_slack(const mem_opt_t *o)
 {
-	int w, score, q_s, r_s;
-	double r;
-	const bb_galn_t *g;
-	if (bns == 0 || gc == 0) return 0;
-	if (a->rb < bns->l_pac && b->rb >= bns->l_pac) return 0;
-	if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
-	w = (int)((a->re - b->rb) - (a->qe - b->qb));
-	w = w > 0 ? w : -w;
-	r = (double)(a->re - b->rb) / (b->re - a->rb) - (double)(a->qe - b->qb) / (b->qe - a->qb);
-	r = r > 0. ? r : -r;
-	if (a->re < b->rb || a->qe < b->qb) {
-		if (w > opt->w << 1 || r >= 0.05f) return 0;
-	} else if (w > opt->w << 2 || r >= 0.05f * 2) return 0;
-	w += a->w + b->w;
-	w = w < opt->w << 2 ? w : opt->w << 2;
-	g = bb_gcache_get(gc, BWAG_G_SCORE, a->qb, b->qe, a->rb, b->re, w, 0);
-	if (!g) return -1;
-	score = g->score;
-	q_s = (int)((double)(b->qe - a->qb) / ((b->qe - b->qb) + (a->qe - a->qb)) * (b->score + a->score) + .499);
-	r_s = (int)((double)(b->re - a->rb) / ((b->re - b->rb) + (a->re - a->rb)) * (b->score + a->score) + .499);
-	if ((double)score / (q_s > r_s ? q_s : r_s) < 0.90f) return 0;
-	*w_out = w;
-	return score;
+	return imax(imax(o->a + o->b, o->o_del + o->e_del), o->o_ins + o->e_ins);
 }
 
-/* bwamem.c:463-515.  Returns the new count, or -1 if a patch alignment is pending on the device
- * (the caller restores the array and retries after the next device round). */
+/* ---------------------------------------------------------------------------------------------------- joining neighbours */
+
+/* Geometry test for joining `left` and `right` (left starts first on the reference): band width for the joint global
+ * alignment, or -1 when the two are not colinear enough.  Thresholds are float constants against a double (bwamem.c:441-449). */
+static int join_band(const mem_opt_t *opt, int64_t l_pac, const mem_alnreg_t *left, const mem_alnreg_t *right)
+{
+	int skew;
+	double slope_gap;
+	if (left->rb < l_pac && right->rb >= l_pac) return -1;                            /* different strands */
+	if (left->qb >= right->qb || left->qe >= right->qe || left->re >= right->re) return -1;   /* not in order on both axes */
+	skew = (int)((left->re - right->rb) - (left->qe - right->qb));
+	if (skew < 0) skew = -skew;
+	slope_gap = (double)(left->re - right->rb) / (right->re - left->rb) - (double)(left->qe - right->qb) / (right->qe - left->qb);   /* order matters */
+	if (slope_gap < 0.) slope_gap = -slope_gap;
+	if (left->re < right->rb || left->qe < right->qb) {   /* a gap between them: stricter */
+		if (skew > opt->w << 1 || slope_gap >= 0.05f) return -1;
+	} else if (skew > opt->w << 2 || slope_gap >= 0.05f * 2) return -1;
+	return imin(skew + left->w + right->w, opt->w << 2);
+}
+
+/* Score of the joint alignment if joining pays: >0 score (band in *band), 0 no, -1 the global alignment is not in the cache
+ * yet (it has been requested; the caller replays the read after the next device round). */
+static int join_score(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, const mem_alnreg_t *left, const mem_alnreg_t *right, int *band)
+{
+	const bb_galn_t *g;
+	int w, by_query, by_ref, sum;
+	if (!bns || !gc) return 0;
+	if ((w = join_band(opt, bns->l_pac, left, right)) < 0) return 0;
+	if ((g = bb_gcache_get(gc, BWAG_G_SCORE, left->qb, right->qe, left->rb, right->re, w, 0)) == 0) return -1;
+	/* the score the two would have if scores scaled with the joint span: the joint alignment must reach 90% of it */
+	sum = right->score + left->score;
+	by_query = (int)((double)(right->qe - left->qb) / (qspan(right) + qspan(left)) * sum + .499);   /* order matters */
+	by_ref = (int)((double)(right->re - left->rb) / (rspan(right) + rspan(left)) * sum + .499);
+	if ((double)g->score / imax(by_query, by_ref) < 0.90f) return 0;
+	*band = w;
+	return g->score;
+}
+
+static void absorb(mem_alnreg_t *keep, mem_alnreg_t *gone, int score, int band)   /* keep := keep + gone joined; gone is dropped */
+{
+	keep->n_comp += gone->n_comp + 1;
+	keep->seedcov = imax(keep->seedcov, gone->seedcov);
+	keep->sub = imax(keep->sub, gone->sub);
+	keep->csub = imax(keep->csub, gone->csub);
+	keep->qb = gone->qb; keep->rb = gone->rb;
+	keep->truesc = keep->score = score;
+	keep->w = band;
+	gone->qb = gone->qe;
+}
+
+static int compact(int n, mem_alnreg_t *a)   /* close the holes left by dropped regions */
+{
+	int i, kept = 0;
+	for (i = 0; i < n; ++i)
+		if (!is_dropped(&a[i])) { if (kept != i) a[kept] = a[i]; ++kept; }
+	return kept;
+}
+
+/* Sweep in order of reference end: each region meets the earlier ones that end within max_chain_gap of its start.  Of two that
+ * overlap by more than mask_level_redun on both axes the lower-scoring goes; an earlier one that is colinear is joined. */
+static int sweep_redundant(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, int n, mem_alnreg_t *a)
+{
+	int i, j;
+	for (i = 1; i < n; ++i) {
+		mem_alnreg_t *cur = &a[i];
+		for (j = i - 1; j >= 0; --j) {
+			mem_alnreg_t *old = &a[j];
+			int64_t ov_ref, ov_qry;
+			if (cur->rid != old->rid || cur->rb >= old->re + opt->max_chain_gap) break;
+			if (old->qe == old->qb) continue;
+			ov_ref = old->re - cur->rb;
+			ov_qry = old->qb < cur->qb ? old->qe - cur->qb : cur->qe - old->qb;
+			if (ov_ref > opt->mask_level_redun * lmin(rspan(old), rspan(cur)) && ov_qry > opt->mask_level_redun * imin(qspan(old), qspan(cur))) {
+				if (cur->score < old->score) { drop(cur); break; }
+				drop(old);
+			} else if (old->rb < cur->rb) {
+				int band, sc = join_score(opt, bns, gc, old, cur, &band);
+				if (sc < 0) return -1;
+				if (sc > 0) absorb(cur, old, sc, band);
+			}
+		}
+	}
+	return 0;
+}
+
+/* Returns the new count, or -1 if a joint alignment is pending on the device (the caller restores the array and retries). */
 int bb_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, bb_gcache_t *gc, int l_query, int n, mem_alnreg_t *a)
 {
-	int m, i, j;
+	int i;
 	(void)l_query;
 	if (n <= 1) return n;
 	sort_regs_by_end(n, a);
 	for (i = 0; i < n; ++i) a[i].n_comp = 1;
-	for (i = 1; i < n; ++i) {
-		mem_alnreg_t *p = &a[i];
-		if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + opt->max_chain_gap) continue;
-		for (j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + opt->max_chain_gap; --j) {
-			mem_alnreg_t *q = &a[j];
-			int64_t o_r, o_q, m_r, m_q;
-			int score, w;
-			if (q->qe == q->qb) continue;
-			o_r = q->re - p->rb;
-			o_q = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
-			m_r = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
-			m_q = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
-			if (o_r > opt->mask_level_redun * m_r && o_q > opt->mask_level_redun * m_q) {
-				if (p->score < q->score) { p->qe = p->qb; break; }
-				else q->qe = q->qb;
-			} else if (q->rb < p->rb && (score = try_patch(opt, bns, gc, q, p, &w)) != 0) {
-				if (score < 0) return -1;
-				p->n_comp += q->n_comp + 1;
-				p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
-				p->sub = p->sub > q->sub ? p->sub : q->sub;
-				p->csub = p->csub > q->csub ? p->csub : q->csub;
-				p->qb = q->qb; p->rb = q->rb;
-				p->truesc = p->score = score;
-				p->w = w;
-				q->qb = q->qe;
-			}
-		}
-	}
-	for (i = 0, m = 0; i < n; ++i)
-		if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
-	n = m;
+	if (sweep_redundant(opt, bns, gc, n, a) < 0) return -1;
+	n = compact(n, a);
 	sort_regs_by_score(n, a);
-	for (i = 1; i < n; ++i)
-		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
-	for (i = 1, m = 1; i < n; ++i)
-		if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
-	return m;
+	for (i = 1; i < n; ++i)   /* exact duplicates (same score, same starts) are neighbours now */
+		if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) drop(&a[i]);
+	return n > 1 ? 1 + compact(n - 1, a + 1) : n;
 }
 
 void bb_regs_make_room(mem_alnreg_v *v) /* room for one more region */
@@ -111,101 +150,106 @@ void bb_regs_make_room(mem_alnreg_v *v) /* room for one more region */
 	} else bb_vec_reserve(*v, v->n + 1);
 }
 
-static void mark_core(const mem_opt_t *opt, int n, mem_alnreg_t *a, bb_int_v *z_)
+/* ------------------------------------------------------------------------------------------------- parents and children */
+
+/* do the query intervals of x and y overlap by mask_level of the shorter one? (float product against an int) */
+static inline int covers(const mem_opt_t *opt, const mem_alnreg_t *x, const mem_alnreg_t *y)
 {
-	bb_int_v z = *z_;
-	int i, tmp;
-	size_t k;
-	tmp = opt->a + opt->b;
-	if (opt->o_del + opt->e_del > tmp) tmp = opt->o_del + opt->e_del;
-	if (opt->o_ins + opt->e_ins > tmp) tmp = opt->o_ins + opt->e_ins;
-	z.n = 0;
-	bb_vec_push(z, 0);
-	for (i = 1; i < n; ++i) {
-		for (k = 0; k < z.n; ++k) {
-			int j = z.a[k];
-			int b_max = a[j].qb > a[i].qb ? a[j].qb : a[i].qb;
-			int e_min = a[j].qe < a[i].qe ? a[j].qe : a[i].qe;
-			if (e_min > b_max) {
-				int min_l = a[i].qe - a[i].qb < a[j].qe - a[j].qb ? a[i].qe - a[i].qb : a[j].qe - a[j].qb;
-				if (e_min - b_max >= min_l * opt->mask_level) {
-					if (a[j].sub == 0) a[j].sub = a[i].score;
-					if (a[j].score - a[i].score <= tmp && (a[j].is_alt || !a[i].is_alt)) ++a[j].sub_n;
-					break;
-				}
-			}
-		}
-		if (k == z.n) bb_vec_push(z, i);
-		else a[i].secondary = z.a[k];
-	}
-	*z_ = z;
+	const int lo = imax(x->qb, y->qb), hi = imin(x->qe, y->qe);
+	return hi > lo && hi - lo >= imin(qspan(x), qspan(y)) * opt->mask_level;
 }
 
-/* bwamem.c:547-584 */
+/* Regions a[0..n) are in rank order.  A region becomes the child of the first earlier parent it overlaps, else a parent itself.
+ * The parent records its first child's score (sub) and counts the children that are as good as itself (sub_n). */
+static void assign_parents(const mem_opt_t *opt, int n, mem_alnreg_t *a, bb_int_v *parents_)
+{
+	bb_int_v parents = *parents_;
+	const int slack = tie_slack(opt);
+	int i;
+	parents.n = 0;
+	bb_vec_push(parents, 0);
+	for (i = 1; i < n; ++i) {
+		size_t k;
+		for (k = 0; k < parents.n; ++k) if (covers(opt, &a[parents.a[k]], &a[i])) break;
+		if (k == parents.n) { bb_vec_push(parents, i); continue; }
+		{
+			mem_alnreg_t *par = &a[parents.a[k]];
+			if (par->sub == 0) par->sub = a[i].score;
+			if (par->score - a[i].score <= slack && (par->is_alt || !a[i].is_alt)) ++par->sub_n;
+			a[i].secondary = parents.a[k];
+		}
+	}
+	*parents_ = parents;
+}
+
+/* Ranks the regions (score, then primary assembly before ALT, then a per-read hash), marks children, and -- when ALT hits are
+ * present -- ranks again with the primary-assembly hits first and marks among those alone.  Returns their number. */
 int bb_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id)
 {
-	int zstack[32];
-	bb_int_v z = {0, 0, 0};
+	int small[32];
+	bb_int_v scratch = {0, 0, 0};
 	int i, n_pri = 0;
 	if (n == 0) return 0;
-	if (n <= 32) { z.a = zstack; z.m = 32; }   /* the usual case: no heap traffic */
+	if (n <= 32) { scratch.a = small; scratch.m = 32; }   /* the usual case: no heap traffic */
 	for (i = 0; i < n; ++i) {
-		a[i].sub = a[i].alt_sc = 0; a[i].secondary = a[i].secondary_all = -1;
-		a[i].hash = bb_mix64((uint64_t)(id + i));
-		if (!a[i].is_alt) ++n_pri;
+		mem_alnreg_t *r = &a[i];
+		r->sub = r->alt_sc = 0;
+		r->secondary = r->secondary_all = -1;
+		r->hash = bb_mix64((uint64_t)(id + i));
+		n_pri += !r->is_alt;
 	}
 	sort_regs_score_hash(n, a);
-	mark_core(opt, n, a, &z);
+	assign_parents(opt, n, a, &scratch);
 	for (i = 0; i < n; ++i) {
-		mem_alnreg_t *p = &a[i];
-		p->secondary_all = i;
-		if (!p->is_alt && p->secondary >= 0 && a[p->secondary].is_alt) p->alt_sc = a[p->secondary].score;
+		mem_alnreg_t *r = &a[i];
+		r->secondary_all = i;   /* for now: this region's rank in the all-hits order */
+		if (!r->is_alt && r->secondary >= 0 && a[r->secondary].is_alt) r->alt_sc = a[r->secondary].score;
 	}
-	if (n_pri >= 0 && n_pri < n) {
-		if (z.a != zstack) bb_vec_reserve(z, (size_t)n);
+	if (n_pri == n) {
+		for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+	} else {
+		int *new_rank;
+		if (scratch.a != small) bb_vec_reserve(scratch, (size_t)n);
+		new_rank = scratch.a;
 		if (n_pri > 0) sort_regs_alt_score_hash(n, a);
-		for (i = 0; i < n; ++i) z.a[a[i].secondary_all] = i;
+		for (i = 0; i < n; ++i) new_rank[a[i].secondary_all] = i;
 		for (i = 0; i < n; ++i) {
-			if (a[i].secondary >= 0) {
-				a[i].secondary_all = z.a[a[i].secondary];
-				if (a[i].is_alt) a[i].secondary = INT_MAX;
-			} else a[i].secondary_all = -1;
+			mem_alnreg_t *r = &a[i];
+			if (r->secondary < 0) { r->secondary_all = -1; continue; }
+			r->secondary_all = new_rank[r->secondary];
+			if (r->is_alt) r->secondary = INT_MAX;
 		}
 		if (n_pri > 0) {
 			for (i = 0; i < n_pri; ++i) { a[i].sub = 0; a[i].secondary = -1; }
-			mark_core(opt, n_pri, a, &z);
+			assign_parents(opt, n_pri, a, &scratch);
 		}
-	} else for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
-	if (z.a != zstack) free(z.a);
+	}
+	if (scratch.a != small) free(scratch.a);
 	return n_pri;
 }
 
-/* bwamem.c:1008-1030 */
-void bb_reorder_primary5(int T, mem_alnreg_v *a)
+/* -5: of the reportable primary hits the one that starts leftmost on the read goes first (bwamem.c:1008-1030) */
+void bb_reorder_primary5(int T, mem_alnreg_v *v)
 {
-	int n_pri = 0, left_st = INT_MAX, left_k = -1;
 	size_t k;
-	mem_alnreg_t t;
-	for (k = 0; k < a->n; ++k)
-		if (a->a[k].secondary < 0 && !a->a[k].is_alt && a->a[k].score >= T) ++n_pri;
-	if (n_pri <= 1) return;
-	for (k = 0; k < a->n; ++k) {
-		mem_alnreg_t *p = &a->a[k];
-		if (p->secondary >= 0 || p->is_alt || p->score < T) continue;
-		if (p->qb < left_st) { left_st = p->qb; left_k = (int)k; }
+	int reportable = 0, best_qb = INT_MAX, pick = -1;
+	for (k = 0; k < v->n; ++k) {
+		const mem_alnreg_t *r = &v->a[k];
+		if (r->secondary >= 0 || r->is_alt || r->score < T) continue;
+		++reportable;
+		if (r->qb < best_qb) { best_qb = r->qb; pick = (int)k; }
 	}
-	if (left_k == 0) return;
-	t = a->a[0]; a->a[0] = a->a[left_k]; a->a[left_k] = t;
-	for (k = 1; k < a->n; ++k) {
-		mem_alnreg_t *p = &a->a[k];
-		if (p->secondary == 0) p->secondary = left_k;
-		else if (p->secondary == left_k) p->secondary = 0;
-		if (p->secondary_all == 0) p->secondary_all = left_k;
-		else if (p->secondary_all == left_k) p->secondary_all = 0;
+	if (reportable <= 1 || pick == 0) return;
+	{ mem_alnreg_t t = v->a[0]; v->a[0] = v->a[pick]; v->a[pick] = t; }
+	for (k = 1; k < v->n; ++k) {   /* references to the two swapped slots follow them */
+		mem_alnreg_t *r = &v->a[k];
+		if (r->secondary == 0) r->secondary = pick; else if (r->secondary == pick) r->secondary = 0;
+		if (r->secondary_all == 0) r->secondary_all = pick; else if (r->secondary_all == pick) r->secondary_all = 0;
 	}
 }
 
-/* bwamem.c:982-1006 */
+/* ------------------------------------------------------------------------------------------------------------------ MAPQ */
+
 /* log of a small non-negative integer (seed coverage, number of sub-optimal hits + 1): the same libm values, tabulated once */
 #define LOGTAB_N 4096
 static double g_logtab[LOGTAB_N];
@@ -218,27 +262,27 @@ static inline double log_of_int(int n)
 	return g_logtab[n];
 }
 
-int bb_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a)
+/* Single-end mapping quality of a region from its score, the best competing score and the seed coverage (bwamem.c:982-1006).
+ * Every line that says "order matters" is a double expression truncated to int: operands and order are the reference's. */
+int bb_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *r)
 {
-	int mapq, l, sub = a->sub ? a->sub : opt->min_seed_len * opt->a;
+	const int span = qspan(r) > rspan(r) ? qspan(r) : (int)rspan(r);
+	int rival = r->sub ? r->sub : opt->min_seed_len * opt->a, q;
 	double identity;
-	sub = a->csub > sub ? a->csub : sub;
-	if (sub >= a->score) return 0;
-	l = a->qe - a->qb > a->re - a->rb ? a->qe - a->qb : (int)(a->re - a->rb);
-	identity = 1. - (double)(l * opt->a - a->score) / (opt->a + opt->b) / l;
-	if (a->score == 0) mapq = 0;
+	if (r->csub > rival) rival = r->csub;
+	if (rival >= r->score) return 0;
+	identity = 1. - (double)(span * opt->a - r->score) / (opt->a + opt->b) / span;   /* order matters */
+	if (r->score == 0) q = 0;
 	else if (opt->mapQ_coef_len > 0) {
-		double tmp;
-		tmp = l < opt->mapQ_coef_len ? 1. : opt->mapQ_coef_fac / log(l);
-		tmp *= identity * identity;
-		mapq = (int)(6.02 * (a->score - sub) / opt->a * tmp * tmp + .499);
+		double scale = span < opt->mapQ_coef_len ? 1. : opt->mapQ_coef_fac / log(span);
+		scale *= identity * identity;
+		q = (int)(6.02 * (r->score - rival) / opt->a * scale * scale + .499);   /* order matters */
 	} else {
-		mapq = (int)(MEM_MAPQ_COEF * (1. - (double)sub / a->score) * log_of_int(a->seedcov) + .499);
-		mapq = identity < 0.95 ? (int)(mapq * identity * identity + .499) : mapq;
+		q = (int)(MEM_MAPQ_COEF * (1. - (double)rival / r->score) * log_of_int(r->seedcov) + .499);   /* order matters */
+		if (identity < 0.95) q = (int)(q * identity * identity + .499);
 	}
-	if (a->sub_n > 0) mapq -= (int)(4.343 * log_of_int(a->sub_n + 1) + .499);
-	if (mapq > 60) mapq = 60;
-	if (mapq < 0) mapq = 0;
-	mapq = (int)(mapq * (1. - a->frac_rep) + .499);
-	return mapq;
+	if (r->sub_n > 0) q -= (int)(4.343 * log_of_int(r->sub_n + 1) + .499);
+	if (q > 60) q = 60;
+	if (q < 0) q = 0;
+	return (int)(q * (1. - r->frac_rep) + .499);
 }
