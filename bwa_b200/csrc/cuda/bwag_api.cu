@@ -226,6 +226,9 @@ static int pick_grid(bwag_ctx_t *c)
 	return 0;
 }
 
+static cudaEvent_t g_trace_ref;   /* BWA_B200_GPUTRACE: origin of the device-clock timeline (see elapsed_at) */
+static int g_gputrace = -1;
+
 extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob)
 {
 	BlobHeader h;
@@ -254,6 +257,11 @@ extern "C" bwag_ctx_t *bwag_ctx_from_blob(int device, void *d_blob, int own_blob
 	c->sa_intv_disk = 1 << h.sa_shift;
 	CKP(cudaStreamCreate(&c->stream));
 	CKP(cudaEventCreate(&c->ev0)); CKP(cudaEventCreate(&c->ev1));
+	if (g_gputrace < 0) {
+		const char *e = getenv("BWA_B200_GPUTRACE");
+		g_gputrace = e && atoi(e) > 0;
+		if (g_gputrace) { CKP(cudaEventCreate(&g_trace_ref)); CKP(cudaEventRecord(g_trace_ref, c->stream)); CKP(cudaEventSynchronize(g_trace_ref)); }
+	}
 	CKP(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
 	CKP(cudaMalloc((void **)&c->d_cnt, sizeof(Counters)));
 	CKP(cudaMallocHost((void **)&c->h_cnt, sizeof(Counters)));
@@ -538,7 +546,20 @@ static int fetch_counters(bwag_ctx_t *c)
 }
 #define H2D(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (c)->stream)); (c)->st.h2d_bytes += (u64)(bytes); } while (0)
 #define D2H(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (c)->stream)); (c)->st.d2h_bytes += (u64)(bytes); } while (0)
-static double elapsed(bwag_ctx_t *c) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); return ms; }
+/* BWA_B200_GPUTRACE=1: every timed stage also prints its start and end on the device clock (ms since the first context was made),
+ * one line per stage and lane, so that tools/gpu_timeline.py can tell how much of a run the GPU sat idle and between which stages */
+static double elapsed_at(bwag_ctx_t *c, int line)
+{
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	if (g_gputrace > 0) {
+		float t0 = 0, t1 = 0;
+		cudaEventElapsedTime(&t0, g_trace_ref, c->ev0); cudaEventElapsedTime(&t1, g_trace_ref, c->ev1);
+		fprintf(stderr, "[gputrace] %p %d %.3f %.3f\n", (void *)c, line, t0, t1);
+	}
+	return ms;
+}
+#define elapsed(c) elapsed_at(c, __LINE__)
 
 /* ------------------------------------------------------------------------------------------------ stage 1 */
 
