@@ -53,7 +53,7 @@ struct Counters {
 	u64 t_dregs, t_tasks, t_max_z, t_text, t_complex;
 	int t_max_lq, t_max_rl;
 	int n_many;      /* reads with more chains than the lane kernel takes (K3) */
-	int pad3;
+	u32 n_swtasks;   /* local alignments the seed-level filter of long reads asks for (K3) */
 };
 
 struct DevBuf { void *p; size_t cap; };
@@ -127,6 +127,7 @@ struct bwag_batch {
 	/* stage 4 */
 	DevBuf d_dregs, d_dreg_beg, d_dreg_n, d_task_beg, d_cflag, d_pe_is, d_rec, d_text, d_ptab;
 	DevBuf d_swtasks, d_swres, d_swpool, d_swscratch; HostBuf h_swres;   /* K6 */
+	DevBuf d_hsp, d_flt_nchn; HostBuf h_hsp;   /* seed-level filter of long reads (K3/K3b) */
 	DevBuf d_sel;
 	HostBuf h_pe_is, h_cflag, h_rec, h_text, h_ptab;
 	int tail_ready;              /* bwag_tail_regs ran on this batch */
@@ -148,6 +149,7 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #endif
 #define K4_SMEM_MAX (96 * 1024)
 #define K4L_SMEM_MAX (200 * 1024)
+#define SEEDSW_MAXLEN 200   /* the seed-level filter aligns windows shorter than this on both axes (bwamem.c:591,612) */
 
 #ifdef BWAG_CUSIM
 unsigned long long bwag_cusim_sector_loads, bwag_cusim_list_acc[5];
@@ -498,6 +500,7 @@ static void batch_free(bwag_batch_t *b)
 	free_dev(&b->d_tasks); free_dev(&b->d_res); free_dev(&b->d_cig); free_dev(&b->d_md);
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
 	free_dev(&b->d_sel); free_dev(&b->d_swtasks); free_dev(&b->d_swres); free_dev(&b->d_swpool); free_dev(&b->d_swscratch); free_host(&b->h_swres);
+	free_dev(&b->d_hsp); free_dev(&b->d_flt_nchn); free_host(&b->h_hsp);
 	free_dev(&b->d_dregs); free_dev(&b->d_dreg_beg); free_dev(&b->d_dreg_n); free_dev(&b->d_task_beg); free_dev(&b->d_cflag); free_dev(&b->d_pe_is); free_dev(&b->d_rec); free_dev(&b->d_text); free_dev(&b->d_ptab);
 	free_host(&b->h_pe_is); free_host(&b->h_cflag); free_host(&b->h_rec); free_host(&b->h_text); free_host(&b->h_ptab);
 	free(b);
@@ -827,6 +830,74 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 
 /* ------------------------------------------------------------------------------------------------ stages 2a+2 fused */
 
+/* K6 over n_tasks tasks that are in b->d_swtasks already (queries/targets: the batch's reads, the reference, or b->d_swpool);
+ * results to b->d_swres.  max_q / max_t: no task is longer.  Records ev0/ev1 around the kernel; the caller fetches the counters. */
+static int localsw_on_device(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, int max_q, int max_t)
+{
+	bwag_ctx_t *c = &b->lc;
+	const int cap_q = ((max_q > 16 ? max_q : 16) + 15) & ~15, cap_t = ((max_t > 16 ? max_t : 16) + 15) & ~15;
+	const int cap_n = cap_q + 16;                                       /* query length rounded up to a whole number of vectors */
+	/* warp per task (vectors in shared memory) when a block's share fits, else lane per task (everything in a global scratch slice) */
+	const size_t w_smem = (size_t)(8 * cap_n + cap_q) * 4;
+	const int warp_ok = w_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K6_WARP") && atoi(getenv("BWA_B200_K6_WARP")) == 0);
+	const i64 per_thread = warp_ok ? (((i64)cap_t * 8 + cap_t + 63) & ~(i64)63) : (((i64)cap_n * 8 + (i64)cap_t * 8 + cap_q + cap_t + 63) & ~(i64)63);   /* per warp / per lane */
+	int grid = c->n_sm * 16;
+	if (warp_ok) {
+#ifndef BWAG_CUSIM
+		int nb = 0;
+		CK(cudaFuncSetAttribute(k_localsw_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_localsw_warp, 128, w_smem));
+		grid = c->n_sm * (nb > 0 ? nb : 1);
+#else
+		grid = 2;
+#endif
+		const i64 need = ((i64)n_tasks + 3) / 4;
+		if (grid > need) grid = (int)need;
+	} else {
+		const i64 need = ((i64)n_tasks + 63) / 64;
+		if (grid > need) grid = (int)need;
+		const i64 max_threads = ((i64)4 << 30) / per_thread;            /* bound the scratch to ~4 GB */
+		if ((i64)grid * 64 > max_threads) grid = (int)(max_threads / 64 > 0 ? max_threads / 64 : 1);
+	}
+	if (buf_reserve(&b->d_swres, sizeof(bwag_swres_t) * (size_t)n_tasks) || buf_reserve(&b->d_swscratch, (size_t)per_thread * (size_t)grid * (warp_ok ? 4 : 64)) ||
+	    buf_reserve(&b->d_swpool, 16)) return 1;
+	SwArgs a;
+	memset(&a, 0, sizeof(a));
+	a.tasks = (const bwag_swtask_t *)b->d_swtasks.p; a.n_tasks = n_tasks; a.par = *par;
+	a.codes = (const uint8_t *)b->d_codes.p; a.pool = (const uint8_t *)b->d_swpool.p; a.res = (bwag_swres_t *)b->d_swres.p;
+	a.scratch = (unsigned char *)b->d_swscratch.p; a.per_thread = per_thread; a.cap_n = cap_n; a.cap_q = cap_q; a.cap_t = cap_t;
+	a.next_task = &c->d_cnt->next_task; a.flags = &c->d_cnt->flags;
+	CK(cudaMemsetAsync(&c->d_cnt->next_task, 0, sizeof(int), c->stream));
+	CK(cudaEventRecord(c->ev0, c->stream));
+	if (warp_ok) BWAG_LAUNCH(k_localsw_warp, grid, 128, w_smem, c->stream, c->ix, a);
+	else BWAG_LAUNCH(k_localsw, grid, 64, 0, c->stream, c->ix, a);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(c->ev1, c->stream));
+	return 0;
+}
+
+extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out)
+{
+	bwag_ctx_t *c = &b->lc;
+	CK(cudaSetDevice(c->device));
+	*out = 0;
+	if (n_tasks <= 0) return 0;
+	int max_q = 16, max_t = 16;
+	for (int t = 0; t < n_tasks; ++t) { if (tasks[t].qlen > max_q) max_q = tasks[t].qlen; if (tasks[t].tlen > max_t) max_t = tasks[t].tlen; }
+	if (buf_reserve(&b->d_swtasks, sizeof(bwag_swtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_swpool, pool_bytes + 16) ||
+	    hbuf_reserve(&b->h_swres, sizeof(bwag_swres_t) * (size_t)n_tasks)) return 1;
+	if (reset_counters(c)) return 1;
+	H2D(c, b->d_swtasks.p, tasks, sizeof(bwag_swtask_t) * (size_t)n_tasks);
+	if (pool && pool_bytes) H2D(c, b->d_swpool.p, pool, pool_bytes);
+	if (localsw_on_device(b, par, n_tasks, max_q, max_t)) return 1;
+	D2H(c, b->h_swres.p, b->d_swres.p, sizeof(bwag_swres_t) * (size_t)n_tasks);
+	if (fetch_counters(c)) return 1;
+	c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_tasks;
+	if (c->h_cnt->flags & 32u) return set_err("local alignment: a task exceeded the scratch capacity");
+	*out = (const bwag_swres_t *)b->h_swres.p;
+	return 0;
+}
+
 extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, const bwag_sw_par_t *par, const bwag_contigs_t *ctg, bwag_cregs_t *out)
 {
 	bwag_ctx_t *c = &b->lc;
@@ -866,12 +937,47 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	k.xchains = (bwag_xchain_t *)b->d_chains.p; k.xseeds = (bwag_xseed_t *)b->d_seeds.p; k.chain_rid = (int *)b->d_chain_rid.p; k.chain_frac = (float *)b->d_chain_frac.p;
 	k.chain_beg = (i64 *)b->d_chain_beg.p; k.reg_base = (i64 *)b->d_reg_base.p; k.n_chains = (int *)b->d_chain_cnt.p;
 	k.max_rlen = &c->d_cnt->max_rlen; k.n_many = &c->d_cnt->n_many; k.many = k4_lane_maxchains();
+	{   /* seed-level filter of long reads (mem_flt_chained_seeds, bwamem.c:626-641): threshold by read length, from the host's libm
+	     * (the value is truncated to an int: bwamem.c:628); no table if no read of the chunk can be long enough */
+		const int L = b->max_len;
+		int any = 0;
+		if (hbuf_reserve(&b->h_hsp, sizeof(int) * (size_t)(L + 2))) return 1;
+		int *tab = (int *)b->h_hsp.p;
+		for (int l = 0; l <= L; ++l) {
+			const double min_l = cp->min_chain_weight ? 1.1f * cp->min_chain_weight : 5.5f * log((double)l);
+			tab[l] = min_l > 0.05f * l ? -1 : (int)(par->a * min_l + .499);
+			if (tab[l] >= 0 && l >= cp->min_seed_len) any = 1;
+		}
+		if (any && !(getenv("BWA_B200_DEVICE_SEEDSW") && atoi(getenv("BWA_B200_DEVICE_SEEDSW")) == 0)) {
+			if (buf_reserve(&b->d_hsp, sizeof(int) * (size_t)(L + 2)) || buf_reserve(&b->d_flt_nchn, sizeof(int) * (size_t)(n + 1)) ||
+			    buf_reserve(&b->d_swtasks, sizeof(bwag_swtask_t) * (size_t)(ns + 1))) return 1;
+			H2D(c, b->d_hsp.p, tab, sizeof(int) * (size_t)(L + 1));
+			k.hsp_tab = (const int *)b->d_hsp.p; k.flt_nchn = (int *)b->d_flt_nchn.p;
+			k.sw_tasks = (bwag_swtask_t *)b->d_swtasks.p; k.n_swtasks = &c->d_cnt->n_swtasks;
+		} else if (any) return BWAG_DECLINED;   /* switched off: the caller chains these reads on the host */
+	}
 	CK(cudaEventRecord(c->ev0, c->stream));
 	BWAG_LAUNCH(k_chain, (n + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, c->stream, k);
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (fetch_counters(c)) return 1;
 	c->st.ms_chain += elapsed(c); ++c->st.n_launch;
+	if (k.hsp_tab) {
+		const int n_sw = (int)c->h_cnt->n_swtasks;
+		if (n_sw > 0) {
+			if (localsw_on_device(b, par, n_sw, SEEDSW_MAXLEN, SEEDSW_MAXLEN)) return 1;
+			if (fetch_counters(c)) return 1;
+			c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_sw;
+			if (c->h_cnt->flags & 32u) return set_err("seed filter: a local alignment exceeded the scratch capacity");
+		}
+		k.sw_res = (const bwag_swres_t *)b->d_swres.p;
+		CK(cudaEventRecord(c->ev0, c->stream));
+		BWAG_LAUNCH(k_chain_emit, (n + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, c->stream, k);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev1, c->stream));
+		if (fetch_counters(c)) return 1;
+		c->st.ms_chain += elapsed(c); ++c->st.n_launch;
+	}
 
 	/* extension over the chains that K3 left in HBM; K3 reported the longest reference window */
 	const int cap_q = (b->max_len + 3) & ~3;
@@ -1229,59 +1335,4 @@ extern "C" int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pe
 
 /* ------------------------------------------------------------------------------------------------ K6 */
 
-extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out)
-{
-	bwag_ctx_t *c = &b->lc;
-	CK(cudaSetDevice(c->device));
-	*out = 0;
-	if (n_tasks <= 0) return 0;
-	int cap_q = 16, cap_t = 16;
-	for (int t = 0; t < n_tasks; ++t) { if (tasks[t].qlen > cap_q) cap_q = tasks[t].qlen; if (tasks[t].tlen > cap_t) cap_t = tasks[t].tlen; }
-	cap_q = (cap_q + 15) & ~15; cap_t = (cap_t + 15) & ~15;
-	const int cap_n = cap_q + 16;                                       /* query length rounded up to a whole number of vectors */
-	/* warp per task (vectors in shared memory) when a block's share fits, else lane per task (everything in a global scratch slice) */
-	const size_t w_smem = (size_t)(8 * cap_n + cap_q) * 4;
-	const int warp_ok = w_smem <= K4_SMEM_MAX && !(getenv("BWA_B200_K6_WARP") && atoi(getenv("BWA_B200_K6_WARP")) == 0);
-	const i64 per_thread = warp_ok ? (((i64)cap_t * 8 + cap_t + 63) & ~(i64)63) : (((i64)cap_n * 8 + (i64)cap_t * 8 + cap_q + cap_t + 63) & ~(i64)63);   /* per warp / per lane */
-	int grid = c->n_sm * 16;
-	if (warp_ok) {
-#ifndef BWAG_CUSIM
-		int nb = 0;
-		CK(cudaFuncSetAttribute(k_localsw_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_SMEM_MAX));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_localsw_warp, 128, w_smem));
-		grid = c->n_sm * (nb > 0 ? nb : 1);
-#else
-		grid = 2;
-#endif
-		const i64 need = ((i64)n_tasks + 3) / 4;
-		if (grid > need) grid = (int)need;
-	} else {
-		const i64 need = ((i64)n_tasks + 63) / 64;
-		if (grid > need) grid = (int)need;
-		const i64 max_threads = ((i64)4 << 30) / per_thread;            /* bound the scratch to ~4 GB */
-		if ((i64)grid * 64 > max_threads) grid = (int)(max_threads / 64 > 0 ? max_threads / 64 : 1);
-	}
-	if (buf_reserve(&b->d_swtasks, sizeof(bwag_swtask_t) * (size_t)n_tasks) || buf_reserve(&b->d_swres, sizeof(bwag_swres_t) * (size_t)n_tasks) ||
-	    buf_reserve(&b->d_swscratch, (size_t)per_thread * (size_t)grid * (warp_ok ? 4 : 64)) || buf_reserve(&b->d_swpool, pool_bytes + 16) ||
-	    hbuf_reserve(&b->h_swres, sizeof(bwag_swres_t) * (size_t)n_tasks)) return 1;
-	if (reset_counters(c)) return 1;
-	H2D(c, b->d_swtasks.p, tasks, sizeof(bwag_swtask_t) * (size_t)n_tasks);
-	if (pool && pool_bytes) H2D(c, b->d_swpool.p, pool, pool_bytes);
-	SwArgs a;
-	memset(&a, 0, sizeof(a));
-	a.tasks = (const bwag_swtask_t *)b->d_swtasks.p; a.n_tasks = n_tasks; a.par = *par;
-	a.codes = (const uint8_t *)b->d_codes.p; a.pool = (const uint8_t *)b->d_swpool.p; a.res = (bwag_swres_t *)b->d_swres.p;
-	a.scratch = (unsigned char *)b->d_swscratch.p; a.per_thread = per_thread; a.cap_n = cap_n; a.cap_q = cap_q; a.cap_t = cap_t;
-	a.next_task = &c->d_cnt->next_task; a.flags = &c->d_cnt->flags;
-	CK(cudaEventRecord(c->ev0, c->stream));
-	if (warp_ok) BWAG_LAUNCH(k_localsw_warp, grid, 128, w_smem, c->stream, c->ix, a);
-	else BWAG_LAUNCH(k_localsw, grid, 64, 0, c->stream, c->ix, a);
-	CK(cudaGetLastError());
-	CK(cudaEventRecord(c->ev1, c->stream));
-	D2H(c, b->h_swres.p, b->d_swres.p, sizeof(bwag_swres_t) * (size_t)n_tasks);
-	if (fetch_counters(c)) return 1;
-	c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_tasks;
-	if (c->h_cnt->flags & 32u) return set_err("local alignment: a task exceeded the scratch capacity");
-	*out = (const bwag_swres_t *)b->h_swres.p;
-	return 0;
-}
+

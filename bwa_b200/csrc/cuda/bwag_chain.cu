@@ -248,6 +248,69 @@ __device__ int chain_weight(const ChainWs &w, const ChainRec &c) /* bwamem.c:239
 	return wq < 1 << 30 ? wq : (1 << 30) - 1;
 }
 
+#define SEEDSW_EXT 50          /* MEM_SHORT_EXT */
+#define SEEDSW_SHORT_LEN 200   /* MEM_SHORT_LEN */
+
+/* Per kept chain: reference window and seed order of mem_chain2aln (bwamem.c:666-691), written to the read's slice of the chain and
+ * seed arrays K4 reads.  by_score: seeds carry the score of the seed-level filter in `pad` (else a seed's score is its length);
+ * chains the filter emptied are skipped.  Returns the number of chains written. */
+__device__ int chain_emit(const ChainArgs &a, ChainWs &w, int rid, int l_query, int n_chn, const int *ord, float frac_rep, i64 sb, bool by_score)
+{
+	int n_out = 0;
+	{
+		i64 s_out = 0;
+		for (int i = 0; i < n_chn; ++i) {
+			const ChainRec &c = w.ch[ord[i]];
+			if (c.kept == 0 || c.n == 0) continue;
+			i64 rmax0 = a.l_pac << 1, rmax1 = 0;
+			int k = 0;
+			for (int s = c.first; s >= 0; s = w.sn[s].next, ++k) {
+				const SeedNode &t = w.sn[s];
+				const i64 bb = t.rbeg - (t.qbeg + dev_max_gap(a, t.qbeg));
+				const i64 ee = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + dev_max_gap(a, l_query - t.qbeg - t.len));
+				if (bb < rmax0) rmax0 = bb;
+				if (ee > rmax1) rmax1 = ee;
+				w.keys[k] = (u64)(by_score ? t.pad : t.len) << 32 | (u32)k;     /* seed score == seed length unless the seed-level filter ran */
+			}
+			if (rmax0 < 0) rmax0 = 0;
+			if (rmax1 > a.l_pac << 1) rmax1 = a.l_pac << 1;
+			const i64 first_rbeg = w.sn[c.first].rbeg;
+			if (rmax0 < a.l_pac && a.l_pac < rmax1) { if (first_rbeg < a.l_pac) rmax1 = a.l_pac; else rmax0 = a.l_pac; }
+			{   /* bns_fetch_seq: clamp to the contig holding the first seed (bntseq.c:426-441) */
+				const i64 mid = first_rbeg;
+				const int crid = dev_pos2rid(a, dev_depos(a, mid));
+				i64 far_beg = a.ctg_off[crid], far_end = far_beg + a.ctg_len[crid];
+				if (mid >= a.l_pac) { const i64 t = far_beg; far_beg = (a.l_pac << 1) - far_end; far_end = (a.l_pac << 1) - t; }
+				if (rmax0 < far_beg) rmax0 = far_beg;
+				if (rmax1 > far_end) rmax1 = far_end;
+			}
+			sort_keys(w.keys, c.n);
+			atomicMax(a.max_rlen, (int)(rmax1 - rmax0));
+			bwag_xchain_t xc;
+			xc.rmax0 = rmax0; xc.rmax1 = rmax1; xc.seed_off = (int32_t)(sb + s_out); xc.n_seeds = c.n;
+			/* seeds of the chain in list order -> temporary order array, then emitted in key order */
+			bwag_xseed_t *xs = a.xseeds + sb + s_out;
+			{
+				int *lst = w.idx;                          /* the kept list is dead by now: node ids in list order */
+				int q = 0;
+				for (int s = c.first; s >= 0; s = w.sn[s].next) lst[q++] = s;
+				for (int q2 = 0; q2 < c.n; ++q2) {
+					const SeedNode &t = w.sn[lst[(u32)w.keys[q2]]];
+					bwag_xseed_t o;
+					o.rbeg = t.rbeg; o.qbeg = t.qbeg; o.len = (u32)t.len | (w.keys[q2] == 0 ? BWAG_XSEED_ZEROKEY : 0);
+					xs[q2] = o;
+				}
+			}
+			a.xchains[sb + n_out] = xc;
+			a.chain_rid[sb + n_out] = c.rid;
+			a.chain_frac[sb + n_out] = frac_rep;
+			s_out += c.n;
+			++n_out;
+		}
+	}
+	return n_out;
+}
+
 __global__ void __launch_bounds__(K3_THREADS)
 k_chain(ChainArgs a)
 {
@@ -256,6 +319,7 @@ k_chain(ChainArgs a)
 	const int n_intv = a.intv_n[rid];
 	const int l_query = (int)(a.off[rid + 1] - a.off[rid]);
 	a.n_chains[rid] = 0; a.reg_base[rid] = 0; a.chain_beg[rid] = 0;
+	if (a.flt_nchn) a.flt_nchn[rid] = -1;
 	if (n_intv == 0 || l_query < a.min_seed_len) return;
 	const bwtintv_t *iv = a.intv + a.intv_beg[rid];
 	const i64 *sbeg = a.seed_beg + a.intv_beg[rid];
@@ -389,57 +453,86 @@ k_chain(ChainArgs a)
 			for (; i < n_chn; ++i) if (w.ch[ord[i]].kept < 3) w.ch[ord[i]].kept = 0;
 		}
 
-		/* ---- per kept chain: reference window and seed order of mem_chain2aln (bwamem.c:666-691) ---- */
-		i64 s_out = 0;
-		for (int i = 0; i < n_chn; ++i) {
-			const ChainRec &c = w.ch[ord[i]];
-			if (c.kept == 0) continue;
-			i64 rmax0 = a.l_pac << 1, rmax1 = 0;
-			int k = 0;
-			for (int s = c.first; s >= 0; s = w.sn[s].next, ++k) {
-				const SeedNode &t = w.sn[s];
-				const i64 bb = t.rbeg - (t.qbeg + dev_max_gap(a, t.qbeg));
-				const i64 ee = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + dev_max_gap(a, l_query - t.qbeg - t.len));
-				if (bb < rmax0) rmax0 = bb;
-				if (ee > rmax1) rmax1 = ee;
-				w.keys[k] = (u64)t.len << 32 | (u32)k;     /* seed score == seed length on this path */
-			}
-			if (rmax0 < 0) rmax0 = 0;
-			if (rmax1 > a.l_pac << 1) rmax1 = a.l_pac << 1;
-			const i64 first_rbeg = w.sn[c.first].rbeg;
-			if (rmax0 < a.l_pac && a.l_pac < rmax1) { if (first_rbeg < a.l_pac) rmax1 = a.l_pac; else rmax0 = a.l_pac; }
-			{   /* bns_fetch_seq: clamp to the contig holding the first seed (bntseq.c:426-441) */
-				const i64 mid = first_rbeg;
-				const int crid = dev_pos2rid(a, dev_depos(a, mid));
-				i64 far_beg = a.ctg_off[crid], far_end = far_beg + a.ctg_len[crid];
-				if (mid >= a.l_pac) { const i64 t = far_beg; far_beg = (a.l_pac << 1) - far_end; far_end = (a.l_pac << 1) - t; }
-				if (rmax0 < far_beg) rmax0 = far_beg;
-				if (rmax1 > far_end) rmax1 = far_end;
-			}
-			sort_keys(w.keys, c.n);
-			atomicMax(a.max_rlen, (int)(rmax1 - rmax0));
-			bwag_xchain_t xc;
-			xc.rmax0 = rmax0; xc.rmax1 = rmax1; xc.seed_off = (int32_t)(sb + s_out); xc.n_seeds = c.n;
-			/* seeds of the chain in list order -> temporary order array, then emitted in key order */
-			bwag_xseed_t *xs = a.xseeds + sb + s_out;
-			{
-				int *lst = w.idx;                          /* the kept list is dead by now: node ids in list order */
-				int q = 0;
-				for (int s = c.first; s >= 0; s = w.sn[s].next) lst[q++] = s;
-				for (int q2 = 0; q2 < c.n; ++q2) {
-					const SeedNode &t = w.sn[lst[(u32)w.keys[q2]]];
-					bwag_xseed_t o;
-					o.rbeg = t.rbeg; o.qbeg = t.qbeg; o.len = (u32)t.len | (w.keys[q2] == 0 ? BWAG_XSEED_ZEROKEY : 0);
-					xs[q2] = o;
+		if (a.hsp_tab && a.hsp_tab[l_query] >= 0) {
+			/* Long read: the seeds of the kept chains first pass the seed-level filter (mem_flt_chained_seeds, bwamem.c:626-641): every
+			 * seed shorter than 200 bp whose 50-bp-padded window is shorter than 200 bp on both axes is aligned locally (K6, next
+			 * launch) and dropped if it scores below hsp_tab[l_query].  This launch lists the alignments; k_chain_emit applies the
+			 * scores and writes the chains.  Chain records, seed lists and `ord` stay in the read's scratch slice meanwhile. */
+			for (int i = 0; i < n_chn; ++i) {
+				const ChainRec &c = w.ch[ord[i]];
+				if (c.kept == 0) continue;
+				for (int sx = c.first; sx >= 0; sx = w.sn[sx].next) {
+					SeedNode &t = w.sn[sx];
+					t.pad = -1;
+					if (t.len >= SEEDSW_SHORT_LEN) continue;
+					int qb = t.qbeg - SEEDSW_EXT, qe = t.qbeg + t.len + SEEDSW_EXT;
+					i64 rb = t.rbeg - SEEDSW_EXT, re = t.rbeg + t.len + SEEDSW_EXT;
+					const i64 mid = (t.rbeg + (t.rbeg + t.len)) >> 1;
+					if (qb < 0) qb = 0;
+					if (qe > l_query) qe = l_query;
+					if (rb < 0) rb = 0;
+					if (re > a.l_pac << 1) re = a.l_pac << 1;
+					if (rb < a.l_pac && a.l_pac < re) { if (mid < a.l_pac) re = a.l_pac; else rb = a.l_pac; }
+					if (qe - qb >= SEEDSW_SHORT_LEN || re - rb >= SEEDSW_SHORT_LEN) continue;
+					{   /* bns_fetch_seq: clamp to the contig that holds the middle of the seed (bntseq.c:426-441) */
+						const int crid = dev_pos2rid(a, dev_depos(a, mid));
+						i64 far_beg = a.ctg_off[crid], far_end = far_beg + a.ctg_len[crid];
+						if (mid >= a.l_pac) { const i64 x = far_beg; far_beg = (a.l_pac << 1) - far_end; far_end = (a.l_pac << 1) - x; }
+						if (rb < far_beg) rb = far_beg;
+						if (re > far_end) re = far_end;
+					}
+					const u32 slot = atomicAdd(a.n_swtasks, 1u);
+					bwag_swtask_t k;
+					k.t_beg = rb; k.q_beg = a.off[rid] + qb; k.tlen = (int)(re - rb); k.qlen = qe - qb;
+					k.xtra = 0;                       /* 16-bit kernel, score only: the filter does not look at the start */
+					k.flags = BWAG_SWF_QREAD | BWAG_SWF_TREF;
+					a.sw_tasks[slot] = k;
+					t.pad = (int)slot;
 				}
 			}
-			a.xchains[sb + n_out] = xc;
-			a.chain_rid[sb + n_out] = c.rid;
-			a.chain_frac[sb + n_out] = frac_rep;
-			s_out += c.n;
-			++n_out;
+			a.flt_nchn[rid] = n_chn;
+			a.chain_frac[sb] = frac_rep;          /* parked in the read's first output slot until k_chain_emit runs */
+			return;
 		}
+		n_out = chain_emit(a, w, rid, l_query, n_chn, ord, frac_rep, sb, false);
 	}
+	a.n_chains[rid] = n_out;
+	if (n_out > a.many) atomicAdd(a.n_many, 1);
+}
+
+/* K3b: the seed-level filter's verdicts are in (K6 ran on the tasks k_chain listed): drop the seeds that scored below the read's
+ * threshold, give the others their score (bwamem.c:631-639), then write the chains as k_chain would have. */
+__global__ void __launch_bounds__(K3_THREADS)
+k_chain_emit(ChainArgs a)
+{
+	const int rid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rid >= a.n_reads) return;
+	const int n_chn = a.flt_nchn[rid];
+	if (n_chn < 0) return;
+	const int l_query = (int)(a.off[rid + 1] - a.off[rid]);
+	const i64 sb = a.seed_beg[a.intv_beg[rid]];
+	const int min_hsp = a.hsp_tab[l_query];
+	ChainWs w;
+	w.bt = reinterpret_cast<BtNode *>(a.s_bt) + sb; w.sn = reinterpret_cast<SeedNode *>(a.s_sn) + sb; w.ch = reinterpret_cast<ChainRec *>(a.s_ch) + sb;
+	w.order = a.s_order + sb; w.idx = a.s_idx + sb; w.keys = a.s_keys + sb;
+	const float frac_rep = a.chain_frac[sb];
+	const int *ord = w.order;
+	for (int i = 0; i < n_chn; ++i) {
+		ChainRec &c = w.ch[ord[i]];
+		if (c.kept == 0) continue;
+		int prev = -1, kept = 0, first = -1;
+		for (int sx = c.first; sx >= 0; sx = w.sn[sx].next) {
+			SeedNode &t = w.sn[sx];
+			int sc = t.pad >= 0 ? a.sw_res[t.pad].score : -1;
+			if (sc >= 0 && sc < min_hsp) continue;             /* dropped: the list skips it */
+			t.pad = sc < 0 ? t.len * a.a : sc;
+			if (prev < 0) first = sx; else w.sn[prev].next = sx;
+			prev = sx; ++kept;
+		}
+		if (prev >= 0) w.sn[prev].next = -1;
+		c.first = first; c.last = prev; c.n = kept;
+	}
+	const int n_out = chain_emit(a, w, rid, l_query, n_chn, ord, frac_rep, sb, true);
 	a.n_chains[rid] = n_out;
 	if (n_out > a.many) atomicAdd(a.n_many, 1);
 }

@@ -59,6 +59,9 @@ struct ChainArgs {
 	i64 *chain_beg, *reg_base; int *n_chains;                          /* per read */
 	int *max_rlen;                                                     /* longest reference window of any chain (sizes K4's scratch) */
 	int *n_many; int many;                                             /* counts the reads with more than `many` chains (they go to the warp-per-read extension kernel) */
+	/* seed-level filter of long reads (mem_flt_chained_seeds): threshold by read length (-1: inactive; NULL: no read of the chunk is
+	 * long enough), the local alignments k_chain asks for, their results for k_chain_emit, per read the number of chains parked */
+	const int *hsp_tab; bwag_swtask_t *sw_tasks; u32 *n_swtasks; const bwag_swres_t *sw_res; int *flt_nchn;
 };
 
 struct RegCompactArgs {
@@ -136,6 +139,7 @@ struct SwArgs {
 	int *next_task; u32 *flags;
 };
 
+__global__ void k_chain_emit(ChainArgs a);
 __global__ void k_localsw(DevIndex ix, SwArgs a);
 __global__ void k_localsw_warp(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);

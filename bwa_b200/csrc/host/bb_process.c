@@ -1027,19 +1027,20 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 	sp.split_width = opt->split_width;
 	sp.max_occ = opt->max_occ;
 	sp.max_mem_intv = opt->max_mem_intv;
-	{   /* chaining on the device when every read of the chunk is short enough that the seed-level SW filter
-	     * (mem_flt_chained_seeds, bwamem.c:626-628) is inactive; otherwise (or if the stage is not provided) on the host */
+	{   /* chaining on the device, including the seed-level SW filter of long reads (mem_flt_chained_seeds, bwamem.c:626-641: K3 lists
+	     * the alignments, K6 makes them, K3b applies them); on the host only if the stage is not provided */
 		static int no_dev_chain = 0;   /* set once if the stage library has no device chaining (the CPU oracle of the tests) */
 		int dev_chain = !__atomic_load_n(&no_dev_chain, __ATOMIC_RELAXED) && !(getenv("BWA_B200_DEVICE_CHAIN") && atoi(getenv("BWA_B200_DEVICE_CHAIN")) == 0);
 		if (j->pre_n) {   /* regions inherited from the parent chunk */
 			j->cregs.n_regs = j->pre_n; j->cregs.reg_beg = j->pre_beg; j->cregs.regs = j->pre_regs; j->have_cregs = 1;
 			dev_chain = 0;
 		}
-		for (i = 0; i < n && dev_chain; ++i) {
-			int l = j->seqs[i].l_seq;
-			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l > 0 ? l : 1);
-			if (l > 0 && !(min_l > 0.05f * l)) dev_chain = 0;
-		}
+		if (getenv("BWA_B200_DEVICE_SEEDSW") && atoi(getenv("BWA_B200_DEVICE_SEEDSW")) == 0)   /* A/B switch: long reads chain and filter on the host */
+			for (i = 0; i < n && dev_chain; ++i) {
+				int l = j->seqs[i].l_seq;
+				double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l > 0 ? l : 1);
+				if (l > 0 && !(min_l > 0.05f * l)) dev_chain = 0;
+			}
 		if (dev_chain) {
 			bwag_chain_par_t cp;
 			bwag_contigs_t ctg;
@@ -1073,6 +1074,7 @@ static bwag_batch_t *run_to_regs(job_t *j, bwag_ctx_t *ctx, const bwag_sw_par_t 
 			}
 			free(c_off); free(c_len); free(c_alt);
 			if (rc == BWAG_UNSUPPORTED) { __atomic_store_n(&no_dev_chain, 1, __ATOMIC_RELAXED); dev_chain = 0; }
+			else if (rc == BWAG_DECLINED) dev_chain = 0;
 			else if (rc != 0) bb_fatal("mem_process_seqs", "chain+extend stage failed: %s", bwag_last_error());
 			else { j->have_cregs = 1; PH(j, "chain_extend"); }
 		}

@@ -103,3 +103,27 @@ def test_small_superblocks_emulated(data):
 def test_small_superblocks_gpu(data):
     from conftest import ROOT
     _sb16(os.path.join(ROOT, "tests", "_build", "bwa-b200-sb16"), data)
+
+
+def _check_seed_filter(binary, data, n_1k, n_pb, pb_len):
+    """Reads long enough for the seed-level filter (mem_flt_chained_seeds, >= ~770 bp): K3 lists the local alignments, K6 makes
+    them, K3b applies them -- counted, equal to the reference, and equal to chaining + filtering on the host (the switch)."""
+    for ref, kw, extra in (("two", dict(tag="sf1k%d" % n_1k, n=n_1k, length=1000, seed=41), []),
+                           ("two", dict(tag="sfpb%d" % n_pb, n=n_pb, length=pb_len, seed=42, err=(0.02, 0.05, 0.03)), ["-x", "pacbio"]),
+                           ("stress", dict(tag="sfst%d" % n_1k, n=n_1k, length=900, seed=43, err=(0.02, 0.01, 0.01), chimeric=0.1), ["-W", "30"])):
+        fa, fqs = data.reads(ref, **kw)
+        args = extra + ["-K", "100000000", "-t", "4", fa] + fqs
+        sam, _, _, _ = _counts(binary, args)
+        assert _counts.sw > 0, (ref, kw)
+        assert sam == ref_sam(args), (ref, kw)
+        s2, _, _, _ = _counts(binary, args, {"BWA_B200_DEVICE_SEEDSW": "0"})
+        assert _counts.sw == 0 and s2 == sam
+
+
+def test_seed_filter_on_device_emulated(data):
+    _check_seed_filter(CUSIMBIN, data, 8, 3, 3000)
+
+
+@pytest.mark.gpu
+def test_seed_filter_on_device_gpu(data):
+    _check_seed_filter(bwa_b200.CLI_PATH, data, 400, 16, 8000)

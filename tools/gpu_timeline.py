@@ -13,11 +13,16 @@ import sys
 
 
 def main():
-    path = sys.argv[1]
-    skip = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
+    import gzip
+    argv = [a for a in sys.argv[1:]]
+    window = 0
+    if "--window" in argv:
+        k = argv.index("--window"); window = int(argv[k + 1]); del argv[k:k + 2]
+    path = argv[0]
+    skip = float(argv[1]) if len(argv) > 1 else 0.0
     src = open(__file__.replace("tools/gpu_timeline.py", "bwa_b200/csrc/cuda/bwag_api.cu")).read().splitlines()
     iv = []
-    for line in open(path, errors="replace"):
+    for line in (gzip.open(path, "rt", errors="replace") if path.endswith(".gz") else open(path, errors="replace")):
         m = re.match(r"\[gputrace\] (\S+) (\d+) ([\d.]+) ([\d.]+)", line)
         if m:
             iv.append((float(m.group(3)), float(m.group(4)), m.group(1), int(m.group(2))))
@@ -28,6 +33,14 @@ def main():
     iv = [x for x in iv if x[0] >= t_first + skip]
     iv.sort()
     t0, t1 = iv[0][0], max(b for _, b, _, _ in iv)
+    if window:
+        k1_line = next(n + 1 for n, text in enumerate(src) if "ms_smem += elapsed" in text)
+        k1 = [x for x in iv if x[3] == k1_line]
+        if len(k1) >= window:
+            best = min(range(len(k1) - window + 1), key=lambda s_: k1[s_ + window - 1][1] - k1[s_][0])
+            t0, t1 = k1[best][0], k1[best + window - 1][1]
+            iv = [(max(a, t0), min(b, t1), l, n) for a, b, l, n in iv if b > t0 and a < t1]
+            print("window: %d seeding stages from the %dth, %.1f ms" % (window, best, t1 - t0))
     span = t1 - t0
     # union and overlap depth by sweeping the end points
     ev = sorted([(a, 1) for a, _, _, _ in iv] + [(b, -1) for _, b, _, _ in iv])
