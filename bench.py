@@ -473,7 +473,7 @@ def main():
             os.environ.pop(k, None)
         else:
             os.environ[k] = v
-    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_chain"] + ks["ms_extend"] + ks["ms_global"] + ks.get("ms_tail", 0.0)) / KSTEPS * a.steps
+    k_ms = (ks["ms_smem"] + ks["ms_sa"] + ks["ms_chain"] + ks["ms_extend"] + ks["ms_global"] + ks.get("ms_tail", 0.0) + ks.get("ms_localsw", 0.0)) / KSTEPS * a.steps
     vals = torch.tensor([dt, k_ms / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -516,7 +516,7 @@ def main():
                          "traffic_note": "DRAM bytes of k_smem + k_smem_fwd per launch from the committed ncu --set full capture (profiles/r2_traffic.json), scaled to the reads of one launch; null when the workload is not the captured one",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
-            "kernels_ms_per_step": {k: ks[k] / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_tail", "ms_h2d", "ms_d2h")},
+            "kernels_ms_per_step": {k: ks.get(k, 0.0) / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_tail", "ms_localsw", "ms_h2d", "ms_d2h")},
             "device_tail": {"reads": st["tail_reads"] // a.steps, "handed_back_to_host_postprocessing": st["tail_complex"] // a.steps,
                             "note": "stage 4 (bwag_tail.cu): de-duplication, CIGAR requests, pairing, MAPQ and SAM records on the device; reads it hands back are re-aligned with host-side post-processing"},
             "work_per_read": {"occ_touches": st["occ_touches"] / (n_reads * a.steps), "sa_touches": st["sa_touches"] / (n_reads * a.steps),

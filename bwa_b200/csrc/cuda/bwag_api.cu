@@ -551,18 +551,17 @@ static int fetch_counters(bwag_ctx_t *c)
 #define D2H(c, dst, src, bytes) do { CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (c)->stream)); (c)->st.d2h_bytes += (u64)(bytes); } while (0)
 /* BWA_B200_GPUTRACE=1: every timed stage also prints its start and end on the device clock (ms since the first context was made),
  * one line per stage and lane, so that tools/gpu_timeline.py can tell how much of a run the GPU sat idle and between which stages */
-static double elapsed_at(bwag_ctx_t *c, int line)
+static double elapsed_at(bwag_ctx_t *c, const char *stage, int line)
 {
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev0, c->ev1);
 	if (g_gputrace > 0) {
 		float t0 = 0, t1 = 0;
 		cudaEventElapsedTime(&t0, g_trace_ref, c->ev0); cudaEventElapsedTime(&t1, g_trace_ref, c->ev1);
-		fprintf(stderr, "[gputrace] %p %d %.3f %.3f\n", (void *)c, line, t0, t1);
+		fprintf(stderr, "[gputrace] %p %s:%d %.3f %.3f\n", (void *)c, stage, line, t0, t1);
 	}
 	return ms;
 }
-#define elapsed(c) elapsed_at(c, __LINE__)
 
 /* ------------------------------------------------------------------------------------------------ stage 1 */
 
@@ -654,7 +653,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		BWAG_LAUNCH(k_seed_post, (n + K1B_THREADS - 1) / K1B_THREADS, K1B_THREADS, 0, c->stream, a);   /* harmless if K1 overflowed: the run is repeated */
 		CK(cudaGetLastError());
 		if (fetch_counters(c)) return 1;
-		c->st.ms_smem += elapsed(c); c->st.n_launch += 2;
+		c->st.ms_smem += elapsed_at(c, "smem", __LINE__); c->st.n_launch += 2;
 		if (!(c->h_cnt->flags & 9u)) break;
 		if (attempt >= 6) return set_err("seeding: output pools keep overflowing (intervals %llu, seeds %llu)", (unsigned long long)c->h_cnt->n_intv, (unsigned long long)c->h_cnt->n_seeds);
 		if (c->h_cnt->flags & 1u) { /* pools too small: the counters say how much is needed */
@@ -677,7 +676,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;
-		c->st.ms_sa += elapsed(c); ++c->st.n_launch;
+		c->st.ms_sa += elapsed_at(c, "sa", __LINE__); ++c->st.n_launch;
 		c->st.sa_touches += c->h_cnt->sa_touches;
 	}
 	b->n_intv = n_intv; b->n_seeds = n_seeds; b->seeded = 1;
@@ -692,7 +691,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	if (n_seeds) D2H(c, b->h_rbeg.p, b->d_rbeg.p, 8 * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	out->intv_beg = (const int64_t *)b->h_intv_beg.p; out->intv_n = (const int32_t *)b->h_intv_n.p; out->intv = (const bwtintv_t *)b->h_intv.p;
 	out->seed_beg = (const int64_t *)b->h_seed_beg.p; out->rbeg = (const int64_t *)b->h_rbeg.p; out->n_intv = n_intv; out->n_seeds = n_seeds;
 	return 0;
@@ -801,7 +800,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	if (n_seeds) H2D(c, b->d_seeds.p, seeds, sizeof(bwag_xseed_t) * (size_t)n_seeds);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_h2d += elapsed(c);
+	c->st.ms_h2d += elapsed_at(c, "h2d", __LINE__);
 	ExtArgs a;
 	memset(&a, 0, sizeof(a));
 	a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n; a.par = *par;
@@ -814,7 +813,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	if (launch_extend(c, a, n)) return 1;
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (fetch_counters(c)) return 1;
-	c->st.ms_extend += elapsed(c); ++c->st.n_launch;
+	c->st.ms_extend += elapsed_at(c, "extend", __LINE__); ++c->st.n_launch;
 	if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
 	c->st.ext_cells += c->h_cnt->ext_cells;
 	if (hbuf_reserve(&b->h_regs, sizeof(bwag_xreg_t) * (size_t)(n_seeds + 1)) || hbuf_reserve(&b->h_nregs, 4 * (size_t)(n + 1))) return 1;
@@ -823,7 +822,7 @@ extern "C" int bwag_extend(bwag_batch_t *b, const bwag_sw_par_t *par, const int3
 	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->regs = (const bwag_xreg_t *)b->h_regs.p;
 	return 0;
 }
@@ -892,7 +891,7 @@ extern "C" int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tas
 	if (localsw_on_device(b, par, n_tasks, max_q, max_t)) return 1;
 	D2H(c, b->h_swres.p, b->d_swres.p, sizeof(bwag_swres_t) * (size_t)n_tasks);
 	if (fetch_counters(c)) return 1;
-	c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_tasks;
+	c->st.ms_localsw += elapsed_at(c, "localsw", __LINE__); ++c->st.n_launch; c->st.sw_tasks += (u64)n_tasks;
 	if (c->h_cnt->flags & 32u) return set_err("local alignment: a task exceeded the scratch capacity");
 	*out = (const bwag_swres_t *)b->h_swres.p;
 	return 0;
@@ -961,13 +960,13 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (fetch_counters(c)) return 1;
-	c->st.ms_chain += elapsed(c); ++c->st.n_launch;
+	c->st.ms_chain += elapsed_at(c, "chain", __LINE__); ++c->st.n_launch;
 	if (k.hsp_tab) {
 		const int n_sw = (int)c->h_cnt->n_swtasks;
 		if (n_sw > 0) {
 			if (localsw_on_device(b, par, n_sw, SEEDSW_MAXLEN, SEEDSW_MAXLEN)) return 1;
 			if (fetch_counters(c)) return 1;
-			c->st.ms_localsw += elapsed(c); ++c->st.n_launch; c->st.sw_tasks += (u64)n_sw;
+			c->st.ms_localsw += elapsed_at(c, "localsw", __LINE__); ++c->st.n_launch; c->st.sw_tasks += (u64)n_sw;
 			if (c->h_cnt->flags & 32u) return set_err("seed filter: a local alignment exceeded the scratch capacity");
 		}
 		k.sw_res = (const bwag_swres_t *)b->d_swres.p;
@@ -976,7 +975,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;
-		c->st.ms_chain += elapsed(c); ++c->st.n_launch;
+		c->st.ms_chain += elapsed_at(c, "chain", __LINE__); ++c->st.n_launch;
 	}
 
 	/* extension over the chains that K3 left in HBM; K3 reported the longest reference window */
@@ -1001,7 +1000,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (!out) {   /* the regions stay in HBM for bwag_tail_regs */
 		if (fetch_counters(c)) return 1;
-		c->st.ms_extend += elapsed(c); ++c->st.n_launch;
+		c->st.ms_extend += elapsed_at(c, "extend", __LINE__); ++c->st.n_launch;
 		if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
 		c->st.ext_cells += c->h_cnt->ext_cells;
 		b->regs_on_device = 1;
@@ -1018,7 +1017,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	BWAG_LAUNCH(k_regs_compact, (n + 127) / 128, 128, 0, c->stream, rc);
 	CK(cudaGetLastError());
 	if (fetch_counters(c)) return 1;
-	c->st.ms_extend += elapsed(c); c->st.n_launch += 2;
+	c->st.ms_extend += elapsed_at(c, "extend", __LINE__); c->st.n_launch += 2;
 	if (c->h_cnt->flags & 2u) return set_err("extension: a read or reference window exceeded the scratch capacity");
 	c->st.ext_cells += c->h_cnt->ext_cells;
 	const i64 n_regs = (i64)c->h_cnt->n_cig;
@@ -1029,7 +1028,7 @@ extern "C" int bwag_chain_extend(bwag_batch_t *b, const bwag_chain_par_t *cp, co
 	D2H(c, b->h_nregs.p, b->d_nregs.p, 4 * (size_t)n);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->reg_beg = (const int64_t *)b->h_creg_beg.p; out->regs = (const bwag_creg_t *)b->h_cregs.p;
 	return 0;
 }
@@ -1062,7 +1061,7 @@ extern "C" int bwag_fetch_cregs(bwag_batch_t *b, int n_sel, const int32_t *sel, 
 	D2H(c, b->h_nregs.p, d_out_n, 4 * (size_t)n_sel);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	out->n_regs = (const int32_t *)b->h_nregs.p; out->reg_beg = (const int64_t *)b->h_creg_beg.p; out->regs = (const bwag_creg_t *)b->h_cregs.p;
 	return 0;
 }
@@ -1124,7 +1123,7 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;
-		c->st.ms_global += elapsed(c); ++c->st.n_launch;
+		c->st.ms_global += elapsed_at(c, "global", __LINE__); ++c->st.n_launch;
 		if (c->h_cnt->flags & 4u) return set_err("global alignment: a task exceeded the scratch capacity");
 		if (!(c->h_cnt->flags & 16u)) break;
 		if (attempt >= 3) return set_err("global alignment: output pools keep overflowing");
@@ -1159,7 +1158,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	H2D(c, b->d_tasks.p, tasks, sizeof(bwag_gtask_t) * (size_t)n_tasks);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_h2d += elapsed(c);
+	c->st.ms_h2d += elapsed_at(c, "h2d", __LINE__);
 	b->tail_ready = 0;   /* the request pool of a preceding bwag_tail_regs is gone */
 	if (run_global(b, par, n_tasks, cap_q, cap_r, cap_z, n_aln, &nc, &nm)) return 1;
 	if (hbuf_reserve(&b->h_res, sizeof(bwag_gres_t) * (size_t)n_tasks) || hbuf_reserve(&b->h_cig, 4 * (size_t)(nc + 1)) || hbuf_reserve(&b->h_md, (size_t)nm + 16)) return 1;
@@ -1169,7 +1168,7 @@ extern "C" int bwag_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_task
 	if (nm) D2H(c, b->h_md.p, b->d_md.p, (size_t)nm);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	out->res = (const bwag_gres_t *)b->h_res.p; out->cigar = (const uint32_t *)b->h_cig.p; out->md = (const char *)b->h_md.p;
 	return 0;
 }
@@ -1241,7 +1240,7 @@ extern "C" int bwag_tail_regs(bwag_batch_t *b, const mem_opt_t *opt, const bwag_
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(c->ev1, c->stream));
 	if (fetch_counters(c)) return 1;
-	c->st.ms_tail += elapsed(c); ++c->st.n_launch;
+	c->st.ms_tail += elapsed_at(c, "tail", __LINE__); ++c->st.n_launch;
 	const i64 n_tasks = (i64)c->h_cnt->t_tasks;
 	if (n_tasks > cap || (i64)c->h_cnt->t_dregs > cap) return set_err("stage 4: more regions than seeds?");
 	if (n_tasks >= ((i64)1 << 31)) return set_err("stage 4: too many alignment requests in one batch; use smaller chunks");
@@ -1257,7 +1256,7 @@ extern "C" int bwag_tail_regs(bwag_batch_t *b, const mem_opt_t *opt, const bwag_
 	if (pe) D2H(c, b->h_pe_is.p, b->d_pe_is.p, 8 * (size_t)(n / 2));
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	b->tail_ready = 1;
 	if (pe_is) *pe_is = pe ? (const uint64_t *)b->h_pe_is.p : 0;
 	if (cflag) *cflag = (const uint8_t *)b->h_cflag.p;
@@ -1315,7 +1314,7 @@ extern "C" int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pe
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;
-		c->st.ms_tail += elapsed(c); ++c->st.n_launch;
+		c->st.ms_tail += elapsed_at(c, "tail", __LINE__); ++c->st.n_launch;
 		if ((i64)c->h_cnt->t_text <= cap_text) break;
 		if (attempt >= 2) return set_err("stage 4: the text pool keeps overflowing");
 		cap_text = (i64)c->h_cnt->t_text + 4096;
@@ -1327,7 +1326,7 @@ extern "C" int bwag_tail_sam(bwag_batch_t *b, const mem_opt_t *opt, const mem_pe
 	if (n_text) D2H(c, b->h_text.p, b->d_text.p, (size_t)n_text);
 	CK(cudaEventRecord(c->ev1, c->stream));
 	CK(stream_wait(c));
-	c->st.ms_d2h += elapsed(c);
+	c->st.ms_d2h += elapsed_at(c, "d2h", __LINE__);
 	c->st.tail_reads += (u64)n; c->st.tail_complex += c->h_cnt->t_complex;
 	out->rec = (const bwag_samrec_t *)b->h_rec.p; out->text = (const char *)b->h_text.p; out->n_text = n_text; out->n_complex = (int64_t)c->h_cnt->t_complex;
 	return 0;

@@ -20,12 +20,11 @@ def main():
         k = argv.index("--window"); window = int(argv[k + 1]); del argv[k:k + 2]
     path = argv[0]
     skip = float(argv[1]) if len(argv) > 1 else 0.0
-    src = open(__file__.replace("tools/gpu_timeline.py", "bwa_b200/csrc/cuda/bwag_api.cu")).read().splitlines()
     iv = []
     for line in (gzip.open(path, "rt", errors="replace") if path.endswith(".gz") else open(path, errors="replace")):
-        m = re.match(r"\[gputrace\] (\S+) (\d+) ([\d.]+) ([\d.]+)", line)
+        m = re.match(r"\[gputrace\] (\S+) (\S+) ([\d.]+) ([\d.]+)", line)
         if m:
-            iv.append((float(m.group(3)), float(m.group(4)), m.group(1), int(m.group(2))))
+            iv.append((float(m.group(3)), float(m.group(4)), m.group(1), m.group(2)))
     if not iv:
         print("no [gputrace] lines")
         return
@@ -34,8 +33,7 @@ def main():
     iv.sort()
     t0, t1 = iv[0][0], max(b for _, b, _, _ in iv)
     if window:
-        k1_line = next(n + 1 for n, text in enumerate(src) if "ms_smem += elapsed" in text)
-        k1 = [x for x in iv if x[3] == k1_line]
+        k1 = [x for x in iv if x[3].startswith("smem:") or x[3] == "654"]   # (654: the seeding timer's line in the first traces, profiles/r2_call8_*)
         if len(k1) >= window:
             best = min(range(len(k1) - window + 1), key=lambda s_: k1[s_ + window - 1][1] - k1[s_][0])
             t0, t1 = k1[best][0], k1[best + window - 1][1]
@@ -59,9 +57,9 @@ def main():
     for a, b, _, ln in iv:
         by[ln][0] += 1
         by[ln][1] += b - a
-    print("by stage (source line of the timer in bwag_api.cu): count, total ms, mean ms")
+    print("by stage (counter the timer adds to : its line in bwag_api.cu): count, total ms, mean ms")
     for ln, (n, tot) in sorted(by.items(), key=lambda kv: -kv[1][1]):
-        print("  %5d  %-60s %6d %10.1f %8.3f" % (ln, src[ln - 1].strip()[:60], n, tot, tot / n))
+        print("  %-16s %6d %10.1f %8.3f" % (ln, n, tot, tot / n))
     gaps.sort(reverse=True)
     print("idle gaps: %d, total %.1f ms; the 10 longest (ms, at ms):" % (len(gaps), sum(g for g, _ in gaps)), [(round(g, 2), round(t - t0, 1)) for g, t in gaps[:10]])
     hist = collections.Counter()
