@@ -48,7 +48,7 @@ struct Counters {
 	u64 n_intv, n_seeds;
 	u64 occ_touches, sa_touches, ext_cells, glb_cells;
 	u64 n_cig, n_md;
-	u32 flags, pad2;
+	u32 flags, n_pre;   /* n_pre: CIGARs made by the lane-per-request kernel (K5L) */
 	/* stage 4 */
 	u64 t_dregs, t_tasks, t_max_z, t_text, t_complex;
 	int t_max_lq, t_max_rl;
@@ -92,7 +92,7 @@ struct bwag_ctx {
 	bwag_stats_t st;
 	int sa_intv_disk;
 	/* scratch reused across batches */
-	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd, s_pack;
+	DevBuf s_k1, s_k1f, s_n3, s_eh, s_rseq, s_qseq, s_z, s_wcig, s_wmd, s_pack, s_zl;
 	int grid_k1, grid_k1f, grid_k2, grid_k4, grid_k5;
 #define N_SPARE 12
 	struct bwag_batch *spare[N_SPARE]; /* batch objects (stream, counters, scratch, device and pinned buffers) kept for later batches */
@@ -128,6 +128,7 @@ struct bwag_batch {
 	DevBuf d_dregs, d_dreg_beg, d_dreg_n, d_task_beg, d_cflag, d_pe_is, d_rec, d_text, d_ptab;
 	DevBuf d_swtasks, d_swres, d_swpool, d_swscratch; HostBuf h_swres;   /* K6 */
 	DevBuf d_hsp, d_flt_nchn; HostBuf h_hsp;   /* seed-level filter of long reads (K3/K3b) */
+	DevBuf d_pre_n, d_pre_score, d_pre_cig;    /* K5L results for the warp kernel */
 	DevBuf d_sel;
 	HostBuf h_pe_is, h_cflag, h_rec, h_text, h_ptab;
 	int tail_ready;              /* bwag_tail_regs ran on this batch */
@@ -291,7 +292,7 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	free_dev(&c->s_pack); free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd);
+	free_dev(&c->s_pack); free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd); free_dev(&c->s_zl);
 	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
 	if (c->dense_sa) cudaFree(c->dense_sa);
 	if (c->ktab) cudaFree(c->ktab);
@@ -501,6 +502,7 @@ static void batch_free(bwag_batch_t *b)
 	free_host(&b->h_res); free_host(&b->h_cig); free_host(&b->h_md);
 	free_dev(&b->d_sel); free_dev(&b->d_swtasks); free_dev(&b->d_swres); free_dev(&b->d_swpool); free_dev(&b->d_swscratch); free_host(&b->h_swres);
 	free_dev(&b->d_hsp); free_dev(&b->d_flt_nchn); free_host(&b->h_hsp);
+	free_dev(&b->d_pre_n); free_dev(&b->d_pre_score); free_dev(&b->d_pre_cig);
 	free_dev(&b->d_dregs); free_dev(&b->d_dreg_beg); free_dev(&b->d_dreg_n); free_dev(&b->d_task_beg); free_dev(&b->d_cflag); free_dev(&b->d_pe_is); free_dev(&b->d_rec); free_dev(&b->d_text); free_dev(&b->d_ptab);
 	free_host(&b->h_pe_is); free_host(&b->h_cflag); free_host(&b->h_rec); free_host(&b->h_text); free_host(&b->h_ptab);
 	free(b);
@@ -1100,6 +1102,25 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 	    buf_reserve(&c->s_qseq, n_warps * (size_t)(cap_q + 2)) || buf_reserve(&c->s_z, n_warps * (size_t)cap_z) ||
 	    buf_reserve(&c->s_wcig, n_warps * (size_t)cap_wcig * 4) || buf_reserve(&c->s_wmd, n_warps * (size_t)cap_wmd)) return 1;
 	if (buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
+	/* K5L for batches of short reads (the requests it cannot take fall through to the warp kernel one by one) */
+	int k5_lane = !c->baseline && cap_q <= K5L_QWORDS * 4 && n_tasks >= 64 && !(getenv("BWA_B200_K5_LANE") && atoi(getenv("BWA_B200_K5_LANE")) == 0);
+	const size_t k5l_smem = (size_t)K5L_RING * K5L_THREADS * 8 + (size_t)K5L_QWORDS * K5L_THREADS * 4;
+	const i64 k5l_cap_z = (i64)(K5L_RING - 1) * (cap_r < 1024 ? cap_r : 1024);   /* cells per lane: the widest band it takes x the longest window */
+	int k5l_grid = 0;
+	if (k5_lane) {
+#ifndef BWAG_CUSIM
+		int nb = 0;
+		CK(cudaFuncSetAttribute(k_global_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5l_smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_global_lane, K5L_THREADS, k5l_smem));
+		k5l_grid = c->n_sm * (nb > 0 ? nb : 1);
+#else
+		k5l_grid = 2;
+#endif
+		const i64 need = ((i64)n_tasks + K5L_THREADS - 1) / K5L_THREADS;
+		if (k5l_grid > need) k5l_grid = (int)need;
+		if (buf_reserve(&b->d_pre_n, 4 * (size_t)n_tasks) || buf_reserve(&b->d_pre_score, 4 * (size_t)n_tasks) || buf_reserve(&b->d_pre_cig, 4 * (size_t)K5L_MAXCIG * (size_t)n_tasks) ||
+		    buf_reserve(&c->s_zl, (size_t)k5l_cap_z * (size_t)k5l_grid * K5L_THREADS)) return 1;
+	}
 	i64 cap_cig = n_aln * 6 + 1024, cap_md = n_aln * 24 + 4096;   /* typical short-read sizes; grown on demand */
 	for (int attempt = 0;; ++attempt) {
 		if (buf_reserve(&b->d_cig, 4 * (size_t)cap_cig) || buf_reserve(&b->d_md, (size_t)cap_md)) return 1;
@@ -1115,6 +1136,18 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 		a.next_task = &c->d_cnt->next_task; a.cells = &c->d_cnt->glb_cells; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
+		if (k5_lane) {   /* DP + backtrack of the short-read CIGAR requests, one lane per request; the warp kernel then adds NM/MD and takes the rest */
+			GlbLaneArgs la;
+			memset(&la, 0, sizeof(la));
+			la.codes = a.codes; la.off = a.off; la.par = *par; la.tasks = a.tasks; la.n_tasks = n_tasks;
+			la.pre_n = (int *)b->d_pre_n.p; la.pre_score = (int *)b->d_pre_score.p; la.pre_cig = (u32 *)b->d_pre_cig.p;
+			la.z = (uint8_t *)c->s_zl.p; la.cap_z = k5l_cap_z; la.next_task = &c->d_cnt->next_task; la.cells = &c->d_cnt->glb_cells; la.n_pre = &c->d_cnt->n_pre;
+			BWAG_LAUNCH(k_global_lane, k5l_grid, K5L_THREADS, k5l_smem, c->stream, c->ix, la);
+			CK(cudaGetLastError());
+			CK(cudaMemsetAsync(&c->d_cnt->next_task, 0, sizeof(int), c->stream));
+			a.pre_n = la.pre_n; a.pre_score = la.pre_score; a.pre_cig = la.pre_cig;
+			++c->st.n_launch;
+		}
 		a.smem_per_warp = k5_sm ? k5_per_warp : 0; a.z_sm_bytes = k5_sm ? k5_zsm : 0;
 		if (k5_sm && k5_fast) BWAG_LAUNCH(k_global_sm_fast, grid, K5_THREADS, k5_smem, c->stream, c->ix, a);
 		else if (k5_sm) BWAG_LAUNCH(k_global_sm, grid, K5_THREADS, k5_smem, c->stream, c->ix, a);
@@ -1124,6 +1157,7 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 		CK(cudaEventRecord(c->ev1, c->stream));
 		if (fetch_counters(c)) return 1;
 		c->st.ms_global += elapsed_at(c, "global", __LINE__); ++c->st.n_launch;
+		if (k5_lane && getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] global alignment: lane-per-request kernel made %u of %d CIGARs, grid %d x %d\n", c->h_cnt->n_pre, n_tasks, k5l_grid, K5L_THREADS);
 		if (c->h_cnt->flags & 4u) return set_err("global alignment: a task exceeded the scratch capacity");
 		if (!(c->h_cnt->flags & 16u)) break;
 		if (attempt >= 3) return set_err("global alignment: output pools keep overflowing");

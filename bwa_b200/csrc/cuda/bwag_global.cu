@@ -214,10 +214,15 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 			__syncwarp();
 			const int want = tk.mode == BWAG_G_REG2ALN;
 			int w2 = tk.w, it = 0, last_sc = -(1 << 30);
+			const bool have_pre = a.pre_n && a.pre_n[tix] >= 0;   /* the lane-per-request kernel made score and CIGAR: only NM/MD are left */
 			for (;;) {
 				if (want) w2 = w2 < p.w << 2 ? w2 : p.w << 2;
 				n_cigar = 0;
-				if (lq == rlen && w2 == 0) {    /* no gap possible: score the diagonal */
+				if (have_pre) {
+					score = a.pre_score[tix]; n_cigar = a.pre_n[tix];
+					for (int x = lane; x < n_cigar; x += 32) cig[x] = a.pre_cig[(i64)tix * K5L_MAXCIG + x];
+					__syncwarp();
+				} else if (lq == rlen && w2 == 0) {    /* no gap possible: score the diagonal */
 					int sc = 0;
 					for (int x = lane; x < lq; x += 32) sc += s_mat[rseq[x] * 5 + qseq[x]];
 					score = __reduce_add_sync(FULL_MASK, sc);
@@ -305,7 +310,7 @@ __device__ __forceinline__ void global_body(const DevIndex &ix, const GlbArgs &a
 					l_md = __shfl_sync(FULL_MASK, l_md, 0);
 					NM = n_mm + n_gap;
 				}
-				if (!want) break;
+				if (!want || have_pre) break;
 				if (score == last_sc || w2 == p.w << 2) break;
 				last_sc = score;
 				w2 <<= 1;

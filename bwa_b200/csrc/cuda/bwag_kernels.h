@@ -95,6 +95,21 @@ struct GlbArgs {
 	int smem_per_warp;   /* k_global_sm: 8*(cap_q+2) + cap_r + cap_q + 2, rounded up to 16, + z_sm_bytes */
 	int z_sm_bytes;      /* backtrack bytes per warp kept in shared memory (tasks whose n_col x rows fit); 0: all in global memory */
 	int *next_task; u64 *cells; u32 *flags;
+	const int *pre_n, *pre_score; const u32 *pre_cig;   /* CIGARs the lane-per-request kernel made already (pre_n[t] < 0: none), K5L_MAXCIG words per request */
+};
+
+/* K5L (bwag_global_lane.cu): DP + backtrack of short-read CIGAR requests, one lane per request */
+#define K5L_THREADS 128
+#define K5L_RING 64      /* (h, e) slots per lane: bands up to 2w+2 = 64 */
+#define K5L_QWORDS 64    /* query words per lane: reads up to 256 bases */
+#define K5L_MAXCIG 16    /* CIGAR operations per request; longer ones are left to the warp kernel */
+struct GlbLaneArgs {
+	const uint8_t *codes; const i64 *off;
+	bwag_sw_par_t par;
+	const bwag_gtask_t *tasks; int n_tasks;
+	int *pre_n, *pre_score; u32 *pre_cig;
+	uint8_t *z; i64 cap_z;   /* direction bytes: cap_z cells per lane, byte-interleaved by lane within a warp's slice */
+	int *next_task; u64 *cells; u32 *n_pre;
 };
 
 /* ---- stage 4 (device tail, bwag_tail.cu) ---- */
@@ -140,6 +155,7 @@ struct SwArgs {
 };
 
 __global__ void k_chain_emit(ChainArgs a);
+__global__ void k_global_lane(DevIndex ix, GlbLaneArgs a);
 __global__ void k_localsw(DevIndex ix, SwArgs a);
 __global__ void k_localsw_warp(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);

@@ -856,6 +856,9 @@ static int tail_wanted(const job_t *j)
 	if (!env || j->sub_map || j->no_tail || __atomic_load_n(&g_no_tail, __ATOMIC_RELAXED)) return 0;
 	if (j->opt->flag & (MEM_F_ALL | MEM_F_REF_HDR | MEM_F_PRIMARY5)) return 0;
 	if ((j->opt->flag & MEM_F_PE) && (j->n & 1)) return 0;
+	/* long noisy reads (thousands of bases) have many regions, region merges and supplementary records: stage 4 would hand nearly all
+	 * of them back after having made their CIGAR requests once already (measured on the pacbio workload: profiles/r2_call9_*) */
+	if (j->n > 0 && j->off && j->off[j->n] / j->n > 1500) return 0;
 	return 1;
 }
 

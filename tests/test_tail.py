@@ -21,6 +21,7 @@ def _counts(binary, args, env=None):
     for m in re.finditer(rb"stage 4: (\d+) reads, (\d+) handed back", p.stderr):
         took += int(m.group(1)); handed += int(m.group(2))
     _counts.sw = sum(int(m.group(1)) for m in re.finditer(rb"K6: (\d+) local alignments", p.stderr))
+    _counts.k5l = sum(int(m.group(1)) for m in re.finditer(rb"lane-per-request kernel made (\d+) of", p.stderr))
     return strip_pg(p.stdout), took, handed, b"lane-per-read kernel" in p.stderr
 
 
@@ -40,9 +41,11 @@ def _check(binary, data, n_c1, n_stress):
         assert took >= n_stress and 0 < handed < took
         if paired:
             assert _counts.sw > 0          # mate rescue ran its local alignments on the device (K6)
-        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}, {"BWA_B200_DEVICE_SW": "0"}):
+        assert _counts.k5l > 0             # CIGARs of the short-read requests came from the lane-per-request kernel (K5L)
+        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}, {"BWA_B200_DEVICE_SW": "0"}, {"BWA_B200_K5_LANE": "0"}):
             s2, t2, _, l2 = _counts(binary, args, env)
             assert s2 == sam
+            assert (_counts.k5l == 0) == ("BWA_B200_K5_LANE" in env)
             assert (t2 == 0) == ("BWA_B200_TAIL" in env) and l2 == ("BWA_B200_K4_LANE" not in env)
             assert (_counts.sw == 0) == ("BWA_B200_DEVICE_SW" in env or not paired)
     # options that keep stage 4 out (-a lists secondary hits, -5 reorders) and options it handles (-M, -Y, -P, -S)
