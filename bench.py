@@ -277,11 +277,14 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="a named workload (overrides --layout/--reads/--read-len): BASELINE.json configs 4-5 and a repeat-rich reference")
     ap.add_argument("--threads", type=int, default=0, help="host threads (0 = all cores / ranks)")
     ap.add_argument("--workdir", default=os.environ.get("BWA_B200_BENCH_DIR", "/tmp/bwa_b200_bench"))
-    ap.add_argument("--cpu-sample", type=int, default=100000)
+    ap.add_argument("--cpu-sample", type=int, default=None, help="reads of the workload the CPU reference aligns (default: 1 M for the cpu_baseline of the B200 arm, the whole step for --impl reference)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("BWA_B200_INFLIGHT", "3")), help="mem_process_seqs calls issued at a time (host threads), as bwa-b200 mem does")
     ap.add_argument("--worker", action="store_true", help="(internal) run the measurement in this process; without it a parent process supervises the run")
     ap.add_argument("--dense-sa", type=int, default=int(os.environ.get("BWA_B200_DENSE_SA", "0")))
     a = ap.parse_args()
+    a.cpu_sample_given = a.cpu_sample is not None
+    if a.cpu_sample is None:
+        a.cpu_sample = 1_000_000   # ~10 s of `bwa mem -t 16`: the whole step of the default workload
     wl = dict(WORKLOADS[a.workload]) if a.workload else {}
     if wl:
         a.layout, a.read_len, a.reads = wl["layout"], wl["read_len"], wl["reads"]
@@ -310,15 +313,16 @@ def main():
         if rank != 0:
             return
         fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, 0, paired, **wl_kw)
-        n_sample = min(a.reads, a.cpu_sample)
-        vals = []
+        # a step = the whole per-step workload (1 M reads: ~10 s on 16 cores) unless --cpu-sample asks for less; the run stops taking
+        # further steps once ~4 minutes are used (the steps done are the ones reported)
+        n_sample = min(a.reads, a.cpu_sample if a.cpu_sample_given else a.reads)
+        vals, t_run = [], time.time()
         for s in range(a.warmup + a.steps):
             t0 = time.time()
             v, n = time_reference(fa, fq, n_sample, ncores, mem_args=mem_args)
-            if s >= a.warmup:
+            if s >= a.warmup or time.time() - t_run > 240:
                 vals.append((v, n, time.time() - t0))
-            if s == 0 and (time.time() - t0) * (a.warmup + a.steps) > 240:   # keep the whole run within minutes
-                vals.append((v, n, time.time() - t0))
+            if time.time() - t_run > 240:   # keep the whole run within minutes
                 break
         v = sum(x[0] for x in vals) / len(vals)
         line = {"impl": "reference", "metric": "reads_per_sec", "value": v, "unit": "reads/s", "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup,

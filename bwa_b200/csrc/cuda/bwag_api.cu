@@ -81,6 +81,8 @@ static int hbuf_reserve(HostBuf *b, size_t bytes)
 
 struct bwag_ctx {
 	int device, own_blob, n_sm;
+	int imported;                /* blob, dense SA and table belong to another process (bwag_ctx_import): closed, not freed */
+	size_t map_bytes[3];         /* (emulator build) sizes of the three shared mappings */
 	void *blob;
 	DevIndex ix;
 	u64 *dense_sa;
@@ -287,6 +289,130 @@ extern "C" bwag_ctx_t *bwag_ctx_create(int device, const bwt_t *bwt, int64_t l_p
 	return c;
 }
 
+/* ------------------------------------------------------------------------------------------------ residency across processes */
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <signal.h>
+#include <errno.h>
+#include <unistd.h>
+struct ShareFile {
+	char magic[8];
+	int32_t version, device, pid, dense_shift, ktab_k, pad;
+	u64 l_pac, blob_bytes, dense_bytes, dense_n, ktab_bytes;
+#ifndef BWAG_CUSIM
+	cudaIpcMemHandle_t h[3];     /* blob, dense SA sample, short-string table */
+#else
+	char name[3][64];            /* emulator build: "device memory" is host memory, the three regions travel as POSIX shared memory */
+#endif
+};
+#define SHARE_MAGIC "BWAB2SHR"
+
+static void shared_close(bwag_ctx_t *c)
+{
+	void *p[3] = { c->blob, (void *)c->dense_sa, (void *)c->ktab };
+	for (int i = 0; i < 3; ++i) {
+		if (!p[i]) continue;
+#ifndef BWAG_CUSIM
+		cudaIpcCloseMemHandle(p[i]);
+#else
+		munmap(p[i], c->map_bytes[i]);
+#endif
+	}
+}
+
+extern "C" void bwag_ctx_unexport(const char *path)
+{
+#ifdef BWAG_CUSIM
+	ShareFile f;
+	FILE *fp = fopen(path, "rb");
+	if (fp) { if (fread(&f, sizeof(f), 1, fp) == 1 && memcmp(f.magic, SHARE_MAGIC, 8) == 0) for (int i = 0; i < 3; ++i) if (f.name[i][0]) shm_unlink(f.name[i]); fclose(fp); }
+#endif
+	unlink(path);
+}
+
+extern "C" int bwag_ctx_export(bwag_ctx_t *c, const char *path)
+{
+	ShareFile f;
+	BlobHeader h;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(&h, c->blob, sizeof(h), cudaMemcpyDeviceToHost));
+	memset(&f, 0, sizeof(f));
+	memcpy(f.magic, SHARE_MAGIC, 8);
+	f.version = 1; f.device = c->device; f.pid = (int32_t)getpid(); f.l_pac = h.l_pac; f.blob_bytes = h.total;
+	f.dense_shift = c->dense_sa ? c->ix.sa_shift : -1; f.dense_n = c->dense_sa ? c->ix.n_sa : 0; f.dense_bytes = c->dense_sa ? c->ix.n_sa * 8 + 32 : 0;
+	f.ktab_k = c->ktab ? c->ix.ktab_k : 0; f.ktab_bytes = c->ktab ? (((((u64)1 << (2 * (c->ix.ktab_k + 1))) - 4) / 3) + 2) * 16 : 0;
+	{
+		void *p[3] = { c->blob, (void *)c->dense_sa, (void *)c->ktab };
+		const u64 bytes[3] = { f.blob_bytes, f.dense_bytes, f.ktab_bytes };
+		for (int i = 0; i < 3; ++i) {
+			if (!p[i]) continue;
+#ifndef BWAG_CUSIM
+			(void)bytes;
+			CK(cudaIpcGetMemHandle(&f.h[i], p[i]));
+#else
+			snprintf(f.name[i], sizeof(f.name[i]), "/bwa_b200.%d.%d", (int)getpid(), i);
+			int fd = shm_open(f.name[i], O_CREAT | O_RDWR | O_TRUNC, 0600);
+			if (fd < 0 || ftruncate(fd, (off_t)bytes[i]) != 0) return set_err("cannot create shared memory %s: %s", f.name[i], strerror(errno));
+			void *m = mmap(0, bytes[i], PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+			close(fd);
+			if (m == MAP_FAILED) return set_err("cannot map shared memory %s: %s", f.name[i], strerror(errno));
+			memcpy(m, p[i], bytes[i]);
+			munmap(m, bytes[i]);
+#endif
+		}
+	}
+	{   /* the file appears complete or not at all */
+		char tmp[4096];
+		snprintf(tmp, sizeof(tmp), "%s.tmp%d", path, (int)getpid());
+		FILE *fp = fopen(tmp, "wb");
+		if (!fp || fwrite(&f, sizeof(f), 1, fp) != 1 || fclose(fp) != 0 || rename(tmp, path) != 0) return set_err("cannot write %s: %s", path, strerror(errno));
+	}
+	return 0;
+}
+
+extern "C" bwag_ctx_t *bwag_ctx_import(const char *path, int64_t l_pac)
+{
+	ShareFile f;
+	FILE *fp = fopen(path, "rb");
+	if (!fp) { set_err("no resident index at %s", path); return 0; }
+	const size_t got = fread(&f, sizeof(f), 1, fp);
+	fclose(fp);
+	if (got != 1 || memcmp(f.magic, SHARE_MAGIC, 8) != 0 || f.version != 1) { set_err("%s is not a resident-index descriptor of this version", path); return 0; }
+	if (kill((pid_t)f.pid, 0) != 0 && errno == ESRCH) { set_err("the process that kept the index resident (pid %d) is gone", f.pid); return 0; }
+	if (l_pac >= 0 && (u64)l_pac != f.l_pac) { set_err("the resident index is not this index (l_pac %llu, expected %lld)", (unsigned long long)f.l_pac, (long long)l_pac); return 0; }
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device is visible: this library has no CPU path"); return 0; }
+	if (f.device >= ndev) { set_err("the resident index lives on device %d, which this process does not see", f.device); return 0; }
+	CKP(cudaSetDevice(f.device));
+	void *p[3] = { 0, 0, 0 };
+	const u64 bytes[3] = { f.blob_bytes, f.dense_bytes, f.ktab_bytes };
+	for (int i = 0; i < 3; ++i) {
+		if (!bytes[i]) continue;
+#ifndef BWAG_CUSIM
+		if (cudaIpcOpenMemHandle(&p[i], f.h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			set_err("cannot open the resident index of pid %d: %s", f.pid, cudaGetErrorString(cudaGetLastError()));
+			for (int k = 0; k < i; ++k) if (p[k]) cudaIpcCloseMemHandle(p[k]);
+			return 0;
+		}
+#else
+		int fd = shm_open(f.name[i], O_RDONLY, 0);
+		void *m = fd >= 0 ? mmap(0, bytes[i], PROT_READ, MAP_SHARED, fd, 0) : MAP_FAILED;
+		if (fd >= 0) close(fd);
+		if (m == MAP_FAILED) { set_err("cannot map the resident index of pid %d (%s): %s", f.pid, f.name[i], strerror(errno)); for (int k = 0; k < i; ++k) if (p[k]) munmap(p[k], bytes[k]); return 0; }
+		p[i] = m;
+#endif
+	}
+	bwag_ctx_t *c = bwag_ctx_from_blob(f.device, p[0], 0);
+	if (!c) return 0;
+	c->imported = 1;
+	for (int i = 0; i < 3; ++i) c->map_bytes[i] = bytes[i];
+	if (p[1]) { c->dense_sa = (u64 *)p[1]; c->ix.sa = c->dense_sa; c->ix.sa_shift = f.dense_shift; c->ix.n_sa = f.dense_n; }
+	if (p[2]) { c->ktab = (ulonglong2 *)p[2]; c->ix.ktab = c->ktab; c->ix.ktab_k = f.ktab_k; }
+	return c;
+}
+
 extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 {
 	if (!c) return;
@@ -294,10 +420,13 @@ extern "C" void bwag_ctx_destroy(bwag_ctx_t *c)
 	cudaStreamSynchronize(c->stream);
 	free_dev(&c->s_pack); free_dev(&c->s_k1); free_dev(&c->s_k1f); free_dev(&c->s_n3); free_dev(&c->s_eh); free_dev(&c->s_rseq); free_dev(&c->s_qseq); free_dev(&c->s_z); free_dev(&c->s_wcig); free_dev(&c->s_wmd); free_dev(&c->s_zl);
 	for (int i = 0; i < N_SPARE; ++i) if (c->spare[i]) { batch_free(c->spare[i]); c->spare[i] = 0; }
-	if (c->dense_sa) cudaFree(c->dense_sa);
-	if (c->ktab) cudaFree(c->ktab);
+	if (c->imported) shared_close(c);
+	else {
+		if (c->dense_sa) cudaFree(c->dense_sa);
+		if (c->ktab) cudaFree(c->ktab);
+		if (c->own_blob && c->blob) cudaFree(c->blob);
+	}
 	if (c->d_tail) cudaFree(c->d_tail);
-	if (c->own_blob && c->blob) cudaFree(c->blob);
 	cudaFree(c->d_cnt); cudaFreeHost(c->h_cnt);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_wait);
 	cudaStreamDestroy(c->stream);
@@ -309,7 +438,7 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 	int s = 0;
 	while ((1 << s) < intv) ++s;
 	if ((1 << s) != intv || s > c->ix.sa_shift) return set_err("dense suffix-array interval must be a power of two not above the current %d", 1 << c->ix.sa_shift);
-	if (s == c->ix.sa_shift) return 0;
+	if (s == c->ix.sa_shift || c->imported) return 0;   /* an imported context keeps the sample of the process that owns the memory */
 	CK(cudaSetDevice(c->device));
 	u64 n_out = (c->ix.seq_len + (u64)intv) / (u64)intv, *out = 0;
 	{   /* leave room for the batch buffers */
@@ -332,6 +461,7 @@ extern "C" int bwag_ctx_densify_sa(bwag_ctx_t *c, int intv)
 extern "C" int bwag_ctx_build_ktab(bwag_ctx_t *c, int K)
 {
 	CK(cudaSetDevice(c->device));
+	if (c->imported) return 0;   /* the table, or its absence, is the owner's */
 	if (K == 0) {   /* as deep as strings still have a few dozen occurrences (their intervals span two Occ blocks): 14 at 3 Gbp = 5.7 GB */
 		int lg = 0;
 		while (lg < 31 && ((u64)1 << (2 * (lg + 1))) <= c->ix.seq_len) ++lg;   /* floor(log4(seq_len)) */

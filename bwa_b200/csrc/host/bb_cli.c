@@ -376,6 +376,7 @@ int main_mem(int argc, char *argv[])
 		if ((e = getenv("BWA_B200_SHARD_IDX")) != 0 && (run.shard_idx = fopen(e, "w")) == 0) bb_fatal("main_mem", "fail to open '%s' for writing", e);
 	}
 	if (g_cli_idx) run.idx = g_cli_idx;
+	else if ((run.idx = bb_idx_from_resident(argv[optind])) != 0) {}   /* kept on the GPU by `bwa-b200 shm` */
 	else if ((run.idx = bwa_idx_load(argv[optind], BWA_IDX_ALL)) == 0) return 1;
 	if (ignore_alt) for (i = 0; i < run.idx->bns->n_seqs; ++i) run.idx->bns->anns[i].is_alt = 0;
 	run.fn1 = argv[optind + 1];
@@ -463,9 +464,10 @@ int main(int argc, char *argv[])
 	bb_puts(&pg, "@PG\tID:bwa\tPN:bwa\tVN:" BB_VERSION "\tCL:");
 	for (i = 0; i < argc; ++i) { if (i) bb_putc(&pg, ' '); bb_puts(&pg, argv[i]); }
 	bwa_pg = pg.s;
+	if (argc >= 2 && strcmp(argv[1], "shm") == 0) { free(pg.s); return bb_shm_main(argc - 1, argv + 1); }
 	if (argc < 2 || strcmp(argv[1], "mem") != 0) {
 		fprintf(stderr, "\nProgram: bwa-b200 (BWA-MEM seed-and-extend on NVIDIA B200)\nVersion: %s\n\nUsage:   bwa-b200 mem [options] <idxbase> <in1.fq> [in2.fq]\n\n", BB_VERSION);
-		fprintf(stderr, "The index is the one written by the reference's `bwa index`.\n\n");
+		fprintf(stderr, "         bwa-b200 shm [-d|-l] [idxbase]      keep an index resident on the GPU between runs\n\nThe index is the one written by the reference's `bwa index`.\n\n");
 		return 1;
 	}
 	ret = main_mem(argc - 1, argv + 1);

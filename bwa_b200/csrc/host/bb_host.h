@@ -135,6 +135,10 @@ int bb_matesw(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, con
 int bb_sam_pe(bb_samctx_t sc[2], const mem_pestat_t pes[4], uint64_t id, bseq1_t s[2], mem_alnreg_v a[2], int rescue_done);
 int bb_rescue_pe(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4], bseq1_t s[2], mem_alnreg_v a[2], bb_swcache_t *swc);   /* swc == NULL: align on the host (SSE2) */
 
+/* ---- an index that stays on the GPU between runs (bb_resident.c) ---- */
+bwaidx_t *bb_idx_from_resident(const char *prefix);
+int bb_shm_main(int argc, char *argv[]);
+
 /* ---- FASTA/FASTQ input (bb_fastq.c) ---- */
 typedef struct bb_fq bb_fq_t;
 bb_fq_t *bb_fq_open(const char *fn);

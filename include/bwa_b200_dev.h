@@ -51,6 +51,16 @@ int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
  * suffix pairs equal over 8192 bases (undecided).  For indexes that did not come from `bwa index` (bwa_b200/index_build.py). */
 int bwag_ctx_verify(bwag_ctx_t *ctx, uint64_t first, uint64_t stride, uint64_t out[4]);
 
+/* Residency across processes (the reference's counterpart is `bwa shm`, bwashm.c:16-122, which parks the index
+ * in POSIX shared memory so that later `bwa mem` runs skip the load).  Device memory lives and dies with its process, so here a
+ * process that keeps the index resident (`bwa-b200 shm idxbase`) EXPORTS it -- CUDA IPC handles of the blob, the dense suffix-array
+ * sample and the short-string table, written to `path` -- and any other process on the same GPU IMPORTS it: a context over the
+ * exporter's memory, ready in milliseconds, nothing read from the index files and nothing uploaded.  bwag_ctx_import returns NULL
+ * (bwag_last_error says why) if the file is missing or stale (exporter gone, other device, other index size). */
+int bwag_ctx_export(bwag_ctx_t *ctx, const char *path);
+bwag_ctx_t *bwag_ctx_import(const char *path, int64_t l_pac);
+void bwag_ctx_unexport(const char *path);   /* remove what bwag_ctx_export left behind (the exporter calls it before it exits) */
+
 /* on != 0: batches begun from now on run the first formulation of the extension / global-alignment row sweeps and do no
  * short-string table lookups (same results, the configuration measured in round 1); 0: the defaults again.  The host's
  * start-up self-check compares the two on a few hundred reads drawn from the reference and stays on the baseline if

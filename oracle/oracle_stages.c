@@ -79,6 +79,9 @@ int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth) { (void)ctx; (void)depth; re
 void bwag_ctx_baseline(bwag_ctx_t *ctx, int on) { (void)ctx; (void)on; }
 int bwag_is_emulator(void) { return 2; }
 int bwag_ctx_verify(bwag_ctx_t *ctx, uint64_t first, uint64_t stride, uint64_t out[4]) { (void)ctx; (void)first; (void)stride; (void)out; return BWAG_UNSUPPORTED; }
+int bwag_ctx_export(bwag_ctx_t *ctx, const char *path) { (void)ctx; (void)path; return BWAG_UNSUPPORTED; }
+bwag_ctx_t *bwag_ctx_import(const char *path, int64_t l_pac) { (void)path; (void)l_pac; return 0; }
+void bwag_ctx_unexport(const char *path) { (void)path; }
 /* stage 4 (the post-processing on the device) has no oracle restatement: the host-side post-processing IS the checker for it */
 int bwag_ctx_set_contigs(bwag_ctx_t *ctx, int n_seqs, const int64_t *offset, const int32_t *len, const uint8_t *is_alt, const char *const *names) { (void)ctx; (void)n_seqs; (void)offset; (void)len; (void)is_alt; (void)names; return BWAG_UNSUPPORTED; }
 int bwag_localsw(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, const bwag_swtask_t *tasks, const uint8_t *pool, size_t pool_bytes, const bwag_swres_t **out) { (void)b; (void)par; (void)n_tasks; (void)tasks; (void)pool; (void)pool_bytes; (void)out; return BWAG_UNSUPPORTED; }
