@@ -1232,8 +1232,11 @@ static int run_global(bwag_batch_t *b, const bwag_sw_par_t *par, int n_tasks, in
 	    buf_reserve(&c->s_qseq, n_warps * (size_t)(cap_q + 2)) || buf_reserve(&c->s_z, n_warps * (size_t)cap_z) ||
 	    buf_reserve(&c->s_wcig, n_warps * (size_t)cap_wcig * 4) || buf_reserve(&c->s_wmd, n_warps * (size_t)cap_wmd)) return 1;
 	if (buf_reserve(&b->d_res, sizeof(bwag_gres_t) * (size_t)n_tasks)) return 1;
-	/* K5L for batches of short reads (the requests it cannot take fall through to the warp kernel one by one) */
-	int k5_lane = !c->baseline && cap_q <= K5L_QWORDS * 4 && n_tasks >= 64 && !(getenv("BWA_B200_K5_LANE") && atoi(getenv("BWA_B200_K5_LANE")) == 0);
+	/* K5L for batches of short reads (the requests it cannot take fall through to the warp kernel one by one).  Off by default: in
+	 * its first form it takes 32 consecutive requests per warp, of which only the quarter that needs a DP is live (8.5 of 32 lanes
+	 * active, 30 ms vs the warp kernel's 11.3 ms per 1 M reads: profiles/r2_call10_*); it needs the requests compacted and bucketed by
+	 * band first.  BWA_B200_K5_LANE=1 switches it on (exact: tests/test_tail.py runs both). */
+	int k5_lane = !c->baseline && cap_q <= K5L_QWORDS * 4 && n_tasks >= 64 && getenv("BWA_B200_K5_LANE") && atoi(getenv("BWA_B200_K5_LANE")) != 0;
 	const size_t k5l_smem = (size_t)K5L_RING * K5L_THREADS * 8 + (size_t)K5L_QWORDS * K5L_THREADS * 4;
 	const i64 k5l_cap_z = (i64)(K5L_RING - 1) * (cap_r < 1024 ? cap_r : 1024);   /* cells per lane: the widest band it takes x the longest window */
 	int k5l_grid = 0;

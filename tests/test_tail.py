@@ -41,11 +41,10 @@ def _check(binary, data, n_c1, n_stress):
         assert took >= n_stress and 0 < handed < took
         if paired:
             assert _counts.sw > 0          # mate rescue ran its local alignments on the device (K6)
-        assert _counts.k5l > 0             # CIGARs of the short-read requests came from the lane-per-request kernel (K5L)
-        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}, {"BWA_B200_DEVICE_SW": "0"}, {"BWA_B200_K5_LANE": "0"}):
+        for env in ({"BWA_B200_TAIL": "0"}, {"BWA_B200_K4_LANE": "0"}, {"BWA_B200_DEVICE_SW": "0"}, {"BWA_B200_K5_LANE": "1"}):
             s2, t2, _, l2 = _counts(binary, args, env)
             assert s2 == sam
-            assert (_counts.k5l == 0) == ("BWA_B200_K5_LANE" in env)
+            assert (_counts.k5l > 0) == ("BWA_B200_K5_LANE" in env)   # the opt-in lane-per-request global alignment made CIGARs
             assert (t2 == 0) == ("BWA_B200_TAIL" in env) and l2 == ("BWA_B200_K4_LANE" not in env)
             assert (_counts.sw == 0) == ("BWA_B200_DEVICE_SW" in env or not paired)
     # options that keep stage 4 out (-a lists secondary hits, -5 reorders) and options it handles (-M, -Y, -P, -S)
