@@ -296,7 +296,10 @@ def main(argv=None):
         print("[bwa_b200.multi] striped ingest: %s" % ("%d batches over %d ranks" % (plan[2], world) if plan else "off (switched off, or the input cannot be cut by byte offset): every rank parses everything"), file=sys.stderr)
     args = ["mem"] + [part if (k > 0 and argv[k - 1] in ("-o", "-f")) else a for k, a in enumerate(argv)]
     arr = (C.c_char_p * (len(args) + 1))(*[a.encode() for a in args], None)
+    import time
+    t_align = time.time()
     rc = L.main_mem(len(args), arr)
+    t_align = time.time() - t_align
     ok = torch.tensor([0 if rc == 0 else 1])
     if world > 1:
         if on_gpu:
@@ -304,6 +307,8 @@ def main(argv=None):
         dist.all_reduce(ok)      # also the barrier before the merge
     if int(ok[0]) != 0:
         raise SystemExit("bwa_b200.multi: a rank failed")
+    if rank == 0:
+        print("[bwa_b200.multi] rank 0 spent %.2f s in main_mem (index already replicated)" % t_align, file=sys.stderr)
     if rank == 0:
         parts = [("%s.part%d" % (out, r), "%s.part%d.idx" % (out, r)) for r in range(world)]
         merge_parts(out, parts)

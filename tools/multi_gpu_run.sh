@@ -1,15 +1,31 @@
 #!/bin/bash
-# N-GPU check (default 2): the weak-scaling benchmark line under torchrun, then the multi-GPU `mem` launcher against the reference's SAM
+# N-GPU check (default 2): the weak-scaling benchmark line under torchrun, then the multi-GPU `mem` launcher: parity against the
+# reference on a small case, and the wall time of its alignment phase on a 16 M-read file with striped ingest on and off
 N=${1:-2}
 cd /root/repo; mkdir -p gpurun_out; O=gpurun_out
 t0=$(date +%s); lap() { echo "[lap] $1 $(( $(date +%s) - t0 )) s"; }
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 4 --warmup 3 > $O/scale_n$N.json 2> $O/scale_n$N.err
-echo "bench rc=$?"; tail -c 900 $O/scale_n$N.json; echo; grep "replicated" $O/scale_n$N.err; lap bench
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 8 --warmup 3 > $O/scale_n$N.json 2> $O/scale_n$N.err
+echo "bench rc=$?"; python -c "
+import json; d=json.loads(open('$O/scale_n$N.json').read().strip().splitlines()[-1]); print('N=%d: e2e %.0f reads/s, %.1f ms/step, value %.0f' % (d['n_gpus'], d['e2e']['value'], d['ms_per_step'], d['value']))"; grep "replicated" $O/scale_n$N.err; lap bench
 D=/tmp/mg; mkdir -p $D
 python tools/gen_data.py ref --out $D/ref.fa --contigs 3 --len 150000 --seed 11 && oracle/_ref/bwa index $D/ref.fa 2>/dev/null
 python tools/gen_data.py reads --ref $D/ref.fa --out $D/r -n 20000 --len 150 --seed 12 --paired
 oracle/_ref/bwa mem -v 1 -t 8 -K 600000 $D/ref.fa $D/r_1.fq $D/r_2.fq 2>/dev/null | grep -v '^@PG' > $D/ref.sam
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 -m bwa_b200.multi -v 1 -t 8 -K 600000 -o $D/out.sam $D/ref.fa $D/r_1.fq $D/r_2.fq > $O/multi_n$N.log 2>&1
-echo "multi rc=$?"; grep -v '^@PG' $D/out.sam > $D/out.nopg.sam
+echo "multi rc=$?"; grep -v '^@PG' $D/out.sam > $D/out.nopg.sam; grep "striped" $O/multi_n$N.log
 echo "multi-GPU mem: ref lines $(wc -l < $D/ref.sam), ours $(wc -l < $D/out.nopg.sam), differing $(diff $D/ref.sam $D/out.nopg.sam | grep -c '^<')" | tee -a $O/multi_n$N.log
-lap multi
+lap multi_parity
+# throughput of the launcher's alignment phase: 16 M reads (the bench's 1 M-read PE files, 16 times over) against the 3 Gbp index
+W=/tmp/bwa_b200_bench; FA=$W/ref_3000.fa; A=$W/reads_pe1000000_150_e10_r0_1.fq; B=$W/reads_pe1000000_150_e10_r0_2.fq
+if [ -f $A ]; then
+  for k in 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16; do cat $A; done > $D/big_1.fq; for k in 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16; do cat $B; done > $D/big_2.fq; ls -la $D/big_1.fq | awk '{print $5, $9}'; lap bigfile
+  for striped in 1 0; do
+    BWA_B200_STRIPED=$striped timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$striped -m bwa_b200.multi -v 1 -t 16 -o $D/big$striped.sam $FA $D/big_1.fq $D/big_2.fq > $O/multi_big_n${N}_striped$striped.log 2>&1
+    echo "N=$N striped=$striped rc=$?: $(grep -h 'striped ingest\|spent' $O/multi_big_n${N}_striped$striped.log | tr '\n' ' ')"; lap big_striped$striped
+  done
+  cmp <(grep -v '^@PG' $D/big1.sam) <(grep -v '^@PG' $D/big0.sam) && echo "striped and unstriped outputs identical ($(wc -l < $D/big1.sam) lines)"
+  /usr/bin/time -f "1 GPU bwa-b200 mem: %e s wall incl. index load" bwa_b200/bwa-b200 mem -v 3 -t 16 $FA $D/big_1.fq $D/big_2.fq 2> $O/single_big.err > $D/big_single.sam; grep "Real time\|wall" $O/single_big.err | tail -2
+  cmp <(grep -v '^@PG' $D/big1.sam) <(grep -v '^@PG' $D/big_single.sam) && echo "N=$N output identical to the single-GPU output"
+  lap single
+fi
+ls -la $O/ | awk '{print $5, $9}' | grep -i "multi\|scale\|single"
