@@ -24,7 +24,7 @@ if [ -f $A ]; then
     echo "N=$N striped=$striped rc=$?: $(grep -h 'striped ingest\|spent' $O/multi_big_n${N}_striped$striped.log | tr '\n' ' ')"; lap big_striped$striped
   done
   cmp <(grep -v '^@PG' $D/big1.sam) <(grep -v '^@PG' $D/big0.sam) && echo "striped and unstriped outputs identical ($(wc -l < $D/big1.sam) lines)"
-  /usr/bin/time -f "1 GPU bwa-b200 mem: %e s wall incl. index load" bwa_b200/bwa-b200 mem -v 3 -t 16 $FA $D/big_1.fq $D/big_2.fq 2> $O/single_big.err > $D/big_single.sam; grep "Real time\|wall" $O/single_big.err | tail -2
+  timeout 900 python -m bwa_b200.multi -v 1 -t 16 -o $D/big_single.sam $FA $D/big_1.fq $D/big_2.fq > $O/single_big.log 2>&1; echo "N=1 rc=$?: $(grep -h 'spent' $O/single_big.log)"
   cmp <(grep -v '^@PG' $D/big1.sam) <(grep -v '^@PG' $D/big_single.sam) && echo "N=$N output identical to the single-GPU output"
   lap single
 fi
