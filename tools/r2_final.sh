@@ -19,6 +19,8 @@ PY
 python bench.py --steps 20 --warmup 5 > $O/r2f_pe.json 2>$O/r2f_pe.err; echo "default workload, the driver's 20 steps (python bench.py --steps 20 --warmup 5):"; line $O/r2f_pe.json; lap pe
 python bench.py > $O/r2f_pe_default.json 2>/dev/null; echo "python bench.py (no flags):"; line $O/r2f_pe_default.json; lap pe_default
 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2f_ref.json 2>/dev/null; echo "reference arm:"; cut -c1-400 $O/r2f_ref.json; lap ref
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2f_launches.csv python bench.py --worker --steps 1 --warmup 1 --cpu-sample 2000 > $O/r2f_launches.log 2>&1; lap ncu_launches
+BWA_B200_SELFCHECK=0 BWA_B200_BENCH_VERIFY=0 BWA_B200_LANES=1 BWA_B200_CHUNK=1000000 timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:^(k_pack_reads|k_smem|k_smem_fwd|k_seed_post|k_sa|k_chain|k_extend_lane|k_extend_sm_fast|k_tail_regs|k_global_sm_fast|k_tail_sam)$' -s 11 -c 11 -o $O/r2f_ncu -f python bench.py --worker --inflight 1 --steps 1 --warmup 1 --cpu-sample 2000 > $O/r2f_ncu.log 2>&1; lap ncu_full
 python bench.py --layout se --steps 20 --warmup 5 --cpu-sample 100000 > $O/r2f_se.json 2>/dev/null; echo "SE:"; line $O/r2f_se.json; lap se
 for w in len36 len75 len300 len1000 pacbio stress; do
   timeout 900 python bench.py --worker --workload $w --steps 4 --warmup 2 > $O/r2f_wl_$w.json 2>$O/r2f_wl_$w.err; echo "workload $w:"; line $O/r2f_wl_$w.json; lap wl_$w
@@ -35,7 +37,5 @@ if [ -f $R1 ]; then
   bwa_b200/bwa-b200 shm -d; echo "after shm -d: $(bwa_b200/bwa-b200 shm -l | wc -l) resident, GPU memory used: $(nvidia-smi --query-gpu=memory.used --format=csv,noheader)"
 fi
 lap resident
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2f_launches.csv python bench.py --worker --steps 1 --warmup 1 --cpu-sample 2000 > $O/r2f_launches.log 2>&1; lap ncu_launches
-BWA_B200_SELFCHECK=0 BWA_B200_BENCH_VERIFY=0 BWA_B200_LANES=1 BWA_B200_CHUNK=1000000 timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:^(k_pack_reads|k_smem|k_smem_fwd|k_seed_post|k_sa|k_chain|k_extend_lane|k_extend_sm_fast|k_tail_regs|k_global_sm_fast|k_tail_sam)$' -s 11 -c 11 -o $O/r2f_ncu -f python bench.py --worker --inflight 1 --steps 1 --warmup 1 --cpu-sample 2000 > $O/r2f_ncu.log 2>&1; lap ncu_full
 BWA_B200_SELFCHECK=0 BWA_B200_BENCH_VERIFY=0 BWA_B200_LANES=1 timeout 600 ncu --set full --import-source on --clock-control none -k 'regex:^(k_localsw_warp|k_chain_emit)$' -c 2 -o $O/r2f_ncu_k6 -f python bench.py --worker --workload len1000 --inflight 1 --steps 1 --warmup 1 --cpu-sample 200 > $O/r2f_ncu_k6.log 2>&1; lap ncu_k6
 ls -la $O/r2f_* | awk '{print $5, $9}'
