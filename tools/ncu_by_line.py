@@ -15,7 +15,7 @@ for l in open(sys.argv[2]):
     if not inside: continue
     m = re.search(r'//## File "(.*)", line (\d+)', l)
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
-    if re.match(r'\s+/\*[0-9a-f]{4}\*/', l): lines.append(cur)
+    if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): lines.append(cur)
 print("sass rows", len(rows), "disasm instructions", len(lines), file=sys.stderr)
 n = min(len(rows), len(lines))
 inst = defaultdict(int); samp = defaultdict(int); thr = defaultdict(int)
