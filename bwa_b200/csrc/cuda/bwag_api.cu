@@ -145,6 +145,9 @@ static void free_host(HostBuf *b) { if (b->p) cudaFreeHost(b->p); b->p = 0; b->c
 #define BWAG_L2_FETCH_DEFAULT 0   /* 0: leave the device's setting */
 #endif
 #define K1_SMEM_MAX (200 * 1024)
+#ifndef K1_COMPACT_DEFAULT
+#define K1_COMPACT_DEFAULT 1   /* k_smem_c unless BWA_B200_K1_COMPACT=0 */
+#endif
 #ifdef BWAG_CUSIM
 #define BWAG_KTAB_MAX_AUTO 5     /* the emulator builds the table one fiber per entry: keep it small */
 #else
@@ -217,6 +220,9 @@ static int pick_grid(bwag_ctx_t *c)
 	CK(cudaGetDeviceProperties(&prop, c->device));
 	c->n_sm = prop.multiProcessorCount;
 	CK(cudaFuncSetAttribute(k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_MAX));
+#ifndef K1_PACKED8
+	CK(cudaFuncSetAttribute(k_smem_c, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_MAX));
+#endif
 	c->grid_k1 = 0;   /* depends on the shared read slots: chosen per launch */
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem_fwd, K1F_THREADS, 0)); c->grid_k1f = c->n_sm * (nb > 0 ? nb : 1);
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sa, K2_THREADS, 0)); c->grid_k2 = c->n_sm * (nb > 0 ? nb : 1);
@@ -340,7 +346,7 @@ extern "C" int bwag_ctx_export(bwag_ctx_t *c, const char *path)
 	CK(cudaMemcpy(&h, c->blob, sizeof(h), cudaMemcpyDeviceToHost));
 	memset(&f, 0, sizeof(f));
 	memcpy(f.magic, SHARE_MAGIC, 8);
-	f.version = 1; f.device = c->device; f.pid = (int32_t)getpid(); f.l_pac = h.l_pac; f.blob_bytes = h.total;
+	f.version = 2; f.device = c->device; f.pid = (int32_t)getpid(); f.l_pac = h.l_pac; f.blob_bytes = h.total;
 	f.dense_shift = c->dense_sa ? c->ix.sa_shift : -1; f.dense_n = c->dense_sa ? c->ix.n_sa : 0; f.dense_bytes = c->dense_sa ? c->ix.n_sa * 8 + 32 : 0;
 	f.ktab_k = c->ktab ? c->ix.ktab_k : 0; f.ktab_bytes = c->ktab ? (((((u64)1 << (2 * (c->ix.ktab_k + 1))) - 4) / 3) + 2) * 16 : 0;
 	{
@@ -379,7 +385,7 @@ extern "C" bwag_ctx_t *bwag_ctx_import(const char *path, int64_t l_pac)
 	if (!fp) { set_err("no resident index at %s", path); return 0; }
 	const size_t got = fread(&f, sizeof(f), 1, fp);
 	fclose(fp);
-	if (got != 1 || memcmp(f.magic, SHARE_MAGIC, 8) != 0 || f.version != 1) { set_err("%s is not a resident-index descriptor of this version", path); return 0; }
+	if (got != 1 || memcmp(f.magic, SHARE_MAGIC, 8) != 0 || f.version != 2) { set_err("%s is not a resident-index descriptor of this version", path); return 0; }
 	if (kill((pid_t)f.pid, 0) != 0 && errno == ESRCH) { set_err("the process that kept the index resident (pid %d) is gone", f.pid); return 0; }
 	if (l_pac >= 0 && (u64)l_pac != f.l_pac) { set_err("the resident index is not this index (l_pac %llu, expected %lld)", (unsigned long long)f.l_pac, (long long)l_pac); return 0; }
 	int ndev = 0;
@@ -726,6 +732,14 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		qstride = 0; pstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16;
 #endif
 		if (smem > K1_SMEM_MAX) { qstride = 0; pstride = 0; nstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
+		/* k_smem_c (compact candidate lists) needs the table and both copies of the read in shared memory; BWA_B200_K1_COMPACT=0 selects k_smem */
+		bool k1c = false;
+#ifndef K1_PACKED8
+		{
+			const char *e = getenv("BWA_B200_K1_COMPACT");
+			k1c = (e ? atoi(e) != 0 : K1_COMPACT_DEFAULT) && qstride && pstride;
+		}
+#endif
 		int grid;
 #ifdef BWAG_CUSIM
 		grid = 2;
@@ -736,7 +750,8 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 			static int cap = -1;
 			int nb;
 			if (cap < 0) { const char *e = getenv("BWA_B200_K1_BLOCKS"); cap = e ? atoi(e) : 0; }
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, smem));
+			if (k1c) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem_c, K1_THREADS, smem));
+			else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smem, K1_THREADS, smem));
 			if (cap > 0 && nb > cap) nb = cap;
 			grid = c->n_sm * (nb > 0 ? nb : 1);
 		}
@@ -779,6 +794,10 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 			CK(cudaGetLastError());
 			++c->st.n_launch;
 		}
+#ifndef K1_PACKED8
+		if (k1c) BWAG_LAUNCH(k_smem_c, grid, K1_THREADS, smem, c->stream, c->ix, a);
+		else
+#endif
 		BWAG_LAUNCH(k_smem, grid, K1_THREADS, smem, c->stream, c->ix, a);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev1, c->stream));

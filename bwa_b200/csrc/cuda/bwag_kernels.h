@@ -162,6 +162,9 @@ __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
 __global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
+#ifndef K1_PACKED8
+__global__ void k_smem_c(DevIndex ix, SeedArgs a);   /* short candidates as mask bits, matches appended at once (bwag_smem.cu) */
+#endif
 __global__ void k_smem_fwd(DevIndex ix, SeedArgs a);
 __global__ void k_seed_post(SeedArgs a);
 __global__ void k_sa(DevIndex ix, SaArgs a);

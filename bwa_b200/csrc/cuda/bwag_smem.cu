@@ -112,6 +112,8 @@ __device__ __forceinline__ void extend_step(const DevIndex &ix, u64 xs, u64 xo, 
  *            reference counts them (bwt.c:194-197): the third pass jumps over that chain and adds t to its counter;
  *   index  = (4^len - 4)/3 + sum_t s[t] * 4^t   (all shorter strings first; first base in the low bits). */
 __device__ __forceinline__ u32 ktab_off(int len) { return ((1u << (2 * len)) - 4u) / 3u; }
+#define KTAB_BT_SHIFT 22                       /* count field of an entry: chain touches in the low bits, the backward-touch bit on top */
+#define KTAB_CT_MASK ((1u << KTAB_BT_SHIFT) - 1u)
 
 /* bwt_extend as extend_step, or -- for lanes with tab set -- the table entry tidx instead.  t12: the touches of this one
  * extension as the reference counts them (valid for every lane whose xs/e2 are the real input interval); ct: the entry's
@@ -216,7 +218,24 @@ __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K)
 			extend_step(ix, x1, x0, x2, 3 - (int)(key >> (2 * t) & 3u), touches, o_s, o_o, o_x2);
 			x0 = o_o; x1 = o_s; x2 = o_x2;
 		}
-		tab[e] = pack_ent(x0, x1, x2, (u32)touches);
+		/* bit 22 of the count field: the backward extension that produces this string from its suffix s[1..] touches two of the
+		 * reference's 128-symbol blocks (bwt.c:194-197) rather than one.  k_smem_c keeps its short candidates as end positions
+		 * only, so it cannot derive that from the input interval as k_smem does. */
+		u32 bt = 0;
+		if (len >= 2) {
+			u64 y0, y1, y2, td = 0;
+			INIT_INTV((int)(key >> 2 & 3u), y0, y1, y2);
+			for (int t = 2; t < len; ++t) {
+				u64 o_s, o_o, o_x2;
+				extend_step(ix, y1, y0, y2, 3 - (int)(key >> (2 * t) & 3u), td, o_s, o_o, o_x2);
+				y0 = o_o; y1 = o_s; y2 = o_x2;
+			}
+			const u64 k = y0 - 1, l = y0 - 1 + y2;
+			const bool kv = k != (u64)-1, lv = l != (u64)-1;
+			const u64 kp = k - (k >= ix.primary), lp = l - (l >= ix.primary);
+			bt = (kv && lv && (kp >> 7) == (lp >> 7)) ? 0u : 1u;
+		}
+		tab[e] = pack_ent(x0, x1, x2, (u32)touches | bt << KTAB_BT_SHIFT);
 	}
 }
 
@@ -270,7 +289,7 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
 		u32 ct;
 		int t12;
 		extend_step3(ix, ik1, ik0, ik2, jump ? 0 : 3 - q[i], jump, tidx, 0, t12, o_s, o_o, o_x2, ct);
-		if (jump) { ik0 = o_o; ik1 = o_s; ik2 = o_x2; i = x + kj; touches += ct; continue; }
+		if (jump) { ik0 = o_o; ik1 = o_s; ik2 = o_x2; i = x + kj; touches += ct & KTAB_CT_MASK; continue; }
 		touches += (u64)t12;
 		if (o_x2 < a.max_mem_intv && i - x >= a.min_seed_len) {     /* bwt.c:366-375 */
 			if (o_x2 > 0) {
@@ -561,6 +580,225 @@ k_smem(DevIndex ix, SeedArgs a)
 		if ((threadIdx.x & 31) == 0 && f) atomicOr(a.flags, f);
 	}
 }
+
+#ifndef K1_PACKED8
+/* ------------------------------------------------------------------------------------------------ K1, compact candidate lists
+ * k_smem with two changes to what a lane keeps between extensions (same extensions, same results, same touch count):
+ *
+ *  - SHORT CANDIDATES ARE ONE BIT.  A backward sweep visits its candidates q[i+1..end) longest first and extends each by q[i].
+ *    When the extended string q[i..end) is at most kc = min(table depth, min_seed_len) bases long, the extension is a table
+ *    lookup keyed by the string alone: the candidate's interval is never read, and if the candidate dies it is shorter than
+ *    min_seed_len, so bwt_smem1's caller drops it (bwamem.c:152).  Such a candidate is fully described by its end, and ends
+ *    of short candidates lie within kc - 1 positions of the sweep's start sx: one bit (end - sx - 1) of a 32-bit mask per
+ *    list.  Lists are ordered by decreasing end, so the candidates with an interval ("long", next string > kc bases) come
+ *    first, in the shared/global slots as before, followed by the mask's bits from high to low.  A candidate whose next string
+ *    outgrows kc is written out with the interval its table entry returned.  In k_smem 53 % of the list accesses went to the
+ *    per-lane global tails (entries 4..); here a list rarely has more than 3 long candidates (a 3 Gbp text has few repeats of 15+
+ *    bases), so the sweep's inner loop is register work between two table/Occ loads.
+ *  - NO PER-CALL RESULT ARRAY.  A match that bwt_smem1 would return is appended to the read's list at once if it is long
+ *    enough (k_smem parked it in a global array and copied it at the end of the call to restore ascending order; K1b sorts
+ *    the read's list by (start, end) anyway, and equal keys are equal intervals).
+ * The touch count of a short candidate's extension comes from the backward-touch bit of the table entry (k_ktab_build). */
+#undef TURN_AROUND
+#undef CALL_DONE
+#define TURN_AROUND() do { ret = (int)ikend; pl ^= 1; n_prev = n_curr; n_curr = 0; rm = cm; cm = 0; rev_first = 1; i = sx - 1; j = 0; st = ST_BWD; } while (0)
+#define CALL_DONE() do { if (pass == 0) x = ret; st = ST_IDLE; } while (0)
+#define EMIT(X0, X1, X2, S, E) do { \
+		if ((int)((E) - (u32)(S)) >= a.min_seed_len) { \
+			if (mem_n < a.cap_mem) { st_intv(mem + mem_n, X0, X1, X2, (u64)(S) << 32 | (E)); ++mem_n; } else overflow |= 8; \
+		} \
+	} while (0)
+/* a candidate for the next backward step (string of NEXT_LEN bases then): a mask bit or a list entry */
+#define PUSH_CAND(NEXT_LEN, X0, X1, X2, E) do { \
+		if ((NEXT_LEN) <= kc) cm |= 1u << ((int)(E) - sx - 1); \
+		else if (n_curr < a.cap_list) { ENT_ST(pl ^ 1, n_curr, X0, X1, X2, E); ++n_curr; } else overflow |= 8; \
+	} while (0)
+
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
+k_smem_c(DevIndex ix, SeedArgs a)
+{
+#ifdef BWAG_CUSIM
+	ulonglong2 *sl = reinterpret_cast<ulonglong2 *>(cusim_dyn_smem);
+#else
+	extern __shared__ ulonglong2 k1_dyn[];
+	ulonglong2 *sl = k1_dyn;
+#endif
+	/* shared: as k_smem: [2 lists][K1_SLOTS][K1_THREADS] entries, K1_THREADS read slots of qstride bytes, K1_THREADS packed copies of pstride bytes */
+	const uint8_t *sq = reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)threadIdx.x * a.qstride;
+	u32 *sp = reinterpret_cast<u32 *>(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)K1_THREADS * a.qstride + (size_t)threadIdx.x * a.pstride));
+	const int ktk = ix.ktab_k;                                           /* the host launches this kernel only with the table and both copies of the reads in shared memory */
+	const int kc = ktk < a.min_seed_len ? ktk : a.min_seed_len;
+	sl += threadIdx.x;
+	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+	/* per-lane global scratch, laid out as for k_smem (the per-call result array in the middle is not used) */
+	ulonglong2 *gl = reinterpret_cast<ulonglong2 *>(a.scratch) + tid * (i64)(4 * a.cap_list + 2 * a.cap_mem);
+	Intv *mem = reinterpret_cast<Intv *>(gl + 2 * a.cap_list) + a.cap_list;
+
+	int rid = -1, len = 0, pass = 2, st = ST_IDLE, x = 0, k2 = 0, old_n = 0;
+	int sx = 0, min_intv = 1, i = 0, j = 0, n_prev = 0, n_curr = 0, rev_first = 0, mem_n = 0, m1_n = 0, last_start = 0, ret = 0;
+	int pl = 0;
+	u32 cm = 0, rm = 0;            /* short candidates: of the list being built / still to visit in this step */
+	bool cur_short = false;        /* the candidate being extended came from the mask: e0..e2 are stale */
+	const uint8_t *q = 0;
+	u64 ik0 = 0, ik1 = 0, ik2 = 0, curr_last_x2 = 0;
+	u32 ikend = 0, pend = 0;
+	u64 e0 = 0, e1 = 0, e2 = 0;
+	u64 touches = 0;
+	u32 overflow = 0;
+
+	for (;;) {
+		bool need = false;
+		int back = 0;
+		for (;;) {
+			if (st == ST_IDLE) {
+				if (pass == 0) {
+					while (x < len && QISN(x)) ++x;
+					if (x >= len) { pass = 1; k2 = 0; old_n = mem_n; continue; }
+					sx = x; min_intv = 1;
+				} else if (pass == 1) {
+					bool found = false;
+					while (k2 < old_n) {
+						Intv p = ld_intv(mem + k2); ++k2;
+						int s = (int)(p.info >> 32), e = (int)(u32)p.info;
+						if (e - s < a.split_len || p.x2 > (u64)a.split_width) continue;
+						sx = (s + e) >> 1; min_intv = (int)p.x2 + 1; found = true;
+						break;
+					}
+					if (!found) { pass = 2; continue; }
+				} else {
+					if (rid >= 0) {
+						const int n3 = a.n3 ? a.n3[rid] : 0;
+						const i64 base = (i64)atomicAdd(a.n_intv, (u64)(mem_n + n3));
+						a.intv_beg[rid] = base; a.intv_n[rid] = mem_n + n3;
+						if (base + mem_n + n3 > a.cap_intv) overflow |= 1;
+						else {
+							Intv *dst = reinterpret_cast<Intv *>(a.intv) + base;
+							const Intv *s3 = a.stage3 + (i64)rid * a.cap3;
+							for (int e = 0; e < mem_n; ++e) { Intv p = ld_intv(mem + e); st_intv(dst + e, p.x0, p.x1, p.x2, p.info); }
+							for (int e = 0; e < n3; ++e) { Intv p = ld_intv(s3 + e); st_intv(dst + mem_n + e, p.x0, p.x1, p.x2, p.info); }
+						}
+					}
+					rid = atomicAdd(a.next_read, 1);
+					if (rid >= a.n_reads) { rid = -1; st = ST_NONE; break; }
+					const i64 o = a.off[rid];
+					len = (int)(a.off[rid + 1] - o);
+					pass = 0; x = 0; mem_n = 0;
+					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
+					{
+						const u32 *g = reinterpret_cast<const u32 *>(a.codes + (o & ~(i64)3));
+						u32 *d = reinterpret_cast<u32 *>(const_cast<uint8_t *>(sq));
+						const int nw = ((int)(o & 3) + len + 3) >> 2;
+						for (int w = 0; w < nw; ++w) d[w] = g[w];
+						q = sq + (o & 3);
+						const int nwp = ((len + 15) >> 4) + 1;
+						const u32 *gp = a.packed + (o >> 4) + 2 * (i64)rid;
+						for (int w = 0; w < nwp; ++w) sp[w] = gp[w];
+					}
+					continue;
+				}
+				INIT_INTV(QBASE(sx), ik0, ik1, ik2);
+				ikend = (u32)sx + 1;
+				i = sx + 1; n_curr = 0; cm = 0; m1_n = 0; st = ST_FWD;
+				continue;
+			}
+			if (st == ST_FWD) {
+				if (i < len && !QISN(i)) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; cur_short = false; break; }
+				PUSH_CAND((int)ikend - sx + 1, ik0, ik1, ik2, ikend);
+				TURN_AROUND();
+				continue;
+			}
+			if (st == ST_BWD) {
+				const int c = i < 0 ? -1 : (QISN(i) ? -1 : QBASE(i));
+				if (c < 0) {
+					if (m1_n == 0 || i + 1 < last_start) {
+						if (n_prev > 0) {   /* the longest candidate; one from the mask is shorter than min_seed_len */
+							u64 p0, p1, p2; u32 pe;
+							ENT_LD(pl, rev_first ? n_prev - 1 : 0, p0, p1, p2, pe);
+							EMIT(p0, p1, p2, i + 1, pe);
+						}
+						++m1_n; last_start = i + 1;
+					}
+					CALL_DONE();
+					continue;
+				}
+				if (j < n_prev) {
+					ENT_LD(pl, rev_first ? n_prev - 1 - j : j, e0, e1, e2, pend);
+					cur_short = false; need = true; back = 1;
+					break;
+				}
+				if (rm) {
+					const int b = 31 - __clz(rm);
+					rm ^= 1u << b;
+					pend = (u32)(sx + 1 + b);
+					cur_short = true; need = true; back = 1;
+					break;
+				}
+				if (n_curr == 0 && cm == 0) { CALL_DONE(); continue; }
+				pl ^= 1;
+				n_prev = n_curr; n_curr = 0; rm = cm; cm = 0; rev_first = 0; --i; j = 0;
+				continue;
+			}
+			break; /* ST_NONE */
+		}
+
+		if (__all_sync(FULL_MASK, st == ST_NONE)) break;
+		if (!need) continue;
+
+		const int cq = QBASE(i);
+		u64 o_s, o_o, o_x2;
+		{
+			const int rlen = back ? (int)pend - i : i + 1 - sx;
+			const bool tab = rlen <= ktk;
+			u32 tidx = 0, ct;
+			int t12;
+			if (tab) {
+				const int pos = back ? i : sx;
+				const u32 win = __funnelshift_r(sp[pos >> 4], sp[(pos >> 4) + 1], (u32)(pos & 15) << 1);
+				tidx = ktab_off(rlen) + (win & ((1u << (2 * rlen)) - 1u));
+			}
+			/* a candidate from the mask passes stale (valid) interval registers; its lane is a table lane, which ignores them */
+			extend_step3(ix, back ? e0 : e1, back ? e1 : e0, e2, back ? cq : 3 - cq, tab, tidx, back, t12, o_s, o_o, o_x2, ct);
+			touches += cur_short ? (u64)(1u + (ct >> KTAB_BT_SHIFT)) : (u64)t12;
+		}
+
+		if (st == ST_FWD) {                 /* bwt.c:307-316 */
+			bool stop = false;
+			if (o_x2 != ik2) {
+				PUSH_CAND((int)ikend - sx + 1, ik0, ik1, ik2, ikend);
+				if (o_x2 < (u64)min_intv) stop = true;
+			}
+			if (stop) TURN_AROUND();
+			else {
+				ik0 = o_o; ik1 = o_s; ik2 = o_x2; ikend = (u32)i + 1;
+				++i;
+				if (i == len) {
+					PUSH_CAND((int)ikend - sx + 1, ik0, ik1, ik2, ikend);
+					TURN_AROUND();
+				}
+			}
+		} else {                            /* ST_BWD, bwt.c:331-343 */
+			const bool first = n_curr == 0 && cm == 0;
+			if (o_x2 < (u64)min_intv) {
+				if (first && (m1_n == 0 || i + 1 < last_start)) {
+					if (!cur_short) EMIT(e0, e1, e2, i + 1, pend);
+					++m1_n; last_start = i + 1;
+				}
+			} else if (first || o_x2 != curr_last_x2) {
+				PUSH_CAND((int)pend - i + 1, o_s, o_o, o_x2, pend);
+				curr_last_x2 = o_x2;
+			}
+			if (!cur_short) ++j;
+		}
+	}
+	{
+		u64 t = touches;
+		for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(FULL_MASK, t, d);
+		if ((threadIdx.x & 31) == 0 && t) atomicAdd(a.occ_touches, t);
+		u32 f = __reduce_or_sync(FULL_MASK, overflow);
+		if ((threadIdx.x & 31) == 0 && f) atomicOr(a.flags, f);
+	}
+}
+#endif /* !K1_PACKED8 */
 
 /* K1b: one lane per read: sort the read's intervals by info, size and fill its share of the seed pool */
 __global__ void __launch_bounds__(K1B_THREADS)

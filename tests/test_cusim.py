@@ -21,8 +21,11 @@ def test_emulated_kernels_sam_vs_reference(data, name, ref, kw, extra):
     assert run_sam(CUSIMBIN, args) == ref_sam(args)
 
 
-def test_emulated_seed_stage_buffers_equal_oracle(data):
-    """bwag_seed of the emulated CUDA kernels vs the CPU oracle, buffer by buffer (intervals and SA positions)."""
+@pytest.mark.parametrize("compact", ["1", "0"])
+def test_emulated_seed_stage_buffers_equal_oracle(data, monkeypatch, compact):
+    """bwag_seed of the emulated CUDA kernels vs the CPU oracle, buffer by buffer (intervals and SA positions); compact: K1 with its
+    short candidates as mask bits (k_smem_c, the default) or with every candidate as a list entry (k_smem)."""
+    monkeypatch.setenv("BWA_B200_K1_COMPACT", compact)
     import ctypes as C
     import os
     import bwa_b200
@@ -45,6 +48,10 @@ def test_emulated_seed_stage_buffers_equal_oracle(data):
     assert len(set(t)) == 1 and t[0] > 0, t   # the Occ-block count (as the reference would touch them) is the oracle's, table or not
     par11 = SeedPar(11, 17, 10, 500, 20)   # a seed length below the table depth + 1: the third pass jumps min_seed_len bases only
     assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=6) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
+    t8 = []
+    par8 = SeedPar(8, 12, 10, 500, 20)     # a table deeper than the seed length: candidates of 8..10 bases keep their intervals (they can be results)
+    assert seed_stage(S, idx.bwt, l_pac, idx.pac, codes, off, par8, ktab=10, touches=t8) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par8, touches=t8)
+    assert t8[0] == t8[1], t8
 
 
 def test_batches_in_flight_keep_order_and_content(data, monkeypatch):

@@ -97,8 +97,11 @@ def test_library_call_and_dense_sa(data):
 from stage_abi import SeedPar, load_reads_as_codes, seed_stage
 
 
-def test_seed_stage_buffers_equal_oracle(data):
-    """bwag_seed of the CUDA library vs the CPU oracle: every interval (x0,x1,x2,info) and every suffix-array position."""
+@pytest.mark.parametrize("compact", ["1", "0"])
+def test_seed_stage_buffers_equal_oracle(data, monkeypatch, compact):
+    """bwag_seed of the CUDA library vs the CPU oracle: every interval (x0,x1,x2,info) and every suffix-array position; with K1's
+    compact candidate lists (k_smem_c) and without (k_smem)."""
+    monkeypatch.setenv("BWA_B200_K1_COMPACT", compact)
     fa, fqs = data.reads("stress", tag="gse", n=4000, seed=3, err=(0.016, 0.002, 0.002), chimeric=0.05)
     L = bwa_b200.lib()
     O = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
@@ -115,6 +118,10 @@ def test_seed_stage_buffers_equal_oracle(data):
     assert len(set(t)) == 1 and t[0] > 0, t   # the roofline's numerator (reference-equivalent Occ-block touches) is the oracle's, table or not
     par11 = SeedPar(11, 17, 10, 500, 20)   # seed length below the table depth: the third pass may only jump min_seed_len bases
     assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par11, ktab=13) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par11)
+    t8 = []
+    par8 = SeedPar(8, 12, 10, 500, 20)     # candidates of 8..10 bases can be results: they keep their intervals
+    assert seed_stage(L, idx.bwt, l_pac, idx.pac, codes, off, par8, ktab=10, touches=t8) == seed_stage(O, idx.bwt, l_pac, idx.pac, codes, off, par8, touches=t8)
+    assert t8[0] == t8[1], t8
 
 
 def test_index_builder_identical_to_bwa_index(data, tmp_path):
