@@ -287,7 +287,7 @@ def main():
         a.cpu_sample = 1_000_000   # ~10 s of `bwa mem -t 16`: the whole step of the default workload
     wl = dict(WORKLOADS[a.workload]) if a.workload else {}
     if wl:
-        a.layout, a.read_len, a.reads = wl["layout"], wl["read_len"], wl["reads"]
+        a.layout, a.read_len, a.reads = wl["layout"], wl["read_len"], int(os.environ.get("BWA_B200_BENCH_WL_READS", wl["reads"]))
         a.ref_mbp = wl.get("ref_mbp", a.ref_mbp)
         a.cpu_sample = min(a.cpu_sample, max(200, 3_000_000 // a.read_len))
     wl_kw = dict(ref=wl.get("ref", "random"), err=wl.get("err", (0.008, 0.001, 0.001)), chimeric=wl.get("chimeric", 0.0))
@@ -496,8 +496,9 @@ def main():
         try:   # DRAM bytes of the seeding kernels per launch, from the committed ncu --set full captures
             tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             # captured on the default configuration (short-string table depth 14) of the 3 Gbp / 150-bp workload: valid there only
+            k1 = "k_smem" if os.environ.get("BWA_B200_K1_COMPACT") == "0" else "k_smem_c"   # the seeding kernel in use (compact candidate lists by default)
             if a.read_len == 150 and a.ref_mbp == 3000 and os.environ.get("BWA_B200_KTAB") is None:
-                traffic = (tr["k_smem"]["dram_bytes_per_read"] + tr["k_smem_fwd"]["dram_bytes_per_read"]) * n_reads
+                traffic = (tr[k1]["dram_bytes_per_read"] + tr["k_smem_fwd"]["dram_bytes_per_read"]) * n_reads
         except Exception:
             pass
         line = {
@@ -515,9 +516,9 @@ def main():
             "e2e": {"value": total_reads / dt_max, "unit": "reads/s", "h2d_bytes_per_step": st["h2d_bytes"] // a.steps, "d2h_bytes_per_step": st["d2h_bytes"] // a.steps},
             "gpu_launches": st["n_launch"],
             "clocks": clocks,
-            "roofline": {"kernel": "k_smem_fwd + k_smem + k_seed_post (SMEM seeding over the FM-index)", "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_smem_fwd + %s + k_seed_post (SMEM seeding over the FM-index)" % ("k_smem" if os.environ.get("BWA_B200_K1_COMPACT") == "0" else "k_smem_c"), "bound": "hbm", "achieved": smem_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": smem_gbs / hbm_peak if hbm_peak else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes of k_smem + k_smem_fwd per launch from the committed ncu --set full capture (profiles/r2_traffic.json), scaled to the reads of one launch; null when the workload is not the captured one",
+                         "traffic_note": "DRAM bytes of the seeding kernel + k_smem_fwd per launch from the committed ncu --set full capture (profiles/r2_traffic.json), scaled to the reads of one launch; null when the workload is not the captured one",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": "64 B x %d Occ-block touches per step" % (st["occ_touches"] // a.steps)},
             "kernels_ms_per_step": {k: ks.get(k, 0.0) / KSTEPS for k in ("ms_smem", "ms_sa", "ms_chain", "ms_extend", "ms_global", "ms_tail", "ms_localsw", "ms_h2d", "ms_d2h")},

@@ -713,6 +713,19 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 	i64 cap_intv = (i64)n * 16 + b->total_bases / 4 + 1024, cap_seeds = (i64)n * 32 + b->total_bases / 2 + 4096;
 	if (getenv("BWA_B200_TEST_SMALL_POOLS")) { cap_intv = n / 2 + 8; cap_seeds = n / 2 + 8; }   /* test hook: start with pools that overflow, so that the repeat-with-reported-sizes path runs */
 	int cap_list = b->max_len + 1, cap_mem = 2 * b->max_len + 64;
+	/* k_smem_c (compact candidate lists, bwag_smem.cu) needs the short-string table; BWA_B200_K1_COMPACT=0 selects k_smem */
+	bool k1c = false;
+#ifndef K1_PACKED8
+	{
+		const char *e = getenv("BWA_B200_K1_COMPACT");
+		k1c = (e ? atoi(e) != 0 : K1_COMPACT_DEFAULT) && c->ix.ktab_k > 0;
+	}
+	/* k_smem_c checks every list and result append, so long reads start with scratch for what they typically need (a few
+	 * candidates with an interval per list, a result per ~4 bases) instead of the worst case: more lanes fit the scratch budget.
+	 * A lane that runs out sets a flag and the stage is repeated with the worst-case sizes. */
+	if (k1c && b->max_len > 2048) { cap_list = 1024; cap_mem = b->max_len / 4 + 256; }
+	if (k1c && getenv("BWA_B200_TEST_SMALL_K1")) { cap_list = 9; cap_mem = 3; }   /* test hook: the repeat-with-larger-scratch path (9: the shared slots + one entry of global tail) */
+#endif
 	SeedArgs a;
 	memset(&a, 0, sizeof(a));
 	for (int attempt = 0;; ++attempt) {
@@ -731,15 +744,13 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 #ifdef K1_NO_QSMEM
 		qstride = 0; pstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16;
 #endif
-		if (smem > K1_SMEM_MAX) { qstride = 0; pstride = 0; nstride = 0; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
-		/* k_smem_c (compact candidate lists) needs the table and both copies of the read in shared memory; BWA_B200_K1_COMPACT=0 selects k_smem */
-		bool k1c = false;
-#ifndef K1_PACKED8
-		{
-			const char *e = getenv("BWA_B200_K1_COMPACT");
-			k1c = (e ? atoi(e) != 0 : K1_COMPACT_DEFAULT) && qstride && pstride;
-		}
-#endif
+		bool want_pack = pstride != 0;
+		if (k1c) {   /* list heads + the packed copy; reads too long for that are read in place (pstride = 0) */
+			qstride = 0;
+			smem = (size_t)2 * K1C_SLOTS * K1_THREADS * 16 + (size_t)K1_THREADS * pstride;
+			if (smem > 44 * 1024) { pstride = 0; smem = (size_t)2 * K1C_SLOTS * K1_THREADS * 16; }   /* the shared copy must not cost a resident block (registers allow 5 per SM): reads up to ~350 bases */
+		} else
+		if (smem > K1_SMEM_MAX) { qstride = 0; pstride = 0; nstride = 0; want_pack = false; smem = (size_t)2 * K1_SLOTS * K1_THREADS * 16; }   /* very long reads stay in global memory */
 		int grid;
 #ifdef BWAG_CUSIM
 		grid = 2;
@@ -757,7 +768,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		}
 #endif
 		const int cap3 = b->max_len / (par->min_seed_len + 1) + 2;
-		size_t per_group = (size_t)(4 * cap_list + 2 * cap_mem) * 16;
+		size_t per_group = (size_t)((k1c ? 2 : 4) * cap_list + 2 * cap_mem) * 16;   /* k_smem_c has no per-call result array */
 		{   /* keep the per-group scratch within ~6 GB: very long reads get fewer groups */
 			size_t budget = (size_t)6 << 30;
 			i64 max_groups = (i64)(budget / per_group);
@@ -769,7 +780,7 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		if (buf_reserve(&c->s_k1, per_group * (size_t)grid * groups_per_block)) return 1;
 		if (buf_reserve(&c->s_k1f, 32 * (size_t)cap3 * (size_t)n + 64) || buf_reserve(&c->s_n3, sizeof(int) * (size_t)(n + 1))) return 1;
 		const size_t pack_words = (size_t)(b->total_bases >> 4) + 2 * (size_t)n + 8, nmask_words = nstride ? (size_t)(b->total_bases >> 5) + 2 * (size_t)n + 8 : 0;
-		if (pstride && buf_reserve(&c->s_pack, 4 * (pack_words + nmask_words))) return 1;
+		if (want_pack && buf_reserve(&c->s_pack, 4 * (pack_words + nmask_words + (size_t)n + 8))) return 1;
 		if (buf_reserve(&b->d_intv_beg, sizeof(i64) * (size_t)(n + 1)) || buf_reserve(&b->d_intv_n, sizeof(int) * (size_t)(n + 1)) ||
 		    buf_reserve(&b->d_intv, 32 * (size_t)cap_intv) || buf_reserve(&b->d_seed_beg, 8 * (size_t)cap_intv) || buf_reserve(&b->d_rbeg, 8 * (size_t)cap_seeds)) return 1;
 		a.codes = (const uint8_t *)b->d_codes.p; a.off = (const i64 *)b->d_off.p; a.n_reads = n;
@@ -781,9 +792,9 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		a.next_read = &c->d_cnt->next_read; a.n_intv = &c->d_cnt->n_intv; a.n_seeds = &c->d_cnt->n_seeds; a.occ_touches = &c->d_cnt->occ_touches; a.flags = &c->d_cnt->flags;
 		if (reset_counters(c)) return 1;
 		CK(cudaEventRecord(c->ev0, c->stream));
-		if (pstride) {   /* the packed copies K1's table lookups key on */
-			a.packed = (const u32 *)c->s_pack.p; a.nmask = nstride ? (const u32 *)c->s_pack.p + pack_words : 0;
-			BWAG_LAUNCH(k_pack_reads, (n + 127) / 128, 128, 0, c->stream, a.codes, a.off, n, (u32 *)c->s_pack.p, nstride ? (u32 *)c->s_pack.p + pack_words : (u32 *)0);
+		if (want_pack) {   /* the packed copies K1's table lookups key on, and which reads have an ambiguous base */
+			a.packed = (const u32 *)c->s_pack.p; a.nmask = nstride ? (const u32 *)c->s_pack.p + pack_words : 0; a.hasn = (const u32 *)c->s_pack.p + pack_words + nmask_words;
+			BWAG_LAUNCH(k_pack_reads, (n + 127) / 128, 128, 0, c->stream, a.codes, a.off, n, (u32 *)c->s_pack.p, nstride ? (u32 *)c->s_pack.p + pack_words : (u32 *)0, (u32 *)c->s_pack.p + pack_words + nmask_words);
 			CK(cudaGetLastError());
 			++c->st.n_launch;
 		}
@@ -805,13 +816,15 @@ extern "C" int bwag_seed(bwag_batch_t *b, const bwag_seed_par_t *par, bwag_seeds
 		CK(cudaGetLastError());
 		if (fetch_counters(c)) return 1;
 		c->st.ms_smem += elapsed_at(c, "smem", __LINE__); c->st.n_launch += 2;
-		if (!(c->h_cnt->flags & 9u)) break;
+		if (!(c->h_cnt->flags & 41u)) break;
 		if (attempt >= 6) return set_err("seeding: output pools keep overflowing (intervals %llu, seeds %llu)", (unsigned long long)c->h_cnt->n_intv, (unsigned long long)c->h_cnt->n_seeds);
 		if (c->h_cnt->flags & 1u) { /* pools too small: the counters say how much is needed */
 			if ((i64)c->h_cnt->n_intv > cap_intv) cap_intv = (i64)c->h_cnt->n_intv + 1024;
 			if ((i64)c->h_cnt->n_seeds > cap_seeds) cap_seeds = (i64)c->h_cnt->n_seeds + 4096;
 		}
-		if (c->h_cnt->flags & 8u) cap_mem *= 4;
+		if (c->h_cnt->flags & 8u) cap_mem = cap_mem * 4 < 2 * b->max_len + 64 || !k1c ? cap_mem * 4 : 2 * b->max_len + 64;
+		if (c->h_cnt->flags & 32u) cap_list = b->max_len + 1;
+		if (getenv("BWA_B200_PROFILE")) fprintf(stderr, "[prof] seeding repeated (flags %u): pools %lld intervals / %lld seeds, per-lane scratch %d list entries / %d results\n", c->h_cnt->flags, (long long)cap_intv, (long long)cap_seeds, cap_list, cap_mem);
 	}
 	c->st.occ_touches += c->h_cnt->occ_touches;
 	const i64 n_intv = (i64)c->h_cnt->n_intv, n_seeds = (i64)c->h_cnt->n_seeds;

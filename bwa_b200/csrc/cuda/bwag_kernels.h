@@ -13,6 +13,7 @@
 #endif
 #endif
 //       /* candidate-list entries per list kept in shared memory */
+#define K1C_SLOTS 8   /* the same for k_smem_c, which keeps no byte copy of the read in shared memory and has the room */
 #define K1B_THREADS 128
 #define K2_THREADS 128
 #define K3_THREADS 128
@@ -38,6 +39,7 @@ struct SeedArgs {
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
 	const u32 *packed;                             /* k_pack_reads: 2-bit copy of every read, read r at word (off[r] >> 4) + 2 r */
 	const u32 *nmask;                              /* k_pack_reads: one bit per base (ambiguous), read r at word (off[r] >> 5) + 2 r; variant K1_PACKED8 only */
+	const u32 *hasn;                               /* k_pack_reads: per read, non-zero if it has an ambiguous base (k_smem_c looks at the bytes of such reads only) */
 	/* outputs */
 	i64 *intv_beg; int *intv_n; bwtintv_t *intv; i64 *seed_beg; i64 *rbeg;
 	i64 cap_intv, cap_seeds;
@@ -160,7 +162,7 @@ __global__ void k_localsw(DevIndex ix, SwArgs a);
 __global__ void k_localsw_warp(DevIndex ix, SwArgs a);
 __global__ void k_occ_pack(DevIndex ix, uint4 *bwt, u64 n_blocks);
 __global__ void k_ktab_build(DevIndex ix, ulonglong2 *tab, int K);
-__global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask);
+__global__ void k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask, u32 *hasn);
 __global__ void k_smem(DevIndex ix, SeedArgs a);
 #ifndef K1_PACKED8
 __global__ void k_smem_c(DevIndex ix, SeedArgs a);   /* short candidates as mask bits, matches appended at once (bwag_smem.cu) */

@@ -309,7 +309,7 @@ k_smem_fwd(DevIndex ix, SeedArgs a)
  * looked up): the keys of the short-string table.  One lane per read, once per batch; K1 used to build this itself, one lane
  * at a time (5 % of its instructions at 1.1 active lanes, profiles/r2_k_smem_by_source_line.txt).  Read r's words start at
  * (off[r] >> 4) + 2 r. */
-__global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask)
+__global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const i64 *off, int n_reads, u32 *packed, u32 *nmask, u32 *hasn)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
@@ -318,11 +318,13 @@ __global__ void __launch_bounds__(128) k_pack_reads(const uint8_t *codes, const 
 	const uint8_t *q = codes + o;
 	u32 *dst = packed + (o >> 4) + 2 * (i64)r;
 	const int nwp = ((len + 15) >> 4) + 1;
+	u32 any_n = 0;
 	for (int w = 0; w < nwp; ++w) {
 		u32 pw = 0;
-		for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) pw |= (u32)(q[idx] & 3) << (2 * t); }
+		for (int t = 0; t < 16; ++t) { const int idx = (w << 4) + t; if (idx < len) { pw |= (u32)(q[idx] & 3) << (2 * t); any_n |= (u32)(q[idx] > 3); } }
 		dst[w] = pw;
 	}
+	if (hasn) hasn[r] = any_n;
 	if (nmask) {   /* one bit per base: ambiguous (variant K1_PACKED8, which keeps no byte copy of the read); read r's words start at (off[r] >> 5) + 2 r */
 		u32 *dn = nmask + (o >> 5) + 2 * (i64)r;
 		const int nwn = (len + 31) >> 5;
@@ -611,8 +613,15 @@ k_smem(DevIndex ix, SeedArgs a)
 /* a candidate for the next backward step (string of NEXT_LEN bases then): a mask bit or a list entry */
 #define PUSH_CAND(NEXT_LEN, X0, X1, X2, E) do { \
 		if ((NEXT_LEN) <= kc) cm |= 1u << ((int)(E) - sx - 1); \
-		else if (n_curr < a.cap_list) { ENT_ST(pl ^ 1, n_curr, X0, X1, X2, E); ++n_curr; } else overflow |= 8; \
+		else if (n_curr < a.cap_list) { CENT_ST(pl ^ 1, n_curr, X0, X1, X2, E); ++n_curr; } else overflow |= 32; \
 	} while (0)
+#define CQISN(i_) (hn && q[i_] > 3)
+#define SPW(w_) (a.pstride ? sp_sh[w_] : spg[w_])   /* a word of the packed copy: shared, or in place (uniform choice) */
+#define CQBASE(i_) ((int)(SPW((i_) >> 4) >> (((i_) & 15) << 1) & 3u))
+#define CENT_ST(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); const ulonglong2 v_ = pack_ent(X0, X1, X2, E); ENT_COUNT(i_ < K1C_SLOTS ? 0 : i_); \
+		if (i_ < K1C_SLOTS) sl[(l_ * K1C_SLOTS + i_) * nthr] = v_; else gl[l_ * a.cap_list + i_] = v_; } while (0)
+#define CENT_LD(l, idx, X0, X1, X2, E) do { const int l_ = (l), i_ = (idx); ulonglong2 v_; ENT_COUNT(i_ < K1C_SLOTS ? 0 : i_); \
+		if (i_ < K1C_SLOTS) v_ = sl[(l_ * K1C_SLOTS + i_) * nthr]; else v_ = gl[l_ * a.cap_list + i_]; unpack_ent(v_, X0, X1, X2, E); } while (0)
 
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k_smem_c(DevIndex ix, SeedArgs a)
@@ -623,16 +632,20 @@ k_smem_c(DevIndex ix, SeedArgs a)
 	extern __shared__ ulonglong2 k1_dyn[];
 	ulonglong2 *sl = k1_dyn;
 #endif
-	/* shared: as k_smem: [2 lists][K1_SLOTS][K1_THREADS] entries, K1_THREADS read slots of qstride bytes, K1_THREADS packed copies of pstride bytes */
-	const uint8_t *sq = reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)threadIdx.x * a.qstride;
-	u32 *sp = reinterpret_cast<u32 *>(const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(sl + 2 * K1_SLOTS * K1_THREADS) + (size_t)K1_THREADS * a.qstride + (size_t)threadIdx.x * a.pstride));
-	const int ktk = ix.ktab_k;                                           /* the host launches this kernel only with the table and both copies of the reads in shared memory */
+	/* shared: [2 lists][K1C_SLOTS][threads] entries, then one 2-bit packed copy of pstride bytes per lane (pstride = 0: reads too long for
+	 * that; the copy k_pack_reads left in global memory is read in place).  No byte copy of the read: bases come from the packed
+	 * copy, and the bytes (global memory) are looked at only in reads that have an ambiguous base at all (hasn). */
+	const int nthr = blockDim.x;
+	u32 *sp_sh = reinterpret_cast<u32 *>(reinterpret_cast<uint8_t *>(sl + 2 * K1C_SLOTS * nthr) + (size_t)threadIdx.x * a.pstride);
+	const u32 *spg = a.packed;
+	bool hn = false;
+	const int ktk = ix.ktab_k;                                           /* the host launches this kernel only with a table */
 	const int kc = ktk < a.min_seed_len ? ktk : a.min_seed_len;
 	sl += threadIdx.x;
 	const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-	/* per-lane global scratch, laid out as for k_smem (the per-call result array in the middle is not used) */
-	ulonglong2 *gl = reinterpret_cast<ulonglong2 *>(a.scratch) + tid * (i64)(4 * a.cap_list + 2 * a.cap_mem);
-	Intv *mem = reinterpret_cast<Intv *>(gl + 2 * a.cap_list) + a.cap_list;
+	/* per-lane global scratch (units of 16 bytes): the tails of the two lists (cap_list entries each), then the read's interval list (cap_mem x 32 B) */
+	ulonglong2 *gl = reinterpret_cast<ulonglong2 *>(a.scratch) + tid * (i64)(2 * a.cap_list + 2 * a.cap_mem);
+	Intv *mem = reinterpret_cast<Intv *>(gl + 2 * a.cap_list);
 
 	int rid = -1, len = 0, pass = 2, st = ST_IDLE, x = 0, k2 = 0, old_n = 0;
 	int sx = 0, min_intv = 1, i = 0, j = 0, n_prev = 0, n_curr = 0, rev_first = 0, mem_n = 0, m1_n = 0, last_start = 0, ret = 0;
@@ -652,7 +665,7 @@ k_smem_c(DevIndex ix, SeedArgs a)
 		for (;;) {
 			if (st == ST_IDLE) {
 				if (pass == 0) {
-					while (x < len && QISN(x)) ++x;
+					while (x < len && CQISN(x)) ++x;
 					if (x >= len) { pass = 1; k2 = 0; old_n = mem_n; continue; }
 					sx = x; min_intv = 1;
 				} else if (pass == 1) {
@@ -683,37 +696,36 @@ k_smem_c(DevIndex ix, SeedArgs a)
 					const i64 o = a.off[rid];
 					len = (int)(a.off[rid + 1] - o);
 					pass = 0; x = 0; mem_n = 0;
-					if (len > a.cap_list || len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
+					if (len >= (1 << 23)) { overflow |= 8; pass = 2; len = 0; }
+					q = a.codes + o;
+					hn = a.hasn[rid] != 0;
 					{
-						const u32 *g = reinterpret_cast<const u32 *>(a.codes + (o & ~(i64)3));
-						u32 *d = reinterpret_cast<u32 *>(const_cast<uint8_t *>(sq));
-						const int nw = ((int)(o & 3) + len + 3) >> 2;
-						for (int w = 0; w < nw; ++w) d[w] = g[w];
-						q = sq + (o & 3);
-						const int nwp = ((len + 15) >> 4) + 1;
 						const u32 *gp = a.packed + (o >> 4) + 2 * (i64)rid;
-						for (int w = 0; w < nwp; ++w) sp[w] = gp[w];
+						if (a.pstride) {
+							const int nwp = ((len + 15) >> 4) + 1;
+							for (int w = 0; w < nwp; ++w) sp_sh[w] = gp[w];
+						} else spg = gp;
 					}
 					continue;
 				}
-				INIT_INTV(QBASE(sx), ik0, ik1, ik2);
+				INIT_INTV(CQBASE(sx), ik0, ik1, ik2);
 				ikend = (u32)sx + 1;
 				i = sx + 1; n_curr = 0; cm = 0; m1_n = 0; st = ST_FWD;
 				continue;
 			}
 			if (st == ST_FWD) {
-				if (i < len && !QISN(i)) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; cur_short = false; break; }
+				if (i < len && !CQISN(i)) { e0 = ik0; e1 = ik1; e2 = ik2; need = true; back = 0; cur_short = false; break; }
 				PUSH_CAND((int)ikend - sx + 1, ik0, ik1, ik2, ikend);
 				TURN_AROUND();
 				continue;
 			}
 			if (st == ST_BWD) {
-				const int c = i < 0 ? -1 : (QISN(i) ? -1 : QBASE(i));
+				const int c = i < 0 ? -1 : (CQISN(i) ? -1 : CQBASE(i));
 				if (c < 0) {
 					if (m1_n == 0 || i + 1 < last_start) {
 						if (n_prev > 0) {   /* the longest candidate; one from the mask is shorter than min_seed_len */
 							u64 p0, p1, p2; u32 pe;
-							ENT_LD(pl, rev_first ? n_prev - 1 : 0, p0, p1, p2, pe);
+							CENT_LD(pl, rev_first ? n_prev - 1 : 0, p0, p1, p2, pe);
 							EMIT(p0, p1, p2, i + 1, pe);
 						}
 						++m1_n; last_start = i + 1;
@@ -722,7 +734,7 @@ k_smem_c(DevIndex ix, SeedArgs a)
 					continue;
 				}
 				if (j < n_prev) {
-					ENT_LD(pl, rev_first ? n_prev - 1 - j : j, e0, e1, e2, pend);
+					CENT_LD(pl, rev_first ? n_prev - 1 - j : j, e0, e1, e2, pend);
 					cur_short = false; need = true; back = 1;
 					break;
 				}
@@ -744,7 +756,7 @@ k_smem_c(DevIndex ix, SeedArgs a)
 		if (__all_sync(FULL_MASK, st == ST_NONE)) break;
 		if (!need) continue;
 
-		const int cq = QBASE(i);
+		const int cq = CQBASE(i);
 		u64 o_s, o_o, o_x2;
 		{
 			const int rlen = back ? (int)pend - i : i + 1 - sx;
@@ -753,7 +765,7 @@ k_smem_c(DevIndex ix, SeedArgs a)
 			int t12;
 			if (tab) {
 				const int pos = back ? i : sx;
-				const u32 win = __funnelshift_r(sp[pos >> 4], sp[(pos >> 4) + 1], (u32)(pos & 15) << 1);
+				const u32 win = __funnelshift_r(SPW(pos >> 4), SPW((pos >> 4) + 1), (u32)(pos & 15) << 1);
 				tidx = ktab_off(rlen) + (win & ((1u << (2 * rlen)) - 1u));
 			}
 			/* a candidate from the mask passes stale (valid) interval registers; its lane is a table lane, which ignores them */

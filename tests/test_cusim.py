@@ -146,3 +146,8 @@ def test_pool_overflow_is_repeated_not_corrupting(data, monkeypatch):
     want = ref_sam(args)
     monkeypatch.setenv("BWA_B200_TEST_SMALL_POOLS", "1")
     assert run_sam(CUSIMBIN, args) == want
+    # K1's per-lane scratch (candidate-list tails, results of a read): long reads start below the worst case and the stage repeats with more
+    monkeypatch.delenv("BWA_B200_TEST_SMALL_POOLS")
+    monkeypatch.setenv("BWA_B200_TEST_SMALL_K1", "1")
+    monkeypatch.setenv("BWA_B200_KTAB", "6")
+    assert run_sam(CUSIMBIN, args) == want

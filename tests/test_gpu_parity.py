@@ -182,3 +182,6 @@ def test_pool_overflow_is_repeated_not_corrupting(data, monkeypatch):
         fa, fqs = data.reads(ref, **kw)
         args = extra + ["-K", "100000000", "-t", "8", fa] + fqs
         assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
+    monkeypatch.delenv("BWA_B200_TEST_SMALL_POOLS")
+    monkeypatch.setenv("BWA_B200_TEST_SMALL_K1", "1")   # K1's per-lane scratch starts too small as well: repeated with the worst-case sizes
+    assert run_sam(bwa_b200.CLI_PATH, args) == ref_sam(args)
