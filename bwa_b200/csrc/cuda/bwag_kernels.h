@@ -37,6 +37,7 @@ struct SeedArgs {
 	int pstride;                                   /* bytes of a lane's 2-bit packed copy of the read (0: no short-string table lookups in K1) */
 	int nstride;                                   /* variant K1_PACKED8 only: bytes of a lane's N bitmap (the byte copy of the read is dropped: qstride = 0) */
 	Intv *stage3; int cap3; int *n3; int *next_read3;   /* third-pass seeds: cap3 slots per read, filled by K1f */
+	int post_copies3;                              /* k_smem_c: K1 only reserves the room of the third-pass seeds in the read's slice, K1b (all lanes busy) copies them */
 	const u32 *packed;                             /* k_pack_reads: 2-bit copy of every read, read r at word (off[r] >> 4) + 2 r */
 	const u32 *nmask;                              /* k_pack_reads: one bit per base (ambiguous), read r at word (off[r] >> 5) + 2 r; variant K1_PACKED8 only */
 	const u32 *hasn;                               /* k_pack_reads: per read, non-zero if it has an ambiguous base (k_smem_c looks at the bytes of such reads only) */

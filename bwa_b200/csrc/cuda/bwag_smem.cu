@@ -685,10 +685,15 @@ k_smem_c(DevIndex ix, SeedArgs a)
 						a.intv_beg[rid] = base; a.intv_n[rid] = mem_n + n3;
 						if (base + mem_n + n3 > a.cap_intv) overflow |= 1;
 						else {
+							/* this lane is alone here (the rest of its warp waits): two entries in flight per round trip (four spill); the third-pass
+							 * seeds are appended by K1b, where every lane has a read */
 							Intv *dst = reinterpret_cast<Intv *>(a.intv) + base;
-							const Intv *s3 = a.stage3 + (i64)rid * a.cap3;
-							for (int e = 0; e < mem_n; ++e) { Intv p = ld_intv(mem + e); st_intv(dst + e, p.x0, p.x1, p.x2, p.info); }
-							for (int e = 0; e < n3; ++e) { Intv p = ld_intv(s3 + e); st_intv(dst + mem_n + e, p.x0, p.x1, p.x2, p.info); }
+							int e = 0;
+							for (; e + 2 <= mem_n; e += 2) {
+								const Intv p0 = ld_intv(mem + e), p1 = ld_intv(mem + e + 1);
+								st_intv(dst + e, p0.x0, p0.x1, p0.x2, p0.info); st_intv(dst + e + 1, p1.x0, p1.x1, p1.x2, p1.info);
+							}
+							if (e < mem_n) { const Intv p0 = ld_intv(mem + e); st_intv(dst + e, p0.x0, p0.x1, p0.x2, p0.info); }
 						}
 					}
 					rid = atomicAdd(a.next_read, 1);
@@ -822,6 +827,11 @@ k_seed_post(SeedArgs a)
 	if (n == 0) return;
 	if (a.intv_beg[rid] + n > a.cap_intv) return;   /* K1 ran out of pool space for this read (flag set, the stage is repeated with larger pools): its slice does not exist */
 	Intv *v = reinterpret_cast<Intv *>(a.intv) + a.intv_beg[rid];
+	if (a.post_copies3 && a.n3) {           /* k_smem_c left the tail of the slice for the third pass's seeds (K1f) */
+		const int n3 = a.n3[rid];
+		const Intv *s3 = a.stage3 + (i64)rid * a.cap3;
+		for (int e = 0; e < n3; ++e) { Intv p = ld_intv(s3 + e); st_intv(v + (n - n3) + e, p.x0, p.x1, p.x2, p.info); }
+	}
 	for (int e = 1; e < n; ++e) {           /* insertion sort; lists are short (about 8 entries for 150-bp reads) */
 		Intv p = ld_intv(v + e);
 		int f = e - 1;
