@@ -346,6 +346,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    bound = None
+    if os.environ.get("BWA_B200_BIND", "1" if world > 1 else "0") == "1":   # one process per GPU: stay on the GPU's NUMA node (host workers, lanes, pinned buffers)
+        bound = bwa_b200.bind_to_gpu_node(local_rank)
+        log("[bench] rank %d: %s" % (rank, "bound to the %d CPUs of GPU %d's NUMA node" % (len(bound), local_rank) if bound else "NUMA node of the GPU unknown, not bound"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fa, fq = make_workload(a.workdir, a.ref_mbp, a.reads, a.read_len, 1000, rank, paired, **wl_kw)
@@ -504,7 +508,7 @@ def main():
         line = {
             "metric": "reads_per_sec", "value": total_reads / k_max if k_max > 0 else None, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * dt_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads,
+            "config": {"workload": workload, "parallelism": "reads sharded over %d GPU(s), full index copy per GPU" % world, "host_threads_per_rank": threads, "numa_bound_cpus": len(bound) if bound else None,
                        "l2": "inputs larger than L2 (resident index %.1f GB = Occ blocks + SA sample + pac + short-string table, reads %.0f MB per step)" % (
                            os.path.getsize(fa + ".bwt") / 1e9 * (1.25 + 16.0 / (a.dense_sa or int(os.environ.get("BWA_B200_SA_INTV", "2")))) + 5.7, n_reads * a.read_len / 1e6),
                        "value_definition": "reads / summed CUDA-event time of the seeding, SA, chaining, extension, global-alignment and post-processing (stage 4) kernels, inputs resident in HBM, measured in two extra single-stream passes after the timed region",

@@ -182,6 +182,29 @@ def mem_process_seqs(opt, index, batch, n_processed=0):
     index.L.mem_process_seqs(opt, i.bwt, i.bns, i.pac, n_processed, batch.n, batch.seqs, None)
 
 
+def bind_to_gpu_node(device_index):
+    """Restrict this process (and the threads it starts afterwards: host workers, lanes) to the CPUs of the NUMA node the GPU hangs
+    off (sysfs local_cpulist of its PCI function), so that pinned buffers are first-touched next to the GPU and the copies do not cross
+    the socket link.  Multi-GPU plumbing: one process per GPU.  Returns the CPU list used, or None if it could not be determined."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if len(cpus) < 4:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def run_cli(args, stdout_path, stderr_path=None, binary=None, timeout=None):
     """Run `bwa-b200 mem ...` as a process."""
     with open(stdout_path, "wb") as so:
