@@ -347,7 +347,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     bound = None
-    if os.environ.get("BWA_B200_BIND", "1" if world > 1 else "0") == "1":   # one process per GPU: stay on the GPU's NUMA node (host workers, lanes, pinned buffers)
+    if os.environ.get("BWA_B200_BIND", "0") == "1":   # opt-in: stay on the GPU's NUMA node (host workers, lanes, pinned buffers); measured at N=2: no gain (profiles/r2_final_n2b_*)
         bound = bwa_b200.bind_to_gpu_node(local_rank)
         log("[bench] rank %d: %s" % (rank, "bound to the %d CPUs of GPU %d's NUMA node" % (len(bound), local_rank) if bound else "NUMA node of the GPU unknown, not bound"))
     if world > 1:

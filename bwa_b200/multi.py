@@ -265,7 +265,7 @@ def main(argv=None):
         if not torch.cuda.is_available():
             raise SystemExit("bwa_b200.multi: no CUDA device; there is no CPU path")
         torch.cuda.set_device(local_rank)
-        if world > 1 and os.environ.get("BWA_B200_BIND", "1") == "1":
+        if world > 1 and os.environ.get("BWA_B200_BIND", "0") == "1":   # opt-in (no gain measured on a 2-GPU box whose GPUs share a node)
             bwa_b200.bind_to_gpu_node(local_rank)   # host workers, lanes and pinned buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl" if on_gpu else "gloo", **({"device_id": torch.device("cuda", local_rank)} if on_gpu else {}))
