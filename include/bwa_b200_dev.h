@@ -42,7 +42,8 @@ int bwag_ctx_densify_sa(bwag_ctx_t *ctx, int intv);
  * (bwt.c:262-275) whose result is that short costs one 16-byte lookup instead of two Occ blocks (results unchanged;
  * two thirds of a read's extensions qualify at depth 12).  depth 0 = choose from the index size: floor(log4(BWT length)) - 2,
  * i.e. as deep as strings still occur a few dozen times (14 at 3 Gbp: 358 M entries, 5.7 GB); depth < 0 = remove the table;
- * depth <= 14. */
+ * depth <= 14.  Entries also carry the reference-equivalent Occ-block touch counts of the extensions they replace (forward chain,
+ * last backward step), so the stage's occ_touches counter is what the reference would count, table or not. */
 int bwag_ctx_build_ktab(bwag_ctx_t *ctx, int depth);
 
 /* Verify the resident FM-index against the resident text: for rows first, first + stride, ... the BWT symbol must be the text base

@@ -57,7 +57,7 @@ def _check(binary, data, n_c1, n_stress):
 
 
 def test_device_tail_emulated(data):
-    _check(CUSIMBIN, data, 160, 120)
+    _check(CUSIMBIN, data, 96, 64)
 
 
 def test_device_tail_fasta_input_and_several_chunks(data, tmp_path, monkeypatch):
