@@ -27,6 +27,9 @@
  *   - a finished read appends its (unsorted) interval list to the batch-wide pool with one atomicAdd;
  *     K1b (one lane per read) sorts each list by (start,end) -- ties are identical intervals -- sizes
  *     the seed pool and writes the BWT rows whose suffix-array values K2 resolves.
+ * The list above is k_smem, the first form (and the kernel of the table-less baseline).  The default since round 2 is k_smem_c
+ * (below): the same lock-step design with the short candidates as bits of a mask, matches appended to the read's list at once,
+ * and no byte copy of the read in shared memory -- half the L2 requests, none of the serial global round trips in the divergent part.
  * HBM-latency/bandwidth bound; algorithmic bytes = 64 B x Occ-block touches as the reference counts
  * them (bwt.c:194-197), accumulated per lane and summed into one counter.
  */
