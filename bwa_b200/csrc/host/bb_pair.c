@@ -316,10 +316,15 @@ static inline double pair_term(const mem_opt_t *opt, const mem_pestat_t *pe, int
 		int64_t n = (int64_t)pe->high - pe->low + 1, k;
 		if (n <= 0 || n > 65536) { double ns = (dist - pe->avg) / pe->std; return .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
 		if (n > m->cap) { m->t = bb_realloc(m->t, (size_t)n * sizeof(double)); m->cap = (int)n; }
-		for (k = 0; k < n; ++k) { double ns = ((pe->low + k) - pe->avg) / pe->std; m->t[k] = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
+		memset(m->t, 0xff, (size_t)n * sizeof(double));   /* all-ones = NaN = "not computed yet": the model changes with every batch, and a thread with a handful of pairs must not pay for 65 k erfc + log (the term itself is never NaN: erfc >= 0, log(0) = -inf) */
+		(void)k;
 		m->avg = pe->avg; m->std = pe->std; m->low = pe->low; m->high = pe->high; m->a = opt->a; m->valid = 1;
 	}
-	return m->t[dist - pe->low];
+	{
+		double *slot = &m->t[dist - pe->low], v = *slot;
+		if (v != v) { double ns = (dist - pe->avg) / pe->std; v = *slot = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a; }
+		return v;
+	}
 }
 
 
